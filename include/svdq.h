@@ -1,0 +1,174 @@
+/*
+ * svdq.h — C ABI of libsvdq.so, the B200 (sm_100a) implementation of the SVD-Hybrid merge hot
+ * path of mgradyn/SVD-Quantization-Task-Merging.
+ *
+ * The reference has no FFI: its "operator API" is a set of module-level Python functions
+ * (src/svd_hybrid/*.py, root quantization_utils.py).  Each entry point below names the
+ * reference functions (file:line, relative to the reference repository root) whose arithmetic
+ * it replaces; INTEGRATION.md shows the ctypes binding a maintainer adds on the reference side.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes only; every pointer is a DEVICE pointer unless the
+ *     name ends in _host.  The library never allocates and never synchronises the device: the
+ *     caller owns all buffers and passes the CUDA stream (cudaStream_t as void*).
+ *   - return value: 0 = ok; < 0 = invalid argument (Python side raises ValueError);
+ *     > 0 = cudaError_t (Python side raises RuntimeError).  svdq_last_error() returns a
+ *     thread-local message for the last non-zero return.
+ *   - dtype codes: 0 = float32, 1 = bfloat16, 2 = float16 (dtype of base / fine-tuned tensors).
+ *   - mask strategy codes: 0 = union, 1 = intersection, 2 = majority (votes >= 0.5 * n_present).
+ *   - NT = n_tasks is the stride of every per-task array; n_tasks <= 16 for the streaming
+ *     passes (<= 32 for svdq_param_solve).
+ *   - "tile" = tile_elems consecutive elements of one parameter (tile_elems % 1024 == 0);
+ *     tiles are numbered parameter by parameter: tile_begin[p] .. tile_begin[p+1]-1.
+ *   - tensor pointer tables: tensors[p*(NT+1) + 0] = base, [.. + 1 + t] = fine-tuned tensor of
+ *     task t (NULL when task t lacks the parameter).  Pointers must be 16-byte aligned
+ *     (8-byte for 16-bit dtypes); mask pointers 4-byte aligned.
+ */
+#ifndef SVDQ_H_
+#define SVDQ_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SVDQ_ABI_VERSION 1
+#define SVDQ_MAX_STREAM_TASKS 16
+#define SVDQ_MAX_TASKS 32
+#define SVDQ_MAX_STAGES 8
+
+int svdq_abi_version(void);
+const char* svdq_last_error(void);
+
+/* size in bytes of the scratch record svdq_rtvq_quantize / svdq_absmax_quantize need per CTA,
+ * and the number of records (scratch = svdq_k4_scratch_bytes() bytes) */
+int64_t svdq_k4_scratch_bytes(void);
+
+/*
+ * K1 — task-vector construction + tall-mask combination + masked Gram, one streaming pass.
+ * Replaces: compute_task_vector (src/svd_hybrid/task_vector_loader.py:103-145),
+ *           combine_masks / compute_{union,intersection,majority}_mask
+ *           (src/svd_hybrid/mask_loader.py:412-485,488-648), apply_mask_to_tensor
+ *           (mask_loader.py:651-679), stack_and_center and the T^T T half of compute_svd
+ *           (src/svd_hybrid/basis.py:63-113,216-249).
+ * masks: [P*NT] table of torch.bool storages (NULL entry = task has no mask for the parameter),
+ *        or NULL when there are no masks at all.
+ * packed/pmask_off: bit-packed combined mask, parameter p at word offset pmask_off[p].
+ * gram: [n_tiles][full ? 2 : 1][NT(NT+1)/2] fp32 partials (upper triangle, row-major);
+ *       the second block (full != 0) is the Gram of the UNMASKED complement, used for the
+ *       whole-model task Gram behind cluster weighting (src/svd_hybrid/clustering.py:227-232).
+ * count: [n_tiles] masked elements per tile.
+ */
+int svdq_tv_mask_gram(int dtype, int n_tasks, int mask_strategy, int full, int64_t n_tiles, int tile_elems,
+                      const void* const* tensors, const uint8_t* const* masks, const int64_t* numel,
+                      const int32_t* tile_param, const int32_t* tile_local, const int64_t* pmask_off,
+                      uint32_t* packed, float* gram, uint32_t* count, void* stream);
+
+/*
+ * K2a — fixed-order fp64 reduction of K1's tile partials per parameter.
+ * gram_masked / gram_all: [P][NT*NT] full symmetric fp64 (gram_all may be NULL); dm: [P].
+ */
+int svdq_gram_reduce(int n_tasks, int full, int64_t n_params, const float* gram, const uint32_t* count,
+                     const int64_t* tile_begin, double* gram_masked, double* gram_all, int64_t* dm, void* stream);
+
+/*
+ * K2b — per-parameter solve (one warp per parameter).
+ * Replaces: the rest of compute_svd (src/svd_hybrid/basis.py:241), compute_energy_spectrum /
+ *           select_rank (basis.py:116-213), construct_basis glue (basis.py:252-409),
+ *           project_to_basis / compress_single_task (src/svd_hybrid/compress.py:6-56),
+ *           asymmetric_quantization / multistage_residual_quantization
+ *           (src/svd_hybrid/rtvq.py:4-103) on the low-energy block, dequantize_and_average
+ *           (src/svd_hybrid/merge.py:61-141) and the gating of src/svd_hybrid/cli.py:319-343.
+ * Inputs : gram_masked [P][NT*NT], dm [P], has_mask [P] (uint8), present [P] (bit t: task t has
+ *          the parameter), weights [NT] fp64 by task position, avg_order [NT] task positions in
+ *          sorted-name order, sign_ref [P][NT*NT] optional Vh_ref[j][t] for test-only sign
+ *          alignment (NULL in production).
+ * Outputs (per parameter, stride NT; S = rtvq_stages):
+ *   info [P][8] int32  : status (0 solved, 1 skipped: mask below min_mask_size, 2 empty),
+ *                        n_active, r = min(Dm, n_active), k, r_eff, 0, 0, 0
+ *   sv [P][NT] fp32 singular values; scal [P][4] = energy_retained, tail_add, 0, 0
+ *   coef [P][NT][NT] raw coefficients coef[t][j]; chigh [P][NT][NT] fp16 bits (j < k)
+ *   codes [P][NT][S][NT] uint8 (i < r-k); qscale/qzp/qres [P][NT][S]
+ *   chat [P][NT][NT] coefficients after fp16 / RTVQ round trip; cbar [P][NT] weighted average
+ *   W [P][NT][NT] with u_d[j] = sum_t (tau_d[t] - mean_d) W[t][j]; gvec [P][NT] = W cbar
+ *   V [P][NT][NT] fp64 right singular vectors V[t][j]
+ */
+int svdq_param_solve(int n_tasks, int64_t n_params, int center, float energy_threshold, int max_rank,
+                     int min_mask_size, int rtvq_bits, int rtvq_stages,
+                     const double* gram_masked, const int64_t* dm, const uint8_t* has_mask, const uint32_t* present,
+                     const double* weights, const int32_t* avg_order, const double* sign_ref,
+                     int32_t* info, float* sv, float* scal, float* coef, uint16_t* chigh, uint8_t* codes,
+                     float* qscale, float* qzp, float* qres, float* chat, float* cbar, float* W, float* gvec,
+                     double* V, void* stream);
+
+/*
+ * K3 — weighted reconstruction + merge (pass 2), optional fused diagnostics.
+ * Replaces: reconstruct_from_coefficients (src/svd_hybrid/merge.py:144-194), the fp16 cast of
+ *           the bases (src/svd_hybrid/cli.py:355-361), reconstruct_from_masked
+ *           (src/svd_hybrid/mask_loader.py:712-763), merge_parameter / merge_all_parameters
+ *           (merge.py:197-426), apply_merged_deltas (merge.py:429-552) and, with diag != 0,
+ *           compute_reconstruction_error / compute_parameter_diagnostics
+ *           (src/svd_hybrid/diagnostics.py:72-231).
+ * out: [P] table of fp32 output tensors (merged = base + delta; parameters without a basis get
+ *      a copy of base).  diag_partials: [n_tiles][5][NT] fp32 (may be NULL when diag == 0).
+ */
+int svdq_reconstruct_merge(int dtype, int n_tasks, int fp16_basis, int diag, int center, int64_t n_tiles,
+                           int tile_elems, const void* const* tensors, const int64_t* numel,
+                           const int32_t* tile_param, const int32_t* tile_local, const int64_t* pmask_off,
+                           const uint8_t* has_mask, const uint32_t* packed, const int32_t* info, const float* W,
+                           const float* cbar, const float* gvec, const float* scal, const float* chat,
+                           float* const* out, float* diag_partials, void* stream);
+
+/* diagnostics finalisation: out [P][NT][6] fp64 = absolute_error, relative_error,
+ * max_absolute_error, mean_absolute_error, original_norm, reconstructed_norm
+ * (src/svd_hybrid/diagnostics.py:110-117) */
+int svdq_diag_finalize(int n_tasks, int64_t n_params, const float* diag_partials, const int64_t* tile_begin,
+                       const int64_t* dm, const int32_t* info, double* out, void* stream);
+
+/*
+ * K5 — materialise the bases in the reference artifact layout
+ * (U_high [Dm x k], U_low [Dm x (r-k)], mean [Dm x 1], rows compacted through the mask:
+ * src/svd_hybrid/basis.py:363-364,398-407; storage layout src/svd_hybrid/storage.py:76-106).
+ * tile_row_off [n_tiles] is produced by svdq_basis_offsets from K1's counts.
+ */
+int svdq_basis_offsets(int64_t n_params, const uint32_t* count, const int64_t* tile_begin, int64_t* tile_row_off,
+                       void* stream);
+int svdq_write_basis(int dtype, int n_tasks, int fp16_basis, int center, int64_t n_tiles, int tile_elems,
+                     const void* const* tensors, const int64_t* numel, const int32_t* tile_param,
+                     const int32_t* tile_local, const int64_t* pmask_off, const uint8_t* has_mask,
+                     const uint32_t* packed, const int32_t* info, const float* W, const int64_t* tile_row_off,
+                     void* const* u_high, void* const* u_low, float* const* mean, void* stream);
+
+/*
+ * K4 — quantisers on arbitrarily long fp32 tensors.
+ * svdq_rtvq_quantize : asymmetric_quantization (src/svd_hybrid/rtvq.py:4-27 =
+ *                      quantization_utils.py:76-99) for stages == 1, and
+ *                      multistage_residual_quantization (rtvq.py:39-82) in general.
+ *                      codes: [stages][codes_ld] uint8 (code_bytes 1) or int16 (code_bytes 2);
+ *                      scale / zp / resnorm: [stages] fp32 device scalars.
+ * svdq_rtvq_dequantize: asymmetric_dequantization / multistage_residual_dequantization
+ *                      (rtvq.py:29-36,85-103; quantization_utils.py:137-172).
+ * svdq_absmax_quantize: absmax_quantization (quantization_utils.py:60-73); q int8 / int16.
+ * scratch: svdq_k4_scratch_bytes() bytes of device memory.
+ */
+int svdq_rtvq_quantize(const float* x, int64_t n, int bits, int stages, void* codes, int64_t codes_ld,
+                       int code_bytes, float* scale, float* zp, float* resnorm, void* scratch, void* stream);
+int svdq_rtvq_dequantize(const void* codes, int64_t codes_ld, int code_bytes, int stages, int64_t n,
+                         const float* scale, const float* zp, float* out, void* stream);
+int svdq_absmax_quantize(const float* x, int64_t n, int bits, void* q, int code_bytes, float* scale, void* scratch,
+                         void* stream);
+
+/*
+ * Mask utilities behind the fine-grained API.
+ * svdq_combine_masks: compute_union/intersection/majority_mask (src/svd_hybrid/mask_loader.py:412-485)
+ *                     over n_masks torch.bool tensors of n elements -> torch.bool out.
+ * svdq_unpack_mask  : packed combined mask -> torch.bool.
+ */
+int svdq_combine_masks(const uint8_t* const* masks, int n_masks, int64_t n, int strategy, uint8_t* out, void* stream);
+int svdq_unpack_mask(const uint32_t* packed, int64_t n, uint8_t* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SVDQ_H_ */

@@ -1,0 +1,85 @@
+"""In-tree build of libsvdq.so (sm_100a) with nvcc; no torch headers, no JIT cache.
+
+``python -m svd_quantization_task_merging_b200.build`` or ``__graft_entry__.build()``.
+The library travels to the GPU box with the repository snapshot (``*.so`` is git-ignored, not
+gpurun-ignored).
+"""
+from __future__ import annotations
+
+import hashlib
+import os
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+from typing import List, Tuple
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+OBJDIR = os.path.join(HERE, "_build")
+LIB = os.path.join(HERE, "libsvdq.so")
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+
+ARCH_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a"]
+COMMON = ["-std=c++17", "-O3", "-lineinfo", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"] + ARCH_FLAGS
+
+# (source, SVDQ_DTYPE or None)
+UNITS: List[Tuple[str, object]] = (
+    [("k1_tv_mask_gram.cu", d) for d in (0, 1, 2)]
+    + [("k3_reconstruct_merge.cu", d) for d in (0, 1, 2)]
+    + [("k5_basis_misc.cu", d) for d in (0, 1, 2)]
+    + [("k2_param_solve.cu", None), ("k4_rtvq_large.cu", None), ("svdq_capi.cu", None)]
+)
+HEADERS = ["svdq_common.cuh", "svdq_kernels.h", "k2_core.h", os.path.join("..", "..", "include", "svdq.h")]
+
+
+def _digest(paths: List[str], extra: str) -> str:
+    h = hashlib.sha256(extra.encode())
+    for p in paths:
+        with open(p, "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()
+
+
+def _compile(unit: Tuple[str, object], verbose: bool) -> str:
+    src, dt = unit
+    stem = os.path.splitext(src)[0] + ("" if dt is None else f"_dt{dt}")
+    obj = os.path.join(OBJDIR, stem + ".o")
+    stamp = obj + ".sha"
+    deps = [os.path.join(CSRC, src)] + [os.path.normpath(os.path.join(CSRC, h)) for h in HEADERS]
+    flags = COMMON + ([] if dt is None else [f"-DSVDQ_DTYPE={dt}"])
+    want = _digest(deps, " ".join(flags))
+    if os.path.exists(obj) and os.path.exists(stamp) and open(stamp).read() == want:
+        return obj
+    cmd = [NVCC] + flags + ["-c", os.path.join(CSRC, src), "-o", obj]
+    if verbose:
+        print(" ".join(cmd), flush=True)
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"nvcc failed for {src} (dtype {dt}):\n{r.stdout}\n{r.stderr}")
+    with open(stamp, "w") as f:
+        f.write(want)
+    return obj
+
+
+def build(force: bool = False, verbose: bool = False, jobs: int = 0) -> str:
+    """Compile every CUDA translation unit for sm_100a and link libsvdq.so.  Returns its path."""
+    os.makedirs(OBJDIR, exist_ok=True)
+    if force:
+        for f in os.listdir(OBJDIR):
+            os.remove(os.path.join(OBJDIR, f))
+    jobs = jobs or min(len(UNITS), os.cpu_count() or 4)
+    with ThreadPoolExecutor(max_workers=jobs) as ex:
+        objs = list(ex.map(lambda u: _compile(u, verbose), UNITS))
+    newest = max(os.path.getmtime(o) for o in objs)
+    if force or not os.path.exists(LIB) or os.path.getmtime(LIB) < newest:
+        cmd = [NVCC, "-shared", "-o", LIB] + objs + ARCH_FLAGS + ["-Xcompiler", "-fPIC", "-cudart", "static"]
+        if verbose:
+            print(" ".join(cmd), flush=True)
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose=True))

@@ -1,0 +1,113 @@
+// K2 — the small batched per-parameter solve between the two streaming passes.
+//   k2_gram_reduce : sums the per-tile partial Grams / counts of K1 in a fixed order (fp64)
+//   k2_param_solve : one warp per parameter runs svdq::solve_param (k2_core.h): centring,
+//                    Jacobi eigensolve, energy rank selection, closed-form coefficients,
+//                    fp16 high block, multi-stage RTVQ low block, weighted average, W matrix.
+// Replaces the rest of torch.linalg.svd (src/svd_hybrid/basis.py:241), select_rank
+// (basis.py:199-211), project_to_basis (compress.py:18-19), the fp16 cast (compress.py:44-45),
+// RTVQ (rtvq.py:55-79) and dequantize_and_average (merge.py:127-139).  Latency-bound, tiny.
+#include "svdq_kernels.h"
+
+namespace svdq {
+
+
+__global__ void __launch_bounds__(kBlock) k2_gram_reduce(const K2ReduceArgs a) {
+    const int p = blockIdx.x, tid = threadIdx.x;
+    const int NT = a.nt, G = tri_count(NT), NACC = a.full ? 2 * G : G;
+    const int64_t t0 = a.tile_begin[p], t1 = a.tile_begin[p + 1];
+    __shared__ double s_part[kBlock / 32][2 * tri_count(16)];
+    __shared__ unsigned long long s_cnt[kBlock / 32];
+    const int lane = tid & 31, warp = tid >> 5;
+
+    // each warp owns tiles warp, warp+8, ...; inside a warp lane l owns accumulator rows l, l+32, ...
+    for (int r = lane; r < NACC; r += 32) {
+        double s = 0.0;
+        for (int64_t t = t0 + warp; t < t1; t += kBlock / 32) s += (double)a.gram[t * NACC + r];
+        s_part[warp][r] = s;
+    }
+    unsigned long long c = 0;
+    for (int64_t t = t0 + tid; t < t1; t += kBlock) c += a.count[t];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if (lane == 0) s_cnt[warp] = c;
+    __syncthreads();
+    for (int r = tid; r < G; r += kBlock) {
+        double m = 0.0, u = 0.0;
+        for (int w = 0; w < kBlock / 32; ++w) {
+            m += s_part[w][r];
+            if (a.full) u += s_part[w][G + r];
+        }
+        // unpack the upper triangle
+        int i = 0, rem = r;
+        while (rem >= NT - i) { rem -= NT - i; ++i; }
+        const int j = i + rem;
+        a.gram_masked[(int64_t)p * NT * NT + i * NT + j] = m;
+        a.gram_masked[(int64_t)p * NT * NT + j * NT + i] = m;
+        if (a.full && a.gram_all) {
+            a.gram_all[(int64_t)p * NT * NT + i * NT + j] = m + u;
+            a.gram_all[(int64_t)p * NT * NT + j * NT + i] = m + u;
+        }
+    }
+    if (tid == 0) {
+        unsigned long long tot = 0;
+        for (int w = 0; w < kBlock / 32; ++w) tot += s_cnt[w];
+        a.dm[p] = (int64_t)tot;
+    }
+}
+
+
+struct WarpLanes {
+    int lane;
+    static constexpr int nl = 32;
+    __device__ __forceinline__ void sync() { __syncwarp(); }
+};
+
+__global__ void __launch_bounds__(32) k2_param_solve(const K2SolveArgs a) {
+    __shared__ SolveScratch sc;
+    const int p = blockIdx.x;
+    const int NT = a.cfg.n_tasks, S = a.cfg.stages;
+    const int64_t nn = (int64_t)NT * NT;
+    SolveIn in;
+    in.G = a.gram_masked + p * nn;
+    in.dm = a.dm[p];
+    in.has_mask = a.has_mask[p];
+    in.present = a.present[p];
+    in.weights = a.weights;
+    in.avg_order = a.avg_order;
+    in.sign_ref = a.sign_ref ? a.sign_ref + p * nn : nullptr;
+    SolveOut out;
+    out.info = a.info + (int64_t)p * 8;
+    out.sv = a.sv + (int64_t)p * NT;
+    out.scal = a.scal + (int64_t)p * 4;
+    out.coef = a.coef + p * nn;
+    out.chigh = a.chigh + p * nn;
+    out.codes = a.codes + p * nn * S;
+    out.qscale = a.qscale + (int64_t)p * NT * S;
+    out.qzp = a.qzp + (int64_t)p * NT * S;
+    out.qres = a.qres + (int64_t)p * NT * S;
+    out.chat = a.chat + p * nn;
+    out.cbar = a.cbar + (int64_t)p * NT;
+    out.W = a.W + p * nn;
+    out.gvec = a.gvec + (int64_t)p * NT;
+    out.V = a.V + p * nn;
+    WarpLanes ln{(int)threadIdx.x};
+    solve_param(a.cfg, in, out, sc, ln);
+}
+
+cudaError_t k2_reduce_launch(const K2ReduceArgs& a, int n_params, cudaStream_t st) {
+    if (n_params <= 0) return cudaSuccess;
+    if (a.nt < 1 || a.nt > 16) return cudaErrorInvalidValue;
+    k2_gram_reduce<<<n_params, kBlock, 0, st>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t k2_solve_launch(const K2SolveArgs& a, int n_params, cudaStream_t st) {
+    if (n_params <= 0) return cudaSuccess;
+    if (a.cfg.n_tasks < 1 || a.cfg.n_tasks > kCoreMaxTasks) return cudaErrorInvalidValue;
+    if (a.cfg.stages < 1 || a.cfg.stages > kCoreMaxStages || a.cfg.bits < 1 || a.cfg.bits > 8)
+        return cudaErrorInvalidValue;
+    k2_param_solve<<<n_params, 32, 0, st>>>(a);
+    return cudaGetLastError();
+}
+
+}  // namespace svdq

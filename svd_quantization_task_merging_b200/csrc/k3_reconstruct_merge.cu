@@ -1,0 +1,298 @@
+// K3 — pass 2 of the SVD-Hybrid merge: re-reads base + N fine-tuned tensors and the packed
+// combined mask, rebuilds each basis row on the fly (u_d = (tau_d - mean_d) W, rounded to fp16
+// when the bases are stored in fp16), contracts it with the averaged coefficients, scatters
+// through the mask and writes merged = base + delta in the same pass.  Optionally accumulates
+// the reference's per-task reconstruction diagnostics.
+//
+// Replaces (paths relative to /root/reference):
+//   U = T V Sigma^-1 (implicit in torch.linalg.svd)      src/svd_hybrid/basis.py:241
+//   fp16 cast of the bases                                src/svd_hybrid/cli.py:355-361
+//   reconstruct_from_coefficients                         src/svd_hybrid/merge.py:180-192
+//   reconstruct_from_masked (scatter)                     src/svd_hybrid/mask_loader.py:750-763
+//   apply_merged_deltas                                   src/svd_hybrid/merge.py:486-488
+//   compute_reconstruction_error (DIAG)                   src/svd_hybrid/diagnostics.py:101-117,205-216
+// Bound: HBM (algorithmic bytes per element: (N+1)*sizeof(T) + 1/8 + 4).
+#include "svdq_kernels.h"
+
+#ifndef SVDQ_DTYPE
+#define SVDQ_DTYPE 0
+#endif
+
+namespace svdq {
+
+
+constexpr int kDiagRows = 5;      // sum e^2, sum |e|, sum rec^2, sum orig^2, max |e|
+
+template <typename T, int NT, bool FP16B, bool DIAG>
+__global__ void __launch_bounds__(kBlock, (NT <= 8 && !DIAG) ? 2 : 1) k3_reconstruct_merge(const K3Args a) {
+    constexpr int NTP = (NT + 3) & ~3;
+    __shared__ __align__(16) float sWT[NT][NTP];        // sWT[j][t] = W[t][j]
+    __shared__ __align__(16) float sChatT[DIAG ? NT : 1][NTP];   // sChatT[j][t] = chat[t][j]
+    __shared__ float sCbar[NT], sG[NT];
+    __shared__ const void* s_ptr[NT + 1];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tile = blockIdx.x;
+    const int p = a.tile_param[tile];
+    const int64_t numel = a.numel[p];
+    const int64_t start = (int64_t)a.tile_local[tile] * a.tile_elems;
+    const int64_t stop = min(start + (int64_t)a.tile_elems, numel);
+    const int status = a.info[(int64_t)p * 8 + 0];
+    const int n_active = a.info[(int64_t)p * 8 + 1];
+    const int r = a.info[(int64_t)p * 8 + 2];
+    const float tail_add = a.scal[(int64_t)p * 4 + 1];
+    const bool has_mask = a.has_mask[p] != 0;
+
+    if (tid <= NT) s_ptr[tid] = a.tensors[(int64_t)p * (NT + 1) + tid];
+    for (int i = tid; i < NT * NTP; i += kBlock) {
+        const int j = i / NTP, t = i % NTP;
+        sWT[j][t] = (t < NT) ? a.W[(int64_t)p * NT * NT + t * NT + j] : 0.0f;
+        if (DIAG) sChatT[j][t] = (t < NT) ? a.chat[(int64_t)p * NT * NT + t * NT + j] : 0.0f;
+    }
+    if (tid < NT) { sCbar[tid] = a.cbar[(int64_t)p * NT + tid]; sG[tid] = a.gvec[(int64_t)p * NT + tid]; }
+    __syncthreads();
+
+    const uint32_t* packed = has_mask ? a.packed + a.pmask_off[p] : nullptr;
+    float* outp = a.out[p];
+    const float inv_n_dummy = 0.0f; (void)inv_n_dummy;
+    const float n_f = (float)(n_active > 0 ? n_active : 1);
+
+    float dacc[DIAG ? kDiagRows * NT : 1];
+    if (DIAG) {
+#pragma unroll
+        for (int i = 0; i < kDiagRows * NT; ++i) dacc[i] = 0.0f;
+    }
+
+    for (int64_t e0 = start; e0 < stop; e0 += kStep) {
+        const int64_t e = e0 + (int64_t)tid * kVec;
+        if (e >= stop) continue;
+        const bool full = e + kVec <= numel;
+        float b[kVec];
+        if (full) Elem<T>::load4(s_ptr[0], e, b);
+        else {
+#pragma unroll
+            for (int c = 0; c < kVec; ++c) b[c] = (e + c < numel) ? Elem<T>::load1(s_ptr[0], e + c) : 0.0f;
+        }
+        float res[kVec];
+        if (status != kSolved) {
+            // parameter without a basis (mask below svd_min_mask_size / no data): merged = base
+#pragma unroll
+            for (int c = 0; c < kVec; ++c) res[c] = b[c];
+        } else {
+            float x[NT][kVec];                   // task vectors, then centred task vectors
+            float mean[kVec];
+#pragma unroll
+            for (int c = 0; c < kVec; ++c) mean[c] = 0.0f;
+#pragma unroll
+            for (int t = 0; t < NT; ++t) {
+                const void* fp = s_ptr[t + 1];
+                if (fp == nullptr) {
+#pragma unroll
+                    for (int c = 0; c < kVec; ++c) x[t][c] = 0.0f;
+                } else if (full) {
+                    float f[kVec];
+                    Elem<T>::load4(fp, e, f);
+#pragma unroll
+                    for (int c = 0; c < kVec; ++c) x[t][c] = Elem<T>::sub(f[c], b[c]);
+                } else {
+#pragma unroll
+                    for (int c = 0; c < kVec; ++c)
+                        x[t][c] = (e + c < numel) ? Elem<T>::sub(Elem<T>::load1(fp, e + c), b[c]) : 0.0f;
+                }
+#pragma unroll
+                for (int c = 0; c < kVec; ++c) mean[c] += x[t][c];
+            }
+            uint32_t bits = 0xFu;
+            if (has_mask) bits = (__ldg(packed + (e >> 5)) >> (int)(e & 31)) & 0xFu;
+
+            float orig[DIAG ? NT : 1][kVec];
+            if (DIAG) {
+#pragma unroll
+                for (int t = 0; t < NT; ++t)
+#pragma unroll
+                    for (int c = 0; c < kVec; ++c) orig[t][c] = x[t][c];
+            }
+#pragma unroll
+            for (int c = 0; c < kVec; ++c) mean[c] = a.center ? __fdiv_rn(mean[c], n_f) : 0.0f;
+#pragma unroll
+            for (int t = 0; t < NT; ++t)
+#pragma unroll
+                for (int c = 0; c < kVec; ++c) x[t][c] = (s_ptr[t + 1] != nullptr) ? x[t][c] - mean[c] : 0.0f;
+
+            float acc[kVec];
+#pragma unroll
+            for (int c = 0; c < kVec; ++c) acc[c] = 0.0f;
+            float rec[DIAG ? NT : 1][kVec];
+            if (DIAG) {
+#pragma unroll
+                for (int t = 0; t < NT; ++t)
+#pragma unroll
+                    for (int c = 0; c < kVec; ++c) rec[t][c] = 0.0f;
+            }
+            if (FP16B || DIAG) {
+                for (int j = 0; j < r; ++j) {
+                    float u[kVec];
+#pragma unroll
+                    for (int c = 0; c < kVec; ++c) u[c] = 0.0f;
+#pragma unroll
+                    for (int t = 0; t < NT; ++t) {
+                        const float w = sWT[j][t];
+#pragma unroll
+                        for (int c = 0; c < kVec; ++c) u[c] = fmaf(x[t][c], w, u[c]);
+                    }
+                    const float cb = sCbar[j];
+#pragma unroll
+                    for (int c = 0; c < kVec; ++c) {
+                        if (FP16B) u[c] = round_fp16(u[c]);
+                        acc[c] = fmaf(u[c], cb, acc[c]);
+                    }
+                    if (DIAG) {
+#pragma unroll
+                        for (int t = 0; t < NT; ++t) {
+                            const float ch = sChatT[j][t];
+#pragma unroll
+                            for (int c = 0; c < kVec; ++c) rec[t][c] = fmaf(u[c], ch, rec[t][c]);
+                        }
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int t = 0; t < NT; ++t) {
+                    const float g = sG[t];
+#pragma unroll
+                    for (int c = 0; c < kVec; ++c) acc[c] = fmaf(x[t][c], g, acc[c]);
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < kVec; ++c) {
+                const bool m = (bits >> c) & 1u;
+                const float val = (acc[c] + mean[c]) + tail_add;
+                res[c] = b[c] + (m ? val : 0.0f);
+            }
+            if (DIAG) {
+#pragma unroll
+                for (int t = 0; t < NT; ++t) {
+                    if (s_ptr[t + 1] == nullptr) continue;
+#pragma unroll
+                    for (int c = 0; c < kVec; ++c) {
+                        const bool m = ((bits >> c) & 1u) && (e + c < numel);
+                        if (m) {
+                            const float er = orig[t][c] - rec[t][c];
+                            dacc[0 * NT + t] = fmaf(er, er, dacc[0 * NT + t]);
+                            dacc[1 * NT + t] += fabsf(er);
+                            dacc[2 * NT + t] = fmaf(rec[t][c], rec[t][c], dacc[2 * NT + t]);
+                            dacc[3 * NT + t] = fmaf(orig[t][c], orig[t][c], dacc[3 * NT + t]);
+                            dacc[4 * NT + t] = fmaxf(dacc[4 * NT + t], fabsf(er));
+                        }
+                    }
+                }
+            }
+        }
+        if (full) stg_stream_f4(outp + e, make_float4(res[0], res[1], res[2], res[3]));
+        else {
+#pragma unroll
+            for (int c = 0; c < kVec; ++c)
+                if (e + c < numel) outp[e + c] = res[c];
+        }
+    }
+
+    if (DIAG) {
+        // CTA reduction of the 5*NT diagnostic rows: sums for rows < 4*NT, max for the rest
+        constexpr int NR = kDiagRows * NT;
+        constexpr int kRows = 16;
+        __shared__ float red[kRows][kBlock + 1];
+        float* dout = a.diag + (int64_t)tile * NR;
+#pragma unroll
+        for (int r0 = 0; r0 < NR; r0 += kRows) {
+#pragma unroll
+            for (int rr = 0; rr < kRows; ++rr)
+                if (r0 + rr < NR) red[rr][tid] = dacc[r0 + rr];
+            __syncthreads();
+#pragma unroll
+            for (int q = 0; q < kRows / (kBlock / 32); ++q) {
+                const int rr = warp * (kRows / (kBlock / 32)) + q;
+                if (r0 + rr < NR) {
+                    const bool is_max = (r0 + rr) >= 4 * NT;
+                    float s = 0.0f;
+#pragma unroll
+                    for (int c = 0; c < kBlock / 32; ++c) {
+                        const float v = red[rr][lane + 32 * c];
+                        s = is_max ? fmaxf(s, v) : s + v;
+                    }
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+                        const float v = __shfl_xor_sync(0xffffffffu, s, o);
+                        s = is_max ? fmaxf(s, v) : s + v;
+                    }
+                    if (lane == 0) dout[r0 + rr] = s;
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+#if SVDQ_DTYPE == 0
+// ---- diagnostics finalisation: per (parameter, task) reduce the tile partials ------------------
+
+__global__ void __launch_bounds__(32) k3_diag_finalize(const K3DiagArgs a) {
+    const int p = blockIdx.x, t = threadIdx.x;
+    if (t >= a.nt) return;
+    const int NT = a.nt, NR = kDiagRows * NT;
+    double se = 0.0, sa = 0.0, sr = 0.0, so = 0.0;
+    float mx = 0.0f;
+    for (int64_t tl = a.tile_begin[p]; tl < a.tile_begin[p + 1]; ++tl) {
+        const float* d = a.diag + tl * NR;
+        se += (double)d[0 * NT + t]; sa += (double)d[1 * NT + t];
+        sr += (double)d[2 * NT + t]; so += (double)d[3 * NT + t];
+        mx = fmaxf(mx, d[4 * NT + t]);
+    }
+    double* o = a.out + ((int64_t)p * NT + t) * 6;
+    const bool solved = a.info[(int64_t)p * 8] == kSolved;
+    const double dm = (double)a.dm[p];
+    const double on = sqrt(so), en = sqrt(se);
+    o[0] = solved ? en : 0.0;
+    o[1] = solved ? (on > 1e-10 ? en / on : 0.0) : 0.0;
+    o[2] = solved ? ((se != se) ? se : (double)mx) : 0.0;     // NaN anywhere -> NaN max (torch.max)
+    o[3] = solved && dm > 0 ? sa / dm : 0.0;
+    o[4] = solved ? on : 0.0;
+    o[5] = solved ? sqrt(sr) : 0.0;
+}
+
+#endif  // SVDQ_DTYPE == 0
+
+// ---- host-side dispatch ---------------------------------------------------------------------------
+template <typename T, int NT>
+static cudaError_t launch_nt(const K3Args& a, int n_tiles, bool fp16b, bool diag, cudaStream_t st) {
+    if (n_tiles <= 0) return cudaSuccess;
+    if (diag) {
+        if (fp16b) k3_reconstruct_merge<T, NT, true, true><<<n_tiles, kBlock, 0, st>>>(a);
+        else       k3_reconstruct_merge<T, NT, false, true><<<n_tiles, kBlock, 0, st>>>(a);
+    } else {
+        if (fp16b) k3_reconstruct_merge<T, NT, true, false><<<n_tiles, kBlock, 0, st>>>(a);
+        else       k3_reconstruct_merge<T, NT, false, false><<<n_tiles, kBlock, 0, st>>>(a);
+    }
+    return cudaGetLastError();
+}
+
+template <>
+cudaError_t k3_launch_dtype<SVDQ_DTYPE>(int nt, const K3Args& a, int n_tiles, bool fp16b, bool diag, cudaStream_t st) {
+    using T = DTypeOf<SVDQ_DTYPE>::type;
+    switch (nt) {
+#define SVDQ_CASE(N) case N: return launch_nt<T, N>(a, n_tiles, fp16b, diag, st);
+        SVDQ_CASE(1) SVDQ_CASE(2) SVDQ_CASE(3) SVDQ_CASE(4) SVDQ_CASE(5) SVDQ_CASE(6) SVDQ_CASE(7) SVDQ_CASE(8)
+        SVDQ_CASE(9) SVDQ_CASE(10) SVDQ_CASE(11) SVDQ_CASE(12) SVDQ_CASE(13) SVDQ_CASE(14) SVDQ_CASE(15) SVDQ_CASE(16)
+#undef SVDQ_CASE
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+#if SVDQ_DTYPE == 0
+cudaError_t k3_diag_launch(const K3DiagArgs& a, int n_params, cudaStream_t st) {
+    if (n_params <= 0) return cudaSuccess;
+    k3_diag_finalize<<<n_params, 32, 0, st>>>(a);
+    return cudaGetLastError();
+}
+#endif
+
+}  // namespace svdq

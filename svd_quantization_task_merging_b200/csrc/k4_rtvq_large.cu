@@ -1,0 +1,244 @@
+// K4 — multi-stage residual quantisation (RTVQ) and the root quantization_utils quantisers on
+// arbitrarily long tensors.
+//
+// Replaces (paths relative to /root/reference):
+//   asymmetric_quantization / _dequantization      src/svd_hybrid/rtvq.py:4-36, quantization_utils.py:76-99,137-172
+//   multistage_residual_quantization / _deq.       src/svd_hybrid/rtvq.py:39-103
+//   absmax_quantization                            quantization_utils.py:60-73
+//
+// The residual is never written to memory: pass q re-reads x and REPLAYS stages 0..q-2 with
+// their (already final) scale / zero-point to rebuild the residual in registers bit-exactly,
+// quantises stage q-1, and reduces min / max / sum-of-squares of the new residual for stage q
+// in the same pass.  S stages cost S+1 reads of x and S code writes; all scalars stay on the
+// device (no host synchronisation between stages).  Bound: HBM.
+#include "svdq_kernels.h"
+
+namespace svdq {
+
+
+
+struct K4PassArgs {
+    const float* x;
+    int64_t n;
+    int bits;
+    int pass;               // q: replay stages 0..q-2, quantise stage q-1 (if q >= 1), stats for stage q
+    int stages;             // S: no stats when pass == S
+    const float* scale;     // [S] device scalars, entries < pass valid
+    const float* zp;        // [S]
+    void* codes;            // [S][codes_ld] uint8 or int16
+    int64_t codes_ld;
+    K4Stats* part;          // [gridDim.x]
+};
+
+__device__ __forceinline__ void stats_update(float v, float& lo, float& hi, int& nan, double& ss) {
+    nan |= (v != v);
+    lo = fminf(lo, v);      // fminf/fmaxf drop NaN; the nan flag restores torch.min/max propagation
+    hi = fmaxf(hi, v);
+    ss += (double)v * (double)v;
+}
+
+template <typename CodeT>
+__global__ void __launch_bounds__(kBlock) k4_rtvq_pass(const K4PassArgs a) {
+    __shared__ QuantScalars s_q[kCoreMaxStages];
+    const int tid = threadIdx.x;
+    if (tid < a.pass && tid < kCoreMaxStages) { s_q[tid].scale = a.scale[tid]; s_q[tid].zp = a.zp[tid]; }
+    __syncthreads();
+    const int q = a.pass;
+    const bool want_stats = q < a.stages;
+    float lo = __int_as_float(0x7f800000), hi = __int_as_float(0xff800000);
+    int nan = 0;
+    double ss = 0.0;
+    CodeT* crow = q >= 1 ? reinterpret_cast<CodeT*>(a.codes) + (int64_t)(q - 1) * a.codes_ld : nullptr;
+
+    const int64_t nvec = (a.n + kVec - 1) / kVec;
+    for (int64_t v = (int64_t)blockIdx.x * kBlock + tid; v < nvec; v += (int64_t)gridDim.x * kBlock) {
+        const int64_t e = v * kVec;
+        const bool full = e + kVec <= a.n;
+        float r[kVec];
+        if (full) { float4 t = ldg_stream_f4(a.x + e); r[0] = t.x; r[1] = t.y; r[2] = t.z; r[3] = t.w; }
+        else {
+#pragma unroll
+            for (int c = 0; c < kVec; ++c) r[c] = (e + c < a.n) ? __ldg(a.x + e + c) : 0.0f;
+        }
+        int code[kVec] = {0, 0, 0, 0};
+        for (int s = 0; s < q; ++s) {
+            const QuantScalars qs = s_q[s];
+#pragma unroll
+            for (int c = 0; c < kVec; ++c) {
+                code[c] = asym_code(r[c], qs, a.bits);
+                r[c] = f_sub(r[c], asym_decode(code[c], qs));
+            }
+        }
+        if (q >= 1) {
+            if (full) {
+                if (sizeof(CodeT) == 1) {
+                    const uint32_t w = (uint32_t)code[0] | ((uint32_t)code[1] << 8) | ((uint32_t)code[2] << 16) |
+                                       ((uint32_t)code[3] << 24);
+                    *reinterpret_cast<uint32_t*>(crow + e) = w;
+                } else {
+                    uint2 w;
+                    w.x = ((uint32_t)code[0] & 0xffffu) | ((uint32_t)code[1] << 16);
+                    w.y = ((uint32_t)code[2] & 0xffffu) | ((uint32_t)code[3] << 16);
+                    *reinterpret_cast<uint2*>(crow + e) = w;
+                }
+            } else {
+#pragma unroll
+                for (int c = 0; c < kVec; ++c)
+                    if (e + c < a.n) crow[e + c] = (CodeT)code[c];
+            }
+        }
+        if (want_stats) {
+#pragma unroll
+            for (int c = 0; c < kVec; ++c)
+                if (e + c < a.n) stats_update(r[c], lo, hi, nan, ss);
+        }
+    }
+    if (!want_stats) return;
+    // CTA reduction in a fixed order
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+        hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+        nan |= __shfl_xor_sync(0xffffffffu, nan, o);
+        ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    }
+    __shared__ K4Stats s_w[kBlock / 32];
+    if ((tid & 31) == 0) { s_w[tid >> 5].lo = lo; s_w[tid >> 5].hi = hi; s_w[tid >> 5].nan = nan; s_w[tid >> 5].sumsq = ss; }
+    __syncthreads();
+    if (tid == 0) {
+        K4Stats t = s_w[0];
+        for (int w = 1; w < kBlock / 32; ++w) {
+            t.lo = fminf(t.lo, s_w[w].lo); t.hi = fmaxf(t.hi, s_w[w].hi); t.nan |= s_w[w].nan; t.sumsq += s_w[w].sumsq;
+        }
+        t.pad = 0;
+        a.part[blockIdx.x] = t;
+    }
+}
+
+// one CTA: reduce the per-CTA stats, emit scale / zero-point / residual norm of stage `stage`
+__global__ void __launch_bounds__(32) k4_finalize(const K4Stats* part, int n_part, int bits, int stage,
+                                                  float* scale, float* zp, float* resnorm) {
+    if (threadIdx.x != 0) return;
+    float lo = part[0].lo, hi = part[0].hi;
+    int nan = part[0].nan;
+    double ss = part[0].sumsq;
+    for (int i = 1; i < n_part; ++i) {
+        lo = fminf(lo, part[i].lo); hi = fmaxf(hi, part[i].hi); nan |= part[i].nan; ss += part[i].sumsq;
+    }
+    if (nan) { lo = __int_as_float(0x7fc00000); hi = lo; }
+    const QuantScalars q = asym_scalars(lo, hi, bits);
+    scale[stage] = q.scale;
+    zp[stage] = q.zp;
+    resnorm[stage] = (float)sqrt(ss);
+}
+
+// sum of the stage dequantisations, left to right from zero (rtvq.py:91-101)
+template <typename CodeT>
+__global__ void __launch_bounds__(kBlock) k4_dequant(const void* codes, int64_t codes_ld, int stages, int64_t n,
+                                                     const float* scale, const float* zp, float* out) {
+    __shared__ QuantScalars s_q[kCoreMaxStages];
+    if (threadIdx.x < stages) { s_q[threadIdx.x].scale = scale[threadIdx.x]; s_q[threadIdx.x].zp = zp[threadIdx.x]; }
+    __syncthreads();
+    const CodeT* c = reinterpret_cast<const CodeT*>(codes);
+    for (int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x; i < n; i += (int64_t)gridDim.x * kBlock) {
+        float acc = 0.0f;
+        for (int s = 0; s < stages; ++s) acc = f_add(acc, asym_decode((int)c[(int64_t)s * codes_ld + i], s_q[s]));
+        out[i] = acc;
+    }
+}
+
+// ---- absmax (quantization_utils.py:60-73): s = (2^(b-1)-1) / max|x| ; q = round(s x), no clamp --
+__global__ void __launch_bounds__(kBlock) k4_absmax_stats(const float* x, int64_t n, K4Stats* part) {
+    float hi = 0.0f;
+    int nan = 0;
+    for (int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x; i < n; i += (int64_t)gridDim.x * kBlock) {
+        const float v = fabsf(__ldg(x + i));
+        nan |= (v != v);
+        hi = fmaxf(hi, v);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+        nan |= __shfl_xor_sync(0xffffffffu, nan, o);
+    }
+    __shared__ float s_hi[kBlock / 32];
+    __shared__ int s_nan[kBlock / 32];
+    if ((threadIdx.x & 31) == 0) { s_hi[threadIdx.x >> 5] = hi; s_nan[threadIdx.x >> 5] = nan; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        K4Stats t; t.lo = 0.0f; t.hi = s_hi[0]; t.nan = s_nan[0]; t.pad = 0; t.sumsq = 0.0;
+        for (int w = 1; w < kBlock / 32; ++w) { t.hi = fmaxf(t.hi, s_hi[w]); t.nan |= s_nan[w]; }
+        part[blockIdx.x] = t;
+    }
+}
+
+__global__ void __launch_bounds__(32) k4_absmax_finalize(const K4Stats* part, int n_part, int bits, float* scale) {
+    if (threadIdx.x != 0) return;
+    float hi = part[0].hi;
+    int nan = part[0].nan;
+    for (int i = 1; i < n_part; ++i) { hi = fmaxf(hi, part[i].hi); nan |= part[i].nan; }
+    if (nan) hi = __int_as_float(0x7fc00000);
+    const float recip = f_div(1.0f, hi);
+    scale[0] = f_mul(recip, (float)((1 << (bits - 1)) - 1));
+}
+
+template <typename CodeT>
+__global__ void __launch_bounds__(kBlock) k4_absmax_quant(const float* x, int64_t n, const float* scale, CodeT* q) {
+    const float s = scale[0];
+    for (int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x; i < n; i += (int64_t)gridDim.x * kBlock) {
+        const float t = rintf(f_mul(s, __ldg(x + i)));
+        q[i] = (t != t) ? (CodeT)0 : (CodeT)(int)t;
+    }
+}
+
+static int grid_for(int64_t n_threads_needed) {
+    int64_t g = (n_threads_needed + kBlock - 1) / kBlock;
+    if (g < 1) g = 1;
+    if (g > kK4MaxGrid) g = kK4MaxGrid;
+    return (int)g;
+}
+
+// Runs the whole S-stage quantisation of x[0..n) on `st`.  part must hold kK4MaxGrid records.
+cudaError_t k4_rtvq_launch(const float* x, int64_t n, int bits, int stages, void* codes, int64_t codes_ld,
+                           int code_bytes, float* scale, float* zp, float* resnorm, K4Stats* part, cudaStream_t st) {
+    if (n <= 0) return cudaSuccess;
+    if (stages < 1 || stages > kCoreMaxStages || bits < 1 || bits > 16) return cudaErrorInvalidValue;
+    if (code_bytes != 1 && code_bytes != 2) return cudaErrorInvalidValue;
+    if (code_bytes == 1 && bits > 8) return cudaErrorInvalidValue;
+    const int grid = grid_for((n + kVec - 1) / kVec);
+    K4PassArgs a;
+    a.x = x; a.n = n; a.bits = bits; a.stages = stages; a.scale = scale; a.zp = zp; a.codes = codes;
+    a.codes_ld = codes_ld; a.part = part;
+    for (int q = 0; q <= stages; ++q) {
+        a.pass = q;
+        if (code_bytes == 1) k4_rtvq_pass<uint8_t><<<grid, kBlock, 0, st>>>(a);
+        else                 k4_rtvq_pass<int16_t><<<grid, kBlock, 0, st>>>(a);
+        if (q < stages) k4_finalize<<<1, 32, 0, st>>>(part, grid, bits, q, scale, zp, resnorm);
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t k4_dequant_launch(const void* codes, int64_t codes_ld, int code_bytes, int stages, int64_t n,
+                              const float* scale, const float* zp, float* out, cudaStream_t st) {
+    if (n <= 0) return cudaSuccess;
+    if (stages < 1 || stages > kCoreMaxStages) return cudaErrorInvalidValue;
+    const int grid = grid_for(n);
+    if (code_bytes == 1) k4_dequant<uint8_t><<<grid, kBlock, 0, st>>>(codes, codes_ld, stages, n, scale, zp, out);
+    else if (code_bytes == 2) k4_dequant<int16_t><<<grid, kBlock, 0, st>>>(codes, codes_ld, stages, n, scale, zp, out);
+    else return cudaErrorInvalidValue;
+    return cudaGetLastError();
+}
+
+cudaError_t k4_absmax_launch(const float* x, int64_t n, int bits, void* q, int code_bytes, float* scale,
+                             K4Stats* part, cudaStream_t st) {
+    if (n <= 0) return cudaSuccess;
+    if (bits < 2 || bits > 16 || (code_bytes != 1 && code_bytes != 2)) return cudaErrorInvalidValue;
+    const int grid = grid_for(n);
+    k4_absmax_stats<<<grid, kBlock, 0, st>>>(x, n, part);
+    k4_absmax_finalize<<<1, 32, 0, st>>>(part, grid, bits, scale);
+    if (code_bytes == 1) k4_absmax_quant<int8_t><<<grid, kBlock, 0, st>>>(x, n, scale, reinterpret_cast<int8_t*>(q));
+    else                 k4_absmax_quant<int16_t><<<grid, kBlock, 0, st>>>(x, n, scale, reinterpret_cast<int16_t*>(q));
+    return cudaGetLastError();
+}
+
+}  // namespace svdq

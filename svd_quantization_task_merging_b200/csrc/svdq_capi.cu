@@ -1,0 +1,240 @@
+// C ABI of libsvdq.so (see include/svdq.h).  Thin argument checking + kernel launches; no
+// allocation, no device synchronisation, no hidden state besides the thread-local error text.
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/svdq.h"
+#include "svdq_kernels.h"
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail_arg(const char* fn, const char* what) {
+    snprintf(g_err, sizeof(g_err), "%s: invalid argument: %s", fn, what);
+    return -1;
+}
+
+int finish(const char* fn, cudaError_t e) {
+    if (e == cudaSuccess) return 0;
+    if (e == cudaErrorInvalidValue) {
+        snprintf(g_err, sizeof(g_err), "%s: invalid argument (unsupported n_tasks / dtype / bits / stages)", fn);
+        (void)cudaGetLastError();
+        return -1;
+    }
+    snprintf(g_err, sizeof(g_err), "%s: CUDA error %d (%s)", fn, (int)e, cudaGetErrorString(e));
+    return (int)e;
+}
+
+#define REQUIRE(cond, what) do { if (!(cond)) return fail_arg(__func__, what); } while (0)
+
+cudaError_t k1_launch(int dtype, int nt, const svdq::K1Args& a, int n_tiles, bool full, cudaStream_t st) {
+    switch (dtype) {
+        case svdq::kF32:  return svdq::k1_launch_dtype<svdq::kF32>(nt, a, n_tiles, full, st);
+        case svdq::kBF16: return svdq::k1_launch_dtype<svdq::kBF16>(nt, a, n_tiles, full, st);
+        case svdq::kF16:  return svdq::k1_launch_dtype<svdq::kF16>(nt, a, n_tiles, full, st);
+        default:          return cudaErrorInvalidValue;
+    }
+}
+cudaError_t k3_launch(int dtype, int nt, const svdq::K3Args& a, int n_tiles, bool fp16b, bool diag, cudaStream_t st) {
+    switch (dtype) {
+        case svdq::kF32:  return svdq::k3_launch_dtype<svdq::kF32>(nt, a, n_tiles, fp16b, diag, st);
+        case svdq::kBF16: return svdq::k3_launch_dtype<svdq::kBF16>(nt, a, n_tiles, fp16b, diag, st);
+        case svdq::kF16:  return svdq::k3_launch_dtype<svdq::kF16>(nt, a, n_tiles, fp16b, diag, st);
+        default:          return cudaErrorInvalidValue;
+    }
+}
+cudaError_t k5_launch(int dtype, int nt, const svdq::K5Args& a, int n_tiles, cudaStream_t st) {
+    switch (dtype) {
+        case svdq::kF32:  return svdq::k5_launch_dtype<svdq::kF32>(nt, a, n_tiles, st);
+        case svdq::kBF16: return svdq::k5_launch_dtype<svdq::kBF16>(nt, a, n_tiles, st);
+        case svdq::kF16:  return svdq::k5_launch_dtype<svdq::kF16>(nt, a, n_tiles, st);
+        default:          return cudaErrorInvalidValue;
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+int svdq_abi_version(void) { return SVDQ_ABI_VERSION; }
+
+const char* svdq_last_error(void) { return g_err; }
+
+int64_t svdq_k4_scratch_bytes(void) { return (int64_t)sizeof(svdq::K4Stats) * svdq::kK4MaxGrid; }
+
+int svdq_tv_mask_gram(int dtype, int n_tasks, int mask_strategy, int full, int64_t n_tiles, int tile_elems,
+                      const void* const* tensors, const uint8_t* const* masks, const int64_t* numel,
+                      const int32_t* tile_param, const int32_t* tile_local, const int64_t* pmask_off,
+                      uint32_t* packed, float* gram, uint32_t* count, void* stream) {
+    REQUIRE(n_tasks >= 1 && n_tasks <= SVDQ_MAX_STREAM_TASKS, "n_tasks must be in [1, 16]");
+    REQUIRE(dtype >= 0 && dtype <= 2, "dtype");
+    REQUIRE(mask_strategy >= 0 && mask_strategy <= 2, "Unknown mask strategy");
+    REQUIRE(tile_elems > 0 && tile_elems % svdq::kStep == 0, "tile_elems must be a positive multiple of 1024");
+    REQUIRE(n_tiles >= 0 && n_tiles < (1ll << 31), "n_tiles");
+    if (n_tiles == 0) return 0;
+    REQUIRE(tensors && numel && tile_param && tile_local && gram && count, "null pointer");
+    REQUIRE(!masks || (pmask_off && packed), "masks given without packed-mask storage");
+    svdq::K1Args a;
+    a.tensors = tensors; a.masks = masks; a.numel = numel; a.tile_param = tile_param; a.tile_local = tile_local;
+    a.pmask_off = pmask_off; a.packed = packed; a.gram = gram; a.count = count; a.tile_elems = tile_elems;
+    a.strategy = mask_strategy;
+    return finish(__func__, k1_launch(dtype, n_tasks, a, (int)n_tiles, full != 0, (cudaStream_t)stream));
+}
+
+int svdq_gram_reduce(int n_tasks, int full, int64_t n_params, const float* gram, const uint32_t* count,
+                     const int64_t* tile_begin, double* gram_masked, double* gram_all, int64_t* dm, void* stream) {
+    REQUIRE(n_tasks >= 1 && n_tasks <= SVDQ_MAX_STREAM_TASKS, "n_tasks must be in [1, 16]");
+    REQUIRE(n_params >= 0 && n_params < (1ll << 31), "n_params");
+    if (n_params == 0) return 0;
+    REQUIRE(gram && count && tile_begin && gram_masked && dm, "null pointer");
+    svdq::K2ReduceArgs a;
+    a.gram = gram; a.count = count; a.tile_begin = tile_begin; a.gram_masked = gram_masked; a.gram_all = gram_all;
+    a.dm = dm; a.nt = n_tasks; a.full = full != 0;
+    return finish(__func__, svdq::k2_reduce_launch(a, (int)n_params, (cudaStream_t)stream));
+}
+
+int svdq_param_solve(int n_tasks, int64_t n_params, int center, float energy_threshold, int max_rank,
+                     int min_mask_size, int rtvq_bits, int rtvq_stages,
+                     const double* gram_masked, const int64_t* dm, const uint8_t* has_mask, const uint32_t* present,
+                     const double* weights, const int32_t* avg_order, const double* sign_ref,
+                     int32_t* info, float* sv, float* scal, float* coef, uint16_t* chigh, uint8_t* codes,
+                     float* qscale, float* qzp, float* qres, float* chat, float* cbar, float* W, float* gvec,
+                     double* V, void* stream) {
+    REQUIRE(n_tasks >= 1 && n_tasks <= SVDQ_MAX_TASKS, "n_tasks must be in [1, 32]");
+    REQUIRE(rtvq_bits >= 1 && rtvq_bits <= 8, "Low bits must be in [1, 8]");
+    REQUIRE(rtvq_stages >= 1 && rtvq_stages <= SVDQ_MAX_STAGES, "RTVQ stages must be in [1, 8]");
+    REQUIRE(energy_threshold > 0.0f && energy_threshold <= 1.0f, "Energy threshold must be in (0, 1]");
+    REQUIRE(n_params >= 0 && n_params < (1ll << 31), "n_params");
+    if (n_params == 0) return 0;
+    REQUIRE(gram_masked && dm && has_mask && present && weights && avg_order, "null input pointer");
+    REQUIRE(info && sv && scal && coef && chigh && codes && qscale && qzp && qres && chat && cbar && W && gvec && V,
+            "null output pointer");
+    svdq::K2SolveArgs a;
+    a.cfg.n_tasks = n_tasks; a.cfg.center = center; a.cfg.energy_threshold = energy_threshold;
+    a.cfg.max_rank = max_rank; a.cfg.min_mask_size = min_mask_size; a.cfg.bits = rtvq_bits; a.cfg.stages = rtvq_stages;
+    a.gram_masked = gram_masked; a.dm = dm; a.has_mask = has_mask; a.present = present; a.weights = weights;
+    a.avg_order = avg_order; a.sign_ref = sign_ref;
+    a.info = info; a.sv = sv; a.scal = scal; a.coef = coef; a.chigh = chigh; a.codes = codes; a.qscale = qscale;
+    a.qzp = qzp; a.qres = qres; a.chat = chat; a.cbar = cbar; a.W = W; a.gvec = gvec; a.V = V;
+    return finish(__func__, svdq::k2_solve_launch(a, (int)n_params, (cudaStream_t)stream));
+}
+
+int svdq_reconstruct_merge(int dtype, int n_tasks, int fp16_basis, int diag, int center, int64_t n_tiles,
+                           int tile_elems, const void* const* tensors, const int64_t* numel,
+                           const int32_t* tile_param, const int32_t* tile_local, const int64_t* pmask_off,
+                           const uint8_t* has_mask, const uint32_t* packed, const int32_t* info, const float* W,
+                           const float* cbar, const float* gvec, const float* scal, const float* chat,
+                           float* const* out, float* diag_partials, void* stream) {
+    REQUIRE(n_tasks >= 1 && n_tasks <= SVDQ_MAX_STREAM_TASKS, "n_tasks must be in [1, 16]");
+    REQUIRE(dtype >= 0 && dtype <= 2, "dtype");
+    REQUIRE(tile_elems > 0 && tile_elems % svdq::kStep == 0, "tile_elems must be a positive multiple of 1024");
+    REQUIRE(n_tiles >= 0 && n_tiles < (1ll << 31), "n_tiles");
+    if (n_tiles == 0) return 0;
+    REQUIRE(tensors && numel && tile_param && tile_local && has_mask && info && W && cbar && gvec && scal && out,
+            "null pointer");
+    REQUIRE(!diag || (diag_partials && chat), "diag requested without diag_partials / chat");
+    svdq::K3Args a;
+    a.tensors = tensors; a.numel = numel; a.tile_param = tile_param; a.tile_local = tile_local;
+    a.pmask_off = pmask_off; a.has_mask = has_mask; a.packed = packed; a.info = info; a.W = W; a.cbar = cbar;
+    a.gvec = gvec; a.scal = scal; a.chat = chat; a.out = out; a.diag = diag_partials; a.tile_elems = tile_elems;
+    a.center = center;
+    return finish(__func__, k3_launch(dtype, n_tasks, a, (int)n_tiles, fp16_basis != 0, diag != 0,
+                                            (cudaStream_t)stream));
+}
+
+int svdq_diag_finalize(int n_tasks, int64_t n_params, const float* diag_partials, const int64_t* tile_begin,
+                       const int64_t* dm, const int32_t* info, double* out, void* stream) {
+    REQUIRE(n_tasks >= 1 && n_tasks <= SVDQ_MAX_STREAM_TASKS, "n_tasks must be in [1, 16]");
+    REQUIRE(n_params >= 0 && n_params < (1ll << 31), "n_params");
+    if (n_params == 0) return 0;
+    REQUIRE(diag_partials && tile_begin && dm && info && out, "null pointer");
+    svdq::K3DiagArgs a;
+    a.diag = diag_partials; a.tile_begin = tile_begin; a.dm = dm; a.info = info; a.out = out; a.nt = n_tasks;
+    return finish(__func__, svdq::k3_diag_launch(a, (int)n_params, (cudaStream_t)stream));
+}
+
+int svdq_basis_offsets(int64_t n_params, const uint32_t* count, const int64_t* tile_begin, int64_t* tile_row_off,
+                       void* stream) {
+    REQUIRE(n_params >= 0 && n_params < (1ll << 31), "n_params");
+    if (n_params == 0) return 0;
+    REQUIRE(count && tile_begin && tile_row_off, "null pointer");
+    return finish(__func__, svdq::k5_offsets_launch(count, tile_begin, tile_row_off, (int)n_params,
+                                                    (cudaStream_t)stream));
+}
+
+int svdq_write_basis(int dtype, int n_tasks, int fp16_basis, int center, int64_t n_tiles, int tile_elems,
+                     const void* const* tensors, const int64_t* numel, const int32_t* tile_param,
+                     const int32_t* tile_local, const int64_t* pmask_off, const uint8_t* has_mask,
+                     const uint32_t* packed, const int32_t* info, const float* W, const int64_t* tile_row_off,
+                     void* const* u_high, void* const* u_low, float* const* mean, void* stream) {
+    REQUIRE(n_tasks >= 1 && n_tasks <= SVDQ_MAX_STREAM_TASKS, "n_tasks must be in [1, 16]");
+    REQUIRE(dtype >= 0 && dtype <= 2, "dtype");
+    REQUIRE(tile_elems > 0 && tile_elems % svdq::kStep == 0, "tile_elems must be a positive multiple of 1024");
+    REQUIRE(n_tiles >= 0 && n_tiles < (1ll << 31), "n_tiles");
+    if (n_tiles == 0) return 0;
+    REQUIRE(tensors && numel && tile_param && tile_local && has_mask && info && W && tile_row_off && u_high && u_low,
+            "null pointer");
+    svdq::K5Args a;
+    a.tensors = tensors; a.numel = numel; a.tile_param = tile_param; a.tile_local = tile_local;
+    a.pmask_off = pmask_off; a.has_mask = has_mask; a.packed = packed; a.info = info; a.W = W;
+    a.tile_row_off = tile_row_off; a.u_high = u_high; a.u_low = u_low; a.mean = mean; a.tile_elems = tile_elems;
+    a.center = center; a.fp16_basis = fp16_basis;
+    return finish(__func__, k5_launch(dtype, n_tasks, a, (int)n_tiles, (cudaStream_t)stream));
+}
+
+int svdq_rtvq_quantize(const float* x, int64_t n, int bits, int stages, void* codes, int64_t codes_ld,
+                       int code_bytes, float* scale, float* zp, float* resnorm, void* scratch, void* stream) {
+    REQUIRE(n >= 0, "n");
+    if (n == 0) return 0;
+    REQUIRE(bits >= 1 && bits <= 16, "bits must be in [1, 16]");
+    REQUIRE(stages >= 1 && stages <= SVDQ_MAX_STAGES, "RTVQ stages must be in [1, 8]");
+    REQUIRE(code_bytes == 1 || code_bytes == 2, "code_bytes");
+    REQUIRE(code_bytes == 2 || bits <= 8, "uint8 codes need bits <= 8");
+    REQUIRE(codes_ld >= n && codes_ld % 4 == 0, "codes_ld must be >= n and a multiple of 4");
+    REQUIRE(x && codes && scale && zp && resnorm && scratch, "null pointer");
+    REQUIRE(((uintptr_t)x & 15) == 0 && ((uintptr_t)codes & 7) == 0, "x must be 16-byte, codes 8-byte aligned");
+    return finish(__func__, svdq::k4_rtvq_launch(x, n, bits, stages, codes, codes_ld, code_bytes, scale, zp, resnorm,
+                                                 (svdq::K4Stats*)scratch, (cudaStream_t)stream));
+}
+
+int svdq_rtvq_dequantize(const void* codes, int64_t codes_ld, int code_bytes, int stages, int64_t n,
+                         const float* scale, const float* zp, float* out, void* stream) {
+    REQUIRE(n >= 0, "n");
+    if (n == 0) return 0;
+    REQUIRE(stages >= 1 && stages <= SVDQ_MAX_STAGES, "stages must be in [1, 8]");
+    REQUIRE(code_bytes == 1 || code_bytes == 2, "code_bytes");
+    REQUIRE(codes && scale && zp && out, "null pointer");
+    return finish(__func__, svdq::k4_dequant_launch(codes, codes_ld, code_bytes, stages, n, scale, zp, out,
+                                                    (cudaStream_t)stream));
+}
+
+int svdq_absmax_quantize(const float* x, int64_t n, int bits, void* q, int code_bytes, float* scale, void* scratch,
+                         void* stream) {
+    REQUIRE(n >= 0, "n");
+    if (n == 0) return 0;
+    REQUIRE(bits >= 2 && bits <= 16, "bits must be in [2, 16]");
+    REQUIRE(code_bytes == 1 || code_bytes == 2, "code_bytes");
+    REQUIRE(x && q && scale && scratch, "null pointer");
+    return finish(__func__, svdq::k4_absmax_launch(x, n, bits, q, code_bytes, scale, (svdq::K4Stats*)scratch,
+                                                   (cudaStream_t)stream));
+}
+
+int svdq_combine_masks(const uint8_t* const* masks, int n_masks, int64_t n, int strategy, uint8_t* out, void* stream) {
+    REQUIRE(n_masks >= 1, "Empty mask list");
+    REQUIRE(n_masks <= SVDQ_MAX_TASKS, "at most 32 masks");
+    REQUIRE(strategy >= 0 && strategy <= 2, "Unknown mask strategy");
+    REQUIRE(n >= 0, "n");
+    if (n == 0) return 0;
+    REQUIRE(masks && out, "null pointer");
+    return finish(__func__, svdq::combine_masks_launch(masks, n_masks, n, strategy, out, (cudaStream_t)stream));
+}
+
+int svdq_unpack_mask(const uint32_t* packed, int64_t n, uint8_t* out, void* stream) {
+    REQUIRE(n >= 0, "n");
+    if (n == 0) return 0;
+    REQUIRE(packed && out, "null pointer");
+    return finish(__func__, svdq::unpack_mask_launch(packed, n, out, (cudaStream_t)stream));
+}
+
+}  // extern "C"

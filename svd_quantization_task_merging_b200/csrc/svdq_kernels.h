@@ -1,0 +1,129 @@
+// Argument blocks and launch entry points shared by the kernel translation units and the C ABI.
+#pragma once
+#include "svdq_common.cuh"
+#include "k2_core.h"
+
+namespace svdq {
+
+struct K1Args {
+    const void* const* tensors;     // [P][NT+1]: base, ft_0 .. ft_{NT-1}; a null ft = task lacks the parameter
+    const uint8_t* const* masks;    // [P][NT] torch.bool storage, null entries = task has no mask; may be null
+    const int64_t* numel;           // [P]
+    const int32_t* tile_param;      // [n_tiles]
+    const int32_t* tile_local;      // [n_tiles] tile index inside its parameter
+    const int64_t* pmask_off;       // [P] word offset of the parameter's packed combined mask
+    uint32_t* packed;               // bit i of word w = combined mask of element 32 w + i
+    float* gram;                    // [n_tiles][FULL ? 2 : 1][G]
+    uint32_t* count;                // [n_tiles] masked elements in the tile
+    int tile_elems;                 // multiple of kStep
+    int strategy;
+};
+
+struct K2ReduceArgs {
+    const float* gram;            // [n_tiles][FULL ? 2 : 1][G]
+    const uint32_t* count;        // [n_tiles]
+    const int64_t* tile_begin;    // [P+1] first tile of each parameter
+    double* gram_masked;          // [P][NT*NT] full symmetric
+    double* gram_all;             // [P][NT*NT] masked + complement (FULL only; may be null)
+    int64_t* dm;                  // [P]
+    int nt;
+    int full;
+};
+
+struct K2SolveArgs {
+    SolveConfig cfg;
+    const double* gram_masked;    // [P][NT*NT]
+    const int64_t* dm;            // [P]
+    const uint8_t* has_mask;      // [P]
+    const uint32_t* present;      // [P]
+    const double* weights;        // [NT]
+    const int32_t* avg_order;     // [NT]
+    const double* sign_ref;       // [P][NT*NT] or null
+    // outputs, strides per parameter as in SolveOut
+    int32_t* info; float* sv; float* scal; float* coef; uint16_t* chigh; uint8_t* codes;
+    float* qscale; float* qzp; float* qres; float* chat; float* cbar; float* W; float* gvec; double* V;
+};
+
+struct K3Args {
+    const void* const* tensors;   // [P][NT+1]
+    const int64_t* numel;         // [P]
+    const int32_t* tile_param;    // [n_tiles]
+    const int32_t* tile_local;    // [n_tiles]
+    const int64_t* pmask_off;     // [P]
+    const uint8_t* has_mask;      // [P]
+    const uint32_t* packed;       // packed combined masks written by K1
+    const int32_t* info;          // [P][8] from K2
+    const float* W;               // [P][NT*NT]  W[t][j]
+    const float* cbar;            // [P][NT]
+    const float* gvec;            // [P][NT]
+    const float* scal;            // [P][4]
+    const float* chat;            // [P][NT*NT]  chat[t][j] (DIAG)
+    float* const* out;            // [P] merged fp32 tensors
+    float* diag;                  // [n_tiles][5][NT] partials (DIAG)
+    int tile_elems;
+    int center;
+};
+
+struct K3DiagArgs {
+    const float* diag;            // [n_tiles][5][NT]
+    const int64_t* tile_begin;    // [P+1]
+    const int64_t* dm;            // [P]
+    const int32_t* info;          // [P][8]
+    double* out;                  // [P][NT][6]: absolute_error, relative_error, max_absolute_error,
+                                  //             mean_absolute_error, original_norm, reconstructed_norm
+    int nt;
+};
+
+constexpr int kK4MaxGrid = 148 * 8;
+
+struct K4Stats {            // one record per CTA, reduced in CTA order by k4_finalize
+    float lo, hi;
+    int nan;
+    int pad;
+    double sumsq;
+};
+
+struct K5Args {
+    const void* const* tensors;   // [P][NT+1]
+    const int64_t* numel;
+    const int32_t* tile_param;
+    const int32_t* tile_local;
+    const int64_t* pmask_off;
+    const uint8_t* has_mask;
+    const uint32_t* packed;
+    const int32_t* info;          // [P][8]
+    const float* W;               // [P][NT*NT]
+    const int64_t* tile_row_off;  // [n_tiles]
+    void* const* u_high;          // [P]  [Dm x k]      (fp16 when fp16_basis else fp32)
+    void* const* u_low;           // [P]  [Dm x (r-k)]
+    float* const* mean;           // [P]  [Dm] or null entries / null table
+    int tile_elems;
+    int center;
+    int fp16_basis;
+};
+
+// launchers (one translation unit per kernel family; K1/K3/K5 additionally one per dtype)
+template <int DT> cudaError_t k1_launch_dtype(int nt, const K1Args& a, int n_tiles, bool full, cudaStream_t st);
+template <int DT> cudaError_t k3_launch_dtype(int nt, const K3Args& a, int n_tiles, bool fp16b, bool diag, cudaStream_t st);
+template <int DT> cudaError_t k5_launch_dtype(int nt, const K5Args& a, int n_tiles, cudaStream_t st);
+cudaError_t k2_reduce_launch(const K2ReduceArgs& a, int n_params, cudaStream_t st);
+cudaError_t k2_solve_launch(const K2SolveArgs& a, int n_params, cudaStream_t st);
+cudaError_t k3_diag_launch(const K3DiagArgs& a, int n_params, cudaStream_t st);
+cudaError_t k5_offsets_launch(const uint32_t* count, const int64_t* tile_begin, int64_t* tile_row_off, int n_params,
+                              cudaStream_t st);
+cudaError_t k4_rtvq_launch(const float* x, int64_t n, int bits, int stages, void* codes, int64_t codes_ld,
+                           int code_bytes, float* scale, float* zp, float* resnorm, K4Stats* part, cudaStream_t st);
+cudaError_t k4_dequant_launch(const void* codes, int64_t codes_ld, int code_bytes, int stages, int64_t n,
+                              const float* scale, const float* zp, float* out, cudaStream_t st);
+cudaError_t k4_absmax_launch(const float* x, int64_t n, int bits, void* q, int code_bytes, float* scale,
+                             K4Stats* part, cudaStream_t st);
+cudaError_t combine_masks_launch(const uint8_t* const* masks, int n_masks, int64_t n, int strategy, uint8_t* out,
+                                 cudaStream_t st);
+cudaError_t unpack_mask_launch(const uint32_t* packed, int64_t n, uint8_t* out, cudaStream_t st);
+
+template <int DT> struct DTypeOf;
+template <> struct DTypeOf<kF32> { using type = float; };
+template <> struct DTypeOf<kBF16> { using type = __nv_bfloat16; };
+template <> struct DTypeOf<kF16> { using type = __half; };
+
+}  // namespace svdq

@@ -1,0 +1,590 @@
+"""Fused SVD-Hybrid merge on one B200: K1 (task vectors + tall masks + Gram) -> K2 (per-parameter
+solve) -> K3 (reconstruct + merge [+ diagnostics]) [-> K5 (materialise bases)].
+
+This is the fast path behind ``run_svd_hybrid_pipeline`` (reference: src/svd_hybrid/cli.py:73-778,
+steps 1-9) and the fine-grained operator mirrors in ``svd_hybrid/``.  All arithmetic runs in
+libsvdq.so (include/svdq.h); torch is used for device memory, streams and host<->device copies.
+
+Data layout in HBM
+  * inputs stay where the caller put them (one device tensor per parameter and state dict) or,
+    when they arrive from the host, are staged into flat per-state-dict arenas;
+  * per launch group (= all parameters of one dtype) small int64/int32 tables describe the work:
+    pointer tables [P][N+1] / [P][N], numel[P], and a tile list (tile -> parameter, local index);
+  * a tile is TILE_ELEMS consecutive elements of one parameter; K1 writes one partial Gram and
+    one masked count per tile, the combined tall mask goes to a bit-packed buffer (1 bit/element);
+  * K2 outputs are SoA arrays with stride N per parameter (see include/svdq.h);
+  * merged parameters are written into one flat fp32 arena and handed out as views.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+import os
+from collections import OrderedDict
+from dataclasses import dataclass, field
+from typing import Dict, List, Mapping, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _native
+from .svd_hybrid.weighting import compute_weights, effective_merge_weights
+
+TILE_ELEMS = 16384          # elements per tile (multiple of 1024); fixes the reduction order
+MAX_STREAM_TASKS = 16
+_FLOAT_DTYPES = {torch.float32: 0, torch.bfloat16: 1, torch.float16: 2}
+_ALIGN = {torch.float32: 16, torch.bfloat16: 8, torch.float16: 8}
+
+
+_PINNED: Dict[Tuple[int, torch.dtype], torch.Tensor] = {}
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _dev(a: np.ndarray, device) -> torch.Tensor:
+    return torch.from_numpy(np.ascontiguousarray(a)).to(device, non_blocking=True)
+
+
+def _aligned_flat(t: torch.Tensor, device, align: int) -> torch.Tensor:
+    """Contiguous, aligned, flattened device view/copy of ``t`` (copy only when needed)."""
+    t = t.detach()
+    if t.device != device:
+        t = t.to(device, non_blocking=True)
+    if not t.is_contiguous():
+        t = t.contiguous()
+    if t.data_ptr() % align:
+        t = t.clone()
+    return t.view(-1)
+
+
+class PackedStateDict(OrderedDict):
+    """A state dict whose tensors are views into ONE flat buffer (``.flat``), element offsets in
+    ``.offsets``.  Lets the engine move a whole checkpoint with a single host->device copy."""
+    flat: torch.Tensor
+    offsets: Dict[str, int]
+
+
+def pack_state_dict(sd: Mapping[str, torch.Tensor], pin: bool = False, align_elems: int = 64) -> PackedStateDict:
+    """Re-home a (host or device) state dict into one flat buffer; all tensors must share a dtype."""
+    dtypes = {v.dtype for v in sd.values()}
+    if len(dtypes) != 1:
+        raise ValueError("pack_state_dict needs a single dtype per state dict")
+    dtype = next(iter(dtypes))
+    offs, n = {}, 0
+    for k, v in sd.items():
+        offs[k] = n
+        n += (v.numel() + align_elems - 1) // align_elems * align_elems
+    dev = next(iter(sd.values())).device
+    flat = torch.zeros(n, dtype=dtype, device=dev)
+    if pin and dev.type == "cpu" and torch.cuda.is_available():
+        flat = flat.pin_memory()
+    out = PackedStateDict()
+    for k, v in sd.items():
+        view = flat[offs[k]: offs[k] + v.numel()].view(v.shape)
+        view.copy_(v)
+        out[k] = view
+    out.flat, out.offsets = flat, offs
+    return out
+
+
+def _to_device_state_dict(sd: Mapping[str, torch.Tensor], device) -> Mapping[str, torch.Tensor]:
+    """Host -> device move of a state dict (one copy when it is packed)."""
+    if isinstance(sd, PackedStateDict) and sd.flat.device != device:
+        flat = sd.flat.to(device, non_blocking=True)
+        out = PackedStateDict((k, flat[o: o + v.numel()].view(v.shape)) for (k, v), o in
+                              zip(sd.items(), sd.offsets.values()))
+        out.flat, out.offsets = flat, sd.offsets
+        return out
+    return sd
+
+
+@dataclass
+class _Group:
+    """All parameters of one dtype: one K1 / K2 / K3 launch each."""
+    dtype: torch.dtype
+    names: List[str] = field(default_factory=list)
+    shapes: List[torch.Size] = field(default_factory=list)
+    numel: List[int] = field(default_factory=list)
+    keep: List[torch.Tensor] = field(default_factory=list)     # keeps staged tensors alive
+    # device tables / workspaces (filled by MergeJob._build_group)
+    t: Dict[str, torch.Tensor] = field(default_factory=dict)
+    n_tiles: int = 0
+    any_mask: bool = False
+    out_off: List[int] = field(default_factory=list)
+    host: Dict[str, np.ndarray] = field(default_factory=dict)
+
+
+class MergeJob:
+    """One SVD-Hybrid merge of N fine-tuned state dicts against a base on one GPU.
+
+    prepare (constructor) -> run() (kernel launches, asynchronous) -> results() (reference-shaped
+    result dict, built lazily from a handful of small device->host copies).
+    """
+
+    def __init__(self, base: Mapping[str, torch.Tensor], finetuned: Mapping[str, Mapping[str, torch.Tensor]],
+                 task_masks: Optional[Mapping[str, Optional[Mapping[str, torch.Tensor]]]], config,
+                 device: Optional[str] = None, *, sign_ref: Optional[Mapping[str, torch.Tensor]] = None,
+                 diagnostics: Optional[bool] = None, materialize_bases: bool = False,
+                 performance: Optional[Dict[str, float]] = None,
+                 cluster_assignments: Optional[Dict[str, int]] = None, param_filter: Optional[Sequence[str]] = None,
+                 tile_elems: int = TILE_ELEMS, cluster_backend: Optional[str] = None):
+        _native.require_cuda()
+        self.cfg = config
+        self.device = torch.device(device or "cuda")
+        if self.device.type != "cuda":
+            raise _native.NativeLibraryError("the SVD-Hybrid merge path runs only on a CUDA device (no CPU fallback)")
+        self.tasks: List[str] = list(config.tasks) if getattr(config, "tasks", None) else list(finetuned.keys())
+        self.N = len(self.tasks)
+        if self.N < 1:
+            raise ValueError("Empty delta list")
+        if self.N > MAX_STREAM_TASKS:
+            raise ValueError(f"n_tasks={self.N}: the streaming kernels support at most {MAX_STREAM_TASKS} task "
+                             f"vectors per merge in this build")
+        if getattr(config, "svd_include_noise", False):
+            raise NotImplementedError("svd_include_noise (noise-region bases) is not part of this build "
+                                      "(SURVEY.md section 8f, rank 4)")
+        if config.svd_mask_strategy not in _native.STRATEGY_CODE:
+            raise ValueError(f"Unknown mask strategy: {config.svd_mask_strategy}")
+        self.tile_elems = int(tile_elems)
+        self.want_diag = config.svd_eval_reconstruction if diagnostics is None else bool(diagnostics)
+        self.materialize = bool(materialize_bases)
+        self.sign_ref = sign_ref
+        self.performance = performance
+        self.fixed_assignments = cluster_assignments
+        self.cluster_mode = config.svd_weighting == "cluster"
+        self.cluster_backend = cluster_backend or os.environ.get("SVDQ_CLUSTER_BACKEND", "exact")
+        self.stages = int(config.svd_rtvq_stages)
+        self.bits = int(config.svd_low_bits)
+        if self.stages > 8:
+            raise ValueError("RTVQ stages must be <= 8 in this build")
+
+        with torch.cuda.device(self.device):
+            self._stage_inputs(base, finetuned, task_masks, param_filter)
+            for g in self.groups.values():
+                self._build_group(g)
+        self._ran = False
+        self._fetched: Optional[Dict[str, Dict[str, np.ndarray]]] = None
+        self.weights: Optional[Dict[str, float]] = None
+        self.cluster_assignments: Optional[Dict[str, int]] = None
+        self.timing: Dict[str, float] = {}
+
+    # ------------------------------------------------------------------------------------------
+    def _stage_inputs(self, base, finetuned, task_masks, param_filter):
+        dev = self.device
+        base_d = _to_device_state_dict(base, dev)
+        fts_d = [(_to_device_state_dict(finetuned[t], dev) if t in finetuned else {}) for t in self.tasks]
+        self.h2d_bytes = 0
+        for sd in [base] + [finetuned[t] for t in self.tasks if t in finetuned]:
+            for v in sd.values():
+                if v.device != dev:
+                    self.h2d_bytes += v.numel() * v.element_size()
+        masks_d: List[Optional[Mapping[str, torch.Tensor]]] = []
+        for t in self.tasks:
+            m = task_masks.get(t) if task_masks else None
+            if m is not None:
+                for v in m.values():
+                    if v.device != dev:
+                        self.h2d_bytes += v.numel() * v.element_size()
+                m = _to_device_state_dict(m, dev)
+            masks_d.append(m)
+
+        self.base_keys = list(base.keys())
+        self.base_ref = base
+        self.groups: "OrderedDict[torch.dtype, _Group]" = OrderedDict()
+        self.passthrough: List[str] = []
+        self._tensors: Dict[str, List[Optional[torch.Tensor]]] = {}
+        self._masks: Dict[str, List[Optional[torch.Tensor]]] = {}
+        self.shapes: Dict[str, torch.Size] = {}
+        wanted = set(param_filter) if param_filter is not None else None
+        for name in sorted(base.keys()):
+            b = base_d[name]
+            if wanted is not None and name not in wanted:
+                self.passthrough.append(name)
+                continue
+            if not torch.is_tensor(b) or b.dtype not in _FLOAT_DTYPES or b.numel() == 0:
+                self.passthrough.append(name)
+                continue
+            row: List[Optional[torch.Tensor]] = [None] * (self.N + 1)
+            any_task = False
+            for i, sd in enumerate(fts_d):
+                f = sd.get(name) if sd else None
+                if f is None or f.shape != b.shape:
+                    continue
+                if f.dtype != b.dtype:
+                    raise ValueError(f"{name}: dtype mismatch between base ({b.dtype}) and task {self.tasks[i]} ({f.dtype})")
+                row[i + 1] = _aligned_flat(f, dev, _ALIGN[b.dtype])
+                any_task = True
+            if not any_task:
+                self.passthrough.append(name)
+                continue
+            row[0] = _aligned_flat(b, dev, _ALIGN[b.dtype])
+            mrow: List[Optional[torch.Tensor]] = [None] * self.N
+            for i, m in enumerate(masks_d):
+                mk = m.get(name) if m else None
+                if mk is None:
+                    continue
+                if mk.shape != b.shape:
+                    mrow = [None] * self.N       # cli.py:330: a mask of the wrong shape is not used
+                    break
+                if mk.dtype != torch.bool:
+                    mk = mk.bool()
+                mrow[i] = _aligned_flat(mk, dev, 4)
+            g = self.groups.setdefault(b.dtype, _Group(dtype=b.dtype))
+            g.names.append(name)
+            g.shapes.append(b.shape)
+            g.numel.append(b.numel())
+            self._tensors[name] = row
+            self._masks[name] = mrow
+            self.shapes[name] = b.shape
+
+    # ------------------------------------------------------------------------------------------
+    def _build_group(self, g: _Group):
+        dev, N, S, te = self.device, self.N, self.stages, self.tile_elems
+        P = len(g.names)
+        numel = np.asarray(g.numel, np.int64)
+        tiles_per = (numel + te - 1) // te
+        tile_begin = np.zeros(P + 1, np.int64)
+        np.cumsum(tiles_per, out=tile_begin[1:])
+        n_tiles = int(tile_begin[-1])
+        tile_param = np.repeat(np.arange(P, dtype=np.int32), tiles_per)
+        tile_local = (np.arange(n_tiles, dtype=np.int64) - np.repeat(tile_begin[:-1], tiles_per)).astype(np.int32)
+        tptr = np.zeros((P, N + 1), np.int64)
+        mptr = np.zeros((P, N), np.int64)
+        present = np.zeros(P, np.uint32)
+        has_mask = np.zeros(P, np.uint8)
+        pm_off = np.zeros(P, np.int64)
+        words = 0
+        out_off, out_total = [], 0
+        for p, name in enumerate(g.names):
+            row, mrow = self._tensors[name], self._masks[name]
+            g.keep.extend(x for x in row if x is not None)
+            g.keep.extend(x for x in mrow if x is not None)
+            for i, x in enumerate(row):
+                tptr[p, i] = 0 if x is None else x.data_ptr()
+            for i in range(N):
+                if row[i + 1] is not None:
+                    present[p] |= np.uint32(1 << i)
+                if mrow[i] is not None:
+                    mptr[p, i] = mrow[i].data_ptr()
+                    has_mask[p] = 1
+            pm_off[p] = words
+            if has_mask[p]:
+                words += (int(numel[p]) + 31) // 32 + 32     # padding: a 4-element step may touch 1 word past
+            out_off.append(out_total)
+            out_total += (int(numel[p]) + 63) // 64 * 64
+        g.any_mask = bool(has_mask.any())
+        g.n_tiles, g.out_off = n_tiles, out_off
+        g.host = dict(numel=numel, tile_begin=tile_begin, has_mask=has_mask, present=present)
+        G = N * (N + 1) // 2
+        full = 2 if self.cluster_mode else 1
+        f32, i32, i64, f64, u8 = torch.float32, torch.int32, torch.int64, torch.float64, torch.uint8
+        z = lambda *shape, dtype=f32: torch.zeros(*shape, dtype=dtype, device=dev)   # noqa: E731
+        g.t = dict(
+            tptr=_dev(tptr, dev), mptr=_dev(mptr, dev) if g.any_mask else None, numel=_dev(numel, dev),
+            tile_param=_dev(tile_param, dev), tile_local=_dev(tile_local, dev), tile_begin=_dev(tile_begin, dev),
+            pm_off=_dev(pm_off, dev), has_mask=_dev(has_mask, dev), present=_dev(present.view(np.int32), dev),
+            packed=z(max(words, 1), dtype=i32), gram=z(max(n_tiles, 1) * full * G), count=z(max(n_tiles, 1), dtype=i32),
+            gram_masked=z(P, N * N, dtype=f64), gram_all=z(P, N * N, dtype=f64) if self.cluster_mode else None,
+            dm=z(P, dtype=i64), info=z(P, 8, dtype=i32), sv=z(P, N), scal=z(P, 4), coef=z(P, N, N),
+            chigh=z(P, N, N, dtype=torch.int16), codes=z(P, N, S, N, dtype=u8), qscale=z(P, N, S), qzp=z(P, N, S),
+            qres=z(P, N, S), chat=z(P, N, N), cbar=z(P, N), W=z(P, N, N), gvec=z(P, N), V=z(P, N, N, dtype=f64),
+            out=torch.empty(out_total, dtype=f32, device=dev),
+            diag=z(max(n_tiles, 1) * 5 * N) if self.want_diag else None,
+            diag_out=z(P, N, 6, dtype=f64) if self.want_diag else None,
+        )
+        optr = np.asarray([g.t["out"].data_ptr() + 4 * o for o in out_off], np.int64)
+        g.t["optr"] = _dev(optr, dev)
+        if self.sign_ref is not None:
+            sr = np.zeros((P, N, N), np.float64)
+            for p, name in enumerate(g.names):
+                v = self.sign_ref.get(name)
+                if v is not None:
+                    v = np.asarray(v.detach().double().cpu().numpy() if torch.is_tensor(v) else v, np.float64)
+                    sr[p, : v.shape[0], : v.shape[1]] = v
+            g.t["sign_ref"] = _dev(sr, dev)
+        else:
+            g.t["sign_ref"] = None
+
+    # ------------------------------------------------------------------------------------------
+    def _weights_table(self) -> Tuple[torch.Tensor, torch.Tensor]:
+        cfg = self.cfg
+        if cfg.svd_weighting == "performance" and self.performance is not None:
+            from .svd_hybrid.weighting import compute_performance_weights
+            self.weights = compute_performance_weights(
+                {t: float(self.performance.get(t, 1.0)) for t in self.tasks}, cfg.svd_weighting_temperature)
+        else:
+            self.weights = compute_weights(self.tasks, weighting_strategy=cfg.svd_weighting,
+                                           performance_file=getattr(cfg, "performance_file", None),
+                                           temperature=cfg.svd_weighting_temperature,
+                                           cluster_assignments=self.cluster_assignments)
+        eff = effective_merge_weights(self.tasks, self.weights,
+                                      self.cluster_assignments if self.cluster_mode else None)
+        w = np.asarray([eff[t] for t in self.tasks], np.float64)
+        order = np.asarray(sorted(range(self.N), key=lambda i: self.tasks[i]), np.int32)
+        return _dev(w, self.device), _dev(order, self.device)
+
+    def _cluster(self):
+        """Whole-model task Gram (K1 by-product) -> host k-means (clustering.py:198-245)."""
+        from .svd_hybrid.clustering import cluster_from_gram
+        if self.fixed_assignments is not None:
+            self.cluster_assignments = dict(self.fixed_assignments)
+            return
+        tot = None
+        for g in self.groups.values():
+            s = g.t["gram_all"].sum(dim=0)
+            tot = s if tot is None else tot + s
+        gram = tot.view(self.N, self.N).cpu().numpy()
+        self.whole_model_gram = gram
+        self.cluster_assignments = cluster_from_gram(gram, self.tasks, self.cfg.svd_cluster_k, "kmeans",
+                                                     backend=self.cluster_backend)
+
+    # ------------------------------------------------------------------------------------------
+    def run(self, record_events: bool = False) -> "MergeJob":
+        """Launch the whole path on the current stream.  Asynchronous except for the k-means
+        round trip of cluster weighting."""
+        cfg, N, te = self.cfg, self.N, self.tile_elems
+        st = _native.stream_ptr()
+        strat = _native.STRATEGY_CODE[cfg.svd_mask_strategy]
+        full = 1 if self.cluster_mode else 0
+        ev = {}
+
+        def mark(name):
+            if record_events:
+                e = torch.cuda.Event(enable_timing=True)
+                e.record()
+                ev[name] = e
+
+        with torch.cuda.device(self.device):
+            mark("start")
+            for g in self.groups.values():
+                t = g.t
+                _native.call("svdq_tv_mask_gram", _FLOAT_DTYPES[g.dtype], N, strat, full, g.n_tiles, te,
+                             _ptr(t["tptr"]), _ptr(t["mptr"]), _ptr(t["numel"]), _ptr(t["tile_param"]),
+                             _ptr(t["tile_local"]), _ptr(t["pm_off"]), _ptr(t["packed"]), _ptr(t["gram"]),
+                             _ptr(t["count"]), st)
+            mark("k1")
+            for g in self.groups.values():
+                t = g.t
+                _native.call("svdq_gram_reduce", N, full, len(g.names), _ptr(t["gram"]), _ptr(t["count"]),
+                             _ptr(t["tile_begin"]), _ptr(t["gram_masked"]), _ptr(t["gram_all"]), _ptr(t["dm"]), st)
+            if self.cluster_mode:
+                self._cluster()
+            w_dev, order_dev = self._weights_table()
+            self._w_keep = (w_dev, order_dev)
+            max_rank = int(cfg.svd_max_rank) if cfg.svd_max_rank is not None else 0
+            for g in self.groups.values():
+                t = g.t
+                _native.call("svdq_param_solve", N, len(g.names), int(bool(cfg.svd_center)),
+                             float(cfg.svd_energy_threshold), max_rank, int(cfg.svd_min_mask_size), self.bits,
+                             self.stages, _ptr(t["gram_masked"]), _ptr(t["dm"]), _ptr(t["has_mask"]),
+                             _ptr(t["present"]), _ptr(w_dev), _ptr(order_dev), _ptr(t["sign_ref"]),
+                             _ptr(t["info"]), _ptr(t["sv"]), _ptr(t["scal"]), _ptr(t["coef"]), _ptr(t["chigh"]),
+                             _ptr(t["codes"]), _ptr(t["qscale"]), _ptr(t["qzp"]), _ptr(t["qres"]), _ptr(t["chat"]),
+                             _ptr(t["cbar"]), _ptr(t["W"]), _ptr(t["gvec"]), _ptr(t["V"]), st)
+            mark("k2")
+            for g in self.groups.values():
+                t = g.t
+                _native.call("svdq_reconstruct_merge", _FLOAT_DTYPES[g.dtype], N, int(bool(cfg.svd_fp16)),
+                             int(self.want_diag), int(bool(cfg.svd_center)), g.n_tiles, te, _ptr(t["tptr"]),
+                             _ptr(t["numel"]), _ptr(t["tile_param"]), _ptr(t["tile_local"]), _ptr(t["pm_off"]),
+                             _ptr(t["has_mask"]), _ptr(t["packed"]), _ptr(t["info"]), _ptr(t["W"]), _ptr(t["cbar"]),
+                             _ptr(t["gvec"]), _ptr(t["scal"]), _ptr(t["chat"]), _ptr(t["optr"]), _ptr(t["diag"]), st)
+            mark("k3")
+            if self.want_diag:
+                for g in self.groups.values():
+                    t = g.t
+                    _native.call("svdq_diag_finalize", N, len(g.names), _ptr(t["diag"]), _ptr(t["tile_begin"]),
+                                 _ptr(t["dm"]), _ptr(t["info"]), _ptr(t["diag_out"]), st)
+            mark("end")
+        self._events = ev
+        self._ran = True
+        self._fetched = None
+        self._bases_done = False
+        return self
+
+    @property
+    def gpu_launches(self) -> int:
+        """Kernels of libsvdq.so launched by one run()."""
+        ng = len(self.groups)
+        return ng * (4 + (1 if self.want_diag else 0))
+
+    def event_times_ms(self) -> Dict[str, float]:
+        ev = self._events
+        torch.cuda.synchronize(self.device)
+        names = ["start", "k1", "k2", "k3", "end"]
+        return {f"{b}": ev[a].elapsed_time(ev[b]) for a, b in zip(names[:-1], names[1:])}
+
+    # ------------------------------------------------------------------------------------------
+    def _fetch(self) -> Dict[torch.dtype, Dict[str, np.ndarray]]:
+        if not self._ran:
+            self.run()
+        if self._fetched is None:
+            out = {}
+            keys = ["info", "sv", "scal", "coef", "chigh", "codes", "qscale", "qzp", "qres", "cbar", "V", "dm"]
+            if self.want_diag:
+                keys.append("diag_out")
+            for dt, g in self.groups.items():
+                out[dt] = {k: g.t[k].cpu().numpy() for k in keys}
+            self._fetched = out
+        return self._fetched
+
+    def merged_deltas_device(self) -> Dict[str, torch.Tensor]:
+        raise NotImplementedError
+
+    def merged_state_dict(self, to_host: bool = False) -> "OrderedDict[str, torch.Tensor]":
+        """merged = base + delta for every base key, in base key order (merge.py:483-494)."""
+        if not self._ran:
+            self.run()
+        fetched = self._fetch()
+        views: Dict[str, torch.Tensor] = {}
+        for dt, g in self.groups.items():
+            flat = g.t["out"]
+            if to_host:
+                if to_host == "reuse":      # one cached pinned buffer per size: results alias it until the next call
+                    key = (flat.numel(), flat.dtype)
+                    host = _PINNED.get(key)
+                    if host is None:
+                        host = _PINNED[key] = torch.empty(flat.shape, dtype=flat.dtype, pin_memory=True)
+                else:
+                    host = torch.empty(flat.shape, dtype=flat.dtype, pin_memory=True)
+                host.copy_(flat, non_blocking=True)
+                flat = host
+            info = fetched[dt]["info"]
+            for p, name in enumerate(g.names):
+                if info[p, 0] != 0:
+                    continue                      # no basis: the reference clones the base parameter
+                views[name] = flat[g.out_off[p]: g.out_off[p] + g.numel[p]].view(g.shapes[p])
+        if to_host:
+            torch.cuda.synchronize(self.device)
+        out: "OrderedDict[str, torch.Tensor]" = OrderedDict()
+        for k in self.base_keys:
+            if k in views:
+                out[k] = views[k]
+            else:
+                b = self.base_ref[k]
+                out[k] = b.clone() if torch.is_tensor(b) else b
+                if torch.is_tensor(b) and not to_host and b.device != self.device:
+                    out[k] = out[k].to(self.device)
+        return out
+
+    # ------------------------------------------------------------------------------------------
+    def _materialize_bases(self):
+        """K5: U_high / U_low / mean compacted to the masked rows, in the artifact dtype."""
+        if self._bases_done:
+            return
+        fetched = self._fetch()
+        cfg, N, te = self.cfg, self.N, self.tile_elems
+        st = _native.stream_ptr()
+        udt = torch.float16 if cfg.svd_fp16 else torch.float32
+        self._basis_tensors: Dict[str, Tuple[torch.Tensor, torch.Tensor, Optional[torch.Tensor]]] = {}
+        with torch.cuda.device(self.device):
+            for dt, g in self.groups.items():
+                t, info, dm = g.t, fetched[dt]["info"], fetched[dt]["dm"]
+                P = len(g.names)
+                uh_ptr, ul_ptr, mn_ptr = np.zeros(P, np.int64), np.zeros(P, np.int64), np.zeros(P, np.int64)
+                for p, name in enumerate(g.names):
+                    if info[p, 0] != 0:
+                        continue
+                    r, k, d = int(info[p, 2]), int(info[p, 3]), int(dm[p])
+                    uh = torch.zeros(d, k, dtype=udt, device=self.device)
+                    ul = torch.zeros(d, r - k, dtype=udt, device=self.device)
+                    mn = torch.zeros(d, 1, dtype=torch.float32, device=self.device) if cfg.svd_center else None
+                    self._basis_tensors[name] = (uh, ul, mn)
+                    uh_ptr[p], ul_ptr[p] = uh.data_ptr(), ul.data_ptr()
+                    mn_ptr[p] = mn.data_ptr() if mn is not None else 0
+                row_off = torch.zeros(max(g.n_tiles, 1), dtype=torch.int64, device=self.device)
+                uh_d, ul_d, mn_d = _dev(uh_ptr, self.device), _dev(ul_ptr, self.device), _dev(mn_ptr, self.device)
+                _native.call("svdq_basis_offsets", P, _ptr(t["count"]), _ptr(t["tile_begin"]), _ptr(row_off), st)
+                _native.call("svdq_write_basis", _FLOAT_DTYPES[g.dtype], N, int(bool(cfg.svd_fp16)),
+                             int(bool(cfg.svd_center)), g.n_tiles, te, _ptr(t["tptr"]), _ptr(t["numel"]),
+                             _ptr(t["tile_param"]), _ptr(t["tile_local"]), _ptr(t["pm_off"]), _ptr(t["has_mask"]),
+                             _ptr(t["packed"]), _ptr(t["info"]), _ptr(t["W"]), _ptr(row_off), _ptr(uh_d), _ptr(ul_d),
+                             _ptr(mn_d) if cfg.svd_center else None, st)
+                g.keep.extend([row_off, uh_d, ul_d, mn_d])
+        self._bases_done = True
+
+    def combined_masks(self) -> Dict[str, torch.Tensor]:
+        """Combined tall masks as torch.bool tensors (what combine_masks returns)."""
+        if not self._ran:
+            self.run()
+        st = _native.stream_ptr()
+        out = {}
+        with torch.cuda.device(self.device):
+            for g in self.groups.values():
+                hm = g.host["has_mask"]
+                pm_off = g.t["pm_off"].cpu().numpy()
+                for p, name in enumerate(g.names):
+                    if not hm[p]:
+                        continue
+                    m = torch.empty(g.numel[p], dtype=torch.bool, device=self.device)
+                    _native.call("svdq_unpack_mask", g.t["packed"].data_ptr() + 4 * int(pm_off[p]), g.numel[p],
+                                 m.data_ptr(), st)
+                    out[name] = m.view(g.shapes[p])
+        return out
+
+    # ------------------------------------------------------------------------------------------
+    def results(self, to_host: bool = False) -> Dict:
+        """{"merged_state_dict", "diagnostics", "bases", "compressed"} as cli.py:773-778."""
+        from .results import LazyBases, LazyCompressed, build_diagnostics
+        merged = self.merged_state_dict(to_host=to_host)
+        fetched = self._fetch()
+        if self.materialize:
+            self._materialize_bases()
+        index = {}
+        for dt, g in self.groups.items():
+            info = fetched[dt]["info"]
+            for p, name in enumerate(g.names):
+                if info[p, 0] == 0:
+                    index[name] = (dt, p)
+        bases = LazyBases(self, index)
+        compressed = LazyCompressed(self, index)
+        if self.want_diag:
+            diag = build_diagnostics(self, index)
+        else:
+            diag = {}
+        diag["task_weights"] = self.weights
+        if self.cluster_assignments:
+            diag["cluster_assignments"] = self.cluster_assignments
+        return {"merged_state_dict": merged, "diagnostics": diag, "bases": bases, "compressed": compressed}
+
+
+def merge_state_dicts(base, finetuned, task_masks, config, device: Optional[str] = None, **kw) -> Dict:
+    """Fused fast path: the whole of run_svd_hybrid_pipeline steps 1-9 (cli.py:146-722) on in-memory
+    state dicts.  Returns the reference's result dict (cli.py:773-778)."""
+    to_host = kw.pop("to_host", False)
+    job = MergeJob(base, finetuned, task_masks, config, device, **kw)
+    job.run()
+    res = job.results(to_host=to_host)
+    res["job"] = job
+    return res
+
+
+def task_vector_gram(task_vectors: Mapping[str, Mapping[str, torch.Tensor]], names: Sequence[str]) -> np.ndarray:
+    """Whole-model N x N Gram of already-formed task vectors via K1 (base = zeros)."""
+    _native.require_cuda()
+    dev = torch.device("cuda")
+    N = len(names)
+    if N > MAX_STREAM_TASKS:
+        raise ValueError(f"at most {MAX_STREAM_TASKS} task vectors")
+    params = sorted({p for n in names for p in task_vectors[n].keys()})
+    total = np.zeros((N, N), np.float64)
+    from .svd_hybrid.config import SVDHybridConfig
+    cfg = SVDHybridConfig(tasks=list(names), svd_weighting="cluster", svd_eval_reconstruction=False)
+    ref = {}
+    for p in params:
+        src = next(task_vectors[n][p] for n in names if p in task_vectors[n])
+        ref[p] = torch.zeros_like(src, device=dev)
+    fts = {n: {p: v.to(dev) for p, v in task_vectors[n].items()} for n in names}
+    job = MergeJob(ref, fts, None, cfg, "cuda", cluster_assignments={n: 0 for n in names})
+    st = _native.stream_ptr()
+    for g in job.groups.values():
+        t = g.t
+        _native.call("svdq_tv_mask_gram", _FLOAT_DTYPES[g.dtype], N, 0, 1, g.n_tiles, job.tile_elems,
+                     _ptr(t["tptr"]), None, _ptr(t["numel"]), _ptr(t["tile_param"]), _ptr(t["tile_local"]),
+                     _ptr(t["pm_off"]), _ptr(t["packed"]), _ptr(t["gram"]), _ptr(t["count"]), st)
+        _native.call("svdq_gram_reduce", N, 1, len(g.names), _ptr(t["gram"]), _ptr(t["count"]),
+                     _ptr(t["tile_begin"]), _ptr(t["gram_masked"]), _ptr(t["gram_all"]), _ptr(t["dm"]), st)
+        total += g.t["gram_all"].sum(dim=0).view(N, N).cpu().numpy()
+    return total

@@ -1,0 +1,171 @@
+"""Reference-shaped views over the packed outputs of a MergeJob.
+
+The reference returns nested dicts of thousands of tiny tensors (cli.py:773-778; layouts in
+basis.py:398-407, compress.py:53-56, rtvq.py:69-75,120-126, diagnostics.py:147-231,261-319).
+Building them eagerly would cost more host time than the whole GPU merge, so they are
+materialised per parameter on access from a handful of small device->host copies.
+"""
+from __future__ import annotations
+
+from collections import OrderedDict
+from collections.abc import Mapping
+from typing import Dict, Tuple
+
+import numpy as np
+import torch
+
+
+def estimate_ratio(n: int, bits: int, stages: int) -> float:
+    """estimate_compression_ratio (src/svd_hybrid/rtvq.py:142-161) for an n-element low block."""
+    return (n * 4) / max(n * bits / 8 * stages + 8 * stages, 1)
+
+
+class _LazyParamMap(Mapping):
+    def __init__(self, job, index: Dict[str, Tuple[torch.dtype, int]]):
+        self._job = job
+        self._index = OrderedDict((k, index[k]) for k in sorted(index))
+        self._cache: Dict[str, dict] = {}
+
+    def __len__(self):
+        return len(self._index)
+
+    def __iter__(self):
+        return iter(self._index)
+
+    def __contains__(self, k):
+        return k in self._index
+
+    def __getitem__(self, k):
+        if k not in self._cache:
+            self._cache[k] = self._build(k)
+        return self._cache[k]
+
+    def _build(self, k):
+        raise NotImplementedError
+
+
+class LazyCompressed(_LazyParamMap):
+    """compressed[param][task] = {"masked": {"c_high_fp16", "c_low_quant"}, "unmasked": None}."""
+
+    def _build(self, name):
+        job = self._job
+        dt, p = self._index[name]
+        f = job._fetch()[dt]
+        info = f["info"][p]
+        r, k = int(info[2]), int(info[3])
+        n_low = r - k
+        present = int(job.groups[dt].host["present"][p])
+        out = OrderedDict()
+        for t, task in enumerate(job.tasks):
+            if not (present >> t) & 1:
+                continue
+            c_high = torch.from_numpy(f["chigh"][p, t, :k].copy().view(np.float16))
+            payloads = []
+            if n_low > 0:
+                for s in range(job.stages):
+                    payloads.append({
+                        "stage": s,
+                        "quantized": torch.from_numpy(f["codes"][p, t, s, :n_low].copy()),
+                        "scale": torch.tensor(f["qscale"][p, t, s]),
+                        "zero_point": torch.tensor(f["qzp"][p, t, s]),
+                        "residual_norm": float(f["qres"][p, t, s]),
+                    })
+            out[task] = {
+                "masked": {
+                    "c_high_fp16": c_high,
+                    "c_low_quant": {"payloads": payloads, "num_bits": job.bits, "num_stages": job.stages,
+                                    "original_shape": torch.Size([n_low]), "original_dtype": "torch.float32"},
+                },
+                "unmasked": None,
+            }
+        return out
+
+    def raw_coefficients(self, name) -> np.ndarray:
+        """coef[t][j] before the fp16 / RTVQ round trip (first r columns valid)."""
+        dt, p = self._index[name]
+        return self._job._fetch()[dt]["coef"][p]
+
+
+class LazyBases(_LazyParamMap):
+    """bases[param] = {"masked": {U_high, U_low, singular_values, k, mean, energy_retained, D, N}, "noise": None}.
+    U_high / U_low / mean are written by the K5 kernel on first access."""
+
+    def meta(self, name) -> Dict:
+        job = self._job
+        dt, p = self._index[name]
+        f = job._fetch()[dt]
+        info = f["info"][p]
+        return {"k": int(info[3]), "r": int(info[2]), "D": int(f["dm"][p]), "N": int(info[1]),
+                "energy_retained": float(f["scal"][p, 0])}
+
+    def _build(self, name):
+        job = self._job
+        job._materialize_bases()
+        dt, p = self._index[name]
+        f = job._fetch()[dt]
+        m = self.meta(name)
+        uh, ul, mn = job._basis_tensors[name]
+        sv = torch.from_numpy(f["sv"][p, : m["r"]].copy()).to(job.device)
+        return {"masked": {"U_high": uh, "U_low": ul, "singular_values": sv, "k": m["k"], "mean": mn,
+                           "energy_retained": m["energy_retained"], "D": m["D"], "N": m["N"]},
+                "noise": None}
+
+    def right_vectors(self, name) -> np.ndarray:
+        """V[t][j] (fp64), the right singular vectors the coefficients were formed from."""
+        dt, p = self._index[name]
+        return self._job._fetch()[dt]["V"][p]
+
+
+_ERR_KEYS = ("absolute_error", "relative_error", "max_absolute_error", "mean_absolute_error", "original_norm",
+             "reconstructed_norm")
+
+
+def build_diagnostics(job, index) -> Dict:
+    """diagnostics.py:234-321 schema from the fused K3 reductions."""
+    cfg = job.cfg
+    out = {"config": {"svd_energy_threshold": cfg.svd_energy_threshold, "svd_max_rank": cfg.svd_max_rank,
+                      "svd_low_bits": cfg.svd_low_bits, "svd_rtvq_stages": cfg.svd_rtvq_stages,
+                      "svd_mask_strategy": cfg.svd_mask_strategy, "svd_weighting": cfg.svd_weighting},
+           "per_parameter": {}, "summary": {}}
+    fetched = job._fetch()
+    ranks, energy, errs, ratios = [], [], [], []
+    for name in sorted(index):
+        dt, p = index[name]
+        g, f = job.groups[dt], fetched[dt]
+        info = f["info"][p]
+        r, k, dm = int(info[2]), int(info[3]), int(f["dm"][p])
+        has_mask = bool(g.host["has_mask"][p])
+        present = int(g.host["present"][p])
+        shape = list(g.shapes[p])
+        d = {"param_name": name, "original_shape": shape,
+             "masked_size": dm if has_mask else np.prod(shape),
+             "unmasked_size": (g.numel[p] - dm) if has_mask else 0,
+             "reconstruction_errors": {}, "compression_ratios": {},
+             "basis": {"k": k, "D": dm, "N": int(info[1]), "energy_retained": float(f["scal"][p, 0])}}
+        rel = []
+        ratio = estimate_ratio(r - k, job.bits, job.stages)
+        for t, task in enumerate(job.tasks):
+            if not (present >> t) & 1:
+                continue
+            row = f["diag_out"][p, t]
+            d["reconstruction_errors"][task] = {key: float(row[i]) for i, key in enumerate(_ERR_KEYS)}
+            d["compression_ratios"][task] = ratio
+            rel.append(float(row[1]))
+        if rel:
+            d["mean_relative_error"] = float(np.mean(rel))
+            d["std_relative_error"] = float(np.std(rel))
+            d["max_relative_error"] = float(np.max(rel))
+            d["min_relative_error"] = float(np.min(rel))
+            errs.append(d["mean_relative_error"])
+        ranks.append(k)
+        energy.append(d["basis"]["energy_retained"])
+        if d["compression_ratios"]:
+            ratios.append(np.mean(list(d["compression_ratios"].values())))
+        out["per_parameter"][name] = d
+    out["summary"] = {"num_parameters": len(out["per_parameter"]),
+                      "average_rank": float(np.mean(ranks)) if ranks else 0,
+                      "std_rank": float(np.std(ranks)) if ranks else 0,
+                      "average_energy_retained": float(np.mean(energy)) if energy else 0,
+                      "average_reconstruction_error": float(np.mean(errs)) if errs else 0,
+                      "average_compression_ratio": float(np.mean(ratios)) if ratios else 0}
+    return out

@@ -1,0 +1,189 @@
+"""Shared helpers of the parity tests: run the oracle and the CUDA path on the same seeded inputs
+and compare them the way SURVEY.md section 8c prescribes (sign alignment, subspace angles,
+NaN-aware equality).  The oracle is only ever the checker here."""
+from __future__ import annotations
+
+from collections import OrderedDict
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+
+from oracle import svd_hybrid_ref as R
+from svd_quantization_task_merging_b200 import synth
+from svd_quantization_task_merging_b200.svd_hybrid.config import SVDHybridConfig
+
+# tolerances (SURVEY.md 8c "stated tolerances to adopt")
+TOL_S = 2e-6            # singular values, relative to sigma_1
+TOL_MERGED = 1e-5       # merged weights, relative L2 per parameter (sign-aligned), when the stored
+                        # artifacts (fp16 c_high bits, RTVQ codes) are identical to the oracle's
+TOL_MERGED_FLIP = 2e-3  # ... when a coefficient sat on a rounding boundary and one fp16 value / code
+                        # differs by one step: bounded by the fp16 / RTVQ step itself
+TOL_COEF = 1e-5         # raw coefficients, abs relative to ||c||_inf
+TOL_DIAG = 1e-4         # diagnostics floats, relative
+TOL_ANGLE = 1e-5        # sine of the largest principal angle between spans
+
+MEDIUM_SHAPES = OrderedDict([
+    ("blk.attn.weight", (300, 70)), ("blk.bias", (4099,)), ("conv.weight", (17, 33, 5)),
+    ("wide.weight", (1, 1, 40000)), ("ln.weight", (768,)), ("tiny", (7,)), ("scalar_like", (1,)),
+])
+
+
+def make_cfgs(tasks, **kw):
+    """-> (RefConfig for the oracle, SVDHybridConfig for the CUDA path) with identical settings."""
+    perf = kw.pop("performance", None)
+    ref = R.RefConfig(tasks=list(tasks), performance=perf, **kw)
+    cfg = SVDHybridConfig(tasks=list(tasks), svd_store_artifacts=False, **kw)
+    return ref, cfg
+
+
+def run_both(shapes, n_tasks: int, mask_p: Optional[float] = None, family: str = "parity", seed: int = 1234,
+             sign_align: bool = True, dtype=torch.float32, device="cuda", **cfg_kw):
+    from svd_quantization_task_merging_b200.engine import merge_state_dicts
+    tasks = synth.task_names(n_tasks)
+    base, fts = synth.make_checkpoints(shapes, tasks, family=family, seed=seed, dtype=dtype)
+    masks = synth.make_masks(shapes, tasks, mask_p, seed=seed + 1) if mask_p is not None else None
+    perf = synth.performance_table(tasks) if cfg_kw.get("svd_weighting") == "performance" else None
+    ref_cfg, cfg = make_cfgs(tasks, performance=perf, **cfg_kw)
+    ref = R.run_reference_path(base, fts, masks, ref_cfg)
+    ref["_base"] = base
+    sign_ref = {p: b["Vh"] for p, b in ref["bases"].items()} if sign_align else None
+    res = merge_state_dicts(base, fts, masks, cfg, device, sign_ref=sign_ref, performance=perf,
+                            cluster_assignments=ref["cluster_assignments"] if cfg.svd_weighting == "cluster" else None)
+    return ref, res, (base, fts, masks, tasks)
+
+
+def rel_l2(a: torch.Tensor, b: torch.Tensor) -> float:
+    a, b = a.double().cpu().flatten(), b.double().cpu().flatten()
+    den = b.norm().item()
+    return (a - b).norm().item() / den if den > 0 else (a - b).norm().item()
+
+
+def nan_positions_equal(a: torch.Tensor, b: torch.Tensor) -> bool:
+    return bool(torch.equal(torch.isnan(a.cpu()), torch.isnan(b.cpu())))
+
+
+def max_principal_sine(A: torch.Tensor, B: torch.Tensor) -> float:
+    """sine of the largest principal angle between span(A) and span(B) (columns)."""
+    A, B = A.double().cpu(), B.double().cpu()
+    if A.shape[1] == 0 and B.shape[1] == 0:
+        return 0.0
+    qa, _ = torch.linalg.qr(A)
+    qb, _ = torch.linalg.qr(B)
+    resid = qb - qa @ (qa.T @ qb)
+    return float(torch.linalg.matrix_norm(resid, ord=2))
+
+
+def fp16_ulp_diff(a: torch.Tensor, b: torch.Tensor) -> int:
+    """largest distance in fp16 representable steps between two fp16 tensors"""
+    ia = a.cpu().view(torch.int16).to(torch.int32)
+    ib = b.cpu().view(torch.int16).to(torch.int32)
+    # map sign-magnitude to a monotone integer line
+    ia = torch.where(ia < 0, -(ia & 0x7fff), ia)
+    ib = torch.where(ib < 0, -(ib & 0x7fff), ib)
+    return int((ia - ib).abs().max().item()) if ia.numel() else 0
+
+
+def compare_run(ref: Dict, res: Dict, check_diag: bool = True, tol_merged: float = TOL_MERGED) -> Dict:
+    """Assert parity of one fused run against the oracle; returns a small report."""
+    job = res["job"]
+    report = {"params": 0, "code_total": 0, "code_equal": 0, "chigh_total": 0, "chigh_equal": 0, "max_merged_rel": 0.0,
+              "flipped_params": []}
+    flipped = set()
+    # same set of parameters got a basis
+    assert sorted(ref["bases"].keys()) == sorted(res["bases"].keys())
+    # combined masks: bit-exact
+    cm = job.combined_masks()
+    assert sorted(cm.keys()) == sorted(k for k in ref["combined_masks"] if k in job.shapes)
+    for name, m in cm.items():
+        assert torch.equal(m.cpu(), ref["combined_masks"][name]), f"combined mask differs: {name}"
+    for name, rb in ref["bases"].items():
+        report["params"] += 1
+        meta = res["bases"].meta(name)
+        S_ref = rb["singular_values"].numpy()
+        dt, p = res["bases"]._index[name]
+        S_new = job._fetch()[dt]["sv"][p][: len(S_ref)]
+        assert meta["D"] == rb["D"] and meta["N"] == rb["N"]
+        assert len(S_ref) == meta["r"]
+        if S_ref[0] > 0:
+            assert np.abs(S_new - S_ref).max() <= TOL_S * S_ref[0] + 1e-30, f"singular values differ: {name}"
+        assert meta["k"] == rb["k"], f"rank differs for {name}: {meta['k']} vs {rb['k']}"
+        assert abs(meta["energy_retained"] - rb["energy_retained"]) <= 1e-5
+        # coefficients / codes
+        comp_new = res["compressed"][name]
+        raw = res["compressed"].raw_coefficients(name)
+        k = rb["k"]
+        for ti, task in enumerate(job.tasks):
+            if task not in ref["compressed"][name] or ref["compressed"][name][task] is None:
+                continue
+            rc = ref["compressed"][name][task]
+            nc = comp_new[task]["masked"]
+            c_ref = torch.cat([rc["c_high_fp32"], rc["c_low_fp32"]]).numpy()
+            finite = np.isfinite(c_ref).all()
+            if finite and len(c_ref):
+                scale = np.abs(c_ref).max()
+                assert np.abs(raw[ti, : len(c_ref)] - c_ref).max() <= 20 * TOL_COEF * scale + 1e-12, \
+                    f"coefficients differ: {name}/{task}"
+            report["chigh_total"] += k
+            eq_h = int((nc["c_high_fp16"].view(torch.int16) == rc["c_high_fp16"].view(torch.int16)).sum())
+            report["chigh_equal"] += eq_h
+            if eq_h != k:
+                flipped.add(name)
+            assert fp16_ulp_diff(nc["c_high_fp16"], rc["c_high_fp16"]) <= 1, f"c_high off by > 1 fp16 ulp: {name}/{task}"
+            pr, pn = rc["c_low_quant"]["payloads"], nc["c_low_quant"]["payloads"]
+            assert len(pr) == len(pn)
+            for a, b in zip(pr, pn):
+                report["code_total"] += a["quantized"].numel()
+                eq_c = int((a["quantized"] == b["quantized"]).sum())
+                report["code_equal"] += eq_c
+                if eq_c != a["quantized"].numel():
+                    flipped.add(name)
+    # merged weights
+    for name, m_ref in ref["merged_state_dict"].items():
+        m_new = res["merged_state_dict"][name]
+        assert m_new.shape == m_ref.shape and m_new.dtype == m_ref.dtype, name
+        assert nan_positions_equal(m_new, m_ref), f"NaN positions differ: {name}"
+        fin = torch.isfinite(m_ref)
+        if name in ref["merged_deltas"]:
+            d_ref = (m_ref - _base_of(ref, name)).double()[fin]
+            d_new = (m_new.cpu() - _base_of(ref, name)).double()[fin]
+            den = d_ref.norm().item()
+            err = (d_new - d_ref).norm().item() / den if den > 0 else (d_new - d_ref).norm().item()
+            report["max_merged_rel"] = max(report["max_merged_rel"], err)
+            tol = TOL_MERGED_FLIP if name in flipped else tol_merged
+            assert err <= tol, f"merged delta differs for {name}: rel L2 {err:.3e} (tol {tol:.0e})"
+        else:
+            assert torch.equal(m_new.cpu(), m_ref), f"untouched parameter changed: {name}"
+    report["flipped_params"] = sorted(flipped)
+    if check_diag and ref["diagnostics"].get("per_parameter") is not None and "per_parameter" in res["diagnostics"]:
+        compare_diagnostics(ref["diagnostics"], res["diagnostics"])
+    return report
+
+
+def _base_of(ref, name):
+    return ref["_base"][name].float()
+
+
+def compare_diagnostics(d_ref: Dict, d_new: Dict, tol: float = TOL_DIAG):
+    assert sorted(d_ref["per_parameter"]) == sorted(d_new["per_parameter"])
+    for name, pr in d_ref["per_parameter"].items():
+        pn = d_new["per_parameter"][name]
+        assert pn["original_shape"] == pr["original_shape"]
+        assert int(pn["masked_size"]) == int(pr["masked_size"]) and int(pn["unmasked_size"]) == int(pr["unmasked_size"])
+        assert pn["basis"]["k"] == pr["basis"]["k"] and pn["basis"]["D"] == pr["basis"]["D"]
+        assert pn["compression_ratios"] == pr["compression_ratios"], name
+        for task, er in pr["reconstruction_errors"].items():
+            en = pn["reconstruction_errors"][task]
+            for key, v in er.items():
+                w = en[key]
+                if np.isnan(v):
+                    assert np.isnan(w), f"{name}/{task}/{key}: expected NaN"
+                else:
+                    scale = max(abs(v), er["original_norm"] * 1e-3 if key != "relative_error" else 1e-3)
+                    assert abs(w - v) <= tol * scale + 1e-12, f"{name}/{task}/{key}: {w} vs {v}"
+    for key, v in d_ref["summary"].items():
+        w = d_new["summary"][key]
+        if isinstance(v, float) and np.isnan(v):
+            assert np.isnan(w)
+        else:
+            assert abs(w - v) <= tol * max(abs(v), 1e-3) + 1e-12, f"summary {key}: {w} vs {v}"

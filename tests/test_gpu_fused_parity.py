@@ -1,0 +1,179 @@
+"""GPU parity of the fused SVD-Hybrid merge (K1 -> K2 -> K3 through the C ABI) against the oracle
+on the same seeded inputs.  Tolerances are the ones written in tests/parity.py."""
+import numpy as np
+import pytest
+import torch
+
+from svd_quantization_task_merging_b200 import synth
+from tests import parity
+
+pytestmark = pytest.mark.gpu
+
+
+def _summary(rep):
+    return (f"params={rep['params']} codes {rep['code_equal']}/{rep['code_total']} "
+            f"c_high {rep['chigh_equal']}/{rep['chigh_total']} max_merged_rel={rep['max_merged_rel']:.2e} "
+            f"flipped={rep['flipped_params']}")
+
+
+@pytest.mark.parametrize("strategy,mask_p", [("union", 0.3), ("intersection", 0.9), ("majority", 0.5), ("union", None)])
+def test_medium_shapes_masks(cuda_device, strategy, mask_p):
+    """configs[0]-style: 8 tasks, energy 0.9, 4-bit x 2 stages, uniform weights; all three tall-mask rules."""
+    ref, res, _ = parity.run_both(parity.MEDIUM_SHAPES, 8, mask_p=mask_p, svd_mask_strategy=strategy,
+                                  svd_energy_threshold=0.9, svd_low_bits=4, svd_rtvq_stages=2)
+    rep = parity.compare_run(ref, res)
+    print(_summary(rep))
+    assert rep["code_equal"] >= 0.98 * rep["code_total"]
+
+
+def test_performance_weighting_three_stages(cuda_device):
+    """configs[1]-style: majority mask, performance-softmax weights (T=5), 4-bit x 3 stages."""
+    ref, res, _ = parity.run_both(parity.MEDIUM_SHAPES, 8, mask_p=0.5, svd_mask_strategy="majority",
+                                  svd_weighting="performance", svd_weighting_temperature=5.0,
+                                  svd_energy_threshold=0.9, svd_rtvq_stages=3)
+    rep = parity.compare_run(ref, res)
+    print(_summary(rep))
+    w_ref, w_new = ref["weights"], res["diagnostics"]["task_weights"]
+    assert w_ref == w_new
+
+
+def test_cluster_weighting(cuda_device):
+    """configs[2]-style: intersection mask, cluster weighting (k=2)."""
+    ref, res, _ = parity.run_both(parity.MEDIUM_SHAPES, 8, mask_p=0.9, svd_mask_strategy="intersection",
+                                  svd_weighting="cluster", svd_cluster_k=2, svd_energy_threshold=0.9)
+    rep = parity.compare_run(ref, res)
+    print(_summary(rep))
+    assert res["diagnostics"]["cluster_assignments"] == ref["cluster_assignments"]
+
+
+def test_cluster_partition_from_gram_matches_full_kmeans(cuda_device):
+    """The k-means partition computed from the K1 whole-model Gram equals the reference's
+    full-feature k-means (clustering.py:198-245) on the same task vectors."""
+    from svd_quantization_task_merging_b200.engine import MergeJob
+    from svd_quantization_task_merging_b200.svd_hybrid.config import SVDHybridConfig
+    from oracle import svd_hybrid_ref as R
+    tasks = synth.task_names(8)
+    base, fts = synth.make_checkpoints(parity.MEDIUM_SHAPES, tasks, family="parity", seed=77)
+    masks = synth.make_masks(parity.MEDIUM_SHAPES, tasks, 0.9, seed=78)
+    cfg = SVDHybridConfig(tasks=tasks, svd_weighting="cluster", svd_mask_strategy="intersection",
+                          svd_energy_threshold=0.9, svd_store_artifacts=False)
+    job = MergeJob(base, fts, masks, cfg, "cuda", cluster_backend="sklearn").run()
+    tvs = {t: R.task_vector(base, fts[t]) for t in tasks}
+    full = R.cluster_tasks_full(tvs, 2)
+    mine = job.cluster_assignments
+    assert all((full[a] == full[b]) == (mine[a] == mine[b]) for a in tasks for b in tasks)
+    # and the Gram itself against fp64 numpy
+    X = np.stack([torch.cat([tvs[t][p].flatten() for p in sorted(tvs[t])]).double().numpy() for t in tasks])
+    G = X @ X.T
+    assert np.abs(job.whole_model_gram - G).max() <= 1e-6 * np.abs(G).max()
+
+
+def test_fp32_basis_no_center(cuda_device):
+    ref, res, _ = parity.run_both(parity.MEDIUM_SHAPES, 6, mask_p=0.5, svd_mask_strategy="union", svd_fp16=False,
+                                  svd_center=False, svd_energy_threshold=0.8, svd_rtvq_stages=2)
+    rep = parity.compare_run(ref, res)
+    print(_summary(rep))
+
+
+@pytest.mark.parametrize("bits,stages", [(2, 1), (2, 4), (4, 1), (8, 2), (3, 3)])
+def test_rtvq_sweep_through_pipeline(cuda_device, bits, stages):
+    """configs[3]-style RTVQ sweep (bits x stages) through the fused path."""
+    ref, res, _ = parity.run_both(synth.toy_shapes(), 8, svd_energy_threshold=0.9, svd_low_bits=bits,
+                                  svd_rtvq_stages=stages)
+    rep = parity.compare_run(ref, res)
+    print(_summary(rep))
+
+
+def test_toy_model_of_reference_integration_test(cuda_device):
+    """tests/test_integration.py:12-19 shapes, 4 tasks, no masks."""
+    ref, res, _ = parity.run_both(synth.toy_shapes(), 4, svd_energy_threshold=0.8, svd_fp16=False)
+    parity.compare_run(ref, res)
+
+
+def test_degenerate_iid_inputs_reproduce_reference_nans(cuda_device):
+    """iid Gaussian task vectors, centred: k = N-1, a 1-element low block, scale = inf -> every merged
+    masked element is NaN in the reference (rtvq.py:17).  Same NaN positions here."""
+    ref, res, _ = parity.run_both(synth.toy_shapes(), 8, family="throughput", svd_energy_threshold=0.95,
+                                  sign_align=True)
+    for name, m in ref["merged_state_dict"].items():
+        assert parity.nan_positions_equal(res["merged_state_dict"][name], m), name
+    assert any(torch.isnan(m).any() for m in ref["merged_state_dict"].values())
+
+
+def test_small_mask_is_skipped(cuda_device):
+    """mask.sum() < svd_min_mask_size -> no basis, parameter stays equal to base (cli.py:332)."""
+    tasks = synth.task_names(4)
+    shapes = {"w": (64, 64), "v": (512,)}
+    base, fts = synth.make_checkpoints(shapes, tasks, family="parity", seed=3)
+    masks = {t: {"w": torch.zeros(64, 64, dtype=torch.bool), "v": torch.ones(512, dtype=torch.bool)} for t in tasks}
+    for t in tasks:
+        masks[t]["w"][0, :5] = True            # 5 < 10 masked elements
+    from oracle import svd_hybrid_ref as R
+    from svd_quantization_task_merging_b200.engine import merge_state_dicts
+    ref_cfg, cfg = parity.make_cfgs(tasks, svd_energy_threshold=0.8)
+    ref = R.run_reference_path(base, fts, masks, ref_cfg)
+    ref["_base"] = base
+    res = merge_state_dicts(base, fts, masks, cfg, "cuda", sign_ref={p: b["Vh"] for p, b in ref["bases"].items()})
+    assert "w" not in res["bases"] and "w" not in ref["bases"]
+    assert torch.equal(res["merged_state_dict"]["w"].cpu(), base["w"])
+    parity.compare_run(ref, res)
+
+
+def test_missing_task_parameter_and_partial_masks(cuda_device):
+    """A task that lacks a parameter, and a task without a mask for a parameter."""
+    tasks = synth.task_names(5)
+    shapes = {"a": (90, 41), "b": (3000,)}
+    base, fts = synth.make_checkpoints(shapes, tasks, family="parity", seed=9)
+    masks = synth.make_masks(shapes, tasks, 0.6, seed=10)
+    del fts[tasks[2]]["b"]
+    del masks[tasks[1]]["a"]
+    masks[tasks[4]] = None
+    from oracle import svd_hybrid_ref as R
+    from svd_quantization_task_merging_b200.engine import merge_state_dicts
+    ref_cfg, cfg = parity.make_cfgs(tasks, svd_energy_threshold=0.85, svd_mask_strategy="majority")
+    ref = R.run_reference_path(base, fts, masks, ref_cfg)
+    ref["_base"] = base
+    # the oracle's Vh has one column per ACTIVE task: scatter it to task positions
+    sign_ref = {}
+    for p, b in ref["bases"].items():
+        active = [i for i, t in enumerate(tasks) if p in fts[t]]
+        vh = torch.zeros(len(tasks), len(tasks), dtype=torch.float64)
+        vh[: b["Vh"].shape[0], active] = b["Vh"].double()
+        sign_ref[p] = vh
+    res = merge_state_dicts(base, fts, masks, cfg, "cuda", sign_ref=sign_ref)
+    rep = parity.compare_run(ref, res)
+    print(_summary(rep))
+
+
+def test_without_sign_hint_matches_at_quantisation_noise_level(cuda_device):
+    """Production mode (no sign hint): singular-vector signs are a free choice, RTVQ is not sign-symmetric,
+    so the merged weights agree with the oracle only at the quantisation-noise level."""
+    ref, res, _ = parity.run_both(parity.MEDIUM_SHAPES, 8, mask_p=0.3, svd_energy_threshold=0.9, sign_align=False)
+    for name, d_ref in ref["merged_deltas"].items():
+        m_new = res["merged_state_dict"][name].cpu()
+        d_new = m_new - ref["_base"][name]
+        if torch.isfinite(d_ref).all() and d_ref.norm() > 0:
+            assert parity.rel_l2(d_new, d_ref) < 5e-2, name
+
+
+def test_bf16_inputs(cuda_device):
+    """bf16 checkpoints (configs[4] dtype): delta is formed in bf16 like `ft - base` on bf16 tensors;
+    the reference's own SVD rejects bf16 on CPU, so the oracle runs on the bf16-rounded deltas in fp32."""
+    from oracle import svd_hybrid_ref as R
+    from svd_quantization_task_merging_b200.engine import merge_state_dicts
+    tasks = synth.task_names(8)
+    shapes = {"w": (256, 130), "b": (1000,)}
+    base, fts = synth.make_checkpoints(shapes, tasks, family="parity", seed=21, dtype=torch.bfloat16)
+    ref_cfg, cfg = parity.make_cfgs(tasks, svd_energy_threshold=0.9)
+    # fp32 stand-in with identical deltas: base32 = base, ft32 = base + bf16(ft - base)
+    base32 = {k: v.float() for k, v in base.items()}
+    fts32 = {t: {k: base32[k] + (fts[t][k] - base[k]).float() for k in base} for t in tasks}
+    ref = R.run_reference_path(base32, fts32, None, ref_cfg)
+    res = merge_state_dicts(base, fts, None, cfg, "cuda", sign_ref={p: b["Vh"] for p, b in ref["bases"].items()})
+    for name, b in ref["bases"].items():
+        assert res["bases"].meta(name)["k"] == b["k"]
+    for name in base:
+        d_ref = ref["merged_deltas"][name]
+        d_new = res["merged_state_dict"][name].cpu() - base32[name]
+        assert res["merged_state_dict"][name].dtype == torch.float32
+        assert parity.rel_l2(d_new, d_ref) < 2e-3, name
