@@ -354,7 +354,10 @@ SVDQ_HD void solve_param(const SolveConfig& cfg, const SolveIn& in, const SolveO
     for (int j = ln.lane; j < n; j += ln.nl) {
         const int src = sc.perm[j];
         const double lam = sc.A[src * kCoreLd + src];
-        sc.sigma[j] = lam > 0.0 ? sqrt(lam) : 0.0;
+        // sqrt(|lambda|): a numerically-zero eigenvalue of the centred Gram comes out as +-1e-17 lambda_1;
+        // LAPACK's singular value there is non-negative round-off dust, never an exact zero, and the
+        // reference's 2-element RTVQ edge (rtvq.py:17) turns NaN only on an exact zero
+        sc.sigma[j] = sqrt(fabs(lam));
         double sgn = 1.0;
         if (in.sign_ref) {
             double dot = 0.0;
