@@ -60,7 +60,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.idx), "-lms", "100"], stdout=subprocess.PIPE,
+                                          "-i", str(self.idx), "-lms", "20"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._pump, daemon=True)
             self.th.start()
@@ -69,16 +69,19 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.rows.append(line.strip())
+            self.rows.append((time.perf_counter(), line.strip()))
 
-    def stop(self):
+    def stop(self, t_begin=None, t_end=None):
+        """Summarise the samples that arrived inside [t_begin, t_end] (the timed region)."""
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.1)
         self.proc.terminate()
         sm, mx, reasons = [], None, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for ts, r in self.rows:
+            if t_begin is not None and not (t_begin <= ts <= t_end + 0.03):
+                continue
             f = [x.strip() for x in r.split(",")]
             if len(f) < 9:
                 continue
@@ -200,12 +203,13 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    for _ in range(args.warmup):
-        job.run()
-    barrier()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    for _ in range(args.warmup):
+        job.run()
+    barrier()
+    t_begin = time.perf_counter()
     k_times = {"k1": 0.0, "k2": 0.0, "k3": 0.0}
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     jobs_events = []
@@ -215,12 +219,13 @@ def run_ours(args):
         jobs_events.append(job._events)
     ev1.record()
     barrier()
+    t_end = time.perf_counter()
     total_ms = ev0.elapsed_time(ev1)
     for ev in jobs_events:
         k_times["k1"] += ev["start"].elapsed_time(ev["k1"])
         k_times["k2"] += ev["k1"].elapsed_time(ev["k2"])
         k_times["k3"] += ev["k2"].elapsed_time(ev["k3"])
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(t_begin, t_end) if rank == 0 else None
     t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -318,7 +323,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="vit-l-14-cluster", choices=sorted(WORKLOADS))

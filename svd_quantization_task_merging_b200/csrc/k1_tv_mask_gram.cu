@@ -37,7 +37,12 @@ __global__ void __launch_bounds__(kBlock, (NT <= 8 && !FULL) ? 2 : 1) k1_tv_mask
     const int64_t start = (int64_t)a.tile_local[tile] * a.tile_elems;
     const int64_t stop = min(start + (int64_t)a.tile_elems, numel);
 
-    if (tid <= NT) s_ptr[tid] = a.tensors[(int64_t)p * (NT + 1) + tid];
+    if (tid <= NT) {
+        // a task that lacks the parameter reads the base tensor instead (delta == 0): the load
+        // sequence stays branch-free; K2 drops the column through its `present` bit mask
+        const void* q = a.tensors[(int64_t)p * (NT + 1) + tid];
+        s_ptr[tid] = q ? q : a.tensors[(int64_t)p * (NT + 1)];
+    }
     if (tid < NT) s_mask[tid] = a.masks ? a.masks[(int64_t)p * NT + tid] : nullptr;
     __syncthreads();
 
@@ -45,6 +50,7 @@ __global__ void __launch_bounds__(kBlock, (NT <= 8 && !FULL) ? 2 : 1) k1_tv_mask
 #pragma unroll
     for (int t = 0; t < NT; ++t) n_present += s_mask[t] != nullptr;
     const bool has_mask = n_present > 0;
+    const bool all_masks = n_present == NT;
     // per-byte vote thresholds: union >= 1, intersection >= n_present, majority 2*votes >= n_present
     const uint32_t thr_bytes = 0x01010101u * (uint32_t)(a.strategy == kUnion ? 1 : n_present);
     const bool majority = a.strategy == kMajority;
@@ -57,51 +63,60 @@ __global__ void __launch_bounds__(kBlock, (NT <= 8 && !FULL) ? 2 : 1) k1_tv_mask
 
     for (int64_t e0 = start; e0 < stop; e0 += kStep) {          // uniform trip count per CTA
         const int64_t e = e0 + (int64_t)tid * kVec;
-        float d[NT][kVec];
-        uint32_t bits = 0;                                       // 4 combined-mask bits of this thread
-        if (e < stop) {
-            const bool full = e + kVec <= numel;
-            const uint32_t valid = full ? 0xFu : ((1u << (int)(numel - e)) - 1u);
-            float b[kVec];
-            if (full) Elem<T>::load4(s_ptr[0], e, b);
-            else {
+        const bool active = e < stop;
+        const bool full = e + kVec <= numel;
+        // ---- phase 1: issue every load of this step back to back (no use in between, so the
+        //      (N+1) tensor loads and N mask loads of a thread are all in flight together) ----------
+        float b[kVec], f[NT][kVec];
+        uint32_t mw[NT];
+        if (active && full) {
+            Elem<T>::load4(s_ptr[0], e, b);
 #pragma unroll
-                for (int c = 0; c < kVec; ++c) b[c] = (e + c < numel) ? Elem<T>::load1(s_ptr[0], e + c) : 0.0f;
+            for (int t = 0; t < NT; ++t) Elem<T>::load4(s_ptr[t + 1], e, f[t]);
+            if (all_masks) {
+#pragma unroll
+                for (int t = 0; t < NT; ++t) mw[t] = ldg_stream_u32(s_mask[t] + e);
+            } else if (has_mask) {
+#pragma unroll
+                for (int t = 0; t < NT; ++t) mw[t] = s_mask[t] ? ldg_stream_u32(s_mask[t] + e) : 0u;
             }
+        } else if (active) {                                     // last, partial vector of a parameter
+#pragma unroll
+            for (int c = 0; c < kVec; ++c) b[c] = (e + c < numel) ? Elem<T>::load1(s_ptr[0], e + c) : 0.0f;
 #pragma unroll
             for (int t = 0; t < NT; ++t) {
-                const void* fp = s_ptr[t + 1];
-                if (fp == nullptr) {
 #pragma unroll
-                    for (int c = 0; c < kVec; ++c) d[t][c] = 0.0f;
-                } else if (full) {
-                    float f[kVec];
-                    Elem<T>::load4(fp, e, f);
-#pragma unroll
-                    for (int c = 0; c < kVec; ++c) d[t][c] = Elem<T>::sub(f[c], b[c]);
-                } else {
+                for (int c = 0; c < kVec; ++c) f[t][c] = (e + c < numel) ? Elem<T>::load1(s_ptr[t + 1], e + c) : 0.0f;
+                mw[t] = 0;
+                if (s_mask[t] != nullptr) {
 #pragma unroll
                     for (int c = 0; c < kVec; ++c)
-                        d[t][c] = (e + c < numel) ? Elem<T>::sub(Elem<T>::load1(fp, e + c), b[c]) : 0.0f;
+                        if (e + c < numel) mw[t] |= (uint32_t)__ldg(s_mask[t] + e + c) << (8 * c);
                 }
             }
+        } else {
+#pragma unroll
+            for (int c = 0; c < kVec; ++c) b[c] = 0.0f;
+#pragma unroll
+            for (int t = 0; t < NT; ++t) {
+                mw[t] = 0;
+#pragma unroll
+                for (int c = 0; c < kVec; ++c) f[t][c] = 0.0f;
+            }
+        }
+        // ---- phase 2: task vectors, combined mask ------------------------------------------------
+        float d[NT][kVec];
+#pragma unroll
+        for (int t = 0; t < NT; ++t)
+#pragma unroll
+            for (int c = 0; c < kVec; ++c) d[t][c] = Elem<T>::sub(f[t][c], b[c]);
+        uint32_t bits = 0;                                       // 4 combined-mask bits of this thread
+        if (active) {
+            const uint32_t valid = full ? 0xFu : ((1u << (int)(numel - e)) - 1u);
             if (has_mask) {
                 uint32_t votes = 0;                              // 4 byte lanes, one per element
 #pragma unroll
-                for (int t = 0; t < NT; ++t) {
-                    const uint8_t* mp = s_mask[t];
-                    if (mp != nullptr) {
-                        uint32_t w;
-                        if (full) w = ldg_stream_u32(mp + e);
-                        else {
-                            w = 0;
-#pragma unroll
-                            for (int c = 0; c < kVec; ++c)
-                                if (e + c < numel) w |= (uint32_t)__ldg(mp + e + c) << (8 * c);
-                        }
-                        votes += __vminu4(w, 0x01010101u);
-                    }
-                }
+                for (int t = 0; t < NT; ++t) votes += __vminu4(mw[t], 0x01010101u);
                 if (majority) votes += votes;                    // 2 * votes (<= 64 per byte)
                 const uint32_t ge = __vcmpgeu4(votes, thr_bytes);   // 0xff per byte where true
                 bits = ((ge >> 7) & 1u) | ((ge >> 14) & 2u) | ((ge >> 21) & 4u) | ((ge >> 28) & 8u);
@@ -109,11 +124,6 @@ __global__ void __launch_bounds__(kBlock, (NT <= 8 && !FULL) ? 2 : 1) k1_tv_mask
             } else {
                 bits = valid;
             }
-        } else {
-#pragma unroll
-            for (int t = 0; t < NT; ++t)
-#pragma unroll
-                for (int c = 0; c < kVec; ++c) d[t][c] = 0.0f;
         }
         cnt += __popc(bits);
 

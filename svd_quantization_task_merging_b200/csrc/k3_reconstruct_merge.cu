@@ -63,47 +63,59 @@ __global__ void __launch_bounds__(kBlock, (NT <= 8 && !DIAG) ? 2 : 1) k3_reconst
         for (int i = 0; i < kDiagRows * NT; ++i) dacc[i] = 0.0f;
     }
 
+    // tasks that lack the parameter: pointer replaced by the base tensor (delta == 0), see K1
+    uint32_t present_bits = 0;
+#pragma unroll
+    for (int t = 0; t < NT; ++t) present_bits |= (s_ptr[t + 1] != nullptr ? 1u : 0u) << t;
+    __syncthreads();
+    if (tid >= 1 && tid <= NT && s_ptr[tid] == nullptr) s_ptr[tid] = s_ptr[0];
+    __syncthreads();
+
     for (int64_t e0 = start; e0 < stop; e0 += kStep) {
         const int64_t e = e0 + (int64_t)tid * kVec;
         if (e >= stop) continue;
         const bool full = e + kVec <= numel;
         float b[kVec];
-        if (full) Elem<T>::load4(s_ptr[0], e, b);
-        else {
-#pragma unroll
-            for (int c = 0; c < kVec; ++c) b[c] = (e + c < numel) ? Elem<T>::load1(s_ptr[0], e + c) : 0.0f;
-        }
         float res[kVec];
         if (status != kSolved) {
             // parameter without a basis (mask below svd_min_mask_size / no data): merged = base
+            if (full) Elem<T>::load4(s_ptr[0], e, b);
+            else {
+#pragma unroll
+                for (int c = 0; c < kVec; ++c) b[c] = (e + c < numel) ? Elem<T>::load1(s_ptr[0], e + c) : 0.0f;
+            }
 #pragma unroll
             for (int c = 0; c < kVec; ++c) res[c] = b[c];
         } else {
-            float x[NT][kVec];                   // task vectors, then centred task vectors
+            // ---- phase 1: all loads of the step back to back ----------------------------------------
+            float x[NT][kVec];                   // fine-tuned values -> task vectors -> centred task vectors
+            uint32_t pword = 0xffffffffu;
+            if (full) {
+                Elem<T>::load4(s_ptr[0], e, b);
+#pragma unroll
+                for (int t = 0; t < NT; ++t) Elem<T>::load4(s_ptr[t + 1], e, x[t]);
+            } else {
+#pragma unroll
+                for (int c = 0; c < kVec; ++c) b[c] = (e + c < numel) ? Elem<T>::load1(s_ptr[0], e + c) : 0.0f;
+#pragma unroll
+                for (int t = 0; t < NT; ++t)
+#pragma unroll
+                    for (int c = 0; c < kVec; ++c)
+                        x[t][c] = (e + c < numel) ? Elem<T>::load1(s_ptr[t + 1], e + c) : 0.0f;
+            }
+            if (has_mask) pword = __ldg(packed + (e >> 5));
+            // ---- phase 2 --------------------------------------------------------------------------------
             float mean[kVec];
 #pragma unroll
             for (int c = 0; c < kVec; ++c) mean[c] = 0.0f;
 #pragma unroll
-            for (int t = 0; t < NT; ++t) {
-                const void* fp = s_ptr[t + 1];
-                if (fp == nullptr) {
+            for (int t = 0; t < NT; ++t)
 #pragma unroll
-                    for (int c = 0; c < kVec; ++c) x[t][c] = 0.0f;
-                } else if (full) {
-                    float f[kVec];
-                    Elem<T>::load4(fp, e, f);
-#pragma unroll
-                    for (int c = 0; c < kVec; ++c) x[t][c] = Elem<T>::sub(f[c], b[c]);
-                } else {
-#pragma unroll
-                    for (int c = 0; c < kVec; ++c)
-                        x[t][c] = (e + c < numel) ? Elem<T>::sub(Elem<T>::load1(fp, e + c), b[c]) : 0.0f;
+                for (int c = 0; c < kVec; ++c) {
+                    x[t][c] = Elem<T>::sub(x[t][c], b[c]);
+                    mean[c] += x[t][c];
                 }
-#pragma unroll
-                for (int c = 0; c < kVec; ++c) mean[c] += x[t][c];
-            }
-            uint32_t bits = 0xFu;
-            if (has_mask) bits = (__ldg(packed + (e >> 5)) >> (int)(e & 31)) & 0xFu;
+            const uint32_t bits = (pword >> (int)(e & 31)) & 0xFu;
 
             float orig[DIAG ? NT : 1][kVec];
             if (DIAG) {
@@ -117,7 +129,7 @@ __global__ void __launch_bounds__(kBlock, (NT <= 8 && !DIAG) ? 2 : 1) k3_reconst
 #pragma unroll
             for (int t = 0; t < NT; ++t)
 #pragma unroll
-                for (int c = 0; c < kVec; ++c) x[t][c] = (s_ptr[t + 1] != nullptr) ? x[t][c] - mean[c] : 0.0f;
+                for (int c = 0; c < kVec; ++c) x[t][c] = ((present_bits >> t) & 1u) ? x[t][c] - mean[c] : 0.0f;
 
             float acc[kVec];
 #pragma unroll
@@ -172,7 +184,7 @@ __global__ void __launch_bounds__(kBlock, (NT <= 8 && !DIAG) ? 2 : 1) k3_reconst
             if (DIAG) {
 #pragma unroll
                 for (int t = 0; t < NT; ++t) {
-                    if (s_ptr[t + 1] == nullptr) continue;
+                    if (!((present_bits >> t) & 1u)) continue;
 #pragma unroll
                     for (int c = 0; c < kVec; ++c) {
                         const bool m = ((bits >> c) & 1u) && (e + c < numel);
