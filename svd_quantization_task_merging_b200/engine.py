@@ -165,6 +165,7 @@ class MergeJob:
             for g in self.groups.values():
                 self._build_group(g)
         self._ran = False
+        self.gram_reduce_hook = None
         self._fetched: Optional[Dict[str, Dict[str, np.ndarray]]] = None
         self.weights: Optional[Dict[str, float]] = None
         self.cluster_assignments: Optional[Dict[str, int]] = None
@@ -194,6 +195,7 @@ class MergeJob:
         self.base_ref = base
         self.groups: "OrderedDict[torch.dtype, _Group]" = OrderedDict()
         self.passthrough: List[str] = []
+        self.filtered_out = set()
         self._tensors: Dict[str, List[Optional[torch.Tensor]]] = {}
         self._masks: Dict[str, List[Optional[torch.Tensor]]] = {}
         self.shapes: Dict[str, torch.Size] = {}
@@ -201,7 +203,7 @@ class MergeJob:
         for name in sorted(base.keys()):
             b = base_d[name]
             if wanted is not None and name not in wanted:
-                self.passthrough.append(name)
+                self.filtered_out.add(name)          # another rank's shard: not returned by this job
                 continue
             if not torch.is_tensor(b) or b.dtype not in _FLOAT_DTYPES or b.numel() == 0:
                 self.passthrough.append(name)
@@ -335,6 +337,8 @@ class MergeJob:
         for g in self.groups.values():
             s = g.t["gram_all"].sum(dim=0)
             tot = s if tot is None else tot + s
+        if self.gram_reduce_hook is not None:       # multi-GPU: sum the per-rank Grams (sharding.allreduce_gram)
+            tot = self.gram_reduce_hook(tot)
         gram = tot.view(self.N, self.N).cpu().numpy()
         self.whole_model_gram = gram
         self.cluster_assignments = cluster_from_gram(gram, self.tasks, self.cfg.svd_cluster_k, "kmeans",
@@ -460,6 +464,8 @@ class MergeJob:
             torch.cuda.synchronize(self.device)
         out: "OrderedDict[str, torch.Tensor]" = OrderedDict()
         for k in self.base_keys:
+            if k in self.filtered_out:
+                continue
             if k in views:
                 out[k] = views[k]
             else:
@@ -588,3 +594,35 @@ def task_vector_gram(task_vectors: Mapping[str, Mapping[str, torch.Tensor]], nam
                      _ptr(t["tile_begin"]), _ptr(t["gram_masked"]), _ptr(t["gram_all"]), _ptr(t["dm"]), st)
         total += g.t["gram_all"].sum(dim=0).view(N, N).cpu().numpy()
     return total
+
+
+def factor_columns(vectors: Sequence[torch.Tensor], center: bool = True, energy_threshold: float = 0.90,
+                   max_rank: Optional[int] = None, fp16: bool = False, sign_ref=None) -> Dict:
+    """Thin SVD + rank selection of the [D x N] matrix whose columns are ``vectors`` (K1 with a zero
+    base -> K2 -> K5).  Backs construct_basis / compute_svd of the fine-grained API.
+
+    -> {"U_high","U_low","singular_values","k","mean","energy_retained","D","N","V","coef"}; V[t][j]
+    are the right singular vectors (fp64), coef[t][j] the closed-form task coefficients."""
+    from .svd_hybrid.config import SVDHybridConfig
+    _native.require_cuda()
+    if len(vectors) == 0:
+        raise ValueError("Empty delta list")
+    dev = torch.device("cuda")
+    cols = [v.detach().to(dev, torch.float32).contiguous().view(-1) for v in vectors]
+    D = cols[0].numel()
+    names = [f"c{i:02d}" for i in range(len(cols))]
+    cfg = SVDHybridConfig(tasks=names, svd_center=bool(center), svd_energy_threshold=float(energy_threshold),
+                          svd_max_rank=max_rank, svd_fp16=bool(fp16), svd_store_artifacts=False,
+                          svd_eval_reconstruction=False)
+    base = {"x": torch.zeros(D, dtype=torch.float32, device=dev)}
+    fts = {n: {"x": c} for n, c in zip(names, cols)}
+    job = MergeJob(base, fts, None, cfg, "cuda", diagnostics=False, materialize_bases=True,
+                   sign_ref={"x": sign_ref} if sign_ref is not None else None)
+    job.run()
+    res = job.results()
+    if "x" not in res["bases"]:
+        raise ValueError("Empty delta list")
+    b = dict(res["bases"]["x"]["masked"])
+    b["V"] = torch.from_numpy(res["bases"].right_vectors("x").copy())
+    b["coef"] = torch.from_numpy(res["compressed"].raw_coefficients("x").copy())
+    return b
