@@ -129,9 +129,10 @@ def compare_run(ref: Dict, res: Dict, check_diag: bool = True, tol_merged: Optio
                 continue
             rc = ref["compressed"][name][task]
             nc = comp_new[task]["masked"]
-            c_ref = torch.cat([rc["c_high_fp32"], rc["c_low_fp32"]]).numpy()
+            has_raw = "c_high_fp32" in rc
+            c_ref = torch.cat([rc["c_high_fp32"], rc["c_low_fp32"]]).numpy() if has_raw else np.zeros(0, np.float32)
             finite = np.isfinite(c_ref).all()
-            if finite and len(c_ref):
+            if has_raw and finite and len(c_ref):
                 scale = np.abs(c_ref).max()
                 # the oracle projects on fp16(U) (cli.py:355-361 before compress.py:18-19); the closed form
                 # Sigma V^T differs from that by the fp16 rounding noise of U averaged over D rows
@@ -214,3 +215,21 @@ def compare_diagnostics(d_ref: Dict, d_new: Dict, tol_exact: float = TOL_DIAG, f
             assert np.isnan(w)
         else:
             assert abs(w - v) <= tol * abs(v) + 1e-6, f"summary {key}: {w} vs {v}"
+
+
+def golden_as_reference(case: Dict) -> Dict:
+    """Re-shape one golden pipeline case (outputs of the REAL reference) into the oracle's result layout."""
+    base = case["base"]
+    bases = {}
+    for p, b in case["bases"].items():
+        d = dict(b["masked"])
+        d["Vh"] = case["Vh"][p]
+        bases[p] = d
+    compressed = {p: {t: (a["masked"] if a.get("masked") is not None else None) for t, a in per.items()}
+                  for p, per in case["compressed"].items()}
+    merged = case["merged_state_dict"]
+    deltas = {p: merged[p] - base[p] for p in case["bases"]}
+    diag = case["diagnostics"]
+    return {"merged_state_dict": merged, "merged_deltas": deltas, "bases": bases, "compressed": compressed,
+            "combined_masks": case["combined_masks"], "diagnostics": diag, "weights": diag["task_weights"],
+            "cluster_assignments": diag.get("cluster_assignments"), "_base": base}

@@ -1,0 +1,288 @@
+"""GPU tests of the reference-facing surface: the CUDA path against golden outputs of the REAL
+reference, the fine-grained operator mirrors, bases as subspaces, the on-disk pipeline + artifact
+layout + reload, and world-size invariance of the parameter-sharded path."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import svd_hybrid_ref as R
+from svd_quantization_task_merging_b200 import sharding, synth
+from svd_quantization_task_merging_b200.svd_hybrid.config import SVDHybridConfig
+from tests import parity
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _gold(name):
+    return torch.load(os.path.join(GOLD, "pipeline_golden.pt"), weights_only=False)[name]
+
+
+# ---- the CUDA path against the real reference's outputs -------------------------------------------------
+@pytest.mark.parametrize("name", ["union_uniform", "majority_performance_3stage", "intersection_cluster",
+                                  "nomask_fp32_nocenter"])
+def test_cuda_path_against_reference_golden(cuda_device, name):
+    from svd_quantization_task_merging_b200.engine import merge_state_dicts
+    case = _gold(name)
+    cfg = SVDHybridConfig(tasks=case["tasks"], svd_max_rank=64, svd_store_artifacts=False, **case["config"])
+    ref = parity.golden_as_reference(case)
+    res = merge_state_dicts(case["base"], case["finetuned"], case["masks"], cfg, "cuda", sign_ref=case["Vh"],
+                            performance=case["performance"], cluster_assignments=ref["cluster_assignments"])
+    rep = parity.compare_run(ref, res)
+    print(name, rep)
+    assert res["diagnostics"]["task_weights"] == ref["weights"]
+
+
+def test_cuda_path_reproduces_reference_nans_golden(cuda_device):
+    from svd_quantization_task_merging_b200.engine import merge_state_dicts
+    case = _gold("iid_degenerate_nan")
+    cfg = SVDHybridConfig(tasks=case["tasks"], svd_max_rank=64, svd_store_artifacts=False, **case["config"])
+    res = merge_state_dicts(case["base"], case["finetuned"], None, cfg, "cuda")
+    for p, m in case["merged_state_dict"].items():
+        assert parity.nan_positions_equal(res["merged_state_dict"][p], m), p
+        assert torch.isnan(m).all()
+        assert res["bases"].meta(p)["k"] == case["bases"][p]["masked"]["k"] == 7
+
+
+def test_cluster_partition_golden_from_gram(cuda_device):
+    """k-means on the K1 whole-model Gram reproduces the reference's own cluster partition."""
+    from svd_quantization_task_merging_b200.engine import MergeJob
+    case = _gold("intersection_cluster")
+    cfg = SVDHybridConfig(tasks=case["tasks"], svd_max_rank=64, svd_store_artifacts=False, **case["config"])
+    gold = case["diagnostics"]["cluster_assignments"]
+    # backend "sklearn" = the reference's very call on an isometric embedding of the Gram.  (The default
+    # "exact" backend returns the global k-means optimum, which coincides with sklearn's best-of-10 whenever
+    # the tasks really form clusters -- tests/test_host_logic.py -- but not on these unclustered toy tasks.)
+    job = MergeJob(case["base"], case["finetuned"], case["masks"], cfg, "cuda", cluster_backend="sklearn").run()
+    mine, ts = job.cluster_assignments, case["tasks"]
+    assert all((mine[a] == mine[b]) == (gold[a] == gold[b]) for a in ts for b in ts)
+    assert mine == gold                                  # same label numbering as well
+
+
+# ---- bases as subspaces ------------------------------------------------------------------------------------
+@pytest.mark.parametrize("fp16", [False, True])
+def test_bases_match_as_subspaces(cuda_device, fp16):
+    from svd_quantization_task_merging_b200.engine import merge_state_dicts
+    tasks = synth.task_names(8)
+    base, fts = synth.make_checkpoints(parity.MEDIUM_SHAPES, tasks, family="parity", seed=11)
+    masks = synth.make_masks(parity.MEDIUM_SHAPES, tasks, 0.5, seed=12)
+    ref_cfg, cfg = parity.make_cfgs(tasks, svd_energy_threshold=0.9, svd_fp16=fp16)
+    ref = R.run_reference_path(base, fts, masks, ref_cfg)
+    res = merge_state_dicts(base, fts, masks, cfg, "cuda", sign_ref={p: b["Vh"] for p, b in ref["bases"].items()},
+                            materialize_bases=True)
+    tol = 2e-3 if fp16 else parity.TOL_ANGLE
+    for p, rb in ref["bases"].items():
+        nb = res["bases"][p]["masked"]
+        assert list(nb.keys()) == ["U_high", "U_low", "singular_values", "k", "mean", "energy_retained", "D", "N"]
+        assert nb["U_high"].shape == rb["U_high"].shape and nb["U_low"].shape == rb["U_low"].shape
+        assert nb["U_high"].dtype == rb["U_high"].dtype == (torch.float16 if fp16 else torch.float32)
+        assert nb["mean"].shape == rb["mean"].shape and nb["singular_values"].shape == rb["singular_values"].shape
+        assert torch.allclose(nb["mean"].cpu(), rb["mean"], rtol=1e-5, atol=1e-9)
+        k = rb["k"]
+        assert parity.max_principal_sine(nb["U_high"].float(), rb["U_high"].float()) <= tol, p
+        # all numerically non-null directions (the centred task matrix has rank N-1: the last left vector
+        # of LAPACK is round-off noise, here it is a zero column)
+        rank = int((rb["singular_values"] > 1e-5 * rb["singular_values"][0]).sum())
+        U_ref = torch.cat([rb["U_high"], rb["U_low"]], 1).float()[:, :rank]
+        U_new = torch.cat([nb["U_high"], nb["U_low"]], 1).float()[:, :rank]
+        assert parity.max_principal_sine(U_new, U_ref) <= tol, p
+        # sign-aligned columns agree entry-wise
+        # LAPACK's own fp32 error on the weakest direction is ~eps * sigma_1 / sigma_j ~ 2e-6 of |u|
+        assert (U_new.cpu() - U_ref).abs().max() <= (2e-3 if fp16 else 1e-4) * U_ref.abs().max()
+        # orthonormality of what we wrote
+        eye = U_new.double().T @ U_new.double()
+        assert (eye.cpu() - torch.eye(rank, dtype=torch.float64)).abs().max() < (2e-3 if fp16 else 1e-5)
+
+
+# ---- fine-grained operator mirrors -----------------------------------------------------------------------------
+def test_mask_strategies_truth_tables_and_golden(cuda_device):
+    from src.svd_hybrid.mask_loader import (combine_masks, compute_intersection_mask, compute_majority_mask,
+                                            compute_union_mask)
+    a = torch.tensor([True, True, False, False])
+    b = torch.tensor([True, False, True, False])
+    c = torch.tensor([True, False, False, False])
+    assert compute_union_mask([a, b]).tolist() == [True, True, True, False]
+    assert compute_intersection_mask([a, b]).tolist() == [True, False, False, False]
+    assert compute_majority_mask([a, b, c]).tolist() == [True, False, False, False]
+    assert compute_majority_mask([a, b]).tolist() == [True, True, True, False]          # votes >= 0.5 * N
+    assert compute_union_mask([a]).tolist() == a.tolist() and compute_union_mask([a]).dtype == torch.bool
+    for fn in (compute_union_mask, compute_intersection_mask, compute_majority_mask):
+        with pytest.raises(ValueError):
+            fn([])
+    assert combine_masks({}, "union", verbose=False) == {}
+    with pytest.raises(ValueError):
+        combine_masks({"t": {"w": a}}, "xor", verbose=False)
+    for case in torch.load(os.path.join(GOLD, "mask_golden.pt"), weights_only=False):
+        for strat in ("union", "intersection", "majority"):
+            mine = combine_masks(case["masks"], strategy=strat, verbose=False)
+            assert sorted(mine) == sorted(case[strat])
+            for name, m in case[strat].items():
+                assert mine[name].dtype == torch.bool and mine[name].shape == m.shape and torch.equal(mine[name], m)
+    big = [torch.rand(3, 100003, generator=torch.Generator().manual_seed(i)) < 0.5 for i in range(5)]
+    for strat in ("union", "intersection", "majority"):
+        assert torch.equal(combine_masks({str(i): {"w": m} for i, m in enumerate(big)}, strat, verbose=False)["w"],
+                           R.combine_mask_list(big, strat))
+
+
+def test_construct_basis_compress_reconstruct_with_mean(cuda_device):
+    """tests/test_mean_handling.py of the reference: centred basis -> compress -> dequantise -> reconstruct must
+    add the mean back; uncentred path < 5 %; exact algebra U_h c_h + U_l c_l (+ mean)."""
+    from src.svd_hybrid.basis import compute_svd, construct_basis
+    from src.svd_hybrid.compress import compress_single_task, project_to_basis
+    from src.svd_hybrid.merge import reconstruct_from_coefficients
+    from src.svd_hybrid.rtvq import RTVQQuantizer
+    g = torch.Generator().manual_seed(0)
+    D, N = 600, 8
+    q, _ = torch.linalg.qr(torch.randn(N, N, generator=g))
+    deltas = list(((q * (0.6 ** torch.arange(N))) @ torch.randn(N, D, generator=g) + 1.0))      # common mean
+    quant = RTVQQuantizer(num_bits=8, num_stages=2)
+    b = construct_basis(deltas, energy_threshold=0.9, max_rank=None, center=True, device="cpu", verbose=False)
+    assert b["mean"].shape == (D, 1) and b["U_high"].shape == (D, b["k"]) and b["U_low"].shape == (D, N - b["k"])
+    assert b["D"] == D and b["N"] == N and b["U_high"].device.type == "cpu"
+    ob = R.build_basis(deltas, 0.9, None, True)
+    assert b["k"] == ob["k"] and torch.allclose(b["singular_values"], ob["singular_values"], rtol=1e-5, atol=1e-5)
+    for d in deltas[:3]:
+        art = compress_single_task(d, b["U_high"], b["U_low"], quant, "cpu", mean=b["mean"])
+        assert art["c_high_fp16"].dtype == torch.float16 and art["c_high_fp16"].device.type == "cpu"
+        c_lo = quant.dequantize(art["c_low_quant"])
+        with_mean = reconstruct_from_coefficients(art["c_high_fp16"].float(), c_lo, b["U_high"], b["U_low"], "cpu",
+                                                  mean=b["mean"])
+        without = reconstruct_from_coefficients(art["c_high_fp16"].float(), c_lo, b["U_high"], b["U_low"], "cpu")
+        e1 = ((with_mean - d).norm() / d.norm()).item()
+        e0 = ((without - d).norm() / d.norm()).item()
+        assert e1 < 0.01 and e0 > 10 * e1
+    # uncentred path
+    b2 = construct_basis(deltas, energy_threshold=0.99, center=False, device="cpu", verbose=False)
+    assert b2["mean"] is None
+    art = compress_single_task(deltas[0], b2["U_high"], b2["U_low"], quant, "cpu", mean=None)
+    rec = reconstruct_from_coefficients(art["c_high_fp16"].float(), quant.dequantize(art["c_low_quant"]),
+                                        b2["U_high"], b2["U_low"], "cpu")
+    assert ((rec - deltas[0]).norm() / deltas[0].norm()).item() < 0.05
+    # exact algebra on a full orthogonal basis (tests/test_mean_handling.py:206-312)
+    Q, _ = torch.linalg.qr(torch.randn(50, 50, generator=g))
+    x = torch.randn(50, generator=g)
+    ch, cl = project_to_basis(x, Q[:, :10], Q[:, 10:])
+    assert torch.allclose(reconstruct_from_coefficients(ch, cl, Q[:, :10], Q[:, 10:], "cpu"), x, atol=1e-5)
+    m = torch.randn(50, 1, generator=g)
+    assert torch.allclose(reconstruct_from_coefficients(ch, cl, Q[:, :10], Q[:, 10:], "cpu", mean=m), x + m.squeeze(), atol=1e-5)
+    # compute_svd keeps the device and reproduces the matrix
+    M = torch.randn(300, 6, generator=g)
+    U, S, Vh = compute_svd(M)
+    assert U.device == M.device and U.shape == (300, 6) and S.shape == (6,) and Vh.shape == (6, 6)
+    assert torch.allclose((U * S) @ Vh, M, atol=1e-4)
+    assert torch.allclose(S, torch.linalg.svdvals(M), rtol=1e-5)
+    Uc, Sc, Vc = compute_svd(M.cuda())
+    assert Uc.is_cuda and Sc.is_cuda and Vc.is_cuda
+
+
+# ---- the on-disk pipeline -------------------------------------------------------------------------------------
+def _write_case(tmp, case):
+    ck, md = tmp / "ckpt", tmp / "masks"
+    ck.mkdir()
+    md.mkdir()
+    torch.save(dict(case["base"]), tmp / "base.pt")
+    for t in case["tasks"]:
+        torch.save(dict(case["finetuned"][t]), ck / f"{t}.pt")
+        if case["masks"] is not None:
+            torch.save(dict(case["masks"][t]), md / f"{t}_mask.pt")
+    return ck, md
+
+
+@pytest.mark.parametrize("name", ["union_uniform", "intersection_cluster"])
+def test_pipeline_on_disk_writes_reference_layout(cuda_device, tmp_path, name, monkeypatch):
+    from src.svd_hybrid.cli import run_svd_hybrid_pipeline
+    monkeypatch.setenv("SVDQ_CLUSTER_BACKEND", "sklearn")      # label-exact parity with the reference's k-means
+    from src.svd_hybrid.storage import load_all_artifacts
+    case = _gold(name)
+    ck, md = _write_case(tmp_path, case)
+    cfg = SVDHybridConfig(tasks=case["tasks"], checkpoint_dir=str(ck), base_model_path=str(tmp_path / "base.pt"),
+                          mask_dir=str(md), svd_store_artifacts=True, svd_eval_reconstruction=True, svd_max_rank=64,
+                          output_dir=str(tmp_path / "out"), artifact_dir=str(tmp_path / "art"), device="cuda",
+                          **case["config"])
+    res = run_svd_hybrid_pipeline(cfg, verbose=False)
+    assert list(res.keys()) == ["merged_state_dict", "diagnostics", "bases", "compressed"]
+    files = sorted(os.path.relpath(os.path.join(r, f), tmp_path) for r, _, fs in os.walk(tmp_path) for f in fs
+                   if os.path.relpath(r, tmp_path).split(os.sep)[0] in ("out", "art"))
+    assert files == case["files"]                        # exactly the files the reference wrote
+    art = load_all_artifacts(str(tmp_path / "art"))
+    gold_diag = case["diagnostics_json"]
+    assert set(art["diagnostics"].keys()) == set(gold_diag.keys())
+    assert json.load(open(tmp_path / "art" / "config.json")).keys() == case["config_json"].keys()
+    for p, gb in case["bases"].items():
+        nb = art["bases"][p]["masked"]
+        g = gb["masked"]
+        assert list(nb.keys()) == list(g.keys())
+        for key in ("U_high", "U_low", "singular_values", "mean"):
+            assert nb[key].shape == g[key].shape and nb[key].dtype == g[key].dtype and nb[key].device.type == "cpu"
+        assert nb["k"] == g["k"] and nb["D"] == g["D"] and nb["N"] == g["N"]
+        for t in case["tasks"]:
+            a, b = art["compressed"][p][t]["masked"], case["compressed"][p][t]["masked"]
+            assert a["c_high_fp16"].dtype == torch.float16 and a["c_high_fp16"].shape == b["c_high_fp16"].shape
+            qa, qb = a["c_low_quant"], b["c_low_quant"]
+            assert list(qa.keys()) == list(qb.keys()) and qa["num_bits"] == qb["num_bits"]
+            assert qa["original_shape"] == qb["original_shape"] and qa["original_dtype"] == qb["original_dtype"]
+            for x, y in zip(qa["payloads"], qb["payloads"]):
+                assert list(x.keys()) == list(y.keys()) and x["quantized"].dtype == torch.uint8
+                assert x["quantized"].shape == y["quantized"].shape and x["scale"].ndim == 0 and x["zero_point"].ndim == 0
+    merged = torch.load(tmp_path / "out" / "merged_state_dict.pt", weights_only=False)
+    for p, m in case["merged_state_dict"].items():
+        assert merged[p].shape == m.shape and merged[p].dtype == m.dtype
+        d_ref = m - case["base"][p]
+        assert parity.rel_l2(merged[p] - case["base"][p], d_ref) < 5e-2     # no sign hint: RTVQ-noise level
+    assert json.load(open(tmp_path / "out" / "weights.json")) == case["diagnostics"]["task_weights"]
+
+
+def test_reload_from_artifacts_unmasked(cuda_device, tmp_path):
+    """reload.reconstruct_from_artifacts re-merges from stored bases + codes (reference reload.py:142-238)."""
+    from src.svd_hybrid.cli import run_svd_hybrid_pipeline
+    from src.svd_hybrid.reload import reconstruct_from_artifacts
+    case = _gold("nomask_fp32_nocenter")
+    ck, _ = _write_case(tmp_path, case)
+    cfg = SVDHybridConfig(tasks=case["tasks"], checkpoint_dir=str(ck), base_model_path=str(tmp_path / "base.pt"),
+                          svd_store_artifacts=True, svd_max_rank=64, output_dir=str(tmp_path / "out"),
+                          artifact_dir=str(tmp_path / "art"), device="cuda", **case["config"])
+    res = run_svd_hybrid_pipeline(cfg, verbose=False)
+    out = reconstruct_from_artifacts(str(tmp_path / "art"), str(tmp_path / "base.pt"), str(tmp_path / "re.pt"), "cpu")
+    for p, m in res["merged_state_dict"].items():
+        assert torch.allclose(out["merged_state_dict"][p], m.cpu(), rtol=1e-4, atol=1e-7), p
+    assert os.path.exists(tmp_path / "re.pt")
+
+
+# ---- world-size invariance of the parameter-sharded path -----------------------------------------------------
+@pytest.mark.parametrize("weighting", ["uniform", "cluster"])
+def test_sharded_results_bit_identical_for_any_world_size(cuda_device, weighting):
+    """Parameters are independent units: processing the shards of world size 2/4/8 (logical ranks, one
+    after the other on this GPU) must reproduce the single-rank result bit for bit."""
+    from svd_quantization_task_merging_b200.engine import MergeJob
+    tasks = synth.task_names(8)
+    shapes = dict(parity.MEDIUM_SHAPES)
+    shapes.update({f"extra{i}.weight": (64 + i, 33) for i in range(9)})
+    base, fts = synth.make_checkpoints(shapes, tasks, family="parity", seed=31)
+    masks = synth.make_masks(shapes, tasks, 0.6, seed=32)
+    cfg = SVDHybridConfig(tasks=tasks, svd_energy_threshold=0.9, svd_weighting=weighting, svd_store_artifacts=False)
+    full = MergeJob(base, fts, masks, cfg, "cuda").run()
+    merged_full = full.merged_state_dict()
+    diag_full = full.results()["diagnostics"]["per_parameter"]
+    gram = torch.from_numpy(full.whole_model_gram).cuda().view(-1) if weighting == "cluster" else None
+    cost = {k: int(np.prod(v)) * 9 for k, v in shapes.items()}
+    for world in (2, 4, 8):
+        owner = sharding.lpt_partition(cost, world)
+        seen = set()
+        for rank in range(world):
+            mine = [n for n, r in owner.items() if r == rank]
+            job = MergeJob(base, fts, masks, cfg, "cuda", param_filter=mine)
+            if gram is not None:
+                job.gram_reduce_hook = lambda g_local: gram.clone()      # what the NCCL all-reduce would deliver
+            job.run()
+            part = job.merged_state_dict()
+            assert sorted(part.keys()) == sorted(mine)
+            d = job.results()["diagnostics"]["per_parameter"]
+            for n in mine:
+                assert torch.equal(part[n], merged_full[n]), (world, rank, n)
+                if n in diag_full:
+                    assert d[n] == diag_full[n], (world, rank, n)
+            seen.update(mine)
+        assert seen == set(shapes)
