@@ -12,7 +12,7 @@
 //   apply_merged_deltas                                   src/svd_hybrid/merge.py:486-488
 //   compute_reconstruction_error (DIAG)                   src/svd_hybrid/diagnostics.py:101-117,205-216
 // Bound: HBM (algorithmic bytes per element: (N+1)*sizeof(T) + 1/8 + 4).
-#include "svdq_kernels.h"
+#include "k3_body.cuh"
 
 #ifndef SVDQ_DTYPE
 #define SVDQ_DTYPE 0
@@ -21,7 +21,6 @@
 namespace svdq {
 
 
-constexpr int kDiagRows = 5;      // sum e^2, sum |e|, sum rec^2, sum orig^2, max |e|
 
 template <typename T, int NT, bool FP16B, bool DIAG>
 __global__ void __launch_bounds__(kBlock, (NT <= 8 && !DIAG) ? 2 : 1) k3_reconstruct_merge(const K3Args a) {
@@ -39,7 +38,9 @@ __global__ void __launch_bounds__(kBlock, (NT <= 8 && !DIAG) ? 2 : 1) k3_reconst
     const int64_t stop = min(start + (int64_t)a.tile_elems, numel);
     const int status = a.info[(int64_t)p * 8 + 0];
     const int n_active = a.info[(int64_t)p * 8 + 1];
-    const int r = a.info[(int64_t)p * 8 + 2];
+    // columns beyond r_eff are zero (null directions): their contribution is tail_add; the fused
+    // diagnostics still walk all r columns so that a NaN coefficient shows up exactly as in the reference
+    const int r = a.info[(int64_t)p * 8 + (DIAG ? 2 : 4)];
     const float tail_add = a.scal[(int64_t)p * 4 + 1];
     const bool has_mask = a.has_mask[p] != 0;
 
@@ -104,101 +105,8 @@ __global__ void __launch_bounds__(kBlock, (NT <= 8 && !DIAG) ? 2 : 1) k3_reconst
                         x[t][c] = (e + c < numel) ? Elem<T>::load1(s_ptr[t + 1], e + c) : 0.0f;
             }
             if (has_mask) pword = __ldg(packed + (e >> 5));
-            // ---- phase 2 --------------------------------------------------------------------------------
-            float mean[kVec];
-#pragma unroll
-            for (int c = 0; c < kVec; ++c) mean[c] = 0.0f;
-#pragma unroll
-            for (int t = 0; t < NT; ++t)
-#pragma unroll
-                for (int c = 0; c < kVec; ++c) {
-                    x[t][c] = Elem<T>::sub(x[t][c], b[c]);
-                    mean[c] += x[t][c];
-                }
-            const uint32_t bits = (pword >> (int)(e & 31)) & 0xFu;
-
-            float orig[DIAG ? NT : 1][kVec];
-            if (DIAG) {
-#pragma unroll
-                for (int t = 0; t < NT; ++t)
-#pragma unroll
-                    for (int c = 0; c < kVec; ++c) orig[t][c] = x[t][c];
-            }
-#pragma unroll
-            for (int c = 0; c < kVec; ++c) mean[c] = a.center ? __fdiv_rn(mean[c], n_f) : 0.0f;
-#pragma unroll
-            for (int t = 0; t < NT; ++t)
-#pragma unroll
-                for (int c = 0; c < kVec; ++c) x[t][c] = ((present_bits >> t) & 1u) ? x[t][c] - mean[c] : 0.0f;
-
-            float acc[kVec];
-#pragma unroll
-            for (int c = 0; c < kVec; ++c) acc[c] = 0.0f;
-            float rec[DIAG ? NT : 1][kVec];
-            if (DIAG) {
-#pragma unroll
-                for (int t = 0; t < NT; ++t)
-#pragma unroll
-                    for (int c = 0; c < kVec; ++c) rec[t][c] = 0.0f;
-            }
-            if (FP16B || DIAG) {
-                for (int j = 0; j < r; ++j) {
-                    float u[kVec];
-#pragma unroll
-                    for (int c = 0; c < kVec; ++c) u[c] = 0.0f;
-#pragma unroll
-                    for (int t = 0; t < NT; ++t) {
-                        const float w = sWT[j][t];
-#pragma unroll
-                        for (int c = 0; c < kVec; ++c) u[c] = fmaf(x[t][c], w, u[c]);
-                    }
-                    const float cb = sCbar[j];
-#pragma unroll
-                    for (int c = 0; c < kVec; ++c) {
-                        if (FP16B) u[c] = round_fp16(u[c]);
-                        acc[c] = fmaf(u[c], cb, acc[c]);
-                    }
-                    if (DIAG) {
-#pragma unroll
-                        for (int t = 0; t < NT; ++t) {
-                            const float ch = sChatT[j][t];
-#pragma unroll
-                            for (int c = 0; c < kVec; ++c) rec[t][c] = fmaf(u[c], ch, rec[t][c]);
-                        }
-                    }
-                }
-            } else {
-#pragma unroll
-                for (int t = 0; t < NT; ++t) {
-                    const float g = sG[t];
-#pragma unroll
-                    for (int c = 0; c < kVec; ++c) acc[c] = fmaf(x[t][c], g, acc[c]);
-                }
-            }
-#pragma unroll
-            for (int c = 0; c < kVec; ++c) {
-                const bool m = (bits >> c) & 1u;
-                const float val = (acc[c] + mean[c]) + tail_add;
-                res[c] = b[c] + (m ? val : 0.0f);
-            }
-            if (DIAG) {
-#pragma unroll
-                for (int t = 0; t < NT; ++t) {
-                    if (!((present_bits >> t) & 1u)) continue;
-#pragma unroll
-                    for (int c = 0; c < kVec; ++c) {
-                        const bool m = ((bits >> c) & 1u) && (e + c < numel);
-                        if (m) {
-                            const float er = orig[t][c] - rec[t][c];
-                            dacc[0 * NT + t] = fmaf(er, er, dacc[0 * NT + t]);
-                            dacc[1 * NT + t] += fabsf(er);
-                            dacc[2 * NT + t] = fmaf(rec[t][c], rec[t][c], dacc[2 * NT + t]);
-                            dacc[3 * NT + t] = fmaf(orig[t][c], orig[t][c], dacc[3 * NT + t]);
-                            dacc[4 * NT + t] = fmaxf(dacc[4 * NT + t], fabsf(er));
-                        }
-                    }
-                }
-            }
+            k3_step<T, NT, FP16B, DIAG>(b, x, pword, e, numel, r, present_bits, a.center, n_f, tail_add, sWT, sChatT,
+                                        sCbar, sG, res, dacc);
         }
         if (full) stg_stream_f4(outp + e, make_float4(res[0], res[1], res[2], res[3]));
         else {

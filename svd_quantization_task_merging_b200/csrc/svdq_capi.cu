@@ -1,6 +1,7 @@
 // C ABI of libsvdq.so (see include/svdq.h).  Thin argument checking + kernel launches; no
 // allocation, no device synchronisation, no hidden state besides the thread-local error text.
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "../../include/svdq.h"
@@ -28,7 +29,35 @@ int finish(const char* fn, cudaError_t e) {
 
 #define REQUIRE(cond, what) do { if (!(cond)) return fail_arg(__func__, what); } while (0)
 
+// SVDQ_STAGED is a bit mask selecting the staged persistent (TMA ring) variant per pass: bit 0 = K1,
+// bit 1 = K3.  Default 1: measured on B200 (ViT-L-14 x 8) the ring wins for pass 1 (2.48 vs 3.22 ms),
+// while pass 2 is instruction-issue-limited and runs faster as 2 CTAs/SM of the direct-load kernel.
+int staged_mask() {
+    static const int m = [] { const char* v = getenv("SVDQ_STAGED"); return v ? atoi(v) : 1; }();
+    return m;
+}
+int sm_count() {
+    static const int n = [] {
+        int dev = 0, v = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) return 148;
+        return v;
+    }();
+    return n;
+}
+bool aligned16(const void* p) { return ((uintptr_t)p & 15u) == 0; }
+
 cudaError_t k1_launch(int dtype, int nt, const svdq::K1Args& a, int n_tiles, bool full, cudaStream_t st) {
+    if ((staged_mask() & 1) && nt <= 8) {
+        cudaError_t e = cudaErrorNotSupported;
+        switch (dtype) {
+            case svdq::kF32:  e = svdq::k1s_launch_dtype<svdq::kF32>(nt, a, n_tiles, full, sm_count(), st); break;
+            case svdq::kBF16: e = svdq::k1s_launch_dtype<svdq::kBF16>(nt, a, n_tiles, full, sm_count(), st); break;
+            case svdq::kF16:  e = svdq::k1s_launch_dtype<svdq::kF16>(nt, a, n_tiles, full, sm_count(), st); break;
+            default: break;
+        }
+        if (e != cudaErrorNotSupported) return e;
+    }
     switch (dtype) {
         case svdq::kF32:  return svdq::k1_launch_dtype<svdq::kF32>(nt, a, n_tiles, full, st);
         case svdq::kBF16: return svdq::k1_launch_dtype<svdq::kBF16>(nt, a, n_tiles, full, st);
@@ -37,6 +66,16 @@ cudaError_t k1_launch(int dtype, int nt, const svdq::K1Args& a, int n_tiles, boo
     }
 }
 cudaError_t k3_launch(int dtype, int nt, const svdq::K3Args& a, int n_tiles, bool fp16b, bool diag, cudaStream_t st) {
+    if ((staged_mask() & 2) && nt <= 8 && !diag) {
+        cudaError_t e = cudaErrorNotSupported;
+        switch (dtype) {
+            case svdq::kF32:  e = svdq::k3s_launch_dtype<svdq::kF32>(nt, a, n_tiles, fp16b, sm_count(), st); break;
+            case svdq::kBF16: e = svdq::k3s_launch_dtype<svdq::kBF16>(nt, a, n_tiles, fp16b, sm_count(), st); break;
+            case svdq::kF16:  e = svdq::k3s_launch_dtype<svdq::kF16>(nt, a, n_tiles, fp16b, sm_count(), st); break;
+            default: break;
+        }
+        if (e != cudaErrorNotSupported) return e;
+    }
     switch (dtype) {
         case svdq::kF32:  return svdq::k3_launch_dtype<svdq::kF32>(nt, a, n_tiles, fp16b, diag, st);
         case svdq::kBF16: return svdq::k3_launch_dtype<svdq::kBF16>(nt, a, n_tiles, fp16b, diag, st);

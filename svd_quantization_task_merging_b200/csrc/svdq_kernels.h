@@ -106,6 +106,9 @@ struct K5Args {
 template <int DT> cudaError_t k1_launch_dtype(int nt, const K1Args& a, int n_tiles, bool full, cudaStream_t st);
 template <int DT> cudaError_t k3_launch_dtype(int nt, const K3Args& a, int n_tiles, bool fp16b, bool diag, cudaStream_t st);
 template <int DT> cudaError_t k5_launch_dtype(int nt, const K5Args& a, int n_tiles, cudaStream_t st);
+// staged persistent variants (TMA bulk copies into a shared-memory ring); cudaErrorNotSupported when nt > 8
+template <int DT> cudaError_t k1s_launch_dtype(int nt, const K1Args& a, int n_tiles, bool full, int n_sm, cudaStream_t st);
+template <int DT> cudaError_t k3s_launch_dtype(int nt, const K3Args& a, int n_tiles, bool fp16b, int n_sm, cudaStream_t st);
 cudaError_t k2_reduce_launch(const K2ReduceArgs& a, int n_params, cudaStream_t st);
 cudaError_t k2_solve_launch(const K2SolveArgs& a, int n_params, cudaStream_t st);
 cudaError_t k3_diag_launch(const K3DiagArgs& a, int n_params, cudaStream_t st);

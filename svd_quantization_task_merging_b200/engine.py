@@ -33,7 +33,7 @@ from .svd_hybrid.weighting import compute_weights, effective_merge_weights
 TILE_ELEMS = 16384          # elements per tile (multiple of 1024); fixes the reduction order
 MAX_STREAM_TASKS = 16
 _FLOAT_DTYPES = {torch.float32: 0, torch.bfloat16: 1, torch.float16: 2}
-_ALIGN = {torch.float32: 16, torch.bfloat16: 8, torch.float16: 8}
+_ALIGN = {torch.float32: 16, torch.bfloat16: 16, torch.float16: 16}   # 16 B: TMA bulk-copy source alignment
 
 
 _PINNED: Dict[Tuple[int, torch.dtype], torch.Tensor] = {}
@@ -232,7 +232,7 @@ class MergeJob:
                     break
                 if mk.dtype != torch.bool:
                     mk = mk.bool()
-                mrow[i] = _aligned_flat(mk, dev, 4)
+                mrow[i] = _aligned_flat(mk, dev, 16)
             g = self.groups.setdefault(b.dtype, _Group(dtype=b.dtype))
             g.names.append(name)
             g.shapes.append(b.shape)
