@@ -21,8 +21,8 @@
  *   - "tile" = tile_elems consecutive elements of one parameter (tile_elems % 1024 == 0);
  *     tiles are numbered parameter by parameter: tile_begin[p] .. tile_begin[p+1]-1.
  *   - tensor pointer tables: tensors[p*(NT+1) + 0] = base, [.. + 1 + t] = fine-tuned tensor of
- *     task t (NULL when task t lacks the parameter).  Pointers must be 16-byte aligned
- *     (8-byte for 16-bit dtypes); mask pointers 4-byte aligned.
+ *     task t (NULL when task t lacks the parameter).  Tensor and mask pointers must be 16-byte
+ *     aligned (source alignment of the TMA bulk copies of the staged kernels).
  */
 #ifndef SVDQ_H_
 #define SVDQ_H_
@@ -56,7 +56,7 @@ int64_t svdq_k4_scratch_bytes(void);
  *        or NULL when there are no masks at all.
  * packed/pmask_off: bit-packed combined mask, parameter p at word offset pmask_off[p].
  * gram: [n_tiles][full ? 2 : 1][NT(NT+1)/2] fp32 partials (upper triangle, row-major);
- *       the second block (full != 0) is the Gram of the UNMASKED complement, used for the
+ *       the second block (full != 0) is the Gram over ALL elements (masked or not): the
  *       whole-model task Gram behind cluster weighting (src/svd_hybrid/clustering.py:227-232).
  * count: [n_tiles] masked elements per tile.
  */

@@ -142,9 +142,9 @@ __global__ void __launch_bounds__(kBlock + 32, 1) k1s_tv_mask_gram(const K1Args 
         const bool majority = a.strategy == kMajority;
         uint32_t* packed = has_mask ? a.packed + a.pmask_off[p] : nullptr;
 
-        float acc[NACC];
+        float2 acc2[G];
 #pragma unroll
-        for (int i = 0; i < NACC; ++i) acc[i] = 0.0f;
+        for (int i = 0; i < G; ++i) acc2[i] = make_float2(0.0f, 0.0f);
         uint32_t cnt = 0;
 
         for (int64_t e0 = start; e0 < stop; e0 += kStep) {
@@ -225,25 +225,44 @@ __global__ void __launch_bounds__(kBlock + 32, 1) k1s_tv_mask_gram(const K1Args 
                 w |= __shfl_xor_sync(0xffffffffu, w, 4);
                 if ((lane & 7) == 0 && active) packed[e >> 5] = w;
             }
+            // packed 2-wide FMAs (fma.rn.f32x2): FULL pairs the masked Gram with the all-element Gram of the
+            // same (i, j); otherwise two consecutive elements share one instruction
+            if (FULL) {
 #pragma unroll
-            for (int c = 0; c < kVec; ++c) {
-                const bool m = (bits >> c) & 1u;
-                float dm[NT], du[NT];
+                for (int c = 0; c < kVec; ++c) {
+                    const bool m = (bits >> c) & 1u;
+                    float2 v[NT];
 #pragma unroll
-                for (int t = 0; t < NT; ++t) {
-                    dm[t] = m ? d[t][c] : 0.0f;
-                    if (FULL) du[t] = m ? 0.0f : d[t][c];
+                    for (int t = 0; t < NT; ++t) v[t] = make_float2(m ? d[t][c] : 0.0f, d[t][c]);
+#pragma unroll
+                    for (int i = 0; i < NT; ++i)
+#pragma unroll
+                        for (int j = i; j < NT; ++j)
+                            acc2[tri_index(i, j, NT)] = __ffma2_rn(v[i], v[j], acc2[tri_index(i, j, NT)]);
                 }
+            } else {
 #pragma unroll
-                for (int i = 0; i < NT; ++i)
+                for (int c = 0; c < kVec; c += 2) {
+                    const bool m0 = (bits >> c) & 1u, m1 = (bits >> (c + 1)) & 1u;
+                    float2 v[NT];
 #pragma unroll
-                    for (int j = i; j < NT; ++j) {
-                        acc[tri_index(i, j, NT)] = fmaf(dm[i], dm[j], acc[tri_index(i, j, NT)]);
-                        if (FULL) acc[G + tri_index(i, j, NT)] = fmaf(du[i], du[j], acc[G + tri_index(i, j, NT)]);
-                    }
+                    for (int t = 0; t < NT; ++t) v[t] = make_float2(m0 ? d[t][c] : 0.0f, m1 ? d[t][c + 1] : 0.0f);
+#pragma unroll
+                    for (int i = 0; i < NT; ++i)
+#pragma unroll
+                        for (int j = i; j < NT; ++j)
+                            acc2[tri_index(i, j, NT)] = __ffma2_rn(v[i], v[j], acc2[tri_index(i, j, NT)]);
+                }
             }
         }
 
+        // unpack the packed accumulators: rows [0, G) masked Gram, rows [G, 2G) all-element Gram (FULL)
+        float acc[NACC];
+#pragma unroll
+        for (int i = 0; i < G; ++i) {
+            if (FULL) { acc[i] = acc2[i].x; acc[G + i] = acc2[i].y; }
+            else acc[i] = acc2[i].x + acc2[i].y;
+        }
         // ---- CTA reduction (consumers only), same order as the non-staged kernel ----------------------
         float* gout = a.gram + (int64_t)tile * NACC;
 #pragma unroll

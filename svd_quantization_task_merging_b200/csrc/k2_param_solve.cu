@@ -44,8 +44,8 @@ __global__ void __launch_bounds__(kBlock) k2_gram_reduce(const K2ReduceArgs a) {
         a.gram_masked[(int64_t)p * NT * NT + i * NT + j] = m;
         a.gram_masked[(int64_t)p * NT * NT + j * NT + i] = m;
         if (a.full && a.gram_all) {
-            a.gram_all[(int64_t)p * NT * NT + i * NT + j] = m + u;
-            a.gram_all[(int64_t)p * NT * NT + j * NT + i] = m + u;
+            a.gram_all[(int64_t)p * NT * NT + i * NT + j] = u;       // second block = Gram over ALL elements
+            a.gram_all[(int64_t)p * NT * NT + j * NT + i] = u;
         }
     }
     if (tid == 0) {

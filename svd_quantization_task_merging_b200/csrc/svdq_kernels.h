@@ -13,7 +13,7 @@ struct K1Args {
     const int32_t* tile_local;      // [n_tiles] tile index inside its parameter
     const int64_t* pmask_off;       // [P] word offset of the parameter's packed combined mask
     uint32_t* packed;               // bit i of word w = combined mask of element 32 w + i
-    float* gram;                    // [n_tiles][FULL ? 2 : 1][G]
+    float* gram;                    // [n_tiles][FULL ? 2 : 1][G]: masked Gram [, Gram over all elements]
     uint32_t* count;                // [n_tiles] masked elements in the tile
     int tile_elems;                 // multiple of kStep
     int strategy;
@@ -24,7 +24,7 @@ struct K2ReduceArgs {
     const uint32_t* count;        // [n_tiles]
     const int64_t* tile_begin;    // [P+1] first tile of each parameter
     double* gram_masked;          // [P][NT*NT] full symmetric
-    double* gram_all;             // [P][NT*NT] masked + complement (FULL only; may be null)
+    double* gram_all;             // [P][NT*NT] Gram over all elements, masked or not (FULL only; may be null)
     int64_t* dm;                  // [P]
     int nt;
     int full;

@@ -204,9 +204,10 @@ def compare_diagnostics(d_ref: Dict, d_new: Dict, tol_exact: float = TOL_DIAG, f
                 if np.isnan(v):
                     assert np.isnan(w), f"{name}/{task}/{key}: expected NaN"
                 else:
-                    # error figures are differences of fp32 quantities that are themselves only accurate to
-                    # ~1e-7 * original_norm: absolute floor of 1e-6 * original_norm (1e-6 for the ratio)
-                    floor = 1e-6 * (er["original_norm"] if key != "relative_error" else 1.0)
+                    # error figures are norms of (orig - rec), a difference of fp32 quantities each carrying a
+                    # few 1e-7 * original_norm of round-off (basis row, coefficient, contraction): absolute floor
+                    # of 5e-6 * original_norm (5e-6 for the ratio)
+                    floor = 5e-6 * (er["original_norm"] if key != "relative_error" else 1.0)
                     assert abs(w - v) <= tol * abs(v) + floor + 1e-12, f"{name}/{task}/{key}: {w} vs {v}"
     tol = 5e-2 if flipped else tol_exact
     for key, v in d_ref["summary"].items():
@@ -214,7 +215,7 @@ def compare_diagnostics(d_ref: Dict, d_new: Dict, tol_exact: float = TOL_DIAG, f
         if isinstance(v, float) and np.isnan(v):
             assert np.isnan(w)
         else:
-            assert abs(w - v) <= tol * abs(v) + 1e-6, f"summary {key}: {w} vs {v}"
+            assert abs(w - v) <= tol * abs(v) + 5e-6, f"summary {key}: {w} vs {v}"
 
 
 def golden_as_reference(case: Dict) -> Dict:

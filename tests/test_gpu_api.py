@@ -143,7 +143,8 @@ def test_construct_basis_compress_reconstruct_with_mean(cuda_device):
     assert b["mean"].shape == (D, 1) and b["U_high"].shape == (D, b["k"]) and b["U_low"].shape == (D, N - b["k"])
     assert b["D"] == D and b["N"] == N and b["U_high"].device.type == "cpu"
     ob = R.build_basis(deltas, 0.9, None, True)
-    assert b["k"] == ob["k"] and torch.allclose(b["singular_values"], ob["singular_values"], rtol=1e-5, atol=1e-5)
+    assert b["k"] == ob["k"]
+    assert (b["singular_values"] - ob["singular_values"]).abs().max() <= 5 * parity.TOL_S * ob["singular_values"][0]
     for d in deltas[:3]:
         art = compress_single_task(d, b["U_high"], b["U_low"], quant, "cpu", mean=b["mean"])
         assert art["c_high_fp16"].dtype == torch.float16 and art["c_high_fp16"].device.type == "cpu"
