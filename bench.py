@@ -195,6 +195,7 @@ def run_ours(args):
     masks = synth.make_masks(shapes, tasks, p, seed=4321 + rank, device=str(dev))
     perf = synth.performance_table(tasks) if cfg.svd_weighting == "performance" else None
     job = MergeJob(base, fts, masks, cfg, str(dev), performance=perf, diagnostics=False)
+    launches_per_step = job.gpu_launches
     torch.cuda.synchronize(dev)
 
     def barrier():
@@ -314,7 +315,7 @@ def run_ours(args):
                            "diagnostics_fused": False, "artifacts_materialised": False,
                            "parallelism": f"parameter-independent, {world} GPU(s), no data-path collective"},
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
-                "gpu_launches": 4 * args.steps, "params_with_basis_per_rank": solved_all}
+                "gpu_launches": launches_per_step * args.steps, "params_with_basis_per_rank": solved_all}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -81,7 +81,8 @@ int svdq_gram_reduce(int n_tasks, int full, int64_t n_params, const float* gram,
  *           (src/svd_hybrid/rtvq.py:4-103) on the low-energy block, dequantize_and_average
  *           (src/svd_hybrid/merge.py:61-141) and the gating of src/svd_hybrid/cli.py:319-343.
  * Inputs : gram_masked [P][NT*NT], dm [P], has_mask [P] (uint8), present [P] (bit t: task t has
- *          the parameter), weights [NT] fp64 by task position, avg_order [NT] task positions in
+ *          the parameter), weights [NT] fp64 by task position (NULL: see svdq_param_average),
+ *          avg_order [NT] task positions in
  *          sorted-name order, sign_ref [P][NT*NT] optional Vh_ref[j][t] for test-only sign
  *          alignment (NULL in production).
  * Outputs (per parameter, stride NT; S = rtvq_stages):
@@ -101,6 +102,17 @@ int svdq_param_solve(int n_tasks, int64_t n_params, int center, float energy_thr
                      int32_t* info, float* sv, float* scal, float* coef, uint16_t* chigh, uint8_t* codes,
                      float* qscale, float* qzp, float* qres, float* chat, float* cbar, float* W, float* gvec,
                      double* V, void* stream);
+
+/*
+ * K2c — weighted average only: svdq_param_solve called with weights == NULL stops after the
+ * coefficients / RTVQ / W; this entry point then forms cbar, gvec and scal[1] once the task weights
+ * are known (cluster weighting derives them from the whole-model Gram on the host meanwhile).
+ * Replaces dequantize_and_average (src/svd_hybrid/merge.py:89-141) and the weight folding of
+ * merge_with_clustering (merge.py:586-626).
+ */
+int svdq_param_average(int n_tasks, int64_t n_params, const uint32_t* present, const double* weights,
+                       const int32_t* avg_order, const int32_t* info, const float* chat, const float* W, float* cbar,
+                       float* gvec, float* scal, void* stream);
 
 /*
  * K3 — weighted reconstruction + merge (pass 2), optional fused diagnostics.

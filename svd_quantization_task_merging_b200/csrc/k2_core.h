@@ -184,6 +184,8 @@ struct SolveScratch {
     double V[kCoreMaxTasks * kCoreLd];     // accumulated rotations, V[t][j]
     double Vs[kCoreMaxTasks * kCoreLd];    // sorted, sign-fixed eigenvectors Vs[t][j]
     double tmp[kCoreMaxTasks];
+    double cs[2 * kCoreMaxTasks];          // (c, s) of the current Jacobi round
+    int pq[2 * kCoreMaxTasks];             // (p, q) of the current Jacobi round (p = -1: no rotation)
     double sigma[kCoreMaxTasks];
     float chat[kCoreMaxTasks * kCoreLd];   // chat[a][j]: fp16-rounded / dequantised coefficient of active task a
     int idx[kCoreMaxTasks];                // active-task compaction: a -> task position
@@ -205,7 +207,8 @@ struct SolveIn {
     int64_t dm;               // masked element count (rows of the task matrix)
     int has_mask;
     uint32_t present;         // bit t set: task t has this parameter
-    const double* weights;    // [NT] merge weights by task position (un-normalised is fine)
+    const double* weights;    // [NT] merge weights by task position (un-normalised is fine); null: solve only,
+                              //      average_param runs later
     const int32_t* avg_order; // [NT] task positions in sorted-name order (merge.py:89)
     const double* sign_ref;   // [NT*NT] optional Vh_ref[j][t] (test-only sign alignment) or null
 };
@@ -231,47 +234,130 @@ struct SolveOut {             // all strides are NT (= cfg.n_tasks); S = cfg.sta
 
 enum SolveStatus : int { kSolved = 0, kSkippedSmallMask = 1, kSkippedEmpty = 2 };
 
-// cyclic Jacobi on the symmetric n x n matrix A (ld kCoreLd); V accumulates rotations.
+// Parallel-order Jacobi eigensolver on the symmetric n x n matrix A (ld kCoreLd); V accumulates the
+// rotations.  One sweep = n-1 (n even) rounds of a round-robin tournament; the <= n/2 rotations of a
+// round touch disjoint index pairs, so their angles are computed side by side (one fp64 div/sqrt
+// latency chain per ROUND instead of per rotation) and applied as A <- J^T A J in two phases.
+// cs: scratch for the (c, s) of the current round, 2 * kCoreMaxTasks doubles.
 template <class L>
-SVDQ_HD void jacobi_eig(double* A, double* V, int n, L& ln) {
+SVDQ_HD void jacobi_eig(double* A, double* V, double* cs, int* pq, int n, L& ln) {
     for (int i = ln.lane; i < n; i += ln.nl)
         for (int j = 0; j < n; ++j) V[i * kCoreLd + j] = (i == j) ? 1.0 : 0.0;
     ln.sync();
-    for (int sweep = 0; sweep < 64; ++sweep) {
+    const int m = (n + 1) & ~1;                 // players in the tournament (one bye when n is odd)
+    const int npairs = m / 2;
+    for (int sweep = 0; sweep < 64 && n > 1; ++sweep) {
         double off = 0.0, dg = 0.0;
         for (int i = 0; i < n; ++i) {
             dg += A[i * kCoreLd + i] * A[i * kCoreLd + i];
             for (int j = i + 1; j < n; ++j) off += A[i * kCoreLd + j] * A[i * kCoreLd + j];
         }
         if (off <= 1e-34 * dg || off == 0.0) break;      // every lane sees the same values
-        for (int p = 0; p < n - 1; ++p) {
-            for (int q = p + 1; q < n; ++q) {
-                const double app = A[p * kCoreLd + p], aqq = A[q * kCoreLd + q], apq = A[p * kCoreLd + q];
-                ln.sync();                                // all lanes have read the pivot block
-                if (fabs(apq) <= 1e-300 || fabs(apq) <= 1e-19 * sqrt(fabs(app * aqq))) continue;
-                const double theta = (aqq - app) / (2.0 * apq);
-                const double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
-                const double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
-                for (int i = ln.lane; i < n; i += ln.nl) {
-                    if (i != p && i != q) {
-                        const double aip = A[i * kCoreLd + p], aiq = A[i * kCoreLd + q];
-                        const double nip = c * aip - s * aiq, niq = s * aip + c * aiq;
-                        A[i * kCoreLd + p] = nip; A[p * kCoreLd + i] = nip;
-                        A[i * kCoreLd + q] = niq; A[q * kCoreLd + i] = niq;
+        for (int round = 0; round < m - 1; ++round) {
+            // ---- rotation angles of this round's disjoint pairs -------------------------------------
+            for (int k = ln.lane; k < npairs; k += ln.nl) {
+                int p = (k == 0) ? (m - 1) : (round + k) % (m - 1);
+                int q = (k == 0) ? round : (round + m - 1 - k) % (m - 1);
+                if (p > q) { const int t = p; p = q; q = t; }
+                double c = 1.0, s = 0.0;
+                bool rot = false;
+                if (q < n) {
+                    const double app = A[p * kCoreLd + p], aqq = A[q * kCoreLd + q], apq = A[p * kCoreLd + q];
+                    if (!(fabs(apq) <= 1e-300 || fabs(apq) <= 1e-19 * sqrt(fabs(app * aqq)))) {
+                        const double theta = (aqq - app) / (2.0 * apq);
+                        const double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+                        c = 1.0 / sqrt(t * t + 1.0);
+                        s = t * c;
+                        rot = true;
                     }
-                    const double vip = V[i * kCoreLd + p], viq = V[i * kCoreLd + q];
-                    V[i * kCoreLd + p] = c * vip - s * viq;
-                    V[i * kCoreLd + q] = s * vip + c * viq;
                 }
-                if (ln.lane == 0) {
-                    A[p * kCoreLd + p] = app - t * apq;
-                    A[q * kCoreLd + q] = aqq + t * apq;
-                    A[p * kCoreLd + q] = 0.0;
-                    A[q * kCoreLd + p] = 0.0;
-                }
-                ln.sync();
+                cs[2 * k] = c; cs[2 * k + 1] = s;
+                pq[2 * k] = rot ? p : -1; pq[2 * k + 1] = q;
             }
+            ln.sync();
+            // ---- A <- A J and V <- V J : item = (pair k, row i) ----------------------------------------
+            for (int it = ln.lane; it < npairs * n; it += ln.nl) {
+                const int k = it / n, i = it % n;
+                const int p = pq[2 * k], q = pq[2 * k + 1];
+                if (p < 0) continue;
+                const double c = cs[2 * k], s = cs[2 * k + 1];
+                const double aip = A[i * kCoreLd + p], aiq = A[i * kCoreLd + q];
+                A[i * kCoreLd + p] = c * aip - s * aiq;
+                A[i * kCoreLd + q] = s * aip + c * aiq;
+                const double vip = V[i * kCoreLd + p], viq = V[i * kCoreLd + q];
+                V[i * kCoreLd + p] = c * vip - s * viq;
+                V[i * kCoreLd + q] = s * vip + c * viq;
+            }
+            ln.sync();
+            // ---- A <- J^T A : item = (pair k, column j) -------------------------------------------------
+            for (int it = ln.lane; it < npairs * n; it += ln.nl) {
+                const int k = it / n, j = it % n;
+                const int p = pq[2 * k], q = pq[2 * k + 1];
+                if (p < 0) continue;
+                const double c = cs[2 * k], s = cs[2 * k + 1];
+                const double apj = A[p * kCoreLd + j], aqj = A[q * kCoreLd + j];
+                A[p * kCoreLd + j] = c * apj - s * aqj;
+                A[q * kCoreLd + j] = s * apj + c * aqj;
+            }
+            ln.sync();
+            // ---- the rotated pivots are zero by construction; keep A exactly symmetric ---------------
+            for (int k = ln.lane; k < npairs; k += ln.nl) {
+                const int p = pq[2 * k], q = pq[2 * k + 1];
+                if (p < 0) continue;
+                A[p * kCoreLd + q] = 0.0;
+                A[q * kCoreLd + p] = 0.0;
+            }
+            ln.sync();
         }
+        // symmetrise (the two phases round the mirrored entries differently)
+        for (int i = ln.lane; i < n; i += ln.nl)
+            for (int j = i + 1; j < n; ++j) {
+                const double v = 0.5 * (A[i * kCoreLd + j] + A[j * kCoreLd + i]);
+                A[i * kCoreLd + j] = v;
+            }
+        ln.sync();
+        for (int i = ln.lane; i < n; i += ln.nl)
+            for (int j = 0; j < i; ++j) A[i * kCoreLd + j] = A[j * kCoreLd + i];
+        ln.sync();
+    }
+    ln.sync();
+}
+
+// Weighted average of the round-tripped coefficients in sorted-name order (merge.py:89-139), the
+// NaN-propagation term of the zero directions, and the fp32-basis shortcut g = W cbar.  Reads only
+// what solve_param wrote (info, chat, W), so it can run as its own tiny launch once the task weights
+// are known (cluster weighting computes them on the host while solve_param runs).
+template <class L>
+SVDQ_HD void average_param(const SolveConfig& cfg, const SolveIn& in, const SolveOut& out, L& ln) {
+    const int NT = cfg.n_tasks;
+    if (out.info[0] != kSolved) return;
+    const int r = out.info[2], r_eff = out.info[4];
+    double wsum = 0.0;
+    for (int o = 0; o < NT; ++o) {
+        const int t = in.avg_order[o];
+        if (in.present >> t & 1u) wsum += in.weights[t];
+    }
+    for (int j = ln.lane; j < r; j += ln.nl) {
+        float acc = 0.0f;
+        for (int o = 0; o < NT; ++o) {
+            const int t = in.avg_order[o];
+            if (!(in.present >> t & 1u)) continue;
+            const float w = (float)(in.weights[t] / wsum);
+            acc = f_add(acc, f_mul(out.chat[t * NT + j], w));
+        }
+        out.cbar[j] = acc;
+    }
+    ln.sync();
+    if (ln.lane == 0) {
+        float tail = 0.0f;
+        for (int j = r_eff; j < r; ++j) tail = f_add(tail, f_mul(0.0f, out.cbar[j]));
+        out.scal[1] = tail;
+    }
+    for (int t = ln.lane; t < NT; t += ln.nl) {
+        double g = 0.0;
+        if (in.present >> t & 1u)
+            for (int j = 0; j < r_eff; ++j) g += (double)out.W[t * NT + j] * (double)out.cbar[j];
+        out.gvec[t] = (float)g;
     }
     ln.sync();
 }
@@ -336,7 +422,7 @@ SVDQ_HD void solve_param(const SolveConfig& cfg, const SolveIn& in, const SolveO
         ln.sync();
     }
 
-    jacobi_eig(sc.A, sc.V, n, ln);
+    jacobi_eig(sc.A, sc.V, sc.cs, sc.pq, n, ln);
 
     // ---- sort descending, sign convention -------------------------------------------------------
     if (ln.lane == 0) {
@@ -421,36 +507,9 @@ SVDQ_HD void solve_param(const SolveConfig& cfg, const SolveIn& in, const SolveO
     }
     ln.sync();
 
-    // ---- weighted average in sorted-name order (merge.py:89-139) ----------------------------------
-    double wsum = 0.0;
-    for (int o = 0; o < NT; ++o) {
-        const int t = in.avg_order[o];
-        if (in.present >> t & 1u) wsum += in.weights[t];
-    }
-    for (int j = ln.lane; j < r; j += ln.nl) {
-        float acc = 0.0f;
-        for (int o = 0; o < NT; ++o) {
-            const int t = in.avg_order[o];
-            if (!(in.present >> t & 1u)) continue;
-            int a = 0;
-            for (int u = 0; u < t; ++u) a += (int)(in.present >> u & 1u);
-            const float w = (float)(in.weights[t] / wsum);
-            acc = f_add(acc, f_mul(sc.chat[a * kCoreLd + j], w));
-        }
-        out.cbar[j] = acc;
-        sc.tmp[j] = (double)acc;
-    }
-    ln.sync();
-    if (ln.lane == 0) {
-        float tail = 0.0f;
-        for (int j = r_eff; j < r; ++j) tail = f_add(tail, f_mul(0.0f, (float)sc.tmp[j]));
-        out.scal[1] = tail;
-    }
-
-    // ---- projection matrix W = H V Sigma^-1 and the fp32-basis shortcut g = W cbar ---------------
+    // ---- projection matrix W = H V Sigma^-1 (independent of the task weights) ----------------------
     for (int a = ln.lane; a < n; a += ln.nl) {
         const int t = sc.idx[a];
-        double g = 0.0;
         for (int j = 0; j < r_eff; ++j) {
             double v = sc.Vs[a * kCoreLd + j];
             if (cfg.center) {
@@ -458,14 +517,13 @@ SVDQ_HD void solve_param(const SolveConfig& cfg, const SolveIn& in, const SolveO
                 for (int b = 0; b < n; ++b) m += sc.Vs[b * kCoreLd + j];
                 v -= m / n;
             }
-            const float w = (float)(v / sc.sigma[j]);
-            out.W[t * NT + j] = w;
-            g += (double)w * sc.tmp[j];
+            out.W[t * NT + j] = (float)(v / sc.sigma[j]);
         }
-        out.gvec[t] = (float)g;
         for (int j = 0; j < n; ++j) out.V[t * NT + j] = sc.Vs[a * kCoreLd + j];
     }
     ln.sync();
+    if (in.weights != nullptr) average_param(cfg, in, out, ln);
 }
+
 
 }  // namespace svdq

@@ -94,6 +94,35 @@ __global__ void __launch_bounds__(32) k2_param_solve(const K2SolveArgs a) {
     solve_param(a.cfg, in, out, sc, ln);
 }
 
+// weighted average only (reads info / chat / W written by k2_param_solve)
+__global__ void __launch_bounds__(32) k2_param_average(const K2SolveArgs a) {
+    const int p = blockIdx.x;
+    const int NT = a.cfg.n_tasks;
+    const int64_t nn = (int64_t)NT * NT;
+    SolveIn in;
+    in.G = nullptr; in.dm = 0; in.has_mask = 0;
+    in.present = a.present[p];
+    in.weights = a.weights;
+    in.avg_order = a.avg_order;
+    in.sign_ref = nullptr;
+    SolveOut out = {};
+    out.info = a.info + (int64_t)p * 8;
+    out.scal = a.scal + (int64_t)p * 4;
+    out.chat = a.chat + p * nn;
+    out.cbar = a.cbar + (int64_t)p * NT;
+    out.W = a.W + p * nn;
+    out.gvec = a.gvec + (int64_t)p * NT;
+    WarpLanes ln{(int)threadIdx.x};
+    average_param(a.cfg, in, out, ln);
+}
+
+cudaError_t k2_average_launch(const K2SolveArgs& a, int n_params, cudaStream_t st) {
+    if (n_params <= 0) return cudaSuccess;
+    if (a.cfg.n_tasks < 1 || a.cfg.n_tasks > kCoreMaxTasks) return cudaErrorInvalidValue;
+    k2_param_average<<<n_params, 32, 0, st>>>(a);
+    return cudaGetLastError();
+}
+
 cudaError_t k2_reduce_launch(const K2ReduceArgs& a, int n_params, cudaStream_t st) {
     if (n_params <= 0) return cudaSuccess;
     if (a.nt < 1 || a.nt > 16) return cudaErrorInvalidValue;

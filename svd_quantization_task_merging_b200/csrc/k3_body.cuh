@@ -60,41 +60,52 @@ __device__ __forceinline__ void k3_step(const float (&b)[kVec], float (&x)[NT][k
             for (int c = 0; c < kVec; ++c) x[t][c] = ((present_bits >> t) & 1u) ? x[t][c] - mean[c] : 0.0f;
     }
 
-    float acc[kVec];
+    // The two tall-skinny contractions run as packed 2-wide FMAs (fma.rn.f32x2): elements (0,1) and (2,3)
+    // of the thread share an instruction; the fp16 round trip of the basis row uses the packed converts.
+    constexpr int kH = kVec / 2;
+    float2 x2[NT][kH];
 #pragma unroll
-    for (int c = 0; c < kVec; ++c) acc[c] = 0.0f;
-    float rec[DIAG ? NT : 1][kVec];
+    for (int t = 0; t < NT; ++t)
+#pragma unroll
+        for (int h = 0; h < kH; ++h) x2[t][h] = make_float2(x[t][2 * h], x[t][2 * h + 1]);
+    float2 acc2[kH];
+#pragma unroll
+    for (int h = 0; h < kH; ++h) acc2[h] = make_float2(0.0f, 0.0f);
+    float2 rec2[DIAG ? NT : 1][kH];
     if (DIAG) {
 #pragma unroll
         for (int t = 0; t < NT; ++t)
 #pragma unroll
-            for (int c = 0; c < kVec; ++c) rec[t][c] = 0.0f;
+            for (int h = 0; h < kH; ++h) rec2[t][h] = make_float2(0.0f, 0.0f);
     }
     if (FP16B || DIAG) {
 #pragma unroll
         for (int j = 0; j < NT; ++j) {               // r <= NT columns; unrolled, uniform early exit
             if (j >= r) break;
-            float u[kVec];
+            float2 u2[kH];
 #pragma unroll
-            for (int c = 0; c < kVec; ++c) u[c] = 0.0f;
+            for (int h = 0; h < kH; ++h) u2[h] = make_float2(0.0f, 0.0f);
 #pragma unroll
             for (int t = 0; t < NT; ++t) {
                 const float w = sWT[j][t];
+                const float2 w2 = make_float2(w, w);
 #pragma unroll
-                for (int c = 0; c < kVec; ++c) u[c] = fmaf(x[t][c], w, u[c]);
+                for (int h = 0; h < kH; ++h) u2[h] = __ffma2_rn(x2[t][h], w2, u2[h]);
             }
             const float cb = sCbar[j];
+            const float2 cb2 = make_float2(cb, cb);
 #pragma unroll
-            for (int c = 0; c < kVec; ++c) {
-                if (FP16B) u[c] = round_fp16(u[c]);
-                acc[c] = fmaf(u[c], cb, acc[c]);
+            for (int h = 0; h < kH; ++h) {
+                if (FP16B) u2[h] = __half22float2(__float22half2_rn(u2[h]));
+                acc2[h] = __ffma2_rn(u2[h], cb2, acc2[h]);
             }
             if (DIAG) {
 #pragma unroll
                 for (int t = 0; t < NT; ++t) {
                     const float ch = sChatT[j][t];
+                    const float2 ch2 = make_float2(ch, ch);
 #pragma unroll
-                    for (int c = 0; c < kVec; ++c) rec[t][c] = fmaf(u[c], ch, rec[t][c]);
+                    for (int h = 0; h < kH; ++h) rec2[t][h] = __ffma2_rn(u2[h], ch2, rec2[t][h]);
                 }
             }
         }
@@ -102,9 +113,20 @@ __device__ __forceinline__ void k3_step(const float (&b)[kVec], float (&x)[NT][k
 #pragma unroll
         for (int t = 0; t < NT; ++t) {
             const float g = sG[t];
+            const float2 g2 = make_float2(g, g);
 #pragma unroll
-            for (int c = 0; c < kVec; ++c) acc[c] = fmaf(x[t][c], g, acc[c]);
+            for (int h = 0; h < kH; ++h) acc2[h] = __ffma2_rn(x2[t][h], g2, acc2[h]);
         }
+    }
+    float acc[kVec];
+#pragma unroll
+    for (int h = 0; h < kH; ++h) { acc[2 * h] = acc2[h].x; acc[2 * h + 1] = acc2[h].y; }
+    float rec[DIAG ? NT : 1][kVec];
+    if (DIAG) {
+#pragma unroll
+        for (int t = 0; t < NT; ++t)
+#pragma unroll
+            for (int h = 0; h < kH; ++h) { rec[t][2 * h] = rec2[t][h].x; rec[t][2 * h + 1] = rec2[t][h].y; }
     }
 #pragma unroll
     for (int c = 0; c < kVec; ++c) {

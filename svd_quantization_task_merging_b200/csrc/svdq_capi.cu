@@ -146,7 +146,7 @@ int svdq_param_solve(int n_tasks, int64_t n_params, int center, float energy_thr
     REQUIRE(energy_threshold > 0.0f && energy_threshold <= 1.0f, "Energy threshold must be in (0, 1]");
     REQUIRE(n_params >= 0 && n_params < (1ll << 31), "n_params");
     if (n_params == 0) return 0;
-    REQUIRE(gram_masked && dm && has_mask && present && weights && avg_order, "null input pointer");
+    REQUIRE(gram_masked && dm && has_mask && present && avg_order, "null input pointer");
     REQUIRE(info && sv && scal && coef && chigh && codes && qscale && qzp && qres && chat && cbar && W && gvec && V,
             "null output pointer");
     svdq::K2SolveArgs a;
@@ -157,6 +157,21 @@ int svdq_param_solve(int n_tasks, int64_t n_params, int center, float energy_thr
     a.info = info; a.sv = sv; a.scal = scal; a.coef = coef; a.chigh = chigh; a.codes = codes; a.qscale = qscale;
     a.qzp = qzp; a.qres = qres; a.chat = chat; a.cbar = cbar; a.W = W; a.gvec = gvec; a.V = V;
     return finish(__func__, svdq::k2_solve_launch(a, (int)n_params, (cudaStream_t)stream));
+}
+
+int svdq_param_average(int n_tasks, int64_t n_params, const uint32_t* present, const double* weights,
+                       const int32_t* avg_order, const int32_t* info, const float* chat, const float* W, float* cbar,
+                       float* gvec, float* scal, void* stream) {
+    REQUIRE(n_tasks >= 1 && n_tasks <= SVDQ_MAX_TASKS, "n_tasks must be in [1, 32]");
+    REQUIRE(n_params >= 0 && n_params < (1ll << 31), "n_params");
+    if (n_params == 0) return 0;
+    REQUIRE(present && weights && avg_order && info && chat && W && cbar && gvec && scal, "null pointer");
+    svdq::K2SolveArgs a = {};
+    a.cfg.n_tasks = n_tasks;
+    a.present = present; a.weights = weights; a.avg_order = avg_order;
+    a.info = const_cast<int32_t*>(info); a.chat = const_cast<float*>(chat); a.W = const_cast<float*>(W);
+    a.cbar = cbar; a.gvec = gvec; a.scal = scal;
+    return finish(__func__, svdq::k2_average_launch(a, (int)n_params, (cudaStream_t)stream));
 }
 
 int svdq_reconstruct_merge(int dtype, int n_tasks, int fp16_basis, int diag, int center, int64_t n_tiles,

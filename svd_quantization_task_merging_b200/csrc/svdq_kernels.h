@@ -111,6 +111,7 @@ template <int DT> cudaError_t k1s_launch_dtype(int nt, const K1Args& a, int n_ti
 template <int DT> cudaError_t k3s_launch_dtype(int nt, const K3Args& a, int n_tiles, bool fp16b, int n_sm, cudaStream_t st);
 cudaError_t k2_reduce_launch(const K2ReduceArgs& a, int n_params, cudaStream_t st);
 cudaError_t k2_solve_launch(const K2SolveArgs& a, int n_params, cudaStream_t st);
+cudaError_t k2_average_launch(const K2SolveArgs& a, int n_params, cudaStream_t st);
 cudaError_t k3_diag_launch(const K3DiagArgs& a, int n_params, cudaStream_t st);
 cudaError_t k5_offsets_launch(const uint32_t* count, const int64_t* tile_begin, int64_t* tile_row_off, int n_params,
                               cudaStream_t st);

@@ -165,6 +165,8 @@ class MergeJob:
             for g in self.groups.values():
                 self._build_group(g)
         self._ran = False
+        self._side = None
+        self._order_dev = _dev(np.asarray(sorted(range(self.N), key=lambda i: self.tasks[i]), np.int32), self.device)
         self.gram_reduce_hook = None
         self._fetched: Optional[Dict[str, Dict[str, np.ndarray]]] = None
         self.weights: Optional[Dict[str, float]] = None
@@ -327,11 +329,10 @@ class MergeJob:
         order = np.asarray(sorted(range(self.N), key=lambda i: self.tasks[i]), np.int32)
         return _dev(w, self.device), _dev(order, self.device)
 
-    def _cluster(self):
-        """Whole-model task Gram (K1 by-product) -> host k-means (clustering.py:198-245)."""
-        from .svd_hybrid.clustering import cluster_from_gram
+    def _cluster_begin(self):
+        """Whole-model task Gram (K1 by-product) -> pinned host copy on a side stream, so that the
+        k-means round trip overlaps the per-parameter solve on the main stream."""
         if self.fixed_assignments is not None:
-            self.cluster_assignments = dict(self.fixed_assignments)
             return
         tot = None
         for g in self.groups.values():
@@ -339,7 +340,26 @@ class MergeJob:
             tot = s if tot is None else tot + s
         if self.gram_reduce_hook is not None:       # multi-GPU: sum the per-rank Grams (sharding.allreduce_gram)
             tot = self.gram_reduce_hook(tot)
-        gram = tot.view(self.N, self.N).cpu().numpy()
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=self.device)
+            self._gram_host = torch.empty(self.N * self.N, dtype=torch.float64, pin_memory=True)
+        ready = torch.cuda.Event()
+        ready.record()
+        self._side.wait_event(ready)
+        with torch.cuda.stream(self._side):
+            self._gram_host.copy_(tot, non_blocking=True)
+            self._gram_done = torch.cuda.Event()
+            self._gram_done.record()
+        self._gram_keep = tot
+
+    def _cluster_end(self):
+        """Host k-means on the Gram (clustering.py:198-245)."""
+        from .svd_hybrid.clustering import cluster_from_gram
+        if self.fixed_assignments is not None:
+            self.cluster_assignments = dict(self.fixed_assignments)
+            return
+        self._gram_done.synchronize()
+        gram = self._gram_host.numpy().reshape(self.N, self.N).copy()
         self.whole_model_gram = gram
         self.cluster_assignments = cluster_from_gram(gram, self.tasks, self.cfg.svd_cluster_k, "kmeans",
                                                      backend=self.cluster_backend)
@@ -373,20 +393,35 @@ class MergeJob:
                 t = g.t
                 _native.call("svdq_gram_reduce", N, full, len(g.names), _ptr(t["gram"]), _ptr(t["count"]),
                              _ptr(t["tile_begin"]), _ptr(t["gram_masked"]), _ptr(t["gram_all"]), _ptr(t["dm"]), st)
-            if self.cluster_mode:
-                self._cluster()
-            w_dev, order_dev = self._weights_table()
-            self._w_keep = (w_dev, order_dev)
             max_rank = int(cfg.svd_max_rank) if cfg.svd_max_rank is not None else 0
-            for g in self.groups.values():
-                t = g.t
-                _native.call("svdq_param_solve", N, len(g.names), int(bool(cfg.svd_center)),
-                             float(cfg.svd_energy_threshold), max_rank, int(cfg.svd_min_mask_size), self.bits,
-                             self.stages, _ptr(t["gram_masked"]), _ptr(t["dm"]), _ptr(t["has_mask"]),
-                             _ptr(t["present"]), _ptr(w_dev), _ptr(order_dev), _ptr(t["sign_ref"]),
-                             _ptr(t["info"]), _ptr(t["sv"]), _ptr(t["scal"]), _ptr(t["coef"]), _ptr(t["chigh"]),
-                             _ptr(t["codes"]), _ptr(t["qscale"]), _ptr(t["qzp"]), _ptr(t["qres"]), _ptr(t["chat"]),
-                             _ptr(t["cbar"]), _ptr(t["W"]), _ptr(t["gvec"]), _ptr(t["V"]), st)
+
+            def solve(w_dev, order_dev):
+                for g in self.groups.values():
+                    t = g.t
+                    _native.call("svdq_param_solve", N, len(g.names), int(bool(cfg.svd_center)),
+                                 float(cfg.svd_energy_threshold), max_rank, int(cfg.svd_min_mask_size), self.bits,
+                                 self.stages, _ptr(t["gram_masked"]), _ptr(t["dm"]), _ptr(t["has_mask"]),
+                                 _ptr(t["present"]), _ptr(w_dev), _ptr(order_dev), _ptr(t["sign_ref"]),
+                                 _ptr(t["info"]), _ptr(t["sv"]), _ptr(t["scal"]), _ptr(t["coef"]), _ptr(t["chigh"]),
+                                 _ptr(t["codes"]), _ptr(t["qscale"]), _ptr(t["qzp"]), _ptr(t["qres"]),
+                                 _ptr(t["chat"]), _ptr(t["cbar"]), _ptr(t["W"]), _ptr(t["gvec"]), _ptr(t["V"]), st)
+
+            if self.cluster_mode:
+                # weights depend on the whole-model Gram: start its D2H on a side stream, run the
+                # weight-independent solve meanwhile, then k-means on the host and the tiny average kernel
+                self._cluster_begin()
+                solve(None, self._order_dev)
+                self._cluster_end()
+                w_dev, order_dev = self._weights_table()
+                for g in self.groups.values():
+                    t = g.t
+                    _native.call("svdq_param_average", N, len(g.names), _ptr(t["present"]), _ptr(w_dev),
+                                 _ptr(order_dev), _ptr(t["info"]), _ptr(t["chat"]), _ptr(t["W"]), _ptr(t["cbar"]),
+                                 _ptr(t["gvec"]), _ptr(t["scal"]), st)
+            else:
+                w_dev, order_dev = self._weights_table()
+                solve(w_dev, order_dev)
+            self._w_keep = (w_dev, order_dev)
             mark("k2")
             for g in self.groups.values():
                 t = g.t
@@ -412,7 +447,7 @@ class MergeJob:
     def gpu_launches(self) -> int:
         """Kernels of libsvdq.so launched by one run()."""
         ng = len(self.groups)
-        return ng * (4 + (1 if self.want_diag else 0))
+        return ng * (4 + (1 if self.want_diag else 0) + (1 if self.cluster_mode else 0))
 
     def event_times_ms(self) -> Dict[str, float]:
         ev = self._events

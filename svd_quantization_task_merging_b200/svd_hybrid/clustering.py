@@ -71,6 +71,20 @@ def _restricted_growth(n: int, k: int, limit: int):
     return rows
 
 
+@functools.lru_cache(maxsize=16)
+def _partition_table(n: int, k: int, limit: int):
+    """Cached enumeration for the exact solver: candidate labelings, their one-hot indicator matrices
+    [k x M x n] and cluster sizes [k x M] (None when the enumeration would exceed ``limit``)."""
+    rows = _restricted_growth(n, k, limit)
+    if rows is None:
+        return None
+    used = rows.max(1) + 1
+    cand = rows[used == min(k, n)] if (used == min(k, n)).any() else rows
+    ind = np.stack([(cand == c).astype(np.float64) for c in range(k)], 0)
+    cnt = np.maximum(ind.sum(2), 1.0)
+    return cand.astype(np.int64), ind, cnt
+
+
 def kmeans_partition_from_gram(gram_normalised: np.ndarray, k: int, exact_limit: int = 200_000,
                                n_init: int = 64, seed: int = 42) -> np.ndarray:
     """Deterministic k-means on points known only through their Gram matrix.
@@ -83,11 +97,12 @@ def kmeans_partition_from_gram(gram_normalised: np.ndarray, k: int, exact_limit:
     n = g.shape[0]
     if k <= 0 or k > n:
         raise ValueError(f"Invalid k={k} for {n} samples")
-    rows = _restricted_growth(n, k, exact_limit)
-    if rows is not None:
-        used = rows.max(1) + 1
-        cand = rows[used == min(k, n)] if (used == min(k, n)).any() else rows
-        return cand[int(np.argmin(_inertia(cand, g, k)))].astype(np.int64)
+    table = _partition_table(n, k, exact_limit)
+    if table is not None:
+        cand, ind, cnt = table
+        # inertia = sum_c ( sum_{i in c} G_ii - (1/|c|) sum_{i,j in c} G_ij ); the first term is trace(G) for all
+        quad = (np.matmul(ind, g) * ind).sum(2)
+        return cand[int(np.argmax((quad / cnt).sum(0)))]
     rng = np.random.default_rng(seed)
     diag = np.diag(g)
     best, best_val = None, np.inf

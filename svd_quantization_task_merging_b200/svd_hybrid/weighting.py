@@ -116,13 +116,16 @@ def effective_merge_weights(task_names: List[str], weights: Dict[str, float],
     for n, c in cluster_assignments.items():
         clusters.setdefault(c, []).append(n)
     ids = list(clusters.keys())
-    score = [sum(weights.get(n, 1.0) for n in clusters[c]) / len(clusters[c]) for c in ids]
-    sm = torch.softmax(torch.tensor(score), dim=0)
-    # apply_weights_to_tensors renormalises the softmax weights in fp32 (sorted cluster ids)
+    score = np.asarray([sum(weights.get(n, 1.0) for n in clusters[c]) / len(clusters[c]) for c in ids], np.float32)
+    # fp32 softmax, then the fp32 renormalisation apply_weights_to_tensors performs (sorted cluster ids);
+    # numpy instead of torch.softmax keeps this off the critical path (a last-ulp difference in exp changes
+    # a weight by ~1e-8 relative)
+    ex = np.exp(score - score.max(), dtype=np.float32)
+    sm = (ex / ex.sum(dtype=np.float32)).astype(np.float32)
     order = sorted(range(len(ids)), key=lambda i: ids[i])
-    wt = torch.tensor([sm[i].item() for i in order], dtype=torch.float32)
-    wt = wt / wt.sum()
-    omega = {ids[i]: wt[j].item() for j, i in enumerate(order)}
+    wt = sm[order]
+    wt = (wt / wt.sum(dtype=np.float32)).astype(np.float32)
+    omega = {ids[i]: float(wt[j]) for j, i in enumerate(order)}
     out = {}
     for c, members in clusters.items():
         tot = sum(weights.get(n, 1.0) for n in members)
