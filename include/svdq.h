@@ -16,8 +16,8 @@
  *     thread-local message for the last non-zero return.
  *   - dtype codes: 0 = float32, 1 = bfloat16, 2 = float16 (dtype of base / fine-tuned tensors).
  *   - mask strategy codes: 0 = union, 1 = intersection, 2 = majority (votes >= 0.5 * n_present).
- *   - NT = n_tasks is the stride of every per-task array; n_tasks <= 16 for the streaming
- *     passes (<= 32 for svdq_param_solve).
+ *   - NT = n_tasks is the stride of every per-task array; n_tasks <= 16 for svdq_tv_mask_gram /
+ *     svdq_gram_reduce / svdq_write_basis, <= 32 everywhere else (see "wide path" below).
  *   - "tile" = tile_elems consecutive elements of one parameter (tile_elems % 1024 == 0);
  *     tiles are numbered parameter by parameter: tile_begin[p] .. tile_begin[p+1]-1.
  *   - tensor pointer tables: tensors[p*(NT+1) + 0] = base, [.. + 1 + t] = fine-tuned tensor of
@@ -64,6 +64,22 @@ int svdq_tv_mask_gram(int dtype, int n_tasks, int mask_strategy, int full, int64
                       const void* const* tensors, const uint8_t* const* masks, const int64_t* numel,
                       const int32_t* tile_param, const int32_t* tile_local, const int64_t* pmask_off,
                       uint32_t* packed, float* gram, uint32_t* count, void* stream);
+
+/*
+ * Wide path, 17..32 task vectors (the Gram accumulators of that many tasks do not fit one thread):
+ * svdq_mask_pack combines the N tall masks once (same reference lines as K1's mask part) into the packed
+ * mask + per-tile counts; svdq_tv_gram_premasked then accumulates the Gram of a SUBSET of <= 16 tasks
+ * (tensors = [P][n_tasks+1] table of that subset) under that pre-combined mask.  The caller runs it for
+ * pairs of task blocks and assembles the N x N Gram.  svdq_param_solve, svdq_reconstruct_merge and
+ * svdq_diag_finalize accept n_tasks <= 32 directly.
+ */
+int svdq_mask_pack(int n_tasks, int mask_strategy, int64_t n_tiles, int tile_elems, const uint8_t* const* masks,
+                   const int64_t* numel, const int32_t* tile_param, const int32_t* tile_local,
+                   const int64_t* pmask_off, uint32_t* packed, uint32_t* count, void* stream);
+int svdq_tv_gram_premasked(int dtype, int n_tasks, int full, int64_t n_tiles, int tile_elems,
+                           const void* const* tensors, const int64_t* numel, const int32_t* tile_param,
+                           const int32_t* tile_local, const int64_t* pmask_off, const uint8_t* has_mask,
+                           const uint32_t* packed, float* gram, uint32_t* count, void* stream);
 
 /*
  * K2a — fixed-order fp64 reduction of K1's tile partials per parameter.

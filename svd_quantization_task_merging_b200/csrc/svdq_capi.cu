@@ -66,6 +66,14 @@ cudaError_t k1_launch(int dtype, int nt, const svdq::K1Args& a, int n_tiles, boo
     }
 }
 cudaError_t k3_launch(int dtype, int nt, const svdq::K3Args& a, int n_tiles, bool fp16b, bool diag, cudaStream_t st) {
+    if (nt > SVDQ_MAX_STREAM_TASKS) {           // 17..32 tasks: runtime-N kernel
+        switch (dtype) {
+            case svdq::kF32:  return svdq::k6_merge_launch_dtype<svdq::kF32>(nt, a, n_tiles, fp16b, diag, st);
+            case svdq::kBF16: return svdq::k6_merge_launch_dtype<svdq::kBF16>(nt, a, n_tiles, fp16b, diag, st);
+            case svdq::kF16:  return svdq::k6_merge_launch_dtype<svdq::kF16>(nt, a, n_tiles, fp16b, diag, st);
+            default:          return cudaErrorInvalidValue;
+        }
+    }
     if ((staged_mask() & 2) && nt <= 8 && !diag) {
         cudaError_t e = cudaErrorNotSupported;
         switch (dtype) {
@@ -118,7 +126,49 @@ int svdq_tv_mask_gram(int dtype, int n_tasks, int mask_strategy, int full, int64
     a.tensors = tensors; a.masks = masks; a.numel = numel; a.tile_param = tile_param; a.tile_local = tile_local;
     a.pmask_off = pmask_off; a.packed = packed; a.gram = gram; a.count = count; a.tile_elems = tile_elems;
     a.strategy = mask_strategy;
+    a.packed_in = nullptr; a.has_mask_in = nullptr;
     return finish(__func__, k1_launch(dtype, n_tasks, a, (int)n_tiles, full != 0, (cudaStream_t)stream));
+}
+
+int svdq_mask_pack(int n_tasks, int mask_strategy, int64_t n_tiles, int tile_elems, const uint8_t* const* masks,
+                   const int64_t* numel, const int32_t* tile_param, const int32_t* tile_local,
+                   const int64_t* pmask_off, uint32_t* packed, uint32_t* count, void* stream) {
+    REQUIRE(n_tasks >= 1 && n_tasks <= SVDQ_MAX_TASKS, "n_tasks must be in [1, 32]");
+    REQUIRE(mask_strategy >= 0 && mask_strategy <= 2, "Unknown mask strategy");
+    REQUIRE(tile_elems > 0 && tile_elems % svdq::kStep == 0, "tile_elems must be a positive multiple of 1024");
+    REQUIRE(n_tiles >= 0 && n_tiles < (1ll << 31), "n_tiles");
+    if (n_tiles == 0) return 0;
+    REQUIRE(numel && tile_param && tile_local && count, "null pointer");
+    REQUIRE(!masks || (pmask_off && packed), "masks given without packed-mask storage");
+    svdq::K6MaskArgs a;
+    a.masks = masks; a.numel = numel; a.tile_param = tile_param; a.tile_local = tile_local; a.pmask_off = pmask_off;
+    a.packed = packed; a.count = count; a.tile_elems = tile_elems; a.strategy = mask_strategy; a.n_tasks = n_tasks;
+    return finish(__func__, svdq::k6_mask_pack_launch(a, (int)n_tiles, (cudaStream_t)stream));
+}
+
+int svdq_tv_gram_premasked(int dtype, int n_tasks, int full, int64_t n_tiles, int tile_elems,
+                           const void* const* tensors, const int64_t* numel, const int32_t* tile_param,
+                           const int32_t* tile_local, const int64_t* pmask_off, const uint8_t* has_mask,
+                           const uint32_t* packed, float* gram, uint32_t* count, void* stream) {
+    REQUIRE(n_tasks >= 1 && n_tasks <= SVDQ_MAX_STREAM_TASKS, "n_tasks must be in [1, 16]");
+    REQUIRE(dtype >= 0 && dtype <= 2, "dtype");
+    REQUIRE(tile_elems > 0 && tile_elems % svdq::kStep == 0, "tile_elems must be a positive multiple of 1024");
+    REQUIRE(n_tiles >= 0 && n_tiles < (1ll << 31), "n_tiles");
+    if (n_tiles == 0) return 0;
+    REQUIRE(tensors && numel && tile_param && tile_local && pmask_off && has_mask && packed && gram && count,
+            "null pointer");
+    svdq::K1Args a;
+    a.tensors = tensors; a.masks = nullptr; a.numel = numel; a.tile_param = tile_param; a.tile_local = tile_local;
+    a.pmask_off = pmask_off; a.packed = nullptr; a.gram = gram; a.count = count; a.tile_elems = tile_elems;
+    a.strategy = 0; a.packed_in = packed; a.has_mask_in = has_mask;
+    // always the direct-load kernel: the staged variant combines the task masks itself
+    cudaError_t e;
+    switch (dtype) {
+        case svdq::kF32:  e = svdq::k1_launch_dtype<svdq::kF32>(n_tasks, a, (int)n_tiles, full != 0, (cudaStream_t)stream); break;
+        case svdq::kBF16: e = svdq::k1_launch_dtype<svdq::kBF16>(n_tasks, a, (int)n_tiles, full != 0, (cudaStream_t)stream); break;
+        default:          e = svdq::k1_launch_dtype<svdq::kF16>(n_tasks, a, (int)n_tiles, full != 0, (cudaStream_t)stream); break;
+    }
+    return finish(__func__, e);
 }
 
 int svdq_gram_reduce(int n_tasks, int full, int64_t n_params, const float* gram, const uint32_t* count,
@@ -180,7 +230,7 @@ int svdq_reconstruct_merge(int dtype, int n_tasks, int fp16_basis, int diag, int
                            const uint8_t* has_mask, const uint32_t* packed, const int32_t* info, const float* W,
                            const float* cbar, const float* gvec, const float* scal, const float* chat,
                            float* const* out, float* diag_partials, void* stream) {
-    REQUIRE(n_tasks >= 1 && n_tasks <= SVDQ_MAX_STREAM_TASKS, "n_tasks must be in [1, 16]");
+    REQUIRE(n_tasks >= 1 && n_tasks <= SVDQ_MAX_TASKS, "n_tasks must be in [1, 32]");
     REQUIRE(dtype >= 0 && dtype <= 2, "dtype");
     REQUIRE(tile_elems > 0 && tile_elems % svdq::kStep == 0, "tile_elems must be a positive multiple of 1024");
     REQUIRE(n_tiles >= 0 && n_tiles < (1ll << 31), "n_tiles");
@@ -199,7 +249,7 @@ int svdq_reconstruct_merge(int dtype, int n_tasks, int fp16_basis, int diag, int
 
 int svdq_diag_finalize(int n_tasks, int64_t n_params, const float* diag_partials, const int64_t* tile_begin,
                        const int64_t* dm, const int32_t* info, double* out, void* stream) {
-    REQUIRE(n_tasks >= 1 && n_tasks <= SVDQ_MAX_STREAM_TASKS, "n_tasks must be in [1, 16]");
+    REQUIRE(n_tasks >= 1 && n_tasks <= SVDQ_MAX_TASKS, "n_tasks must be in [1, 32]");
     REQUIRE(n_params >= 0 && n_params < (1ll << 31), "n_params");
     if (n_params == 0) return 0;
     REQUIRE(diag_partials && tile_begin && dm && info && out, "null pointer");

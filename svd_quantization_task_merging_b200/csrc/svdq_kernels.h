@@ -17,6 +17,11 @@ struct K1Args {
     uint32_t* count;                // [n_tiles] masked elements in the tile
     int tile_elems;                 // multiple of kStep
     int strategy;
+    // pre-combined mask mode (n_tasks > 16 runs the Gram in several task-subset launches that must all see
+    // the SAME combined mask): masks == nullptr, packed_in = packed combined masks written by k6_mask_pack,
+    // has_mask_in[P] says which parameters have one.  packed is not written in this mode.
+    const uint32_t* packed_in;
+    const uint8_t* has_mask_in;
 };
 
 struct K2ReduceArgs {
@@ -74,6 +79,17 @@ struct K3DiagArgs {
     int nt;
 };
 
+struct K6MaskArgs {              // mask combination + packing for the wide (17..32 tasks) path
+    const uint8_t* const* masks;    // [P][n_tasks] (null entries allowed) or null
+    const int64_t* numel;
+    const int32_t* tile_param;
+    const int32_t* tile_local;
+    const int64_t* pmask_off;
+    uint32_t* packed;
+    uint32_t* count;                // [n_tiles]
+    int tile_elems, strategy, n_tasks;
+};
+
 constexpr int kK4MaxGrid = 148 * 8;
 
 struct K4Stats {            // one record per CTA, reduced in CTA order by k4_finalize
@@ -109,6 +125,9 @@ template <int DT> cudaError_t k5_launch_dtype(int nt, const K5Args& a, int n_til
 // staged persistent variants (TMA bulk copies into a shared-memory ring); cudaErrorNotSupported when nt > 8
 template <int DT> cudaError_t k1s_launch_dtype(int nt, const K1Args& a, int n_tiles, bool full, int n_sm, cudaStream_t st);
 template <int DT> cudaError_t k3s_launch_dtype(int nt, const K3Args& a, int n_tiles, bool fp16b, int n_sm, cudaStream_t st);
+cudaError_t k6_mask_pack_launch(const K6MaskArgs& a, int n_tiles, cudaStream_t st);
+template <int DT> cudaError_t k6_merge_launch_dtype(int n_tasks, const K3Args& a, int n_tiles, bool fp16b, bool diag,
+                                                    cudaStream_t st);
 cudaError_t k2_reduce_launch(const K2ReduceArgs& a, int n_params, cudaStream_t st);
 cudaError_t k2_solve_launch(const K2SolveArgs& a, int n_params, cudaStream_t st);
 cudaError_t k2_average_launch(const K2SolveArgs& a, int n_params, cudaStream_t st);

@@ -31,7 +31,8 @@ from . import _native
 from .svd_hybrid.weighting import compute_weights, effective_merge_weights
 
 TILE_ELEMS = 16384          # elements per tile (multiple of 1024); fixes the reduction order
-MAX_STREAM_TASKS = 16
+MAX_STREAM_TASKS = 16      # register-resident Gram (one K1 launch)
+MAX_TASKS = 32             # wide path: Gram over pairs of 8-task blocks, runtime-N pass 2
 _FLOAT_DTYPES = {torch.float32: 0, torch.bfloat16: 1, torch.float16: 2}
 _ALIGN = {torch.float32: 16, torch.bfloat16: 16, torch.float16: 16}   # 16 B: TMA bulk-copy source alignment
 
@@ -139,9 +140,9 @@ class MergeJob:
         self.N = len(self.tasks)
         if self.N < 1:
             raise ValueError("Empty delta list")
-        if self.N > MAX_STREAM_TASKS:
-            raise ValueError(f"n_tasks={self.N}: the streaming kernels support at most {MAX_STREAM_TASKS} task "
-                             f"vectors per merge in this build")
+        if self.N > MAX_TASKS:
+            raise ValueError(f"n_tasks={self.N}: at most {MAX_TASKS} task vectors per merge")
+        self.wide = self.N > MAX_STREAM_TASKS          # 17..32 tasks: blocked Gram + runtime-N pass 2
         if getattr(config, "svd_include_noise", False):
             raise NotImplementedError("svd_include_noise (noise-region bases) is not part of this build "
                                       "(SURVEY.md section 8f, rank 4)")
@@ -298,6 +299,18 @@ class MergeJob:
             diag=z(max(n_tiles, 1) * 5 * N) if self.want_diag else None,
             diag_out=z(P, N, 6, dtype=f64) if self.want_diag else None,
         )
+        g.sub = []
+        if self.wide:
+            blocks = [list(range(b, min(b + 8, N))) for b in range(0, N, 8)]
+            for bi in range(len(blocks)):
+                for bj in range(bi + 1, len(blocks)):
+                    idx = np.asarray(blocks[bi] + blocks[bj], np.int64)
+                    nl = len(idx)
+                    sub_ptr = np.concatenate([tptr[:, :1], tptr[:, 1 + idx]], axis=1)
+                    gl = nl * (nl + 1) // 2
+                    g.sub.append(dict(idx=torch.from_numpy(idx).to(dev), n=nl, tptr=_dev(sub_ptr, dev),
+                                      gram=z(max(n_tiles, 1) * full * gl), gm=z(P, nl * nl, dtype=f64),
+                                      ga=z(P, nl * nl, dtype=f64) if self.cluster_mode else None))
         optr = np.asarray([g.t["out"].data_ptr() + 4 * o for o in out_off], np.int64)
         g.t["optr"] = _dev(optr, dev)
         if self.sign_ref is not None:
@@ -382,17 +395,40 @@ class MergeJob:
 
         with torch.cuda.device(self.device):
             mark("start")
-            for g in self.groups.values():
-                t = g.t
-                _native.call("svdq_tv_mask_gram", _FLOAT_DTYPES[g.dtype], N, strat, full, g.n_tiles, te,
-                             _ptr(t["tptr"]), _ptr(t["mptr"]), _ptr(t["numel"]), _ptr(t["tile_param"]),
-                             _ptr(t["tile_local"]), _ptr(t["pm_off"]), _ptr(t["packed"]), _ptr(t["gram"]),
-                             _ptr(t["count"]), st)
-            mark("k1")
-            for g in self.groups.values():
-                t = g.t
-                _native.call("svdq_gram_reduce", N, full, len(g.names), _ptr(t["gram"]), _ptr(t["count"]),
-                             _ptr(t["tile_begin"]), _ptr(t["gram_masked"]), _ptr(t["gram_all"]), _ptr(t["dm"]), st)
+            if not self.wide:
+                for g in self.groups.values():
+                    t = g.t
+                    _native.call("svdq_tv_mask_gram", _FLOAT_DTYPES[g.dtype], N, strat, full, g.n_tiles, te,
+                                 _ptr(t["tptr"]), _ptr(t["mptr"]), _ptr(t["numel"]), _ptr(t["tile_param"]),
+                                 _ptr(t["tile_local"]), _ptr(t["pm_off"]), _ptr(t["packed"]), _ptr(t["gram"]),
+                                 _ptr(t["count"]), st)
+                mark("k1")
+                for g in self.groups.values():
+                    t = g.t
+                    _native.call("svdq_gram_reduce", N, full, len(g.names), _ptr(t["gram"]), _ptr(t["count"]),
+                                 _ptr(t["tile_begin"]), _ptr(t["gram_masked"]), _ptr(t["gram_all"]), _ptr(t["dm"]), st)
+            else:
+                # 17..32 tasks: combine the masks once, then one Gram launch per pair of 8-task blocks
+                for g in self.groups.values():
+                    t = g.t
+                    P = len(g.names)
+                    _native.call("svdq_mask_pack", N, strat, g.n_tiles, te, _ptr(t["mptr"]), _ptr(t["numel"]),
+                                 _ptr(t["tile_param"]), _ptr(t["tile_local"]), _ptr(t["pm_off"]), _ptr(t["packed"]),
+                                 _ptr(t["count"]), st)
+                    gm_full = t["gram_masked"].view(P, N, N)
+                    ga_full = t["gram_all"].view(P, N, N) if self.cluster_mode else None
+                    for sub in g.sub:
+                        _native.call("svdq_tv_gram_premasked", _FLOAT_DTYPES[g.dtype], sub["n"], full, g.n_tiles, te,
+                                     _ptr(sub["tptr"]), _ptr(t["numel"]), _ptr(t["tile_param"]), _ptr(t["tile_local"]),
+                                     _ptr(t["pm_off"]), _ptr(t["has_mask"]), _ptr(t["packed"]), _ptr(sub["gram"]),
+                                     _ptr(t["count"]), st)
+                        _native.call("svdq_gram_reduce", sub["n"], full, P, _ptr(sub["gram"]), _ptr(t["count"]),
+                                     _ptr(t["tile_begin"]), _ptr(sub["gm"]), _ptr(sub["ga"]), _ptr(t["dm"]), st)
+                        ix = sub["idx"]
+                        gm_full[:, ix[:, None], ix[None, :]] = sub["gm"].view(P, sub["n"], sub["n"])
+                        if ga_full is not None:
+                            ga_full[:, ix[:, None], ix[None, :]] = sub["ga"].view(P, sub["n"], sub["n"])
+                mark("k1")
             max_rank = int(cfg.svd_max_rank) if cfg.svd_max_rank is not None else 0
 
             def solve(w_dev, order_dev):
@@ -515,6 +551,9 @@ class MergeJob:
         """K5: U_high / U_low / mean compacted to the masked rows, in the artifact dtype."""
         if self._bases_done:
             return
+        if self.wide:
+            raise NotImplementedError("materialising U_high / U_low for more than 16 task vectors is not part of "
+                                      "this build (K5 is register-tiled for N <= 16)")
         fetched = self._fetch()
         cfg, N, te = self.cfg, self.N, self.tile_elems
         st = _native.stream_ptr()
@@ -608,7 +647,7 @@ def task_vector_gram(task_vectors: Mapping[str, Mapping[str, torch.Tensor]], nam
     dev = torch.device("cuda")
     N = len(names)
     if N > MAX_STREAM_TASKS:
-        raise ValueError(f"at most {MAX_STREAM_TASKS} task vectors")
+        raise ValueError(f"task_vector_gram: at most {MAX_STREAM_TASKS} task vectors")
     params = sorted({p for n in names for p in task_vectors[n].keys()})
     total = np.zeros((N, N), np.float64)
     from .svd_hybrid.config import SVDHybridConfig

@@ -5,7 +5,7 @@ encoders (the reference notebook builds its base state dict that way) and the
 HF Llama layout for the capacity config.  Two input families:
 
 * ``throughput``: base ~ N(0, 0.02^2), deltas iid N(0, 0.01^2).
-* ``parity``:     deltas with a decaying spectrum, ``D = (A diag(0.6^j)) C + 1e-4 E``,
+* ``parity``:     deltas with a decaying spectrum, ``D = (A diag(d^j)) C + 1e-4 E`` (d = 0.6 up to 8 tasks),
   so that the selected rank stays away from the reference's NaN edge
   (a 1-element low-energy block divides by max-min = 0, rtvq.py:17).
 """
@@ -114,7 +114,11 @@ def make_checkpoints(shapes, tasks: List[str], family: str = "throughput", seed:
     mix = None
     if family == "parity":
         q, _ = torch.linalg.qr(torch.randn(n, n, generator=g, device=device, dtype=torch.float32))
-        mix = q * (0.6 ** torch.arange(n, device=device, dtype=torch.float32))[None, :]
+        # 0.6^j for up to 8 tasks; for more tasks the decay is slowed so that the weakest direction stays at
+        # ~0.028 of the strongest (= 0.6^7), clear of the 1e-4 noise floor: near-degenerate singular values
+        # make the singular VECTORS ill-defined and parity against LAPACK meaningless
+        decay = 0.6 if n <= 8 else 0.028 ** (1.0 / (n - 1))
+        mix = q * (decay ** torch.arange(n, device=device, dtype=torch.float32))[None, :]
     for name, shp in shapes.items():
         numel = 1
         for d in shp:

@@ -15,6 +15,7 @@ from svd_quantization_task_merging_b200.svd_hybrid.config import SVDHybridConfig
 
 # tolerances (SURVEY.md 8c "stated tolerances to adopt")
 TOL_S = 2e-6            # singular values, relative to sigma_1
+TOL_S_GRAM = 2e-9       # ... for sigma_j << sigma_1: |d sigma_j| <= TOL_S_GRAM * sigma_1^2 / sigma_j (Gram route)
 TOL_MERGED = 1e-5       # merged weights, relative L2 per parameter (sign-aligned), fp32 bases, when the stored
                         # artifacts (fp16 c_high bits, RTVQ codes) are identical to the oracle's
 TOL_MERGED_FP16B = 1e-4 # ... with fp16 bases: LAPACK's fp32 left vectors carry an error of ~eps * sigma_1 / sigma_j
@@ -112,7 +113,12 @@ def compare_run(ref: Dict, res: Dict, check_diag: bool = True, tol_merged: Optio
         assert meta["D"] == rb["D"] and meta["N"] == rb["N"]
         assert len(S_ref) == meta["r"]
         if S_ref[0] > 0:
-            assert np.abs(S_new - S_ref).max() <= TOL_S * S_ref[0] + 1e-30, f"singular values differ: {name}"
+            # Gram route: lambda_j is resolved to ~eps_G * lambda_1, so sigma_j to eps_G * sigma_1^2 / (2 sigma_j);
+            # that exceeds TOL_S * sigma_1 only for directions below ~1e-3 sigma_1 (< 1e-6 of the energy)
+            tol_j = np.maximum(TOL_S * S_ref[0], TOL_S_GRAM * S_ref[0] ** 2 / np.maximum(S_ref, 1e-30))
+            null = S_ref <= 1e-5 * S_ref[0]                     # numerically-null direction: round-off in both
+            tol_j[null] = 1e-4 * S_ref[0]
+            assert (np.abs(S_new - S_ref) <= tol_j + 1e-30).all(), f"singular values differ: {name}"
         assert meta["k"] == rb["k"], f"rank differs for {name}: {meta['k']} vs {rb['k']}"
         assert abs(meta["energy_retained"] - rb["energy_retained"]) <= 1e-5
         # A low-energy block of <= 2 coefficients one of which belongs to the numerically-null direction of
@@ -144,9 +150,14 @@ def compare_run(ref: Dict, res: Dict, check_diag: bool = True, tol_merged: Optio
             report["chigh_equal"] += eq_h
             if eq_h != k:
                 flipped.add(name)
-            # closed-form vs projected-on-fp16(U) coefficients differ by ~2.4e-4 / sqrt(D) relative
-            ulps = 1 if meta["D"] >= 256 else 8
-            assert fp16_ulp_diff(nc["c_high_fp16"], rc["c_high_fp16"]) <= ulps, f"c_high off by > {ulps} fp16 ulp: {name}/{task}"
+            # fp16 high block: within one fp16 ulp of the element, or -- for an element much smaller than the
+            # vector's scale, whose own ulp is below the coefficient noise -- within the raw-coefficient tolerance
+            a16, b16 = nc["c_high_fp16"].float(), rc["c_high_fp16"].float()
+            ulp = torch.maximum(b16.abs() * 2.0 ** -10, torch.tensor(2.0 ** -24))
+            tol_h = (max(20 * TOL_COEF, 3e-3 / np.sqrt(max(meta["D"], 1))) if job.cfg.svd_fp16 else 20 * TOL_COEF)
+            scale_h = float(b16.abs().max()) if b16.numel() else 0.0
+            okh = (a16 - b16).abs() <= torch.maximum(ulp, torch.tensor(tol_h * scale_h))
+            assert bool(okh.all()) or not torch.isfinite(b16).all(), f"c_high differs: {name}/{task}"
             pr, pn = rc["c_low_quant"]["payloads"], nc["c_low_quant"]["payloads"]
             assert len(pr) == len(pn)
             for a, b in zip(pr, pn):

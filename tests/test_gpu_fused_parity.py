@@ -177,3 +177,24 @@ def test_bf16_inputs(cuda_device):
         d_new = res["merged_state_dict"][name].cpu() - base32[name]
         assert res["merged_state_dict"][name].dtype == torch.float32
         assert parity.rel_l2(d_new, d_ref) < 2e-3, name
+
+
+# ---- wide path: 17..32 task vectors (BASELINE configs[3]: 20 tasks, RTVQ sweep) -----------------------------
+@pytest.mark.parametrize("n_tasks,bits,stages,strategy,mask_p", [
+    (20, 4, 2, "union", 0.3), (20, 2, 4, "majority", 0.5), (20, 8, 1, "intersection", 0.9), (20, 4, 3, "union", None),
+    (17, 4, 2, "majority", 0.5), (32, 4, 2, "union", 0.3)])
+def test_wide_path_20_tasks_rtvq_sweep(cuda_device, n_tasks, bits, stages, strategy, mask_p):
+    shapes = {"blk.attn.weight": (300, 70), "blk.bias": (4099,), "wide.weight": (1, 1, 40000), "ln.weight": (768,)}
+    ref, res, _ = parity.run_both(shapes, n_tasks, mask_p=mask_p, svd_mask_strategy=strategy,
+                                  svd_energy_threshold=0.9, svd_low_bits=bits, svd_rtvq_stages=stages)
+    rep = parity.compare_run(ref, res)
+    print(_summary(rep))
+    assert rep["code_equal"] >= 0.9 * rep["code_total"]
+
+
+def test_wide_path_cluster_and_fp32_basis(cuda_device):
+    shapes = {"a.weight": (257, 64), "b": (5000,)}
+    ref, res, _ = parity.run_both(shapes, 20, mask_p=0.9, svd_mask_strategy="intersection", svd_weighting="cluster",
+                                  svd_cluster_k=2, svd_energy_threshold=0.9, svd_fp16=False)
+    rep = parity.compare_run(ref, res)
+    print(_summary(rep))
