@@ -37,60 +37,91 @@ __device__ __forceinline__ void stats_update(float v, float& lo, float& hi, int&
     ss += (double)v * (double)v;
 }
 
+// The dequantised value of a code depends only on (stage, code): 2^bits values per stage.  They are
+// tabulated once per CTA with the exactly-rounded IEEE expression (q - zp) / scale, so the per-element
+// replay costs a shared-memory lookup instead of a division and stays bit-exact.
 template <typename CodeT>
 __global__ void __launch_bounds__(kBlock) k4_rtvq_pass(const K4PassArgs a) {
     __shared__ QuantScalars s_q[kCoreMaxStages];
+    __shared__ float s_lut[sizeof(CodeT) == 1 ? kCoreMaxStages : 1][sizeof(CodeT) == 1 ? 256 : 1];
     const int tid = threadIdx.x;
-    if (tid < a.pass && tid < kCoreMaxStages) { s_q[tid].scale = a.scale[tid]; s_q[tid].zp = a.zp[tid]; }
-    __syncthreads();
     const int q = a.pass;
+    if (tid < q && tid < kCoreMaxStages) { s_q[tid].scale = a.scale[tid]; s_q[tid].zp = a.zp[tid]; }
+    __syncthreads();
     const bool want_stats = q < a.stages;
+    if (sizeof(CodeT) == 1) {
+        const int levels = 1 << a.bits;
+        for (int i = tid; i < q * levels; i += kBlock) {
+            const int s = i / levels, c = i % levels;
+            s_lut[s][c] = asym_decode(c, s_q[s]);
+        }
+        __syncthreads();
+    }
     float lo = __int_as_float(0x7f800000), hi = __int_as_float(0xff800000);
     int nan = 0;
     double ss = 0.0;
     CodeT* crow = q >= 1 ? reinterpret_cast<CodeT*>(a.codes) + (int64_t)(q - 1) * a.codes_ld : nullptr;
+    const float qmax = (float)((1 << a.bits) - 1);
 
     const int64_t nvec = (a.n + kVec - 1) / kVec;
-    for (int64_t v = (int64_t)blockIdx.x * kBlock + tid; v < nvec; v += (int64_t)gridDim.x * kBlock) {
-        const int64_t e = v * kVec;
-        const bool full = e + kVec <= a.n;
-        float r[kVec];
-        if (full) { float4 t = ldg_stream_f4(a.x + e); r[0] = t.x; r[1] = t.y; r[2] = t.z; r[3] = t.w; }
-        else {
+    constexpr int kUnroll = 2;                      // two 128-bit loads in flight per thread
+    const int64_t stride = (int64_t)gridDim.x * kBlock;
+    for (int64_t v0 = (int64_t)blockIdx.x * kBlock + tid; v0 < nvec; v0 += stride * kUnroll) {
+        float r[kUnroll][kVec];
+        bool fullv[kUnroll], act[kUnroll];
 #pragma unroll
-            for (int c = 0; c < kVec; ++c) r[c] = (e + c < a.n) ? __ldg(a.x + e + c) : 0.0f;
-        }
-        int code[kVec] = {0, 0, 0, 0};
-        for (int s = 0; s < q; ++s) {
-            const QuantScalars qs = s_q[s];
+        for (int u = 0; u < kUnroll; ++u) {
+            const int64_t e = (v0 + u * stride) * kVec;
+            act[u] = v0 + u * stride < nvec;
+            fullv[u] = act[u] && e + kVec <= a.n;
+            if (fullv[u]) { const float4 t = ldg_stream_f4(a.x + e); r[u][0] = t.x; r[u][1] = t.y; r[u][2] = t.z; r[u][3] = t.w; }
+            else {
 #pragma unroll
-            for (int c = 0; c < kVec; ++c) {
-                code[c] = asym_code(r[c], qs, a.bits);
-                r[c] = f_sub(r[c], asym_decode(code[c], qs));
+                for (int c = 0; c < kVec; ++c) r[u][c] = (act[u] && e + c < a.n) ? __ldg(a.x + e + c) : 0.0f;
             }
         }
-        if (q >= 1) {
-            if (full) {
-                if (sizeof(CodeT) == 1) {
-                    const uint32_t w = (uint32_t)code[0] | ((uint32_t)code[1] << 8) | ((uint32_t)code[2] << 16) |
-                                       ((uint32_t)code[3] << 24);
-                    *reinterpret_cast<uint32_t*>(crow + e) = w;
-                } else {
-                    uint2 w;
-                    w.x = ((uint32_t)code[0] & 0xffffu) | ((uint32_t)code[1] << 16);
-                    w.y = ((uint32_t)code[2] & 0xffffu) | ((uint32_t)code[3] << 16);
-                    *reinterpret_cast<uint2*>(crow + e) = w;
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+            if (!act[u]) continue;
+            const int64_t e = (v0 + u * stride) * kVec;
+            int code[kVec] = {0, 0, 0, 0};
+            for (int s = 0; s < q; ++s) {
+                const QuantScalars qs = s_q[s];
+                const bool need_res = (s < q - 1) || want_stats;
+#pragma unroll
+                for (int c = 0; c < kVec; ++c) {
+                    float t = rintf(f_add(f_mul(qs.scale, r[u][c]), qs.zp));
+                    t = (t != t) ? 0.0f : fminf(fmaxf(t, 0.0f), qmax);       // NaN -> code 0 (torch .to(uint8))
+                    code[c] = (int)t;
+                    if (need_res) {
+                        const float d = sizeof(CodeT) == 1 ? s_lut[s][code[c]] : asym_decode(code[c], qs);
+                        r[u][c] = f_sub(r[u][c], d);
+                    }
                 }
-            } else {
+            }
+            if (q >= 1) {
+                if (fullv[u]) {
+                    if (sizeof(CodeT) == 1) {
+                        const uint32_t w = (uint32_t)code[0] | ((uint32_t)code[1] << 8) | ((uint32_t)code[2] << 16) |
+                                           ((uint32_t)code[3] << 24);
+                        *reinterpret_cast<uint32_t*>(crow + e) = w;
+                    } else {
+                        uint2 w;
+                        w.x = ((uint32_t)code[0] & 0xffffu) | ((uint32_t)code[1] << 16);
+                        w.y = ((uint32_t)code[2] & 0xffffu) | ((uint32_t)code[3] << 16);
+                        *reinterpret_cast<uint2*>(crow + e) = w;
+                    }
+                } else {
+#pragma unroll
+                    for (int c = 0; c < kVec; ++c)
+                        if (e + c < a.n) crow[e + c] = (CodeT)code[c];
+                }
+            }
+            if (want_stats) {
 #pragma unroll
                 for (int c = 0; c < kVec; ++c)
-                    if (e + c < a.n) crow[e + c] = (CodeT)code[c];
+                    if (e + c < a.n) stats_update(r[u][c], lo, hi, nan, ss);
             }
-        }
-        if (want_stats) {
-#pragma unroll
-            for (int c = 0; c < kVec; ++c)
-                if (e + c < a.n) stats_update(r[c], lo, hi, nan, ss);
         }
     }
     if (!want_stats) return;
@@ -115,16 +146,24 @@ __global__ void __launch_bounds__(kBlock) k4_rtvq_pass(const K4PassArgs a) {
     }
 }
 
-// one CTA: reduce the per-CTA stats, emit scale / zero-point / residual norm of stage `stage`
+// one warp: reduce the per-CTA stats in a fixed order, emit scale / zero-point / residual norm of `stage`
 __global__ void __launch_bounds__(32) k4_finalize(const K4Stats* part, int n_part, int bits, int stage,
                                                   float* scale, float* zp, float* resnorm) {
-    if (threadIdx.x != 0) return;
-    float lo = part[0].lo, hi = part[0].hi;
-    int nan = part[0].nan;
-    double ss = part[0].sumsq;
-    for (int i = 1; i < n_part; ++i) {
+    const int lane = threadIdx.x;
+    float lo = __int_as_float(0x7f800000), hi = __int_as_float(0xff800000);
+    int nan = 0;
+    double ss = 0.0;
+    for (int i = lane; i < n_part; i += 32) {
         lo = fminf(lo, part[i].lo); hi = fmaxf(hi, part[i].hi); nan |= part[i].nan; ss += part[i].sumsq;
     }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+        hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+        nan |= __shfl_xor_sync(0xffffffffu, nan, o);
+        ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    }
+    if (lane != 0) return;
     if (nan) { lo = __int_as_float(0x7fc00000); hi = lo; }
     const QuantScalars q = asym_scalars(lo, hi, bits);
     scale[stage] = q.scale;
@@ -205,6 +244,7 @@ cudaError_t k4_rtvq_launch(const float* x, int64_t n, int bits, int stages, void
     if (stages < 1 || stages > kCoreMaxStages || bits < 1 || bits > 16) return cudaErrorInvalidValue;
     if (code_bytes != 1 && code_bytes != 2) return cudaErrorInvalidValue;
     if (code_bytes == 1 && bits > 8) return cudaErrorInvalidValue;
+    if (code_bytes == 2 && stages != 1) return cudaErrorInvalidValue;   // int16 codes: single-stage quantiser only
     const int grid = grid_for((n + kVec - 1) / kVec);
     K4PassArgs a;
     a.x = x; a.n = n; a.bits = bits; a.stages = stages; a.scale = scale; a.zp = zp; a.codes = codes;
