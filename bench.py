@@ -234,6 +234,37 @@ def run_ours(args):
     ms_per_step = total_ms / args.steps
     value = n_params * world / (ms_per_step * 1e-3)
 
+    # secondary figures: the same merge with the per-task reconstruction diagnostics fused into
+    # pass 2, and with the bases (U_high / U_low fp16, mean) materialised in the artifact layout
+    secondary = None
+    if args.secondary and world == 1:
+        def timed(fn, n):
+            fn()
+            torch.cuda.synchronize(dev)
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record()
+            for _ in range(n):
+                fn()
+            a1.record()
+            torch.cuda.synchronize(dev)
+            return a0.elapsed_time(a1) / n
+        jd = MergeJob(base, fts, masks, cfg, str(dev), performance=perf, diagnostics=True)
+        ms_diag = timed(jd.run, 5)
+        del jd
+        torch.cuda.empty_cache()
+
+        def with_bases():
+            job._bases_done = False
+            job._materialize_bases()
+        job.run()
+        ms_art = timed(with_bases, 2)
+        job._basis_tensors = {}
+        torch.cuda.empty_cache()
+        secondary = {"with_fused_diagnostics": {"ms_per_step": ms_diag, "value": n_params / (ms_diag * 1e-3)},
+                     "basis_materialisation_extra_ms": ms_art,
+                     "with_artifacts": {"ms_per_step": ms_per_step + ms_art,
+                                        "value": n_params / ((ms_per_step + ms_art) * 1e-3)}}
+
     # NCCL is used only to gather diagnostics scalars (parameters are independent: no data-path collective)
     fetched = job._fetch()
     solved = sum(int((f["info"][:, 0] == 0).sum()) for f in fetched.values())
@@ -315,7 +346,8 @@ def run_ours(args):
                            "diagnostics_fused": False, "artifacts_materialised": False,
                            "parallelism": f"parameter-independent, {world} GPU(s), no data-path collective"},
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
-                "gpu_launches": launches_per_step * args.steps, "params_with_basis_per_rank": solved_all}
+                "gpu_launches": launches_per_step * args.steps, "params_with_basis_per_rank": solved_all,
+                "secondary": secondary}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -330,6 +362,7 @@ def main():
     ap.add_argument("--workload", default="vit-l-14-cluster", choices=sorted(WORKLOADS))
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--secondary", action="store_true", help="also time the fused-diagnostics and artifact variants")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
