@@ -168,6 +168,56 @@ def get_cluster_members(cluster_assignments: Dict[str, int]) -> Dict[int, List[s
     return out
 
 
+def flatten_task_vectors(task_vectors: Dict[str, Dict[str, torch.Tensor]]) -> Tuple[np.ndarray, List[str]]:
+    """[N x P_total] host feature matrix in sorted task / sorted parameter order, zero-filled where a task lacks
+    a parameter (clustering.py:55-120).  Kept for API parity; the pipeline clusters from the Gram instead."""
+    names = sorted(task_vectors.keys())
+    params = sorted({p for tv in task_vectors.values() for p in tv})
+    rows = []
+    for n in names:
+        tv = task_vectors[n]
+        parts = []
+        for p in params:
+            if p in tv:
+                parts.append(tv[p].flatten())
+            else:
+                ref = next(t[p] for t in task_vectors.values() if p in t)
+                parts.append(torch.zeros_like(ref).flatten())
+        rows.append(torch.cat(parts, dim=0).cpu().numpy())
+    return np.stack(rows, axis=0), names
+
+
+def compute_cluster_statistics(task_vectors: Dict[str, Dict[str, torch.Tensor]],
+                               cluster_assignments: Dict[str, int]) -> Dict[int, Dict]:
+    """Per-cluster size / members / distances to the centroid (clustering.py:278-316)."""
+    feats, names = flatten_task_vectors(task_vectors)
+    idx = {n: i for i, n in enumerate(names)}
+    out = {}
+    for cid, members in get_cluster_members(cluster_assignments).items():
+        f = feats[[idx[m] for m in members]]
+        d = np.linalg.norm(f - f.mean(axis=0), axis=1)
+        out[cid] = {"size": len(members), "members": members, "mean_distance_to_centroid": float(d.mean()),
+                    "max_distance_to_centroid": float(d.max()), "min_distance_to_centroid": float(d.min())}
+    return out
+
+
+def merge_by_cluster(task_vectors: Dict[str, Dict[str, torch.Tensor]], cluster_assignments: Dict[str, int],
+                     weights: Dict[str, float], device: str = "cpu") -> Dict[int, Dict[str, torch.Tensor]]:
+    """Weighted average of raw task vectors inside each cluster (clustering.py:319-371)."""
+    from .weighting import apply_weights_to_tensors
+    out = {}
+    for cid, members in get_cluster_members(cluster_assignments).items():
+        cw = {n: weights.get(n, 1.0) for n in members}
+        tot = sum(cw.values())
+        cw = {n: v / tot for n, v in cw.items()}
+        params = set()
+        for n in members:
+            params.update(task_vectors[n].keys())
+        out[cid] = {p: apply_weights_to_tensors({n: task_vectors[n][p] for n in members if p in task_vectors[n]}, cw, device)
+                    for p in params}
+    return out
+
+
 def merge_cluster_results(cluster_merged: Dict[int, Dict[str, torch.Tensor]], cluster_performance: Dict[int, float],
                           device: str = "cpu") -> Dict[str, torch.Tensor]:
     """softmax(cluster score)-weighted average of per-cluster results (clustering.py:374-425)."""
