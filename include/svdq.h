@@ -179,9 +179,13 @@ int svdq_write_basis(int dtype, int n_tasks, int fp16_basis, int center, int64_t
  *                      (rtvq.py:29-36,85-103; quantization_utils.py:137-172).
  * svdq_absmax_quantize: absmax_quantization (quantization_utils.py:60-73); q int8 / int16.
  * scratch: svdq_k4_scratch_bytes() bytes of device memory.
+ * packed (optional, may be NULL): additionally receives the codes bit-packed, `bits` per code, [stages][packed_ld]
+ *          32-bit words (bits in {1,2,4,8}); assembled with warp shuffles.  The reference stores one uint8 per
+ *          code, so this is an extra, denser copy -- `codes` is always written in the reference layout.
  */
 int svdq_rtvq_quantize(const float* x, int64_t n, int bits, int stages, void* codes, int64_t codes_ld,
-                       int code_bytes, float* scale, float* zp, float* resnorm, void* scratch, void* stream);
+                       int code_bytes, float* scale, float* zp, float* resnorm, void* scratch, uint32_t* packed,
+                       int64_t packed_ld, void* stream);
 int svdq_rtvq_dequantize(const void* codes, int64_t codes_ld, int code_bytes, int stages, int64_t n,
                          const float* scale, const float* zp, float* out, void* stream);
 int svdq_absmax_quantize(const float* x, int64_t n, int bits, void* q, int code_bytes, float* scale, void* scratch,

@@ -35,7 +35,7 @@ _SIGNATURES = {
     "svdq_diag_finalize": (C.c_int, [_i32, _i64] + [_vp] * 6),
     "svdq_basis_offsets": (C.c_int, [_i64] + [_vp] * 4),
     "svdq_write_basis": (C.c_int, [_i32, _i32, _i32, _i32, _i64, _i32] + [_vp] * 14),
-    "svdq_rtvq_quantize": (C.c_int, [_vp, _i64, _i32, _i32, _vp, _i64, _i32] + [_vp] * 5),
+    "svdq_rtvq_quantize": (C.c_int, [_vp, _i64, _i32, _i32, _vp, _i64, _i32] + [_vp] * 5 + [_i64, _vp]),
     "svdq_rtvq_dequantize": (C.c_int, [_vp, _i64, _i32, _i32, _i64] + [_vp] * 4),
     "svdq_absmax_quantize": (C.c_int, [_vp, _i64, _i32, _vp, _i32] + [_vp] * 3),
     "svdq_combine_masks": (C.c_int, [_vp, _i32, _i64, _i32, _vp, _vp]),

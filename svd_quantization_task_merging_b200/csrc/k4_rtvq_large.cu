@@ -27,6 +27,8 @@ struct K4PassArgs {
     const float* zp;        // [S]
     void* codes;            // [S][codes_ld] uint8 or int16
     int64_t codes_ld;
+    uint32_t* packed;       // optional [S][packed_ld] words: codes bit-packed, `bits` per code, little-endian
+    int64_t packed_ld;      //          (bits in {1, 2, 4, 8}); the reference layout stays one uint8 per code
     K4Stats* part;          // [gridDim.x]
 };
 
@@ -66,7 +68,10 @@ __global__ void __launch_bounds__(kBlock) k4_rtvq_pass(const K4PassArgs a) {
     const int64_t nvec = (a.n + kVec - 1) / kVec;
     constexpr int kUnroll = 2;                      // two 128-bit loads in flight per thread
     const int64_t stride = (int64_t)gridDim.x * kBlock;
-    for (int64_t v0 = (int64_t)blockIdx.x * kBlock + tid; v0 < nvec; v0 += stride * kUnroll) {
+    // uniform trip count for every thread of the grid (the packed-code path uses full-warp shuffles)
+    const int64_t n_iter = (nvec + stride * kUnroll - 1) / (stride * kUnroll);
+    for (int64_t it = 0; it < n_iter; ++it) {
+        const int64_t v0 = (int64_t)blockIdx.x * kBlock + tid + it * stride * kUnroll;
         float r[kUnroll][kVec];
         bool fullv[kUnroll], act[kUnroll];
 #pragma unroll
@@ -121,6 +126,29 @@ __global__ void __launch_bounds__(kBlock) k4_rtvq_pass(const K4PassArgs a) {
 #pragma unroll
                 for (int c = 0; c < kVec; ++c)
                     if (e + c < a.n) stats_update(r[u][c], lo, hi, nan, ss);
+            }
+        }
+        // ---- optional bit-packed copy of the codes, assembled with warp shuffles: a thread holds
+        //      4 * bits bits, 32 / (4 * bits) neighbouring lanes share one 32-bit word ------------------
+        if (a.packed != nullptr && q >= 1 && sizeof(CodeT) == 1) {
+            const int lane = tid & 31;
+            const int per_thread = kVec * a.bits;                 // 4, 8, 16 or 32 bits
+            const int lanes_per_word = 32 / per_thread;           // 8, 4, 2 or 1
+#pragma unroll
+            for (int u = 0; u < kUnroll; ++u) {
+                const int64_t v = v0 + u * stride;                // vector index of this thread (lane-contiguous)
+                uint32_t w = 0;
+                if (act[u]) {
+                    const int64_t e = v * kVec;
+                    const uint8_t* cr = reinterpret_cast<const uint8_t*>(crow);
+#pragma unroll
+                    for (int c = 0; c < kVec; ++c)
+                        if (e + c < a.n) w |= (uint32_t)cr[e + c] << (c * a.bits);
+                    w <<= (lane % lanes_per_word) * per_thread;
+                }
+                for (int o = 1; o < lanes_per_word; o <<= 1) w |= __shfl_xor_sync(0xffffffffu, w, o);
+                if (act[u] && (lane % lanes_per_word) == 0)
+                    a.packed[(int64_t)(q - 1) * a.packed_ld + v / lanes_per_word] = w;
             }
         }
     }
@@ -239,7 +267,8 @@ static int grid_for(int64_t n_threads_needed) {
 
 // Runs the whole S-stage quantisation of x[0..n) on `st`.  part must hold kK4MaxGrid records.
 cudaError_t k4_rtvq_launch(const float* x, int64_t n, int bits, int stages, void* codes, int64_t codes_ld,
-                           int code_bytes, float* scale, float* zp, float* resnorm, K4Stats* part, cudaStream_t st) {
+                           int code_bytes, float* scale, float* zp, float* resnorm, K4Stats* part, uint32_t* packed,
+                           int64_t packed_ld, cudaStream_t st) {
     if (n <= 0) return cudaSuccess;
     if (stages < 1 || stages > kCoreMaxStages || bits < 1 || bits > 16) return cudaErrorInvalidValue;
     if (code_bytes != 1 && code_bytes != 2) return cudaErrorInvalidValue;
@@ -249,6 +278,9 @@ cudaError_t k4_rtvq_launch(const float* x, int64_t n, int bits, int stages, void
     K4PassArgs a;
     a.x = x; a.n = n; a.bits = bits; a.stages = stages; a.scale = scale; a.zp = zp; a.codes = codes;
     a.codes_ld = codes_ld; a.part = part;
+    const bool packable = code_bytes == 1 && (bits == 1 || bits == 2 || bits == 4 || bits == 8);
+    if (packed != nullptr && !packable) return cudaErrorInvalidValue;
+    a.packed = packed; a.packed_ld = packed_ld;
     for (int q = 0; q <= stages; ++q) {
         a.pass = q;
         if (code_bytes == 1) k4_rtvq_pass<uint8_t><<<grid, kBlock, 0, st>>>(a);

@@ -288,7 +288,8 @@ int svdq_write_basis(int dtype, int n_tasks, int fp16_basis, int center, int64_t
 }
 
 int svdq_rtvq_quantize(const float* x, int64_t n, int bits, int stages, void* codes, int64_t codes_ld,
-                       int code_bytes, float* scale, float* zp, float* resnorm, void* scratch, void* stream) {
+                       int code_bytes, float* scale, float* zp, float* resnorm, void* scratch, uint32_t* packed,
+                       int64_t packed_ld, void* stream) {
     REQUIRE(n >= 0, "n");
     if (n == 0) return 0;
     REQUIRE(bits >= 1 && bits <= 16, "bits must be in [1, 16]");
@@ -298,8 +299,9 @@ int svdq_rtvq_quantize(const float* x, int64_t n, int bits, int stages, void* co
     REQUIRE(codes_ld >= n && codes_ld % 4 == 0, "codes_ld must be >= n and a multiple of 4");
     REQUIRE(x && codes && scale && zp && resnorm && scratch, "null pointer");
     REQUIRE(((uintptr_t)x & 15) == 0 && ((uintptr_t)codes & 7) == 0, "x must be 16-byte, codes 8-byte aligned");
+    REQUIRE(!packed || packed_ld * 32 >= n * bits, "packed_ld too small");
     return finish(__func__, svdq::k4_rtvq_launch(x, n, bits, stages, codes, codes_ld, code_bytes, scale, zp, resnorm,
-                                                 (svdq::K4Stats*)scratch, (cudaStream_t)stream));
+                                                 (svdq::K4Stats*)scratch, packed, packed_ld, (cudaStream_t)stream));
 }
 
 int svdq_rtvq_dequantize(const void* codes, int64_t codes_ld, int code_bytes, int stages, int64_t n,

@@ -135,7 +135,8 @@ cudaError_t k3_diag_launch(const K3DiagArgs& a, int n_params, cudaStream_t st);
 cudaError_t k5_offsets_launch(const uint32_t* count, const int64_t* tile_begin, int64_t* tile_row_off, int n_params,
                               cudaStream_t st);
 cudaError_t k4_rtvq_launch(const float* x, int64_t n, int bits, int stages, void* codes, int64_t codes_ld,
-                           int code_bytes, float* scale, float* zp, float* resnorm, K4Stats* part, cudaStream_t st);
+                           int code_bytes, float* scale, float* zp, float* resnorm, K4Stats* part, uint32_t* packed,
+                           int64_t packed_ld, cudaStream_t st);
 cudaError_t k4_dequant_launch(const void* codes, int64_t codes_ld, int code_bytes, int stages, int64_t n,
                               const float* scale, const float* zp, float* out, cudaStream_t st);
 cudaError_t k4_absmax_launch(const float* x, int64_t n, int bits, void* q, int code_bytes, float* scale,

@@ -21,8 +21,8 @@ def _gpu_f32(x: torch.Tensor) -> torch.Tensor:
     return y
 
 
-def _quantize_device(x: torch.Tensor, bits: int, stages: int, code_bytes: int):
-    """x: flat fp32 CUDA tensor -> (codes[stages, ld], scale[stages], zp[stages], resnorm[stages])."""
+def _quantize_device(x: torch.Tensor, bits: int, stages: int, code_bytes: int, packed: bool = False):
+    """x: flat fp32 CUDA tensor -> (codes[stages, ld], scale[stages], zp[stages], resnorm[stages][, packed words])."""
     n = x.numel()
     ld = (n + 15) // 16 * 16
     cdt = torch.uint8 if code_bytes == 1 else torch.int16
@@ -31,9 +31,16 @@ def _quantize_device(x: torch.Tensor, bits: int, stages: int, code_bytes: int):
     zp = torch.zeros_like(scale)
     rn = torch.zeros_like(scale)
     scratch = torch.empty(_native.load().svdq_k4_scratch_bytes(), dtype=torch.uint8, device=x.device)
+    pk, pld = None, 0
+    if packed:
+        pld = (n * bits + 31) // 32 + 8
+        pk = torch.zeros(stages, pld, dtype=torch.int32, device=x.device)
     with torch.cuda.device(x.device):
         _native.call("svdq_rtvq_quantize", x.data_ptr(), n, bits, stages, codes.data_ptr(), ld, code_bytes,
-                     scale.data_ptr(), zp.data_ptr(), rn.data_ptr(), scratch.data_ptr(), _native.stream_ptr())
+                     scale.data_ptr(), zp.data_ptr(), rn.data_ptr(), scratch.data_ptr(),
+                     pk.data_ptr() if pk is not None else None, pld, _native.stream_ptr())
+    if packed:
+        return codes, scale, zp, rn, pk
     return codes, scale, zp, rn
 
 
@@ -68,16 +75,24 @@ def asymmetric_dequantization(quantized: torch.Tensor, scale: torch.Tensor, zero
 
 
 def multistage_residual_quantization(tensor: torch.Tensor, num_bits: int = 4, num_stages: int = 2,
-                                     verbose: bool = False) -> List[Dict]:
-    """rtvq.py:39-82.  Payload tensors are returned on the CPU like the reference."""
+                                     verbose: bool = False, packed: bool = False) -> List[Dict]:
+    """rtvq.py:39-82.  Payload tensors are returned on the CPU like the reference.  ``packed=True`` (an
+    addition, bits in {1,2,4,8}) adds a "packed" int32 tensor per stage: the same codes, ``num_bits`` each."""
     if tensor.numel() == 0:
         return []
     x = _gpu_f32(tensor)
-    codes, scale, zp, rn = _quantize_device(x, num_bits, num_stages, 1)
+    out = _quantize_device(x, num_bits, num_stages, 1, packed=packed)
+    codes, scale, zp, rn = out[:4]
     codes_h = codes[:, : x.numel()].cpu()
     scale_h, zp_h, rn_h = scale.cpu(), zp.cpu(), rn.cpu()
-    return [{"stage": s, "quantized": codes_h[s].clone().view(tensor.shape), "scale": scale_h[s].clone(),
-             "zero_point": zp_h[s].clone(), "residual_norm": rn_h[s].item()} for s in range(num_stages)]
+    pay = [{"stage": s, "quantized": codes_h[s].clone().view(tensor.shape), "scale": scale_h[s].clone(),
+            "zero_point": zp_h[s].clone(), "residual_norm": rn_h[s].item()} for s in range(num_stages)]
+    if packed:
+        words = (x.numel() * num_bits + 31) // 32
+        pk = out[4][:, :words].cpu()
+        for s in range(num_stages):
+            pay[s]["packed"] = pk[s].clone()
+    return pay
 
 
 def multistage_residual_dequantization(payloads: List[Dict], device: str = "cpu") -> torch.Tensor:

@@ -51,7 +51,7 @@ def test_invalid_arguments_are_value_errors_without_touching_the_gpu():
     rc = lib.svdq_param_solve(8, 1, 1, C.c_float(0.9), 0, 10, 9, 2, *([None] * 22))
     assert rc < 0 and b"Low bits" in lib.svdq_last_error()
     # zero-sized work is a no-op, not an error
-    assert lib.svdq_rtvq_quantize(None, 0, 4, 2, None, 0, 1, None, None, None, None, None) == 0
+    assert lib.svdq_rtvq_quantize(None, 0, 4, 2, None, 0, 1, None, None, None, None, None, 0, None) == 0
     assert lib.svdq_unpack_mask(None, 0, None, None) == 0
 
 

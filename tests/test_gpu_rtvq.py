@@ -133,3 +133,19 @@ def test_full_size_tensor_roundtrip_property(cuda_device):
     d = rtvq.multistage_residual_dequantization(pay, device="cuda")
     step = 1.0 / pay[-1]["scale"].item()
     assert (x - d).abs().max().item() <= 0.51 * step * 1.01
+
+
+@pytest.mark.parametrize("bits,n", [(4, 1000), (2, 4099), (8, 77), (1, 130), (4, 1 << 18)])
+def test_warp_packed_codes_equal_the_byte_codes(cuda_device, bits, n):
+    """The optional bit-packed copy (assembled with warp shuffles) holds exactly the reference-layout codes."""
+    from svd_quantization_task_merging_b200.svd_hybrid import rtvq
+    x = torch.randn(n, generator=torch.Generator().manual_seed(n + bits)) * 0.01
+    pay = rtvq.multistage_residual_quantization(x, bits, 2, packed=True)
+    for p in pay:
+        words = p["packed"].numpy().view(np.uint32)
+        codes = p["quantized"].numpy().astype(np.uint32)
+        unpacked = np.zeros(len(words) * (32 // bits), np.uint32)
+        for i in range(32 // bits):
+            unpacked[i:: 32 // bits] = (words >> (i * bits)) & ((1 << bits) - 1)
+        assert np.array_equal(unpacked[:n], codes)
+        assert (unpacked[n:] == 0).all()
