@@ -54,7 +54,8 @@ int64_t svdq_k4_scratch_bytes(void);
  *           (src/svd_hybrid/basis.py:63-113,216-249).
  * masks: [P*NT] table of torch.bool storages (NULL entry = task has no mask for the parameter),
  *        or NULL when there are no masks at all.
- * packed/pmask_off: bit-packed combined mask, parameter p at word offset pmask_off[p].
+ * packed/pmask_off: bit-packed combined mask, parameter p at word offset pmask_off[p] (a multiple of 4 words
+ *       lets pass 2 stream the mask words through its TMA ring; any offset is accepted).
  * gram: [n_tiles][full ? 2 : 1][NT(NT+1)/2] fp32 partials (upper triangle, row-major);
  *       the second block (full != 0) is the Gram over ALL elements (masked or not): the
  *       whole-model task Gram behind cluster weighting (src/svd_hybrid/clustering.py:227-232).

@@ -43,7 +43,7 @@ template <> struct SmemElem3<__half> {
 
 template <typename T, int NT>
 __host__ __device__ constexpr int k3s_smem_bytes() {
-    return kK3Stages * (NT + 1) * kStep * (int)sizeof(T) + 2 * kK3Stages * 8 + kK3Stages * 4 + 64;
+    return kK3Stages * ((NT + 1) * kStep * (int)sizeof(T) + kStep / 8) + 2 * kK3Stages * 8 + kK3Stages * 4 + 64;
 }
 
 template <typename T, int NT, bool FP16B>
@@ -51,7 +51,9 @@ __global__ void __launch_bounds__(kK3Consumers + 32, 1) k3s_reconstruct_merge(co
     constexpr int NTP = (NT + 3) & ~3;
     constexpr int STAGES = kK3Stages;
     constexpr int kTensorBytes = kStep * (int)sizeof(T);
-    constexpr int kStageBytes = (NT + 1) * kTensorBytes;
+    constexpr int kMaskBytes = kStep / 8;                          // 1024 mask bits of the chunk
+    constexpr int kStageBytes = (NT + 1) * kTensorBytes + kMaskBytes;
+    constexpr int kMaskOff = (NT + 1) * kTensorBytes;
     extern __shared__ __align__(128) unsigned char smem[];
     unsigned char* stage_base = smem;
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * kStageBytes);
@@ -82,10 +84,16 @@ __global__ void __launch_bounds__(kK3Consumers + 32, 1) k3s_reconstruct_merge(co
             const int64_t start = (int64_t)a.tile_local[tile] * a.tile_elems;
             const int64_t stop = min(start + (int64_t)a.tile_elems, numel);
             const bool solved = a.info[(int64_t)p * 8] == kSolved;
+            // the mask words ride the ring only when their row starts 16-byte aligned (TMA source alignment);
+            // otherwise the consumers read them directly
+            const bool has_mask = a.has_mask[p] != 0 &&
+                                  ((reinterpret_cast<uintptr_t>(a.packed + a.pmask_off[p]) & 15u) == 0);
             const unsigned char* my_ptr = nullptr;
             if (is_tensor) {
                 const void* q = a.tensors[(int64_t)p * (NT + 1) + lane];
                 my_ptr = reinterpret_cast<const unsigned char*>(q ? q : a.tensors[(int64_t)p * (NT + 1)]);
+            } else if (lane == NT + 1 && has_mask) {
+                my_ptr = reinterpret_cast<const unsigned char*>(a.packed + a.pmask_off[p]);   // 16-byte aligned rows
             }
             for (int64_t e0 = start; e0 < stop; e0 += kStep) {
                 if (lane == 0) mbar_wait(&empty[ps.stage], ps.phase ^ 1u);
@@ -94,11 +102,14 @@ __global__ void __launch_bounds__(kK3Consumers + 32, 1) k3s_reconstruct_merge(co
                 if (e0 + kStep <= numel && solved) {
                     if (lane == 0) {
                         s_direct[ps.stage] = 0;
-                        mbar_arrive_expect_tx(&full[ps.stage], (uint32_t)kStageBytes);
+                        mbar_arrive_expect_tx(&full[ps.stage],
+                                              (uint32_t)((NT + 1) * kTensorBytes + (has_mask ? kMaskBytes : 0)));
                     }
                     __syncwarp();
                     if (is_tensor)
                         bulk_g2s(sb + lane * kTensorBytes, my_ptr + e0 * (int64_t)sizeof(T), kTensorBytes, &full[ps.stage]);
+                    else if (my_ptr != nullptr)
+                        bulk_g2s(sb + kMaskOff, my_ptr + e0 / 8, kMaskBytes, &full[ps.stage]);
                 } else if (lane == 0) {
                     s_direct[ps.stage] = 1;          // tail chunk, or a parameter without a basis (only base is read)
                     mbar_arrive(&full[ps.stage]);
@@ -146,6 +157,7 @@ __global__ void __launch_bounds__(kK3Consumers + 32, 1) k3s_reconstruct_merge(co
         const float tail_add = a.scal[(int64_t)p * 4 + 1];
         const bool has_mask = a.has_mask[p] != 0;
         const uint32_t* packed = has_mask ? a.packed + a.pmask_off[p] : nullptr;
+        const bool mask_in_ring = has_mask && ((reinterpret_cast<uintptr_t>(packed) & 15u) == 0);
         float* outp = a.out[p];
         const float n_f = (float)(n_active > 0 ? n_active : 1);
         const uint32_t present_bits = s_present;
@@ -162,10 +174,13 @@ __global__ void __launch_bounds__(kK3Consumers + 32, 1) k3s_reconstruct_merge(co
             uint32_t pword = 0xffffffffu;
             mbar_wait(&full[ps.stage], ps.phase);
             const unsigned char* sb = stage_base + ps.stage * kStageBytes;
+            bool staged_mask = false;
             if (!s_direct[ps.stage]) {
                 SmemElem3<T>::load4(sb, tid, b);
 #pragma unroll
                 for (int t = 0; t < NT; ++t) SmemElem3<T>::load4(sb + (t + 1) * kTensorBytes, tid, x[t]);
+                if (mask_in_ring) pword = *reinterpret_cast<const uint32_t*>(sb + kMaskOff + (tid >> 3) * 4);
+                staged_mask = mask_in_ring || !has_mask;
             } else if (active) {
                 if (fullv) Elem<T>::load4(s_ptr[0], e, b);
                 else {
@@ -185,7 +200,7 @@ __global__ void __launch_bounds__(kK3Consumers + 32, 1) k3s_reconstruct_merge(co
                     }
                 }
             }
-            if (active && has_mask && status == kSolved) pword = __ldg(packed + (e >> 5));
+            if (!staged_mask && active && has_mask && status == kSolved) pword = __ldg(packed + (e >> 5));
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty[ps.stage]);
             ps.advance<STAGES>();

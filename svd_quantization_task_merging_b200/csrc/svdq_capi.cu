@@ -30,10 +30,10 @@ int finish(const char* fn, cudaError_t e) {
 #define REQUIRE(cond, what) do { if (!(cond)) return fail_arg(__func__, what); } while (0)
 
 // SVDQ_STAGED is a bit mask selecting the staged persistent (TMA ring) variant per pass: bit 0 = K1,
-// bit 1 = K3.  Default 1: measured on B200 (ViT-L-14 x 8) the ring wins for pass 1 (2.48 vs 3.22 ms),
-// while pass 2 is instruction-issue-limited and runs faster as 2 CTAs/SM of the direct-load kernel.
+// bit 1 = K3 (A/B switch; 0 = direct-load kernels).  Default 3: measured on B200 (ViT-L-14 x 8) the ring
+// wins for both passes (pass 1: 2.24 vs 3.19 ms, pass 2: 1.95 vs 2.16 ms).
 int staged_mask() {
-    static const int m = [] { const char* v = getenv("SVDQ_STAGED"); return v ? atoi(v) : 1; }();
+    static const int m = [] { const char* v = getenv("SVDQ_STAGED"); return v ? atoi(v) : 3; }();
     return m;
 }
 int sm_count() {

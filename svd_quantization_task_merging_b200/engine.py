@@ -276,7 +276,7 @@ class MergeJob:
                     has_mask[p] = 1
             pm_off[p] = words
             if has_mask[p]:
-                words += (int(numel[p]) + 31) // 32 + 32     # padding: a 4-element step may touch 1 word past
+                words += ((int(numel[p]) + 31) // 32 + 32 + 3) // 4 * 4     # rows start 16-byte aligned (TMA source)
             out_off.append(out_total)
             out_total += (int(numel[p]) + 63) // 64 * 64
         g.any_mask = bool(has_mask.any())
