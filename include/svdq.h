@@ -132,6 +132,25 @@ int svdq_param_average(int n_tasks, int64_t n_params, const uint32_t* present, c
                        float* gvec, float* scal, void* stream);
 
 /*
+ * K7 — exact projection on the STORED basis for selected (small) parameters, n_tasks <= 8.
+ * Replaces project_to_basis / compress_single_task (src/svd_hybrid/compress.py:6-56) literally: the basis row is
+ * rebuilt, rounded to fp16 when fp16_basis (the cast of src/svd_hybrid/cli.py:355-361 precedes the projection in
+ * the reference) and contracted with (tau_t - mean) over the masked rows.  sel_tile_param / sel_tile_local list
+ * the tiles of the selected parameters; proj receives one [NT*NT] partial c[t][j] per tile.
+ * svdq_param_requantize then sums the partials of parameter p (tiles sel_tile_begin[p] .. sel_tile_begin[p+1]-1,
+ * an empty range = keep the closed-form coefficients), overwrites coef and redoes chigh / codes / chat.
+ * Call order: svdq_param_solve(weights = NULL) -> svdq_project_exact -> svdq_param_requantize -> svdq_param_average.
+ */
+int svdq_project_exact(int dtype, int n_tasks, int fp16_basis, int center, int64_t n_sel_tiles, int tile_elems,
+                       const void* const* tensors, const int64_t* numel, const int32_t* sel_tile_param,
+                       const int32_t* sel_tile_local, const int64_t* pmask_off, const uint8_t* has_mask,
+                       const uint32_t* packed, const int32_t* info, const float* W, float* proj, void* stream);
+int svdq_param_requantize(int n_tasks, int64_t n_params, int rtvq_bits, int rtvq_stages, const int64_t* sel_tile_begin,
+                          const float* proj, const uint32_t* present, const int32_t* info, float* coef,
+                          uint16_t* chigh, uint8_t* codes, float* qscale, float* qzp, float* qres, float* chat,
+                          void* stream);
+
+/*
  * K3 — weighted reconstruction + merge (pass 2), optional fused diagnostics.
  * Replaces: reconstruct_from_coefficients (src/svd_hybrid/merge.py:144-194), the fp16 cast of
  *           the bases (src/svd_hybrid/cli.py:355-361), reconstruct_from_masked

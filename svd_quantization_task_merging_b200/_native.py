@@ -31,6 +31,8 @@ _SIGNATURES = {
     "svdq_gram_reduce": (C.c_int, [_i32, _i32, _i64] + [_vp] * 7),
     "svdq_param_solve": (C.c_int, [_i32, _i64, _i32, _f32, _i32, _i32, _i32, _i32] + [_vp] * 22),
     "svdq_param_average": (C.c_int, [_i32, _i64] + [_vp] * 10),
+    "svdq_project_exact": (C.c_int, [_i32, _i32, _i32, _i32, _i64, _i32] + [_vp] * 11),
+    "svdq_param_requantize": (C.c_int, [_i32, _i64, _i32, _i32] + [_vp] * 12),
     "svdq_reconstruct_merge": (C.c_int, [_i32, _i32, _i32, _i32, _i32, _i64, _i32] + [_vp] * 16),
     "svdq_diag_finalize": (C.c_int, [_i32, _i64] + [_vp] * 6),
     "svdq_basis_offsets": (C.c_int, [_i64] + [_vp] * 4),

@@ -187,7 +187,6 @@ struct SolveScratch {
     double cs[2 * kCoreMaxTasks];          // (c, s) of the current Jacobi round
     int pq[2 * kCoreMaxTasks];             // (p, q) of the current Jacobi round (p = -1: no rotation)
     double sigma[kCoreMaxTasks];
-    float chat[kCoreMaxTasks * kCoreLd];   // chat[a][j]: fp16-rounded / dequantised coefficient of active task a
     int idx[kCoreMaxTasks];                // active-task compaction: a -> task position
     int perm[kCoreMaxTasks];
     int n, r, k, r_eff;
@@ -319,6 +318,34 @@ SVDQ_HD void jacobi_eig(double* A, double* V, double* cs, int* pq, int n, L& ln)
         for (int i = ln.lane; i < n; i += ln.nl)
             for (int j = 0; j < i; ++j) A[i * kCoreLd + j] = A[j * kCoreLd + i];
         ln.sync();
+    }
+    ln.sync();
+}
+
+// fp16 high block + multi-stage RTVQ low block of the coefficients in out.coef (compress.py:44-51,
+// rtvq.py:39-82): writes chigh, codes, qscale / qzp / qres and the round-tripped coefficients chat.
+// Reads only info and coef, so it also serves as the re-quantisation step after an exact projection.
+template <class L>
+SVDQ_HD void quantize_param(const SolveConfig& cfg, const uint32_t present, const SolveOut& out, L& ln) {
+    const int NT = cfg.n_tasks, S = cfg.stages;
+    if (out.info[0] != kSolved) return;
+    const int r = out.info[2], k = out.info[3];
+    const int n_low = r - k;
+    for (int t = ln.lane; t < NT; t += ln.nl) {
+        if (!(present >> t & 1u)) continue;
+        float c[kCoreMaxTasks];
+        for (int j = 0; j < r; ++j) c[j] = out.coef[t * NT + j];
+        for (int j = 0; j < k; ++j) {
+            const uint16_t h = f32_to_f16_bits(c[j]);
+            out.chigh[t * NT + j] = h;
+            out.chat[t * NT + j] = f16_bits_to_f32(h);
+        }
+        if (n_low > 0) {
+            float deq[kCoreMaxTasks];
+            rtvq_short(c + k, n_low, cfg.bits, S, out.codes + (size_t)t * S * NT, NT,
+                       out.qscale + t * S, out.qzp + t * S, out.qres + t * S, deq);
+            for (int i = 0; i < n_low; ++i) out.chat[t * NT + k + i] = deq[i];
+        }
     }
     ln.sync();
 }
@@ -484,28 +511,13 @@ SVDQ_HD void solve_param(const SolveConfig& cfg, const SolveIn& in, const SolveO
     const int k = sc.k, r_eff = sc.r_eff;
     const int n_low = r - k;
 
-    // ---- per task: coefficients, fp16 high block, RTVQ low block ---------------------------------
+    // ---- per task: closed-form coefficients c[t][j] = sigma_j V[t][j] ---------------------------------
     for (int a = ln.lane; a < n; a += ln.nl) {
         const int t = sc.idx[a];
-        float c[kCoreMaxTasks];
-        for (int j = 0; j < r; ++j) {
-            c[j] = (float)(sc.sigma[j] * sc.Vs[a * kCoreLd + j]);
-            out.coef[t * NT + j] = c[j];
-        }
-        for (int j = 0; j < k; ++j) {
-            const uint16_t h = f32_to_f16_bits(c[j]);
-            out.chigh[t * NT + j] = h;
-            sc.chat[a * kCoreLd + j] = f16_bits_to_f32(h);
-        }
-        if (n_low > 0) {
-            float deq[kCoreMaxTasks];
-            rtvq_short(c + k, n_low, cfg.bits, S, out.codes + (size_t)t * S * NT, NT,
-                       out.qscale + t * S, out.qzp + t * S, out.qres + t * S, deq);
-            for (int i = 0; i < n_low; ++i) sc.chat[a * kCoreLd + k + i] = deq[i];
-        }
-        for (int j = 0; j < r; ++j) out.chat[t * NT + j] = sc.chat[a * kCoreLd + j];
+        for (int j = 0; j < r; ++j) out.coef[t * NT + j] = (float)(sc.sigma[j] * sc.Vs[a * kCoreLd + j]);
     }
     ln.sync();
+    quantize_param(cfg, in.present, out, ln);
 
     // ---- projection matrix W = H V Sigma^-1 (independent of the task weights) ----------------------
     for (int a = ln.lane; a < n; a += ln.nl) {

@@ -116,6 +116,47 @@ __global__ void __launch_bounds__(32) k2_param_average(const K2SolveArgs a) {
     average_param(a.cfg, in, out, ln);
 }
 
+// re-quantisation after the exact projection (K7): sum the tile partials in a fixed order (fp64), overwrite the
+// coefficients of the selected parameters and redo their fp16 / RTVQ step
+__global__ void __launch_bounds__(32) k2_param_requantize(const K2RequantArgs a) {
+    const int p = blockIdx.x, lane = threadIdx.x;
+    const int NT = a.cfg.n_tasks, S = a.cfg.stages;
+    const int64_t nn = (int64_t)NT * NT;
+    const int64_t t0 = a.sel_tile_begin[p], t1 = a.sel_tile_begin[p + 1];
+    if (t1 <= t0 || a.info[(int64_t)p * 8] != kSolved) return;
+    // only the columns with a basis direction are re-projected: a numerically-null direction keeps its
+    // closed-form coefficient (round-off dust, like LAPACK's; an exact zero there would turn the
+    // reference's 2-element RTVQ edge into NaN, rtvq.py:17)
+    const int r = a.info[(int64_t)p * 8 + 4];
+    float* coef = a.coef + p * nn;
+    for (int i = lane; i < NT * NT; i += 32) {
+        const int j = i % NT;
+        if (j >= r) continue;
+        double s = 0.0;
+        for (int64_t tl = t0; tl < t1; ++tl) s += (double)a.proj[tl * nn + i];
+        coef[i] = (float)s;
+    }
+    __syncwarp();
+    SolveOut out = {};
+    out.info = const_cast<int32_t*>(a.info) + (int64_t)p * 8;
+    out.coef = coef;
+    out.chigh = a.chigh + p * nn;
+    out.codes = a.codes + p * nn * S;
+    out.qscale = a.qscale + (int64_t)p * NT * S;
+    out.qzp = a.qzp + (int64_t)p * NT * S;
+    out.qres = a.qres + (int64_t)p * NT * S;
+    out.chat = a.chat + p * nn;
+    WarpLanes ln{lane};
+    quantize_param(a.cfg, a.present[p], out, ln);
+}
+
+cudaError_t k2_requant_launch(const K2RequantArgs& a, int n_params, cudaStream_t st) {
+    if (n_params <= 0) return cudaSuccess;
+    if (a.cfg.n_tasks < 1 || a.cfg.n_tasks > kCoreMaxTasks) return cudaErrorInvalidValue;
+    k2_param_requantize<<<n_params, 32, 0, st>>>(a);
+    return cudaGetLastError();
+}
+
 cudaError_t k2_average_launch(const K2SolveArgs& a, int n_params, cudaStream_t st) {
     if (n_params <= 0) return cudaSuccess;
     if (a.cfg.n_tasks < 1 || a.cfg.n_tasks > kCoreMaxTasks) return cudaErrorInvalidValue;

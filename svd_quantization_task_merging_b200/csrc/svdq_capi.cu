@@ -224,6 +224,47 @@ int svdq_param_average(int n_tasks, int64_t n_params, const uint32_t* present, c
     return finish(__func__, svdq::k2_average_launch(a, (int)n_params, (cudaStream_t)stream));
 }
 
+int svdq_project_exact(int dtype, int n_tasks, int fp16_basis, int center, int64_t n_sel_tiles, int tile_elems,
+                       const void* const* tensors, const int64_t* numel, const int32_t* sel_tile_param,
+                       const int32_t* sel_tile_local, const int64_t* pmask_off, const uint8_t* has_mask,
+                       const uint32_t* packed, const int32_t* info, const float* W, float* proj, void* stream) {
+    REQUIRE(n_tasks >= 1 && n_tasks <= 8, "exact projection supports n_tasks in [1, 8]");
+    REQUIRE(dtype >= 0 && dtype <= 2, "dtype");
+    REQUIRE(tile_elems > 0 && tile_elems % svdq::kStep == 0, "tile_elems must be a positive multiple of 1024");
+    REQUIRE(n_sel_tiles >= 0 && n_sel_tiles < (1ll << 31), "n_sel_tiles");
+    if (n_sel_tiles == 0) return 0;
+    REQUIRE(tensors && numel && sel_tile_param && sel_tile_local && has_mask && info && W && proj, "null pointer");
+    svdq::K7Args a;
+    a.tensors = tensors; a.numel = numel; a.tile_param = sel_tile_param; a.tile_local = sel_tile_local;
+    a.pmask_off = pmask_off; a.has_mask = has_mask; a.packed = packed; a.info = info; a.W = W; a.proj = proj;
+    a.tile_elems = tile_elems; a.center = center; a.fp16_basis = fp16_basis;
+    cudaError_t e;
+    switch (dtype) {
+        case svdq::kF32:  e = svdq::k7_launch_dtype<svdq::kF32>(n_tasks, a, (int)n_sel_tiles, (cudaStream_t)stream); break;
+        case svdq::kBF16: e = svdq::k7_launch_dtype<svdq::kBF16>(n_tasks, a, (int)n_sel_tiles, (cudaStream_t)stream); break;
+        default:          e = svdq::k7_launch_dtype<svdq::kF16>(n_tasks, a, (int)n_sel_tiles, (cudaStream_t)stream); break;
+    }
+    return finish(__func__, e);
+}
+
+int svdq_param_requantize(int n_tasks, int64_t n_params, int rtvq_bits, int rtvq_stages, const int64_t* sel_tile_begin,
+                          const float* proj, const uint32_t* present, const int32_t* info, float* coef,
+                          uint16_t* chigh, uint8_t* codes, float* qscale, float* qzp, float* qres, float* chat,
+                          void* stream) {
+    REQUIRE(n_tasks >= 1 && n_tasks <= SVDQ_MAX_TASKS, "n_tasks must be in [1, 32]");
+    REQUIRE(rtvq_bits >= 1 && rtvq_bits <= 8, "Low bits must be in [1, 8]");
+    REQUIRE(rtvq_stages >= 1 && rtvq_stages <= SVDQ_MAX_STAGES, "RTVQ stages must be in [1, 8]");
+    REQUIRE(n_params >= 0 && n_params < (1ll << 31), "n_params");
+    if (n_params == 0) return 0;
+    REQUIRE(sel_tile_begin && proj && present && info && coef && chigh && codes && qscale && qzp && qres && chat,
+            "null pointer");
+    svdq::K2RequantArgs a = {};
+    a.cfg.n_tasks = n_tasks; a.cfg.bits = rtvq_bits; a.cfg.stages = rtvq_stages;
+    a.sel_tile_begin = sel_tile_begin; a.proj = proj; a.present = present; a.info = info; a.coef = coef;
+    a.chigh = chigh; a.codes = codes; a.qscale = qscale; a.qzp = qzp; a.qres = qres; a.chat = chat;
+    return finish(__func__, svdq::k2_requant_launch(a, (int)n_params, (cudaStream_t)stream));
+}
+
 int svdq_reconstruct_merge(int dtype, int n_tasks, int fp16_basis, int diag, int center, int64_t n_tiles,
                            int tile_elems, const void* const* tensors, const int64_t* numel,
                            const int32_t* tile_param, const int32_t* tile_local, const int64_t* pmask_off,

@@ -90,6 +90,29 @@ struct K6MaskArgs {              // mask combination + packing for the wide (17.
     int tile_elems, strategy, n_tasks;
 };
 
+struct K7Args {                  // exact projection on the stored (fp16) basis for selected parameters
+    const void* const* tensors;
+    const int64_t* numel;
+    const int32_t* tile_param;      // [n_sel_tiles] tiles of the selected parameters only
+    const int32_t* tile_local;
+    const int64_t* pmask_off;
+    const uint8_t* has_mask;
+    const uint32_t* packed;
+    const int32_t* info;            // [P][8]
+    const float* W;                 // [P][NT*NT]
+    float* proj;                    // [n_sel_tiles][NT*NT] partial coefficients c[t][j]
+    int tile_elems, center, fp16_basis;
+};
+
+struct K2RequantArgs {
+    SolveConfig cfg;
+    const int64_t* sel_tile_begin;  // [P+1] first selected tile of each parameter (empty range: not selected)
+    const float* proj;              // [n_sel_tiles][NT*NT]
+    const uint32_t* present;        // [P]
+    const int32_t* info;            // [P][8]
+    float* coef; uint16_t* chigh; uint8_t* codes; float* qscale; float* qzp; float* qres; float* chat;
+};
+
 constexpr int kK4MaxGrid = 148 * 8;
 
 struct K4Stats {            // one record per CTA, reduced in CTA order by k4_finalize
@@ -131,6 +154,8 @@ template <int DT> cudaError_t k6_merge_launch_dtype(int n_tasks, const K3Args& a
 cudaError_t k2_reduce_launch(const K2ReduceArgs& a, int n_params, cudaStream_t st);
 cudaError_t k2_solve_launch(const K2SolveArgs& a, int n_params, cudaStream_t st);
 cudaError_t k2_average_launch(const K2SolveArgs& a, int n_params, cudaStream_t st);
+cudaError_t k2_requant_launch(const K2RequantArgs& a, int n_params, cudaStream_t st);
+template <int DT> cudaError_t k7_launch_dtype(int nt, const K7Args& a, int n_tiles, cudaStream_t st);
 cudaError_t k3_diag_launch(const K3DiagArgs& a, int n_params, cudaStream_t st);
 cudaError_t k5_offsets_launch(const uint32_t* count, const int64_t* tile_begin, int64_t* tile_row_off, int n_params,
                               cudaStream_t st);

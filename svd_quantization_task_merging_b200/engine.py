@@ -33,6 +33,7 @@ from .svd_hybrid.weighting import compute_weights, effective_merge_weights
 TILE_ELEMS = 16384          # elements per tile (multiple of 1024); fixes the reduction order
 MAX_STREAM_TASKS = 16      # register-resident Gram (one K1 launch)
 MAX_TASKS = 32             # wide path: Gram over pairs of 8-task blocks, runtime-N pass 2
+EXACT_MAX_NUMEL = 262144   # projection="auto": parameters up to this size are re-projected on the stored basis
 _FLOAT_DTYPES = {torch.float32: 0, torch.bfloat16: 1, torch.float16: 2}
 _ALIGN = {torch.float32: 16, torch.bfloat16: 16, torch.float16: 16}   # 16 B: TMA bulk-copy source alignment
 
@@ -130,7 +131,8 @@ class MergeJob:
                  diagnostics: Optional[bool] = None, materialize_bases: bool = False,
                  performance: Optional[Dict[str, float]] = None,
                  cluster_assignments: Optional[Dict[str, int]] = None, param_filter: Optional[Sequence[str]] = None,
-                 tile_elems: int = TILE_ELEMS, cluster_backend: Optional[str] = None):
+                 tile_elems: int = TILE_ELEMS, cluster_backend: Optional[str] = None,
+                 projection: Optional[str] = None):
         _native.require_cuda()
         self.cfg = config
         self.device = torch.device(device or "cuda")
@@ -156,6 +158,15 @@ class MergeJob:
         self.fixed_assignments = cluster_assignments
         self.cluster_mode = config.svd_weighting == "cluster"
         self.cluster_backend = cluster_backend or os.environ.get("SVDQ_CLUSTER_BACKEND", "exact")
+        # coefficients: "closed" = Sigma V^T for every parameter; "exact" = re-project every parameter on the stored
+        # (fp16) basis like the reference does (one more read of the inputs); "auto" = exact for parameters of at
+        # most EXACT_MAX_NUMEL elements, where the closed form's 2.4e-4/sqrt(Dm) deviation can flip an fp16 value or
+        # an RTVQ code, closed form above (deviation below LAPACK's own round-off).  Needs fp16 bases and N <= 8.
+        self.projection = projection or os.environ.get("SVDQ_PROJECTION", "auto")
+        if self.projection not in ("closed", "auto", "exact"):
+            raise ValueError(f"projection must be closed | auto | exact, got {self.projection}")
+        if not config.svd_fp16 or self.N > 8:
+            self.projection = "closed"
         self.stages = int(config.svd_rtvq_stages)
         self.bits = int(config.svd_low_bits)
         if self.stages > 8:
@@ -299,6 +310,19 @@ class MergeJob:
             diag=z(max(n_tiles, 1) * 5 * N) if self.want_diag else None,
             diag_out=z(P, N, 6, dtype=f64) if self.want_diag else None,
         )
+        # exact-projection selection: tiles of the selected parameters
+        g.sel = None
+        if self.projection != "closed":
+            pick = np.ones(P, bool) if self.projection == "exact" else (numel <= EXACT_MAX_NUMEL)
+            if pick.any():
+                sel_tiles = np.where(pick, tiles_per, 0)
+                sel_begin = np.zeros(P + 1, np.int64)
+                np.cumsum(sel_tiles, out=sel_begin[1:])
+                n_sel = int(sel_begin[-1])
+                sp = np.repeat(np.arange(P, dtype=np.int32), sel_tiles)
+                sl = (np.arange(n_sel, dtype=np.int64) - np.repeat(sel_begin[:-1], sel_tiles)).astype(np.int32)
+                g.sel = dict(n=n_sel, begin=_dev(sel_begin, dev), param=_dev(sp, dev), local=_dev(sl, dev),
+                             proj=z(max(n_sel, 1) * N * N))
         g.sub = []
         if self.wide:
             blocks = [list(range(b, min(b + 8, N))) for b in range(0, N, 8)]
@@ -442,18 +466,44 @@ class MergeJob:
                                  _ptr(t["codes"]), _ptr(t["qscale"]), _ptr(t["qzp"]), _ptr(t["qres"]),
                                  _ptr(t["chat"]), _ptr(t["cbar"]), _ptr(t["W"]), _ptr(t["gvec"]), _ptr(t["V"]), st)
 
-            if self.cluster_mode:
-                # weights depend on the whole-model Gram: start its D2H on a side stream, run the
-                # weight-independent solve meanwhile, then k-means on the host and the tiny average kernel
-                self._cluster_begin()
-                solve(None, self._order_dev)
-                self._cluster_end()
-                w_dev, order_dev = self._weights_table()
+            def project_exact():
+                # re-project the selected (small) parameters on the stored basis and re-quantise them (K7)
+                for g in self.groups.values():
+                    if g.sel is None:
+                        continue
+                    t, sel = g.t, g.sel
+                    _native.call("svdq_project_exact", _FLOAT_DTYPES[g.dtype], N, int(bool(cfg.svd_fp16)),
+                                 int(bool(cfg.svd_center)), sel["n"], te, _ptr(t["tptr"]), _ptr(t["numel"]),
+                                 _ptr(sel["param"]), _ptr(sel["local"]), _ptr(t["pm_off"]), _ptr(t["has_mask"]),
+                                 _ptr(t["packed"]), _ptr(t["info"]), _ptr(t["W"]), _ptr(sel["proj"]), st)
+                    _native.call("svdq_param_requantize", N, len(g.names), self.bits, self.stages, _ptr(sel["begin"]),
+                                 _ptr(sel["proj"]), _ptr(t["present"]), _ptr(t["info"]), _ptr(t["coef"]),
+                                 _ptr(t["chigh"]), _ptr(t["codes"]), _ptr(t["qscale"]), _ptr(t["qzp"]),
+                                 _ptr(t["qres"]), _ptr(t["chat"]), st)
+
+            def average(w_dev, order_dev):
                 for g in self.groups.values():
                     t = g.t
                     _native.call("svdq_param_average", N, len(g.names), _ptr(t["present"]), _ptr(w_dev),
                                  _ptr(order_dev), _ptr(t["info"]), _ptr(t["chat"]), _ptr(t["W"]), _ptr(t["cbar"]),
                                  _ptr(t["gvec"]), _ptr(t["scal"]), st)
+
+            any_exact = any(g.sel is not None for g in self.groups.values())
+            if self.cluster_mode:
+                # weights depend on the whole-model Gram: start its D2H on a side stream, run the
+                # weight-independent solve meanwhile, then k-means on the host and the tiny average kernel
+                self._cluster_begin()
+                solve(None, self._order_dev)
+                if any_exact:
+                    project_exact()
+                self._cluster_end()
+                w_dev, order_dev = self._weights_table()
+                average(w_dev, order_dev)
+            elif any_exact:
+                w_dev, order_dev = self._weights_table()
+                solve(None, order_dev)
+                project_exact()
+                average(w_dev, order_dev)
             else:
                 w_dev, order_dev = self._weights_table()
                 solve(w_dev, order_dev)
@@ -483,7 +533,9 @@ class MergeJob:
     def gpu_launches(self) -> int:
         """Kernels of libsvdq.so launched by one run()."""
         ng = len(self.groups)
-        return ng * (4 + (1 if self.want_diag else 0) + (1 if self.cluster_mode else 0))
+        any_exact = any(g.sel is not None for g in self.groups.values())
+        return ng * (4 + (1 if self.want_diag else 0) + (1 if (self.cluster_mode or any_exact) else 0)
+                     + (2 if any_exact else 0))
 
     def event_times_ms(self) -> Dict[str, float]:
         ev = self._events

@@ -28,7 +28,9 @@ def test_integration_md_stub_runs_and_matches_engine(cuda_device):
     w = {t: 1.0 / len(tasks) for t in tasks}
     out, tables = ns["merge_on_gpu"](base, [fts[t] for t in tasks], [masks[t] for t in tasks], cfg, w)
     torch.cuda.synchronize()
-    res = merge_state_dicts(base, fts, masks, cfg, "cuda")
+    # the stub is the minimal K1 -> K2 -> K3 chain (closed-form coefficients everywhere); the engine's default
+    # additionally re-projects small parameters (K7), so compare against projection="closed"
+    res = merge_state_dicts(base, fts, masks, cfg, "cuda", projection="closed")
     for n in shapes:
         assert torch.equal(out[n], res["merged_state_dict"][n]), n
     assert (tables["info"][:, 0] == 0).all()
