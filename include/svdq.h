@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define SVDQ_ABI_VERSION 1
+#define SVDQ_ABI_VERSION 2
 #define SVDQ_MAX_STREAM_TASKS 16
 #define SVDQ_MAX_TASKS 32
 #define SVDQ_MAX_STAGES 8
@@ -57,8 +57,11 @@ int64_t svdq_k4_scratch_bytes(void);
  * packed/pmask_off: bit-packed combined mask, parameter p at word offset pmask_off[p] (a multiple of 4 words
  *       lets pass 2 stream the mask words through its TMA ring; any offset is accepted).
  * gram: [n_tiles][full ? 2 : 1][NT(NT+1)/2] fp32 partials (upper triangle, row-major);
- *       the second block (full != 0) is the Gram over ALL elements (masked or not): the
- *       whole-model task Gram behind cluster weighting (src/svd_hybrid/clustering.py:227-232).
+ *       full == 1: the second block is the Gram over ALL elements (masked or not), the
+ *       whole-model task Gram behind cluster weighting (src/svd_hybrid/clustering.py:227-232);
+ *       full == 2: the second block is the Gram over the elements OUTSIDE the combined mask, the
+ *       noise region of svd_include_noise (get_unmasked_portion, src/svd_hybrid/mask_loader.py:682-709;
+ *       src/svd_hybrid/cli.py:336-338) -- svdq_gram_reduce then forms all = masked + complement.
  * count: [n_tiles] masked elements per tile.
  */
 int svdq_tv_mask_gram(int dtype, int n_tasks, int mask_strategy, int full, int64_t n_tiles, int tile_elems,
@@ -85,9 +88,15 @@ int svdq_tv_gram_premasked(int dtype, int n_tasks, int full, int64_t n_tiles, in
 /*
  * K2a — fixed-order fp64 reduction of K1's tile partials per parameter.
  * gram_masked / gram_all: [P][NT*NT] full symmetric fp64 (gram_all may be NULL); dm: [P].
+ * full == 2 (noise region): gram_noise [P][NT*NT] = Gram of the rows outside the mask, dm_noise [P] = their
+ * count, non-zero only where the reference builds a noise basis (src/svd_hybrid/cli.py:330-338,
+ * src/svd_hybrid/basis.py:455-466): the parameter has a mask, the masked count passes min_mask_size, and
+ * at least one element is unmasked.  numel / has_mask / gram_noise / dm_noise may be NULL otherwise.
  */
-int svdq_gram_reduce(int n_tasks, int full, int64_t n_params, const float* gram, const uint32_t* count,
-                     const int64_t* tile_begin, double* gram_masked, double* gram_all, int64_t* dm, void* stream);
+int svdq_gram_reduce(int n_tasks, int full, int64_t n_params, int min_mask_size, const float* gram,
+                     const uint32_t* count, const int64_t* tile_begin, const int64_t* numel, const uint8_t* has_mask,
+                     double* gram_masked, double* gram_all, int64_t* dm, double* gram_noise, int64_t* dm_noise,
+                     void* stream);
 
 /*
  * K2b — per-parameter solve (one warp per parameter).
@@ -140,8 +149,10 @@ int svdq_param_average(int n_tasks, int64_t n_params, const uint32_t* present, c
  * svdq_param_requantize then sums the partials of parameter p (tiles sel_tile_begin[p] .. sel_tile_begin[p+1]-1,
  * an empty range = keep the closed-form coefficients), overwrites coef and redoes chigh / codes / chat.
  * Call order: svdq_param_solve(weights = NULL) -> svdq_project_exact -> svdq_param_requantize -> svdq_param_average.
+ * region: 0 = rows inside the combined mask, 1 = rows outside it (noise region; info / W of the noise solve).
  */
-int svdq_project_exact(int dtype, int n_tasks, int fp16_basis, int center, int64_t n_sel_tiles, int tile_elems,
+int svdq_project_exact(int dtype, int n_tasks, int fp16_basis, int center, int region, int64_t n_sel_tiles,
+                       int tile_elems,
                        const void* const* tensors, const int64_t* numel, const int32_t* sel_tile_param,
                        const int32_t* sel_tile_local, const int64_t* pmask_off, const uint8_t* has_mask,
                        const uint32_t* packed, const int32_t* info, const float* W, float* proj, void* stream);
@@ -160,13 +171,18 @@ int svdq_param_requantize(int n_tasks, int64_t n_params, int rtvq_bits, int rtvq
  *           (src/svd_hybrid/diagnostics.py:72-231).
  * out: [P] table of fp32 output tensors (merged = base + delta; parameters without a basis get
  *      a copy of base).  diag_partials: [n_tiles][5][NT] fp32 (may be NULL when diag == 0).
+ * noise_*: outputs of a second svdq_param_solve over gram_noise / dm_noise (svd_include_noise): the unmasked
+ *      positions then receive noise_shrink * (U_noise cbar_noise + mean) instead of 0 (merge.py:257-284,
+ *      mask_loader.py:757-760).  All NULL = no noise region.  The diagnostics stay those of the masked region.
  */
 int svdq_reconstruct_merge(int dtype, int n_tasks, int fp16_basis, int diag, int center, int64_t n_tiles,
                            int tile_elems, const void* const* tensors, const int64_t* numel,
                            const int32_t* tile_param, const int32_t* tile_local, const int64_t* pmask_off,
                            const uint8_t* has_mask, const uint32_t* packed, const int32_t* info, const float* W,
                            const float* cbar, const float* gvec, const float* scal, const float* chat,
-                           float* const* out, float* diag_partials, void* stream);
+                           float* const* out, float* diag_partials, const int32_t* noise_info, const float* noise_W,
+                           const float* noise_cbar, const float* noise_gvec, const float* noise_scal,
+                           float noise_shrink, void* stream);
 
 /* diagnostics finalisation: out [P][NT][6] fp64 = absolute_error, relative_error,
  * max_absolute_error, mean_absolute_error, original_norm, reconstructed_norm
@@ -179,10 +195,12 @@ int svdq_diag_finalize(int n_tasks, int64_t n_params, const float* diag_partials
  * (U_high [Dm x k], U_low [Dm x (r-k)], mean [Dm x 1], rows compacted through the mask:
  * src/svd_hybrid/basis.py:363-364,398-407; storage layout src/svd_hybrid/storage.py:76-106).
  * tile_row_off [n_tiles] is produced by svdq_basis_offsets from K1's counts.
+ * region: 0 = the rows inside the combined mask; 1 = the rows outside it (the "noise" basis of
+ * src/svd_hybrid/basis.py:455-466, with info / W of the noise solve; numel is needed for the offsets).
  */
-int svdq_basis_offsets(int64_t n_params, const uint32_t* count, const int64_t* tile_begin, int64_t* tile_row_off,
-                       void* stream);
-int svdq_write_basis(int dtype, int n_tasks, int fp16_basis, int center, int64_t n_tiles, int tile_elems,
+int svdq_basis_offsets(int64_t n_params, int region, int tile_elems, const uint32_t* count, const int64_t* tile_begin,
+                       const int64_t* numel, int64_t* tile_row_off, void* stream);
+int svdq_write_basis(int dtype, int n_tasks, int fp16_basis, int center, int region, int64_t n_tiles, int tile_elems,
                      const void* const* tensors, const int64_t* numel, const int32_t* tile_param,
                      const int32_t* tile_local, const int64_t* pmask_off, const uint8_t* has_mask,
                      const uint32_t* packed, const int32_t* info, const float* W, const int64_t* tile_row_off,

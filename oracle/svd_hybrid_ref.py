@@ -295,16 +295,22 @@ def reconstruct(c_hi: Tensor, c_lo: Tensor, basis: Dict) -> Tensor:
     return out
 
 
-def scatter_masked(vals: Tensor, mask: Tensor, shape) -> Tensor:
-    """reconstruct_from_masked (mask_loader.py:712-763) without a noise region."""
+def scatter_masked(vals: Tensor, mask: Tensor, shape, unmasked_vals: Optional[Tensor] = None) -> Tensor:
+    """reconstruct_from_masked (mask_loader.py:712-763); unmasked_vals = the noise region (:757-760)."""
     flat = mask.flatten()
     out = torch.zeros_like(flat, dtype=vals.dtype)
     out[flat] = vals
+    if unmasked_vals is not None:
+        out[~flat] = unmasked_vals
     return out.view(shape)
 
 
 def merge_deltas(compressed: Dict[str, Dict[str, Dict]], bases: Dict[str, Dict], masks: Dict[str, Tensor],
-                 weights: Dict[str, float], shapes: Dict[str, torch.Size]) -> Dict[str, Tensor]:
+                 weights: Dict[str, float], shapes: Dict[str, torch.Size],
+                 noise: Optional[Tuple[Dict, Dict, float]] = None) -> Dict[str, Tensor]:
+    """merge_all_parameters / merge_parameter (merge.py:197-426).  ``noise`` = (compressed_noise, bases_noise,
+    noise_shrink) when svd_include_noise: the unmasked positions get shrink * (U_n c_n + mean_n)
+    (merge.py:257-284); without it they stay zero."""
     out = {}
     for name in sorted(compressed.keys()):
         c_hi, c_lo = average_coeffs(compressed[name], weights)
@@ -312,8 +318,13 @@ def merge_deltas(compressed: Dict[str, Dict[str, Dict]], bases: Dict[str, Dict],
             out[name] = torch.zeros(shapes[name])
             continue
         vec = reconstruct(c_hi, c_lo, bases[name])
+        rest = None
+        if noise is not None and noise[1].get(name) is not None:
+            n_hi, n_lo = average_coeffs(noise[0].get(name, {}), weights)
+            if n_hi is not None:
+                rest = reconstruct(n_hi, n_lo, noise[1][name]) * noise[2]
         m = masks.get(name)
-        out[name] = scatter_masked(vec, m, shapes[name]) if m is not None else vec.view(shapes[name])
+        out[name] = scatter_masked(vec, m, shapes[name], rest) if m is not None else vec.view(shapes[name])
     return out
 
 
@@ -326,7 +337,7 @@ def weighted_stack(tensors: Dict, weights: Dict) -> Tensor:
     return (st * w).sum(0)
 
 
-def merge_deltas_clustered(compressed, bases, masks, weights, assignments, shapes) -> Dict[str, Tensor]:
+def merge_deltas_clustered(compressed, bases, masks, weights, assignments, shapes, noise=None) -> Dict[str, Tensor]:
     clusters: Dict[int, List[str]] = {}
     for n, c in assignments.items():
         clusters.setdefault(c, []).append(n)
@@ -336,7 +347,11 @@ def merge_deltas_clustered(compressed, bases, masks, weights, assignments, shape
         tot = sum(cw.values())
         cw = {n: v / tot for n, v in cw.items()}
         sub = {p: {n: art[n] for n in members if n in art} for p, art in compressed.items()}
-        per_cluster[cid] = merge_deltas(sub, bases, masks, cw, shapes)
+        sub_noise = None
+        if noise is not None:
+            sub_noise = ({p: {n: art[n] for n in members if n in art} for p, art in noise[0].items()},
+                         noise[1], noise[2])
+        per_cluster[cid] = merge_deltas(sub, bases, masks, cw, shapes, sub_noise)
         score[cid] = sum(weights.get(n, 1.0) for n in members) / len(members)
     ids = list(per_cluster.keys())
     sm = torch.softmax(torch.tensor([score.get(c, 1.0) for c in ids]), 0)
@@ -431,8 +446,10 @@ def run_reference_path(base: Dict[str, Tensor], finetuned: Dict[str, Dict[str, T
     ``finetuned`` is keyed by task in ``cfg.tasks`` order.  ``assignments`` lets
     the caller inject a k-means partition (the full-feature clustering is
     minutes on ViT-L-14); when None and weighting == "cluster" the full
-    reference clustering is run.  Noise-region processing (svd_include_noise)
-    is not restated: SURVEY.md section 8f ranks it after this round's scope.
+    reference clustering is run.  With cfg.svd_include_noise the rows outside
+    the combined mask get their own basis / coefficients (result keys
+    "bases_noise", "compressed_noise"; cli.py:336-351, basis.py:455-466,
+    compress.py:91-107) and are merged with svd_noise_shrink (merge.py:257-284).
     """
     import time
     tick = time.perf_counter
@@ -454,9 +471,17 @@ def run_reference_path(base: Dict[str, Tensor], finetuned: Dict[str, Dict[str, T
     # step 4: bases (cli.py:317-379)
     t0 = tick()
     bases: Dict[str, Optional[Dict]] = {}
+    bases_noise: Dict[str, Optional[Dict]] = {}
+
+    def half(b):
+        if cfg.svd_fp16:
+            b["U_high"] = b["U_high"].half()
+            b["U_low"] = b["U_low"].half()
+        return b
+
     for p in names:
         m = masks.get(p)
-        cols = []
+        cols, rest = [], []
         for t in cfg.tasks:
             if p not in tvs[t]:
                 continue
@@ -464,34 +489,44 @@ def run_reference_path(base: Dict[str, Tensor], finetuned: Dict[str, Dict[str, T
             if m is not None and m.shape == d.shape:
                 if m.sum() >= cfg.svd_min_mask_size:
                     cols.append(d.flatten()[m.flatten()])
+                    if cfg.svd_include_noise:
+                        rest.append(d.flatten()[~m.flatten()])       # get_unmasked_portion, mask_loader.py:682-709
             else:
                 cols.append(d.flatten())
         if cols and len(cols[0]) > 0:
-            b = build_basis(cols, cfg.svd_energy_threshold, cfg.svd_max_rank, cfg.svd_center)
-            if cfg.svd_fp16:
-                b["U_high"] = b["U_high"].half()
-                b["U_low"] = b["U_low"].half()
-            bases[p] = b
+            bases[p] = half(build_basis(cols, cfg.svd_energy_threshold, cfg.svd_max_rank, cfg.svd_center))
+            if cfg.svd_include_noise and rest and len(rest[0]) > 0:  # basis.py:455-466
+                bases_noise[p] = half(build_basis(rest, cfg.svd_energy_threshold, cfg.svd_max_rank, cfg.svd_center))
     tm["basis"] = tick() - t0
 
     # step 5: compression (compress.py:114-207)
     t0 = tick()
     compressed: Dict[str, Dict[str, Dict]] = {}
+    compressed_noise: Dict[str, Dict[str, Dict]] = {}
     for p in sorted(bases.keys()):
         b, m = bases[p], masks.get(p)
-        per_task = {}
+        bn = bases_noise.get(p)
+        per_task, per_task_noise = {}, {}
         for t in cfg.tasks:
             if p not in tvs[t]:
                 continue
             d = tvs[t][p]
+            y = None
             if m is not None and m.shape == d.shape:
                 x = d.flatten()[m.flatten()] if m.sum() >= cfg.svd_min_mask_size else torch.tensor([])
+                if bn is not None:
+                    y = d.flatten()[~m.flatten()]
             else:
                 x = d.flatten()
             per_task[t] = (compress_task(x, b["U_high"], b["U_low"], b["mean"], cfg.svd_low_bits,
                                          cfg.svd_rtvq_stages) if len(x) > 0 else None)
+            if y is not None and len(y) > 0:                         # compress.py:91-107
+                per_task_noise[t] = compress_task(y, bn["U_high"], bn["U_low"], bn["mean"], cfg.svd_low_bits,
+                                                  cfg.svd_rtvq_stages)
         if per_task:
             compressed[p] = per_task
+        if per_task_noise:
+            compressed_noise[p] = per_task_noise
     tm["compress"] = tick() - t0
 
     # step 6: weights
@@ -503,10 +538,11 @@ def run_reference_path(base: Dict[str, Tensor], finetuned: Dict[str, Dict[str, T
 
     # step 7-8: merge + apply
     t0 = tick()
+    noise = (compressed_noise, bases_noise, cfg.svd_noise_shrink) if cfg.svd_include_noise else None
     if cfg.svd_weighting == "cluster" and assignments is not None:
-        deltas = merge_deltas_clustered(compressed, bases, masks, weights, assignments, shapes)
+        deltas = merge_deltas_clustered(compressed, bases, masks, weights, assignments, shapes, noise)
     else:
-        deltas = merge_deltas(compressed, bases, masks, weights, shapes)
+        deltas = merge_deltas(compressed, bases, masks, weights, shapes, noise)
     merged = {}
     for p, b in base.items():
         merged[p] = b + deltas[p] if p in deltas else b.clone()
@@ -519,5 +555,6 @@ def run_reference_path(base: Dict[str, Tensor], finetuned: Dict[str, Dict[str, T
         diag["cluster_assignments"] = assignments
     tm["diagnostics"] = tick() - t0
     return {"merged_state_dict": merged, "diagnostics": diag, "bases": bases, "compressed": compressed,
+            "bases_noise": bases_noise, "compressed_noise": compressed_noise,
             "weights": weights, "cluster_assignments": assignments, "combined_masks": masks,
             "task_vectors": tvs, "merged_deltas": deltas}

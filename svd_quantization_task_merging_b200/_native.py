@@ -12,7 +12,7 @@ from typing import Optional
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libsvdq.so")
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 DTYPE_CODE = {"float32": 0, "bfloat16": 1, "float16": 2}
 STRATEGY_CODE = {"union": 0, "intersection": 1, "majority": 2}
@@ -28,15 +28,15 @@ _SIGNATURES = {
     "svdq_tv_mask_gram": (C.c_int, [_i32, _i32, _i32, _i32, _i64, _i32] + [_vp] * 10),
     "svdq_mask_pack": (C.c_int, [_i32, _i32, _i64, _i32] + [_vp] * 8),
     "svdq_tv_gram_premasked": (C.c_int, [_i32, _i32, _i32, _i64, _i32] + [_vp] * 10),
-    "svdq_gram_reduce": (C.c_int, [_i32, _i32, _i64] + [_vp] * 7),
+    "svdq_gram_reduce": (C.c_int, [_i32, _i32, _i64, _i32] + [_vp] * 11),
     "svdq_param_solve": (C.c_int, [_i32, _i64, _i32, _f32, _i32, _i32, _i32, _i32] + [_vp] * 22),
     "svdq_param_average": (C.c_int, [_i32, _i64] + [_vp] * 10),
-    "svdq_project_exact": (C.c_int, [_i32, _i32, _i32, _i32, _i64, _i32] + [_vp] * 11),
+    "svdq_project_exact": (C.c_int, [_i32, _i32, _i32, _i32, _i32, _i64, _i32] + [_vp] * 11),
     "svdq_param_requantize": (C.c_int, [_i32, _i64, _i32, _i32] + [_vp] * 12),
-    "svdq_reconstruct_merge": (C.c_int, [_i32, _i32, _i32, _i32, _i32, _i64, _i32] + [_vp] * 16),
+    "svdq_reconstruct_merge": (C.c_int, [_i32, _i32, _i32, _i32, _i32, _i64, _i32] + [_vp] * 20 + [_f32, _vp]),
     "svdq_diag_finalize": (C.c_int, [_i32, _i64] + [_vp] * 6),
-    "svdq_basis_offsets": (C.c_int, [_i64] + [_vp] * 4),
-    "svdq_write_basis": (C.c_int, [_i32, _i32, _i32, _i32, _i64, _i32] + [_vp] * 14),
+    "svdq_basis_offsets": (C.c_int, [_i64, _i32, _i32] + [_vp] * 5),
+    "svdq_write_basis": (C.c_int, [_i32, _i32, _i32, _i32, _i32, _i64, _i32] + [_vp] * 14),
     "svdq_rtvq_quantize": (C.c_int, [_vp, _i64, _i32, _i32, _vp, _i64, _i32] + [_vp] * 5 + [_i64, _vp]),
     "svdq_rtvq_dequantize": (C.c_int, [_vp, _i64, _i32, _i32, _i64] + [_vp] * 4),
     "svdq_absmax_quantize": (C.c_int, [_vp, _i64, _i32, _vp, _i32] + [_vp] * 3),

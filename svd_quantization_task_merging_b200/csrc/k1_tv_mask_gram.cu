@@ -58,6 +58,7 @@ __global__ void __launch_bounds__(kBlock, (NT <= 8 && !FULL) ? 2 : 1) k1_tv_mask
     uint32_t* packed = (has_mask && !premasked) ? a.packed + a.pmask_off[p] : nullptr;
     const uint32_t* packed_in = (has_mask && premasked) ? a.packed_in + a.pmask_off[p] : nullptr;
 
+    const bool comp = a.second_complement != 0;   // FULL: second block = Gram of the UNMASKED elements (noise region)
     float2 acc2[G];
 #pragma unroll
     for (int i = 0; i < G; ++i) acc2[i] = make_float2(0.0f, 0.0f);
@@ -143,14 +144,14 @@ __global__ void __launch_bounds__(kBlock, (NT <= 8 && !FULL) ? 2 : 1) k1_tv_mask
         }
 
         // packed 2-wide FMAs (fma.rn.f32x2): FULL pairs the masked Gram with the all-element Gram of the
-        // same (i, j); otherwise two consecutive elements share one instruction
+        // same (i, j) -- or, with second_complement, with the Gram of the unmasked elements; otherwise two consecutive elements share one instruction
         if (FULL) {
 #pragma unroll
             for (int c = 0; c < kVec; ++c) {
                 const bool m = (bits >> c) & 1u;
                 float2 v[NT];
 #pragma unroll
-                for (int t = 0; t < NT; ++t) v[t] = make_float2(m ? d[t][c] : 0.0f, d[t][c]);
+                for (int t = 0; t < NT; ++t) v[t] = make_float2(m ? d[t][c] : 0.0f, (comp && m) ? 0.0f : d[t][c]);
 #pragma unroll
                 for (int i = 0; i < NT; ++i)
 #pragma unroll

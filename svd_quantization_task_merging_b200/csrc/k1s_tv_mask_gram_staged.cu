@@ -142,6 +142,7 @@ __global__ void __launch_bounds__(kBlock + 32, 1) k1s_tv_mask_gram(const K1Args 
         const bool majority = a.strategy == kMajority;
         uint32_t* packed = has_mask ? a.packed + a.pmask_off[p] : nullptr;
 
+        const bool comp = a.second_complement != 0;
         float2 acc2[G];
 #pragma unroll
         for (int i = 0; i < G; ++i) acc2[i] = make_float2(0.0f, 0.0f);
@@ -233,7 +234,7 @@ __global__ void __launch_bounds__(kBlock + 32, 1) k1s_tv_mask_gram(const K1Args 
                     const bool m = (bits >> c) & 1u;
                     float2 v[NT];
 #pragma unroll
-                    for (int t = 0; t < NT; ++t) v[t] = make_float2(m ? d[t][c] : 0.0f, d[t][c]);
+                    for (int t = 0; t < NT; ++t) v[t] = make_float2(m ? d[t][c] : 0.0f, (comp && m) ? 0.0f : d[t][c]);
 #pragma unroll
                     for (int i = 0; i < NT; ++i)
 #pragma unroll

@@ -44,14 +44,23 @@ __global__ void __launch_bounds__(kBlock) k2_gram_reduce(const K2ReduceArgs a) {
         a.gram_masked[(int64_t)p * NT * NT + i * NT + j] = m;
         a.gram_masked[(int64_t)p * NT * NT + j * NT + i] = m;
         if (a.full && a.gram_all) {
-            a.gram_all[(int64_t)p * NT * NT + i * NT + j] = u;       // second block = Gram over ALL elements
-            a.gram_all[(int64_t)p * NT * NT + j * NT + i] = u;
+            const double all = a.full == 2 ? m + u : u;              // second block: all elements / complement
+            a.gram_all[(int64_t)p * NT * NT + i * NT + j] = all;
+            a.gram_all[(int64_t)p * NT * NT + j * NT + i] = all;
+        }
+        if (a.full == 2 && a.gram_noise) {
+            a.gram_noise[(int64_t)p * NT * NT + i * NT + j] = u;
+            a.gram_noise[(int64_t)p * NT * NT + j * NT + i] = u;
         }
     }
     if (tid == 0) {
         unsigned long long tot = 0;
         for (int w = 0; w < kBlock / 32; ++w) tot += s_cnt[w];
         a.dm[p] = (int64_t)tot;
+        if (a.full == 2 && a.dm_noise) {
+            const bool on = a.has_mask[p] != 0 && (int64_t)tot >= (int64_t)a.min_mask_size && tot > 0;
+            a.dm_noise[p] = on ? a.numel[p] - (int64_t)tot : 0;
+        }
     }
 }
 

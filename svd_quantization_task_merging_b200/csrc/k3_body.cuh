@@ -10,18 +10,28 @@ namespace svdq {
 
 constexpr int kDiagRows = 5;      // sum e^2, sum |e|, sum rec^2, sum orig^2, max |e|
 
-template <int NT> struct K3Shared {
-    static constexpr int NTP = (NT + 3) & ~3;
+// Second coefficient set of a parameter: the basis of the elements OUTSIDE the combined mask (svd_include_noise,
+// src/svd_hybrid/basis.py:455-466); its reconstruction is scaled by svd_noise_shrink (merge.py:257-284) and
+// scattered to the unmasked positions (mask_loader.py:757-760).
+template <int NT> struct K3NoiseSet {
+    const float (*sWT)[(NT + 3) & ~3] = nullptr;
+    const float* sCbar = nullptr;
+    const float* sG = nullptr;
+    int r = 0;
+    float tail_add = 0.0f;
+    float shrink = 1.0f;
+    bool on = false;
 };
 
 // x: in = fine-tuned values, scratch afterwards.  res: out = merged values.
-template <typename T, int NT, bool FP16B, bool DIAG>
+template <typename T, int NT, bool FP16B, bool DIAG, bool NOISE = false>
 __device__ __forceinline__ void k3_step(const float (&b)[kVec], float (&x)[NT][kVec], const uint32_t pword,
                                         const int64_t e, const int64_t numel, const int r, const uint32_t present_bits,
                                         const int center, const float n_f, const float tail_add,
                                         const float (*sWT)[(NT + 3) & ~3], const float (*sChatT)[(NT + 3) & ~3],
                                         const float* sCbar, const float* sG, float (&res)[kVec],
-                                        float (&dacc)[DIAG ? kDiagRows * NT : 1]) {
+                                        float (&dacc)[DIAG ? kDiagRows * NT : 1],
+                                        const K3NoiseSet<NT>& ns = K3NoiseSet<NT>()) {
     struct { int center; } a{center};
     float mean[kVec];
 #pragma unroll
@@ -121,6 +131,49 @@ __device__ __forceinline__ void k3_step(const float (&b)[kVec], float (&x)[NT][k
     float acc[kVec];
 #pragma unroll
     for (int h = 0; h < kH; ++h) { acc[2 * h] = acc2[h].x; acc[2 * h + 1] = acc2[h].y; }
+    // noise region: the same centred task vectors contracted with the second (unmasked-rows) coefficient set;
+    // every element belongs to exactly one region, the select happens at the store
+    float accn[NOISE ? kVec : 1];
+    if (NOISE) {
+        float2 an2[kH];
+#pragma unroll
+        for (int h = 0; h < kH; ++h) an2[h] = make_float2(0.0f, 0.0f);
+        if (ns.on) {
+            if (FP16B) {
+#pragma unroll
+                for (int j = 0; j < NT; ++j) {
+                    if (j >= ns.r) break;
+                    float2 u2[kH];
+#pragma unroll
+                    for (int h = 0; h < kH; ++h) u2[h] = make_float2(0.0f, 0.0f);
+#pragma unroll
+                    for (int t = 0; t < NT; ++t) {
+                        const float w = ns.sWT[j][t];
+                        const float2 w2 = make_float2(w, w);
+#pragma unroll
+                        for (int h = 0; h < kH; ++h) u2[h] = __ffma2_rn(x2[t][h], w2, u2[h]);
+                    }
+                    const float cb = ns.sCbar[j];
+                    const float2 cb2 = make_float2(cb, cb);
+#pragma unroll
+                    for (int h = 0; h < kH; ++h) {
+                        u2[h] = __half22float2(__float22half2_rn(u2[h]));
+                        an2[h] = __ffma2_rn(u2[h], cb2, an2[h]);
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int t = 0; t < NT; ++t) {
+                    const float g = ns.sG[t];
+                    const float2 g2 = make_float2(g, g);
+#pragma unroll
+                    for (int h = 0; h < kH; ++h) an2[h] = __ffma2_rn(x2[t][h], g2, an2[h]);
+                }
+            }
+        }
+#pragma unroll
+        for (int h = 0; h < kH; ++h) { accn[2 * h] = an2[h].x; accn[2 * h + 1] = an2[h].y; }
+    }
     float rec[DIAG ? NT : 1][kVec];
     if (DIAG) {
 #pragma unroll
@@ -132,7 +185,9 @@ __device__ __forceinline__ void k3_step(const float (&b)[kVec], float (&x)[NT][k
     for (int c = 0; c < kVec; ++c) {
         const bool m = (bits >> c) & 1u;
         const float val = (acc[c] + mean[c]) + tail_add;
-        res[c] = b[c] + (m ? val : 0.0f);
+        float other = 0.0f;
+        if (NOISE) other = ns.on ? __fmul_rn((accn[c] + mean[c]) + ns.tail_add, ns.shrink) : 0.0f;
+        res[c] = b[c] + (m ? val : other);
     }
     if (DIAG) {
 #pragma unroll

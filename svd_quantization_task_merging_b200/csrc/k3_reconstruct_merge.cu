@@ -22,12 +22,14 @@ namespace svdq {
 
 
 
-template <typename T, int NT, bool FP16B, bool DIAG>
+template <typename T, int NT, bool FP16B, bool DIAG, bool NOISE>
 __global__ void __launch_bounds__(kBlock, (NT <= 8 && !DIAG) ? 2 : 1) k3_reconstruct_merge(const K3Args a) {
     constexpr int NTP = (NT + 3) & ~3;
     __shared__ __align__(16) float sWT[NT][NTP];        // sWT[j][t] = W[t][j]
     __shared__ __align__(16) float sChatT[DIAG ? NT : 1][NTP];   // sChatT[j][t] = chat[t][j]
     __shared__ float sCbar[NT], sG[NT];
+    __shared__ __align__(16) float sWTn[NOISE ? NT : 1][NTP];    // noise-region set (svd_include_noise)
+    __shared__ float sCbarN[NOISE ? NT : 1], sGn[NOISE ? NT : 1];
     __shared__ const void* s_ptr[NT + 1];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -51,6 +53,19 @@ __global__ void __launch_bounds__(kBlock, (NT <= 8 && !DIAG) ? 2 : 1) k3_reconst
         if (DIAG) sChatT[j][t] = (t < NT) ? a.chat[(int64_t)p * NT * NT + t * NT + j] : 0.0f;
     }
     if (tid < NT) { sCbar[tid] = a.cbar[(int64_t)p * NT + tid]; sG[tid] = a.gvec[(int64_t)p * NT + tid]; }
+    K3NoiseSet<NT> ns;
+    if (NOISE) {
+        ns.on = status == kSolved && a.info_n[(int64_t)p * 8 + 0] == kSolved;
+        ns.r = a.info_n[(int64_t)p * 8 + 4];
+        ns.tail_add = a.scal_n[(int64_t)p * 4 + 1];
+        ns.shrink = a.noise_shrink;
+        ns.sWT = sWTn; ns.sCbar = sCbarN; ns.sG = sGn;
+        for (int i = tid; i < NT * NTP; i += kBlock) {
+            const int j = i / NTP, t = i % NTP;
+            sWTn[j][t] = (t < NT) ? a.W_n[(int64_t)p * NT * NT + t * NT + j] : 0.0f;
+        }
+        if (tid < NT) { sCbarN[tid] = a.cbar_n[(int64_t)p * NT + tid]; sGn[tid] = a.gvec_n[(int64_t)p * NT + tid]; }
+    }
     __syncthreads();
 
     const uint32_t* packed = has_mask ? a.packed + a.pmask_off[p] : nullptr;
@@ -105,8 +120,8 @@ __global__ void __launch_bounds__(kBlock, (NT <= 8 && !DIAG) ? 2 : 1) k3_reconst
                         x[t][c] = (e + c < numel) ? Elem<T>::load1(s_ptr[t + 1], e + c) : 0.0f;
             }
             if (has_mask) pword = __ldg(packed + (e >> 5));
-            k3_step<T, NT, FP16B, DIAG>(b, x, pword, e, numel, r, present_bits, a.center, n_f, tail_add, sWT, sChatT,
-                                        sCbar, sG, res, dacc);
+            k3_step<T, NT, FP16B, DIAG, NOISE>(b, x, pword, e, numel, r, present_bits, a.center, n_f, tail_add, sWT,
+                                               sChatT, sCbar, sG, res, dacc, ns);
         }
         if (full) stg_stream_f4(outp + e, make_float4(res[0], res[1], res[2], res[3]));
         else {
@@ -185,13 +200,20 @@ __global__ void __launch_bounds__(32) k3_diag_finalize(const K3DiagArgs a) {
 template <typename T, int NT>
 static cudaError_t launch_nt(const K3Args& a, int n_tiles, bool fp16b, bool diag, cudaStream_t st) {
     if (n_tiles <= 0) return cudaSuccess;
+    const bool noise = a.info_n != nullptr;
+#define SVDQ_GO(F, D)                                                                          \
+    do {                                                                                       \
+        if (noise) k3_reconstruct_merge<T, NT, F, D, true><<<n_tiles, kBlock, 0, st>>>(a);     \
+        else       k3_reconstruct_merge<T, NT, F, D, false><<<n_tiles, kBlock, 0, st>>>(a);    \
+    } while (0)
     if (diag) {
-        if (fp16b) k3_reconstruct_merge<T, NT, true, true><<<n_tiles, kBlock, 0, st>>>(a);
-        else       k3_reconstruct_merge<T, NT, false, true><<<n_tiles, kBlock, 0, st>>>(a);
+        if (fp16b) SVDQ_GO(true, true);
+        else       SVDQ_GO(false, true);
     } else {
-        if (fp16b) k3_reconstruct_merge<T, NT, true, false><<<n_tiles, kBlock, 0, st>>>(a);
-        else       k3_reconstruct_merge<T, NT, false, false><<<n_tiles, kBlock, 0, st>>>(a);
+        if (fp16b) SVDQ_GO(true, false);
+        else       SVDQ_GO(false, false);
     }
+#undef SVDQ_GO
     return cudaGetLastError();
 }
 

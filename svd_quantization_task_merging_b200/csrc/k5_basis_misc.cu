@@ -19,11 +19,19 @@ namespace svdq {
 
 #if SVDQ_DTYPE == 0
 __global__ void __launch_bounds__(32) k5_tile_offsets(const uint32_t* count, const int64_t* tile_begin,
-                                                      int64_t* tile_row_off) {
+                                                      int64_t* tile_row_off, const int64_t* numel_inv,
+                                                      int tile_elems) {
     if (threadIdx.x != 0) return;
     const int p = blockIdx.x;
     int64_t acc = 0;
-    for (int64_t t = tile_begin[p]; t < tile_begin[p + 1]; ++t) { tile_row_off[t] = acc; acc += count[t]; }
+    for (int64_t t = tile_begin[p]; t < tile_begin[p + 1]; ++t) {
+        tile_row_off[t] = acc;
+        if (numel_inv) {       // rows OUTSIDE the mask: elements of the tile minus the masked count
+            const int64_t lo = (t - tile_begin[p]) * (int64_t)tile_elems;
+            const int64_t in_tile = min((int64_t)tile_elems, numel_inv[p] - lo);
+            acc += in_tile - (int64_t)count[t];
+        } else acc += count[t];
+    }
 }
 
 
@@ -61,7 +69,10 @@ __global__ void __launch_bounds__(kBlock) k5_write_basis(const K5Args a) {
         uint32_t bits = 0;
         if (e < stop) {
             const uint32_t valid = (e + kVec <= numel) ? 0xFu : ((1u << (int)(numel - e)) - 1u);
-            bits = has_mask ? ((__ldg(packed + (e >> 5)) >> (int)(e & 31)) & valid) : valid;
+            if (has_mask) {
+                const uint32_t w = __ldg(packed + (e >> 5));
+                bits = ((a.invert ? ~w : w) >> (int)(e & 31)) & valid;
+            } else bits = a.invert ? 0u : valid;
         }
         // block-wide exclusive scan of popc(bits) in element order
         const uint32_t mine = __popc(bits);
@@ -159,9 +170,9 @@ cudaError_t k5_launch_dtype<SVDQ_DTYPE>(int nt, const K5Args& a, int n_tiles, cu
 
 #if SVDQ_DTYPE == 0
 cudaError_t k5_offsets_launch(const uint32_t* count, const int64_t* tile_begin, int64_t* tile_row_off, int n_params,
-                              cudaStream_t st) {
+                              const int64_t* numel_if_inverted, int tile_elems, cudaStream_t st) {
     if (n_params <= 0) return cudaSuccess;
-    k5_tile_offsets<<<n_params, 32, 0, st>>>(count, tile_begin, tile_row_off);
+    k5_tile_offsets<<<n_params, 32, 0, st>>>(count, tile_begin, tile_row_off, numel_if_inverted, tile_elems);
     return cudaGetLastError();
 }
 

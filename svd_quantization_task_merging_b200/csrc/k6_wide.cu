@@ -116,13 +116,20 @@ template <> struct Elem2<__half> {
 };
 
 // RP: compile-time bound on the number of basis columns (24 or 32)
-template <typename T, int RP, bool FP16B, bool DIAG>
+// NOISE (svd_include_noise): a second coefficient set for the rows outside the combined mask; every element
+// picks the set of its own region (index 0 = masked rows, 1 = the rest), so the two elements of a thread may
+// read different rows of sW -- the region stride is padded by 4 floats to keep the two 16-byte reads on
+// different banks.
+template <typename T, int RP, bool FP16B, bool DIAG, bool NOISE>
 __global__ void __launch_bounds__(kBlock) k6_reconstruct_merge(const K3Args a, const int n_tasks) {
     extern __shared__ __align__(16) float dyn[];                  // DIAG: [5 * n_tasks][kBlock] accumulators
-    __shared__ __align__(16) float sW[kMaxTasks][RP];             // sW[t][j] = W[t][j]
+    constexpr int NREG = NOISE ? 2 : 1;
+    constexpr int kRegStride = kMaxTasks * RP + 4;
+    __shared__ __align__(16) float sWf[NREG * kRegStride];        // sW(g, t, j) = W_g[t][j]
     __shared__ float sChat[DIAG ? kMaxTasks : 1][RP];
-    __shared__ float sCbar[RP], sSW[RP];
+    __shared__ float sCbar[NREG][RP], sSW[NREG][RP];
     __shared__ const void* s_ptr[kMaxTasks + 1];
+#define SW(g, t, j) sWf[(g) * kRegStride + (t) * RP + (j)]
     const int N = n_tasks;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tile = blockIdx.x;
@@ -135,20 +142,30 @@ __global__ void __launch_bounds__(kBlock) k6_reconstruct_merge(const K3Args a, c
     const int r = a.info[(int64_t)p * 8 + (DIAG ? 2 : 4)];
     const float tail_add = a.scal[(int64_t)p * 4 + 1];
     const bool has_mask = a.has_mask[p] != 0;
+    const bool noise_on = NOISE && status == kSolved && a.info_n[(int64_t)p * 8 + 0] == kSolved;
+    const int r_n = noise_on ? a.info_n[(int64_t)p * 8 + 4] : 0;
+    const float tail_n = noise_on ? a.scal_n[(int64_t)p * 4 + 1] : 0.0f;
     if (tid <= N) s_ptr[tid] = a.tensors[(int64_t)p * (N + 1) + tid];
     for (int i = tid; i < kMaxTasks * RP; i += kBlock) {
         const int t = i / RP, j = i % RP;
         const bool ok = t < N && j < N;
-        sW[t][j] = ok ? a.W[(int64_t)p * N * N + t * N + j] : 0.0f;
+        SW(0, t, j) = ok ? a.W[(int64_t)p * N * N + t * N + j] : 0.0f;
+        if (NOISE) SW(NREG - 1, t, j) = (ok && noise_on) ? a.W_n[(int64_t)p * N * N + t * N + j] : 0.0f;
         if (DIAG) sChat[t][j] = ok ? a.chat[(int64_t)p * N * N + t * N + j] : 0.0f;
     }
-    if (tid < RP) sCbar[tid] = tid < N ? a.cbar[(int64_t)p * N + tid] : 0.0f;
+    if (tid < RP) {
+        sCbar[0][tid] = tid < N ? a.cbar[(int64_t)p * N + tid] : 0.0f;
+        if (NOISE) sCbar[NREG - 1][tid] = (tid < N && noise_on) ? a.cbar_n[(int64_t)p * N + tid] : 0.0f;
+    }
     if (DIAG) for (int i = tid; i < kDiagRows * N * kBlock; i += kBlock) dyn[i] = 0.0f;
     __syncthreads();
     if (tid < RP) {                                               // column sums of W over the active tasks
-        float s = 0.0f;
-        for (int t = 0; t < N; ++t) if (s_ptr[t + 1] != nullptr) s += sW[t][tid];
-        sSW[tid] = s;
+#pragma unroll
+        for (int g = 0; g < NREG; ++g) {
+            float s = 0.0f;
+            for (int t = 0; t < N; ++t) if (s_ptr[t + 1] != nullptr) s += SW(g, t, tid);
+            sSW[g][tid] = s;
+        }
     }
     __syncthreads();
     const uint32_t* packed = has_mask ? a.packed + a.pmask_off[p] : nullptr;
@@ -167,6 +184,10 @@ __global__ void __launch_bounds__(kBlock) k6_reconstruct_merge(const K3Args a, c
 #pragma unroll
             for (int j = 0; j < RP; ++j) { u[j][0] = 0.0f; u[j][1] = 0.0f; }
             float mean[kWVec] = {0.0f, 0.0f};
+            uint32_t bits = 0x3u;
+            if (has_mask) bits = (__ldg(packed + (e >> 5)) >> (int)(e & 31)) & 0x3u;
+            // region of each of the thread's two elements (0 = masked rows)
+            const int g0 = (NOISE && !(bits & 1u)) ? NREG - 1 : 0, g1 = (NOISE && !(bits & 2u)) ? NREG - 1 : 0;
             for (int t = 0; t < N; ++t) {                        // stream the tasks once
                 const void* fp = s_ptr[t + 1];
                 if (fp == nullptr) continue;
@@ -176,38 +197,40 @@ __global__ void __launch_bounds__(kBlock) k6_reconstruct_merge(const K3Args a, c
                 mean[0] += x0; mean[1] += x1;
 #pragma unroll
                 for (int j = 0; j < RP; j += 4) {
-                    const float4 w = *reinterpret_cast<const float4*>(&sW[t][j]);
-                    u[j + 0][0] = fmaf(x0, w.x, u[j + 0][0]); u[j + 0][1] = fmaf(x1, w.x, u[j + 0][1]);
-                    u[j + 1][0] = fmaf(x0, w.y, u[j + 1][0]); u[j + 1][1] = fmaf(x1, w.y, u[j + 1][1]);
-                    u[j + 2][0] = fmaf(x0, w.z, u[j + 2][0]); u[j + 2][1] = fmaf(x1, w.z, u[j + 2][1]);
-                    u[j + 3][0] = fmaf(x0, w.w, u[j + 3][0]); u[j + 3][1] = fmaf(x1, w.w, u[j + 3][1]);
+                    const float4 w = *reinterpret_cast<const float4*>(&SW(g0, t, j));
+                    const float4 v = NOISE ? *reinterpret_cast<const float4*>(&SW(g1, t, j)) : w;
+                    u[j + 0][0] = fmaf(x0, w.x, u[j + 0][0]); u[j + 0][1] = fmaf(x1, v.x, u[j + 0][1]);
+                    u[j + 1][0] = fmaf(x0, w.y, u[j + 1][0]); u[j + 1][1] = fmaf(x1, v.y, u[j + 1][1]);
+                    u[j + 2][0] = fmaf(x0, w.z, u[j + 2][0]); u[j + 2][1] = fmaf(x1, v.z, u[j + 2][1]);
+                    u[j + 3][0] = fmaf(x0, w.w, u[j + 3][0]); u[j + 3][1] = fmaf(x1, v.w, u[j + 3][1]);
                 }
             }
 #pragma unroll
             for (int c = 0; c < kWVec; ++c) mean[c] = a.center ? __fdiv_rn(mean[c], n_f) : 0.0f;
             // u = (tau - mean) W = tau W - mean * colsum(W); fp16 round trip; contract with cbar
             float acc[kWVec] = {0.0f, 0.0f};
+            const int gsel[kWVec] = {g0, g1};
+            const int rsel[kWVec] = {g0 ? r_n : r, g1 ? r_n : r};
 #pragma unroll
             for (int j = 0; j < RP; ++j) {
-                if (j < r) {
 #pragma unroll
-                    for (int c = 0; c < kWVec; ++c) {
-                        float v = fmaf(-mean[c], sSW[j], u[j][c]);
+                for (int c = 0; c < kWVec; ++c) {
+                    if (j < rsel[c]) {
+                        float v = fmaf(-mean[c], sSW[gsel[c]][j], u[j][c]);
                         if (FP16B) v = round_fp16(v);
                         u[j][c] = v;
-                        acc[c] = fmaf(v, sCbar[j], acc[c]);
+                        acc[c] = fmaf(v, sCbar[gsel[c]][j], acc[c]);
+                    } else {
+                        u[j][c] = 0.0f;
                     }
-                } else {
-                    u[j][0] = 0.0f; u[j][1] = 0.0f;
                 }
             }
-            uint32_t bits = 0x3u;
-            if (has_mask) bits = (__ldg(packed + (e >> 5)) >> (int)(e & 31)) & 0x3u;
 #pragma unroll
             for (int c = 0; c < kWVec; ++c) {
                 const bool m = (bits >> c) & 1u;
-                const float val = (acc[c] + mean[c]) + tail_add;
-                res[c] = b[c] + (m ? val : 0.0f);
+                float val = (acc[c] + mean[c]) + (gsel[c] ? tail_n : tail_add);
+                if (NOISE && !m) val = noise_on ? __fmul_rn(val, a.noise_shrink) : 0.0f;
+                res[c] = b[c] + ((m || NOISE) ? val : 0.0f);
             }
             if (DIAG) {
                 for (int t = 0; t < N; ++t) {
@@ -265,18 +288,25 @@ template <typename T, int RP>
 static cudaError_t launch_wide(const K3Args& a, int n_tasks, int n_tiles, bool fp16b, bool diag, cudaStream_t st) {
     const size_t dsm = diag ? (size_t)kDiagRows * n_tasks * kBlock * sizeof(float) : 0;
     cudaError_t e = cudaSuccess;
-#define SVDQ_GO(F, D)                                                                                            \
+    const bool noise = a.info_n != nullptr;
+#define SVDQ_GO2(F, D, Z)                                                                                        \
     do {                                                                                                         \
-        if (dsm) e = cudaFuncSetAttribute(k6_reconstruct_merge<T, RP, F, D>,                                     \
+        if (dsm) e = cudaFuncSetAttribute(k6_reconstruct_merge<T, RP, F, D, Z>,                                  \
                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm);                \
         if (e != cudaSuccess) return e;                                                                          \
-        k6_reconstruct_merge<T, RP, F, D><<<n_tiles, kBlock, dsm, st>>>(a, n_tasks);                             \
+        k6_reconstruct_merge<T, RP, F, D, Z><<<n_tiles, kBlock, dsm, st>>>(a, n_tasks);                          \
+    } while (0)
+#define SVDQ_GO(F, D)                                                                                            \
+    do {                                                                                                         \
+        if (noise) SVDQ_GO2(F, D, true);                                                                         \
+        else SVDQ_GO2(F, D, false);                                                                              \
     } while (0)
     if (fp16b && diag) SVDQ_GO(true, true);
     else if (fp16b) SVDQ_GO(true, false);
     else if (diag) SVDQ_GO(false, true);
     else SVDQ_GO(false, false);
 #undef SVDQ_GO
+#undef SVDQ_GO2
     return cudaGetLastError();
 }
 
@@ -290,4 +320,5 @@ cudaError_t k6_merge_launch_dtype<SVDQ_DTYPE>(int n_tasks, const K3Args& a, int 
     return launch_wide<T, 32>(a, n_tasks, n_tiles, fp16b, diag, st);
 }
 
+#undef SW
 }  // namespace svdq

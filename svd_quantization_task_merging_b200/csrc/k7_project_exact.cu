@@ -81,7 +81,10 @@ __global__ void __launch_bounds__(kBlock, 1) k7_project_exact(const K7Args a) {
                 for (int c = 0; c < kVec; ++c) { x[t][c] = Elem<T>::sub(f[c], b[c]); mean[c] += x[t][c]; }
             }
             uint32_t bits = full ? 0xFu : ((1u << (int)(numel - e)) - 1u);
-            if (has_mask) bits &= (__ldg(packed + (e >> 5)) >> (int)(e & 31)) & 0xFu;
+            if (has_mask) {
+                const uint32_t w = __ldg(packed + (e >> 5));
+                bits &= ((a.invert ? ~w : w) >> (int)(e & 31)) & 0xFu;
+            } else if (a.invert) bits = 0;
 #pragma unroll
             for (int c = 0; c < kVec; ++c) mean[c] = a.center ? __fdiv_rn(mean[c], n_f) : 0.0f;
 #pragma unroll

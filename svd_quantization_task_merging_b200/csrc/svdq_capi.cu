@@ -74,7 +74,7 @@ cudaError_t k3_launch(int dtype, int nt, const svdq::K3Args& a, int n_tiles, boo
             default:          return cudaErrorInvalidValue;
         }
     }
-    if ((staged_mask() & 2) && nt <= 8 && !diag) {
+    if ((staged_mask() & 2) && nt <= 8 && !diag && a.info_n == nullptr) {
         cudaError_t e = cudaErrorNotSupported;
         switch (dtype) {
             case svdq::kF32:  e = svdq::k3s_launch_dtype<svdq::kF32>(nt, a, n_tiles, fp16b, sm_count(), st); break;
@@ -126,7 +126,8 @@ int svdq_tv_mask_gram(int dtype, int n_tasks, int mask_strategy, int full, int64
     a.tensors = tensors; a.masks = masks; a.numel = numel; a.tile_param = tile_param; a.tile_local = tile_local;
     a.pmask_off = pmask_off; a.packed = packed; a.gram = gram; a.count = count; a.tile_elems = tile_elems;
     a.strategy = mask_strategy;
-    a.packed_in = nullptr; a.has_mask_in = nullptr;
+    a.packed_in = nullptr; a.has_mask_in = nullptr; a.second_complement = full == 2;
+    REQUIRE(full >= 0 && full <= 2, "full must be 0 (masked), 1 (+ all elements) or 2 (+ complement)");
     return finish(__func__, k1_launch(dtype, n_tasks, a, (int)n_tiles, full != 0, (cudaStream_t)stream));
 }
 
@@ -160,7 +161,8 @@ int svdq_tv_gram_premasked(int dtype, int n_tasks, int full, int64_t n_tiles, in
     svdq::K1Args a;
     a.tensors = tensors; a.masks = nullptr; a.numel = numel; a.tile_param = tile_param; a.tile_local = tile_local;
     a.pmask_off = pmask_off; a.packed = nullptr; a.gram = gram; a.count = count; a.tile_elems = tile_elems;
-    a.strategy = 0; a.packed_in = packed; a.has_mask_in = has_mask;
+    a.strategy = 0; a.packed_in = packed; a.has_mask_in = has_mask; a.second_complement = full == 2;
+    REQUIRE(full >= 0 && full <= 2, "full must be 0 (masked), 1 (+ all elements) or 2 (+ complement)");
     // always the direct-load kernel: the staged variant combines the task masks itself
     cudaError_t e;
     switch (dtype) {
@@ -171,15 +173,22 @@ int svdq_tv_gram_premasked(int dtype, int n_tasks, int full, int64_t n_tiles, in
     return finish(__func__, e);
 }
 
-int svdq_gram_reduce(int n_tasks, int full, int64_t n_params, const float* gram, const uint32_t* count,
-                     const int64_t* tile_begin, double* gram_masked, double* gram_all, int64_t* dm, void* stream) {
+int svdq_gram_reduce(int n_tasks, int full, int64_t n_params, int min_mask_size, const float* gram,
+                     const uint32_t* count, const int64_t* tile_begin, const int64_t* numel, const uint8_t* has_mask,
+                     double* gram_masked, double* gram_all, int64_t* dm, double* gram_noise, int64_t* dm_noise,
+                     void* stream) {
     REQUIRE(n_tasks >= 1 && n_tasks <= SVDQ_MAX_STREAM_TASKS, "n_tasks must be in [1, 16]");
     REQUIRE(n_params >= 0 && n_params < (1ll << 31), "n_params");
+    REQUIRE(full >= 0 && full <= 2, "full must be 0 (masked), 1 (+ all elements) or 2 (+ complement)");
     if (n_params == 0) return 0;
     REQUIRE(gram && count && tile_begin && gram_masked && dm, "null pointer");
+    REQUIRE(full == 2 || (!gram_noise && !dm_noise), "noise-region outputs need full == 2");
+    REQUIRE(!dm_noise || (numel && has_mask), "dm_noise needs numel and has_mask");
     svdq::K2ReduceArgs a;
     a.gram = gram; a.count = count; a.tile_begin = tile_begin; a.gram_masked = gram_masked; a.gram_all = gram_all;
-    a.dm = dm; a.nt = n_tasks; a.full = full != 0;
+    a.dm = dm; a.nt = n_tasks; a.full = full;
+    a.gram_noise = gram_noise; a.dm_noise = dm_noise; a.numel = numel; a.has_mask = has_mask;
+    a.min_mask_size = min_mask_size;
     return finish(__func__, svdq::k2_reduce_launch(a, (int)n_params, (cudaStream_t)stream));
 }
 
@@ -224,7 +233,8 @@ int svdq_param_average(int n_tasks, int64_t n_params, const uint32_t* present, c
     return finish(__func__, svdq::k2_average_launch(a, (int)n_params, (cudaStream_t)stream));
 }
 
-int svdq_project_exact(int dtype, int n_tasks, int fp16_basis, int center, int64_t n_sel_tiles, int tile_elems,
+int svdq_project_exact(int dtype, int n_tasks, int fp16_basis, int center, int region, int64_t n_sel_tiles,
+                       int tile_elems,
                        const void* const* tensors, const int64_t* numel, const int32_t* sel_tile_param,
                        const int32_t* sel_tile_local, const int64_t* pmask_off, const uint8_t* has_mask,
                        const uint32_t* packed, const int32_t* info, const float* W, float* proj, void* stream) {
@@ -237,7 +247,8 @@ int svdq_project_exact(int dtype, int n_tasks, int fp16_basis, int center, int64
     svdq::K7Args a;
     a.tensors = tensors; a.numel = numel; a.tile_param = sel_tile_param; a.tile_local = sel_tile_local;
     a.pmask_off = pmask_off; a.has_mask = has_mask; a.packed = packed; a.info = info; a.W = W; a.proj = proj;
-    a.tile_elems = tile_elems; a.center = center; a.fp16_basis = fp16_basis;
+    a.tile_elems = tile_elems; a.center = center; a.fp16_basis = fp16_basis; a.invert = region == 1;
+    REQUIRE(region == 0 || region == 1, "region must be 0 (masked rows) or 1 (rows outside the mask)");
     cudaError_t e;
     switch (dtype) {
         case svdq::kF32:  e = svdq::k7_launch_dtype<svdq::kF32>(n_tasks, a, (int)n_sel_tiles, (cudaStream_t)stream); break;
@@ -270,7 +281,9 @@ int svdq_reconstruct_merge(int dtype, int n_tasks, int fp16_basis, int diag, int
                            const int32_t* tile_param, const int32_t* tile_local, const int64_t* pmask_off,
                            const uint8_t* has_mask, const uint32_t* packed, const int32_t* info, const float* W,
                            const float* cbar, const float* gvec, const float* scal, const float* chat,
-                           float* const* out, float* diag_partials, void* stream) {
+                           float* const* out, float* diag_partials, const int32_t* noise_info, const float* noise_W,
+                           const float* noise_cbar, const float* noise_gvec, const float* noise_scal,
+                           float noise_shrink, void* stream) {
     REQUIRE(n_tasks >= 1 && n_tasks <= SVDQ_MAX_TASKS, "n_tasks must be in [1, 32]");
     REQUIRE(dtype >= 0 && dtype <= 2, "dtype");
     REQUIRE(tile_elems > 0 && tile_elems % svdq::kStep == 0, "tile_elems must be a positive multiple of 1024");
@@ -284,6 +297,10 @@ int svdq_reconstruct_merge(int dtype, int n_tasks, int fp16_basis, int diag, int
     a.pmask_off = pmask_off; a.has_mask = has_mask; a.packed = packed; a.info = info; a.W = W; a.cbar = cbar;
     a.gvec = gvec; a.scal = scal; a.chat = chat; a.out = out; a.diag = diag_partials; a.tile_elems = tile_elems;
     a.center = center;
+    REQUIRE(!noise_info || (noise_W && noise_cbar && noise_gvec && noise_scal && packed && pmask_off),
+            "noise region requested without its W / cbar / gvec / scal tables or without packed masks");
+    a.info_n = noise_info; a.W_n = noise_W; a.cbar_n = noise_cbar; a.gvec_n = noise_gvec; a.scal_n = noise_scal;
+    a.noise_shrink = noise_shrink;
     return finish(__func__, k3_launch(dtype, n_tasks, a, (int)n_tiles, fp16_basis != 0, diag != 0,
                                             (cudaStream_t)stream));
 }
@@ -299,16 +316,19 @@ int svdq_diag_finalize(int n_tasks, int64_t n_params, const float* diag_partials
     return finish(__func__, svdq::k3_diag_launch(a, (int)n_params, (cudaStream_t)stream));
 }
 
-int svdq_basis_offsets(int64_t n_params, const uint32_t* count, const int64_t* tile_begin, int64_t* tile_row_off,
-                       void* stream) {
+int svdq_basis_offsets(int64_t n_params, int region, int tile_elems, const uint32_t* count, const int64_t* tile_begin,
+                       const int64_t* numel, int64_t* tile_row_off, void* stream) {
     REQUIRE(n_params >= 0 && n_params < (1ll << 31), "n_params");
+    REQUIRE(region == 0 || region == 1, "region must be 0 (masked rows) or 1 (rows outside the mask)");
     if (n_params == 0) return 0;
     REQUIRE(count && tile_begin && tile_row_off, "null pointer");
+    REQUIRE(region == 0 || (numel && tile_elems > 0), "region 1 needs numel and tile_elems");
     return finish(__func__, svdq::k5_offsets_launch(count, tile_begin, tile_row_off, (int)n_params,
+                                                    region == 1 ? numel : nullptr, tile_elems,
                                                     (cudaStream_t)stream));
 }
 
-int svdq_write_basis(int dtype, int n_tasks, int fp16_basis, int center, int64_t n_tiles, int tile_elems,
+int svdq_write_basis(int dtype, int n_tasks, int fp16_basis, int center, int region, int64_t n_tiles, int tile_elems,
                      const void* const* tensors, const int64_t* numel, const int32_t* tile_param,
                      const int32_t* tile_local, const int64_t* pmask_off, const uint8_t* has_mask,
                      const uint32_t* packed, const int32_t* info, const float* W, const int64_t* tile_row_off,
@@ -324,7 +344,8 @@ int svdq_write_basis(int dtype, int n_tasks, int fp16_basis, int center, int64_t
     a.tensors = tensors; a.numel = numel; a.tile_param = tile_param; a.tile_local = tile_local;
     a.pmask_off = pmask_off; a.has_mask = has_mask; a.packed = packed; a.info = info; a.W = W;
     a.tile_row_off = tile_row_off; a.u_high = u_high; a.u_low = u_low; a.mean = mean; a.tile_elems = tile_elems;
-    a.center = center; a.fp16_basis = fp16_basis;
+    a.center = center; a.fp16_basis = fp16_basis; a.invert = region == 1;
+    REQUIRE(region == 0 || region == 1, "region must be 0 (masked rows) or 1 (rows outside the mask)");
     return finish(__func__, k5_launch(dtype, n_tasks, a, (int)n_tiles, (cudaStream_t)stream));
 }
 

@@ -22,6 +22,9 @@ struct K1Args {
     // has_mask_in[P] says which parameters have one.  packed is not written in this mode.
     const uint32_t* packed_in;
     const uint8_t* has_mask_in;
+    // FULL only: 0 = second block is the Gram over ALL elements, 1 = over the elements OUTSIDE the combined mask
+    // (the noise region of svd_include_noise; all = masked + complement is then formed by k2_gram_reduce)
+    int second_complement;
 };
 
 struct K2ReduceArgs {
@@ -32,7 +35,15 @@ struct K2ReduceArgs {
     double* gram_all;             // [P][NT*NT] Gram over all elements, masked or not (FULL only; may be null)
     int64_t* dm;                  // [P]
     int nt;
-    int full;
+    int full;                     // 0 masked only, 1 second block = all elements, 2 second block = complement
+    // full == 2 (noise region, basis.py:455-466): complement Gram and its row count.  A parameter has a noise
+    // region iff it has a mask, the masked region passes the svd_min_mask_size gate (cli.py:332) and at least
+    // one element lies outside the mask.
+    double* gram_noise;           // [P][NT*NT] or null
+    int64_t* dm_noise;            // [P] or null
+    const int64_t* numel;         // [P]   (full == 2)
+    const uint8_t* has_mask;      // [P]   (full == 2)
+    int min_mask_size;
 };
 
 struct K2SolveArgs {
@@ -67,6 +78,13 @@ struct K3Args {
     float* diag;                  // [n_tiles][5][NT] partials (DIAG)
     int tile_elems;
     int center;
+    // noise region (svd_include_noise): second solve over the rows outside the mask; all null = off
+    const int32_t* info_n;        // [P][8]
+    const float* W_n;             // [P][NT*NT]
+    const float* cbar_n;          // [P][NT]
+    const float* gvec_n;          // [P][NT]
+    const float* scal_n;          // [P][4]
+    float noise_shrink;
 };
 
 struct K3DiagArgs {
@@ -102,6 +120,7 @@ struct K7Args {                  // exact projection on the stored (fp16) basis 
     const float* W;                 // [P][NT*NT]
     float* proj;                    // [n_sel_tiles][NT*NT] partial coefficients c[t][j]
     int tile_elems, center, fp16_basis;
+    int invert;                     // 1 = project the rows OUTSIDE the combined mask (noise region)
 };
 
 struct K2RequantArgs {
@@ -139,6 +158,7 @@ struct K5Args {
     int tile_elems;
     int center;
     int fp16_basis;
+    int invert;                   // 1 = rows outside the combined mask (noise basis, basis.py:455-466)
 };
 
 // launchers (one translation unit per kernel family; K1/K3/K5 additionally one per dtype)
@@ -158,7 +178,7 @@ cudaError_t k2_requant_launch(const K2RequantArgs& a, int n_params, cudaStream_t
 template <int DT> cudaError_t k7_launch_dtype(int nt, const K7Args& a, int n_tiles, cudaStream_t st);
 cudaError_t k3_diag_launch(const K3DiagArgs& a, int n_params, cudaStream_t st);
 cudaError_t k5_offsets_launch(const uint32_t* count, const int64_t* tile_begin, int64_t* tile_row_off, int n_params,
-                              cudaStream_t st);
+                              const int64_t* numel_if_inverted, int tile_elems, cudaStream_t st);
 cudaError_t k4_rtvq_launch(const float* x, int64_t n, int bits, int stages, void* codes, int64_t codes_ld,
                            int code_bytes, float* scale, float* zp, float* resnorm, K4Stats* part, uint32_t* packed,
                            int64_t packed_ld, cudaStream_t st);

@@ -132,7 +132,7 @@ class MergeJob:
                  performance: Optional[Dict[str, float]] = None,
                  cluster_assignments: Optional[Dict[str, int]] = None, param_filter: Optional[Sequence[str]] = None,
                  tile_elems: int = TILE_ELEMS, cluster_backend: Optional[str] = None,
-                 projection: Optional[str] = None):
+                 projection: Optional[str] = None, sign_ref_noise: Optional[Mapping[str, torch.Tensor]] = None):
         _native.require_cuda()
         self.cfg = config
         self.device = torch.device(device or "cuda")
@@ -145,15 +145,17 @@ class MergeJob:
         if self.N > MAX_TASKS:
             raise ValueError(f"n_tasks={self.N}: at most {MAX_TASKS} task vectors per merge")
         self.wide = self.N > MAX_STREAM_TASKS          # 17..32 tasks: blocked Gram + runtime-N pass 2
-        if getattr(config, "svd_include_noise", False):
-            raise NotImplementedError("svd_include_noise (noise-region bases) is not part of this build "
-                                      "(SURVEY.md section 8f, rank 4)")
+        # noise region (svd_include_noise): a second basis over the rows outside the combined mask, reconstructed
+        # with svd_noise_shrink into the unmasked positions (cli.py:336-351, basis.py:455-466, merge.py:257-284)
+        self.noise = bool(getattr(config, "svd_include_noise", False))
+        self.noise_shrink = float(getattr(config, "svd_noise_shrink", 0.5))
         if config.svd_mask_strategy not in _native.STRATEGY_CODE:
             raise ValueError(f"Unknown mask strategy: {config.svd_mask_strategy}")
         self.tile_elems = int(tile_elems)
         self.want_diag = config.svd_eval_reconstruction if diagnostics is None else bool(diagnostics)
         self.materialize = bool(materialize_bases)
         self.sign_ref = sign_ref
+        self.sign_ref_noise = sign_ref_noise
         self.performance = performance
         self.fixed_assignments = cluster_assignments
         self.cluster_mode = config.svd_weighting == "cluster"
@@ -294,22 +296,30 @@ class MergeJob:
         g.n_tiles, g.out_off = n_tiles, out_off
         g.host = dict(numel=numel, tile_begin=tile_begin, has_mask=has_mask, present=present)
         G = N * (N + 1) // 2
-        full = 2 if self.cluster_mode else 1
+        full = 2 if (self.cluster_mode or self.noise) else 1
         f32, i32, i64, f64, u8 = torch.float32, torch.int32, torch.int64, torch.float64, torch.uint8
         z = lambda *shape, dtype=f32: torch.zeros(*shape, dtype=dtype, device=dev)   # noqa: E731
+
+        def solve_outputs():
+            return dict(info=z(P, 8, dtype=i32), sv=z(P, N), scal=z(P, 4), coef=z(P, N, N),
+                        chigh=z(P, N, N, dtype=torch.int16), codes=z(P, N, S, N, dtype=u8), qscale=z(P, N, S),
+                        qzp=z(P, N, S), qres=z(P, N, S), chat=z(P, N, N), cbar=z(P, N), W=z(P, N, N), gvec=z(P, N),
+                        V=z(P, N, N, dtype=f64))
         g.t = dict(
             tptr=_dev(tptr, dev), mptr=_dev(mptr, dev) if g.any_mask else None, numel=_dev(numel, dev),
             tile_param=_dev(tile_param, dev), tile_local=_dev(tile_local, dev), tile_begin=_dev(tile_begin, dev),
             pm_off=_dev(pm_off, dev), has_mask=_dev(has_mask, dev), present=_dev(present.view(np.int32), dev),
             packed=z(max(words, 1), dtype=i32), gram=z(max(n_tiles, 1) * full * G), count=z(max(n_tiles, 1), dtype=i32),
             gram_masked=z(P, N * N, dtype=f64), gram_all=z(P, N * N, dtype=f64) if self.cluster_mode else None,
-            dm=z(P, dtype=i64), info=z(P, 8, dtype=i32), sv=z(P, N), scal=z(P, 4), coef=z(P, N, N),
-            chigh=z(P, N, N, dtype=torch.int16), codes=z(P, N, S, N, dtype=u8), qscale=z(P, N, S), qzp=z(P, N, S),
-            qres=z(P, N, S), chat=z(P, N, N), cbar=z(P, N), W=z(P, N, N), gvec=z(P, N), V=z(P, N, N, dtype=f64),
+            dm=z(P, dtype=i64), **solve_outputs(),
             out=torch.empty(out_total, dtype=f32, device=dev),
             diag=z(max(n_tiles, 1) * 5 * N) if self.want_diag else None,
             diag_out=z(P, N, 6, dtype=f64) if self.want_diag else None,
         )
+        # noise region: its own Gram, row count and solve outputs (same layout as the masked region's)
+        g.tn = None
+        if self.noise:
+            g.tn = dict(gram=z(P, N * N, dtype=f64), dm=z(P, dtype=i64), no_gate=z(P, dtype=u8), **solve_outputs())
         # exact-projection selection: tiles of the selected parameters
         g.sel = None
         if self.projection != "closed":
@@ -334,19 +344,24 @@ class MergeJob:
                     gl = nl * (nl + 1) // 2
                     g.sub.append(dict(idx=torch.from_numpy(idx).to(dev), n=nl, tptr=_dev(sub_ptr, dev),
                                       gram=z(max(n_tiles, 1) * full * gl), gm=z(P, nl * nl, dtype=f64),
-                                      ga=z(P, nl * nl, dtype=f64) if self.cluster_mode else None))
+                                      ga=z(P, nl * nl, dtype=f64) if self.cluster_mode else None,
+                                      gn=z(P, nl * nl, dtype=f64) if self.noise else None))
         optr = np.asarray([g.t["out"].data_ptr() + 4 * o for o in out_off], np.int64)
         g.t["optr"] = _dev(optr, dev)
-        if self.sign_ref is not None:
+        def sign_table(ref):
+            if ref is None:
+                return None
             sr = np.zeros((P, N, N), np.float64)
             for p, name in enumerate(g.names):
-                v = self.sign_ref.get(name)
+                v = ref.get(name)
                 if v is not None:
                     v = np.asarray(v.detach().double().cpu().numpy() if torch.is_tensor(v) else v, np.float64)
                     sr[p, : v.shape[0], : v.shape[1]] = v
-            g.t["sign_ref"] = _dev(sr, dev)
-        else:
-            g.t["sign_ref"] = None
+            return _dev(sr, dev)
+
+        g.t["sign_ref"] = sign_table(self.sign_ref)
+        if g.tn is not None:
+            g.tn["sign_ref"] = sign_table(self.sign_ref_noise)
 
     # ------------------------------------------------------------------------------------------
     def _weights_table(self) -> Tuple[torch.Tensor, torch.Tensor]:
@@ -408,7 +423,8 @@ class MergeJob:
         cfg, N, te = self.cfg, self.N, self.tile_elems
         st = _native.stream_ptr()
         strat = _native.STRATEGY_CODE[cfg.svd_mask_strategy]
-        full = 1 if self.cluster_mode else 0
+        full = 2 if self.noise else (1 if self.cluster_mode else 0)   # second Gram block: complement / all / none
+        mms = int(cfg.svd_min_mask_size)
         ev = {}
 
         def mark(name):
@@ -429,8 +445,10 @@ class MergeJob:
                 mark("k1")
                 for g in self.groups.values():
                     t = g.t
-                    _native.call("svdq_gram_reduce", N, full, len(g.names), _ptr(t["gram"]), _ptr(t["count"]),
-                                 _ptr(t["tile_begin"]), _ptr(t["gram_masked"]), _ptr(t["gram_all"]), _ptr(t["dm"]), st)
+                    tn = g.tn or {}
+                    _native.call("svdq_gram_reduce", N, full, len(g.names), mms, _ptr(t["gram"]), _ptr(t["count"]),
+                                 _ptr(t["tile_begin"]), _ptr(t["numel"]), _ptr(t["has_mask"]), _ptr(t["gram_masked"]),
+                                 _ptr(t["gram_all"]), _ptr(t["dm"]), _ptr(tn.get("gram")), _ptr(tn.get("dm")), st)
             else:
                 # 17..32 tasks: combine the masks once, then one Gram launch per pair of 8-task blocks
                 for g in self.groups.values():
@@ -441,30 +459,46 @@ class MergeJob:
                                  _ptr(t["count"]), st)
                     gm_full = t["gram_masked"].view(P, N, N)
                     ga_full = t["gram_all"].view(P, N, N) if self.cluster_mode else None
+                    gn_full = g.tn["gram"].view(P, N, N) if self.noise else None
                     for sub in g.sub:
                         _native.call("svdq_tv_gram_premasked", _FLOAT_DTYPES[g.dtype], sub["n"], full, g.n_tiles, te,
                                      _ptr(sub["tptr"]), _ptr(t["numel"]), _ptr(t["tile_param"]), _ptr(t["tile_local"]),
                                      _ptr(t["pm_off"]), _ptr(t["has_mask"]), _ptr(t["packed"]), _ptr(sub["gram"]),
                                      _ptr(t["count"]), st)
-                        _native.call("svdq_gram_reduce", sub["n"], full, P, _ptr(sub["gram"]), _ptr(t["count"]),
-                                     _ptr(t["tile_begin"]), _ptr(sub["gm"]), _ptr(sub["ga"]), _ptr(t["dm"]), st)
+                        _native.call("svdq_gram_reduce", sub["n"], full, P, mms, _ptr(sub["gram"]), _ptr(t["count"]),
+                                     _ptr(t["tile_begin"]), _ptr(t["numel"]), _ptr(t["has_mask"]), _ptr(sub["gm"]),
+                                     _ptr(sub["ga"]), _ptr(t["dm"]), _ptr(sub["gn"]),
+                                     _ptr(g.tn["dm"]) if self.noise else None, st)
                         ix = sub["idx"]
                         gm_full[:, ix[:, None], ix[None, :]] = sub["gm"].view(P, sub["n"], sub["n"])
                         if ga_full is not None:
                             ga_full[:, ix[:, None], ix[None, :]] = sub["ga"].view(P, sub["n"], sub["n"])
+                        if gn_full is not None:
+                            gn_full[:, ix[:, None], ix[None, :]] = sub["gn"].view(P, sub["n"], sub["n"])
                 mark("k1")
             max_rank = int(cfg.svd_max_rank) if cfg.svd_max_rank is not None else 0
 
+            def regions(g):
+                # (region code, solve inputs, solve outputs): 0 = rows inside the combined mask; 1 = noise region,
+                # solved from the complement Gram without the svd_min_mask_size gate (that gate is already folded
+                # into dm_noise by svdq_gram_reduce)
+                t = g.t
+                out = [(0, t["gram_masked"], t["dm"], t["has_mask"], t)]
+                if g.tn is not None:
+                    out.append((1, g.tn["gram"], g.tn["dm"], g.tn["no_gate"], g.tn))
+                return out
+
             def solve(w_dev, order_dev):
                 for g in self.groups.values():
-                    t = g.t
-                    _native.call("svdq_param_solve", N, len(g.names), int(bool(cfg.svd_center)),
-                                 float(cfg.svd_energy_threshold), max_rank, int(cfg.svd_min_mask_size), self.bits,
-                                 self.stages, _ptr(t["gram_masked"]), _ptr(t["dm"]), _ptr(t["has_mask"]),
-                                 _ptr(t["present"]), _ptr(w_dev), _ptr(order_dev), _ptr(t["sign_ref"]),
-                                 _ptr(t["info"]), _ptr(t["sv"]), _ptr(t["scal"]), _ptr(t["coef"]), _ptr(t["chigh"]),
-                                 _ptr(t["codes"]), _ptr(t["qscale"]), _ptr(t["qzp"]), _ptr(t["qres"]),
-                                 _ptr(t["chat"]), _ptr(t["cbar"]), _ptr(t["W"]), _ptr(t["gvec"]), _ptr(t["V"]), st)
+                    for _, gram, dm, gate, o in regions(g):
+                        _native.call("svdq_param_solve", N, len(g.names), int(bool(cfg.svd_center)),
+                                     float(cfg.svd_energy_threshold), max_rank, mms, self.bits,
+                                     self.stages, _ptr(gram), _ptr(dm), _ptr(gate),
+                                     _ptr(g.t["present"]), _ptr(w_dev), _ptr(order_dev), _ptr(o["sign_ref"]),
+                                     _ptr(o["info"]), _ptr(o["sv"]), _ptr(o["scal"]), _ptr(o["coef"]),
+                                     _ptr(o["chigh"]), _ptr(o["codes"]), _ptr(o["qscale"]), _ptr(o["qzp"]),
+                                     _ptr(o["qres"]), _ptr(o["chat"]), _ptr(o["cbar"]), _ptr(o["W"]),
+                                     _ptr(o["gvec"]), _ptr(o["V"]), st)
 
             def project_exact():
                 # re-project the selected (small) parameters on the stored basis and re-quantise them (K7)
@@ -472,21 +506,22 @@ class MergeJob:
                     if g.sel is None:
                         continue
                     t, sel = g.t, g.sel
-                    _native.call("svdq_project_exact", _FLOAT_DTYPES[g.dtype], N, int(bool(cfg.svd_fp16)),
-                                 int(bool(cfg.svd_center)), sel["n"], te, _ptr(t["tptr"]), _ptr(t["numel"]),
-                                 _ptr(sel["param"]), _ptr(sel["local"]), _ptr(t["pm_off"]), _ptr(t["has_mask"]),
-                                 _ptr(t["packed"]), _ptr(t["info"]), _ptr(t["W"]), _ptr(sel["proj"]), st)
-                    _native.call("svdq_param_requantize", N, len(g.names), self.bits, self.stages, _ptr(sel["begin"]),
-                                 _ptr(sel["proj"]), _ptr(t["present"]), _ptr(t["info"]), _ptr(t["coef"]),
-                                 _ptr(t["chigh"]), _ptr(t["codes"]), _ptr(t["qscale"]), _ptr(t["qzp"]),
-                                 _ptr(t["qres"]), _ptr(t["chat"]), st)
+                    for reg, _, _, _, o in regions(g):
+                        _native.call("svdq_project_exact", _FLOAT_DTYPES[g.dtype], N, int(bool(cfg.svd_fp16)),
+                                     int(bool(cfg.svd_center)), reg, sel["n"], te, _ptr(t["tptr"]), _ptr(t["numel"]),
+                                     _ptr(sel["param"]), _ptr(sel["local"]), _ptr(t["pm_off"]), _ptr(t["has_mask"]),
+                                     _ptr(t["packed"]), _ptr(o["info"]), _ptr(o["W"]), _ptr(sel["proj"]), st)
+                        _native.call("svdq_param_requantize", N, len(g.names), self.bits, self.stages,
+                                     _ptr(sel["begin"]), _ptr(sel["proj"]), _ptr(t["present"]), _ptr(o["info"]),
+                                     _ptr(o["coef"]), _ptr(o["chigh"]), _ptr(o["codes"]), _ptr(o["qscale"]),
+                                     _ptr(o["qzp"]), _ptr(o["qres"]), _ptr(o["chat"]), st)
 
             def average(w_dev, order_dev):
                 for g in self.groups.values():
-                    t = g.t
-                    _native.call("svdq_param_average", N, len(g.names), _ptr(t["present"]), _ptr(w_dev),
-                                 _ptr(order_dev), _ptr(t["info"]), _ptr(t["chat"]), _ptr(t["W"]), _ptr(t["cbar"]),
-                                 _ptr(t["gvec"]), _ptr(t["scal"]), st)
+                    for _, _, _, _, o in regions(g):
+                        _native.call("svdq_param_average", N, len(g.names), _ptr(g.t["present"]), _ptr(w_dev),
+                                     _ptr(order_dev), _ptr(o["info"]), _ptr(o["chat"]), _ptr(o["W"]), _ptr(o["cbar"]),
+                                     _ptr(o["gvec"]), _ptr(o["scal"]), st)
 
             any_exact = any(g.sel is not None for g in self.groups.values())
             if self.cluster_mode:
@@ -510,12 +545,14 @@ class MergeJob:
             self._w_keep = (w_dev, order_dev)
             mark("k2")
             for g in self.groups.values():
-                t = g.t
+                t, tn = g.t, (g.tn or {})
                 _native.call("svdq_reconstruct_merge", _FLOAT_DTYPES[g.dtype], N, int(bool(cfg.svd_fp16)),
                              int(self.want_diag), int(bool(cfg.svd_center)), g.n_tiles, te, _ptr(t["tptr"]),
                              _ptr(t["numel"]), _ptr(t["tile_param"]), _ptr(t["tile_local"]), _ptr(t["pm_off"]),
                              _ptr(t["has_mask"]), _ptr(t["packed"]), _ptr(t["info"]), _ptr(t["W"]), _ptr(t["cbar"]),
-                             _ptr(t["gvec"]), _ptr(t["scal"]), _ptr(t["chat"]), _ptr(t["optr"]), _ptr(t["diag"]), st)
+                             _ptr(t["gvec"]), _ptr(t["scal"]), _ptr(t["chat"]), _ptr(t["optr"]), _ptr(t["diag"]),
+                             _ptr(tn.get("info")), _ptr(tn.get("W")), _ptr(tn.get("cbar")), _ptr(tn.get("gvec")),
+                             _ptr(tn.get("scal")), self.noise_shrink, st)
             mark("k3")
             if self.want_diag:
                 for g in self.groups.values():
@@ -534,8 +571,9 @@ class MergeJob:
         """Kernels of libsvdq.so launched by one run()."""
         ng = len(self.groups)
         any_exact = any(g.sel is not None for g in self.groups.values())
-        return ng * (4 + (1 if self.want_diag else 0) + (1 if (self.cluster_mode or any_exact) else 0)
-                     + (2 if any_exact else 0))
+        nreg = 2 if self.noise else 1
+        return ng * (3 + nreg + (1 if self.want_diag else 0) + (nreg if (self.cluster_mode or any_exact) else 0)
+                     + (2 * nreg if any_exact else 0))
 
     def event_times_ms(self) -> Dict[str, float]:
         ev = self._events
@@ -550,10 +588,10 @@ class MergeJob:
         if self._fetched is None:
             out = {}
             keys = ["info", "sv", "scal", "coef", "chigh", "codes", "qscale", "qzp", "qres", "cbar", "V", "dm"]
-            if self.want_diag:
-                keys.append("diag_out")
             for dt, g in self.groups.items():
-                out[dt] = {k: g.t[k].cpu().numpy() for k in keys}
+                out[dt] = {k: g.t[k].cpu().numpy() for k in keys + (["diag_out"] if self.want_diag else [])}
+                if g.tn is not None:      # noise region: same tables, key suffix "_n"
+                    out[dt].update({k + "_n": g.tn[k].cpu().numpy() for k in keys})
             self._fetched = out
         return self._fetched
 
@@ -610,31 +648,38 @@ class MergeJob:
         cfg, N, te = self.cfg, self.N, self.tile_elems
         st = _native.stream_ptr()
         udt = torch.float16 if cfg.svd_fp16 else torch.float32
+        # name -> (U_high, U_low, mean) per region; "noise" only with svd_include_noise
         self._basis_tensors: Dict[str, Tuple[torch.Tensor, torch.Tensor, Optional[torch.Tensor]]] = {}
+        self._noise_basis_tensors: Dict[str, Tuple[torch.Tensor, torch.Tensor, Optional[torch.Tensor]]] = {}
         with torch.cuda.device(self.device):
             for dt, g in self.groups.items():
-                t, info, dm = g.t, fetched[dt]["info"], fetched[dt]["dm"]
+                t = g.t
                 P = len(g.names)
-                uh_ptr, ul_ptr, mn_ptr = np.zeros(P, np.int64), np.zeros(P, np.int64), np.zeros(P, np.int64)
-                for p, name in enumerate(g.names):
-                    if info[p, 0] != 0:
-                        continue
-                    r, k, d = int(info[p, 2]), int(info[p, 3]), int(dm[p])
-                    uh = torch.zeros(d, k, dtype=udt, device=self.device)
-                    ul = torch.zeros(d, r - k, dtype=udt, device=self.device)
-                    mn = torch.zeros(d, 1, dtype=torch.float32, device=self.device) if cfg.svd_center else None
-                    self._basis_tensors[name] = (uh, ul, mn)
-                    uh_ptr[p], ul_ptr[p] = uh.data_ptr(), ul.data_ptr()
-                    mn_ptr[p] = mn.data_ptr() if mn is not None else 0
-                row_off = torch.zeros(max(g.n_tiles, 1), dtype=torch.int64, device=self.device)
-                uh_d, ul_d, mn_d = _dev(uh_ptr, self.device), _dev(ul_ptr, self.device), _dev(mn_ptr, self.device)
-                _native.call("svdq_basis_offsets", P, _ptr(t["count"]), _ptr(t["tile_begin"]), _ptr(row_off), st)
-                _native.call("svdq_write_basis", _FLOAT_DTYPES[g.dtype], N, int(bool(cfg.svd_fp16)),
-                             int(bool(cfg.svd_center)), g.n_tiles, te, _ptr(t["tptr"]), _ptr(t["numel"]),
-                             _ptr(t["tile_param"]), _ptr(t["tile_local"]), _ptr(t["pm_off"]), _ptr(t["has_mask"]),
-                             _ptr(t["packed"]), _ptr(t["info"]), _ptr(t["W"]), _ptr(row_off), _ptr(uh_d), _ptr(ul_d),
-                             _ptr(mn_d) if cfg.svd_center else None, st)
-                g.keep.extend([row_off, uh_d, ul_d, mn_d])
+                for reg in ((0, 1) if g.tn is not None else (0,)):
+                    sfx, o = ("", g.t) if reg == 0 else ("_n", g.tn)
+                    store = self._basis_tensors if reg == 0 else self._noise_basis_tensors
+                    info, dm = fetched[dt]["info" + sfx], fetched[dt]["dm" + sfx]
+                    uh_ptr, ul_ptr, mn_ptr = np.zeros(P, np.int64), np.zeros(P, np.int64), np.zeros(P, np.int64)
+                    for p, name in enumerate(g.names):
+                        if info[p, 0] != 0:
+                            continue
+                        r, k, d = int(info[p, 2]), int(info[p, 3]), int(dm[p])
+                        uh = torch.zeros(d, k, dtype=udt, device=self.device)
+                        ul = torch.zeros(d, r - k, dtype=udt, device=self.device)
+                        mn = torch.zeros(d, 1, dtype=torch.float32, device=self.device) if cfg.svd_center else None
+                        store[name] = (uh, ul, mn)
+                        uh_ptr[p], ul_ptr[p] = uh.data_ptr(), ul.data_ptr()
+                        mn_ptr[p] = mn.data_ptr() if mn is not None else 0
+                    row_off = torch.zeros(max(g.n_tiles, 1), dtype=torch.int64, device=self.device)
+                    uh_d, ul_d, mn_d = _dev(uh_ptr, self.device), _dev(ul_ptr, self.device), _dev(mn_ptr, self.device)
+                    _native.call("svdq_basis_offsets", P, reg, te, _ptr(t["count"]), _ptr(t["tile_begin"]),
+                                 _ptr(t["numel"]), _ptr(row_off), st)
+                    _native.call("svdq_write_basis", _FLOAT_DTYPES[g.dtype], N, int(bool(cfg.svd_fp16)),
+                                 int(bool(cfg.svd_center)), reg, g.n_tiles, te, _ptr(t["tptr"]), _ptr(t["numel"]),
+                                 _ptr(t["tile_param"]), _ptr(t["tile_local"]), _ptr(t["pm_off"]), _ptr(t["has_mask"]),
+                                 _ptr(t["packed"]), _ptr(o["info"]), _ptr(o["W"]), _ptr(row_off), _ptr(uh_d),
+                                 _ptr(ul_d), _ptr(mn_d) if cfg.svd_center else None, st)
+                    g.keep.extend([row_off, uh_d, ul_d, mn_d])
         self._bases_done = True
 
     def combined_masks(self) -> Dict[str, torch.Tensor]:
@@ -716,8 +761,9 @@ def task_vector_gram(task_vectors: Mapping[str, Mapping[str, torch.Tensor]], nam
         _native.call("svdq_tv_mask_gram", _FLOAT_DTYPES[g.dtype], N, 0, 1, g.n_tiles, job.tile_elems,
                      _ptr(t["tptr"]), None, _ptr(t["numel"]), _ptr(t["tile_param"]), _ptr(t["tile_local"]),
                      _ptr(t["pm_off"]), _ptr(t["packed"]), _ptr(t["gram"]), _ptr(t["count"]), st)
-        _native.call("svdq_gram_reduce", N, 1, len(g.names), _ptr(t["gram"]), _ptr(t["count"]),
-                     _ptr(t["tile_begin"]), _ptr(t["gram_masked"]), _ptr(t["gram_all"]), _ptr(t["dm"]), st)
+        _native.call("svdq_gram_reduce", N, 1, len(g.names), 0, _ptr(t["gram"]), _ptr(t["count"]),
+                     _ptr(t["tile_begin"]), None, None, _ptr(t["gram_masked"]), _ptr(t["gram_all"]), _ptr(t["dm"]),
+                     None, None, st)
         total += g.t["gram_all"].sum(dim=0).view(N, N).cpu().numpy()
     return total
 

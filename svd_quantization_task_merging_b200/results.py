@@ -45,75 +45,86 @@ class _LazyParamMap(Mapping):
 
 
 class LazyCompressed(_LazyParamMap):
-    """compressed[param][task] = {"masked": {"c_high_fp16", "c_low_quant"}, "unmasked": None}."""
+    """compressed[param][task] = {"masked": {"c_high_fp16", "c_low_quant"}, "unmasked": same | None}
+    (compress.py:77-108; "unmasked" only with svd_include_noise and a non-empty noise region)."""
+
+    def _region(self, f, p, t, sfx):
+        job = self._job
+        info = f["info" + sfx][p]
+        if info[0] != 0:
+            return None
+        r, k = int(info[2]), int(info[3])
+        n_low = r - k
+        c_high = torch.from_numpy(f["chigh" + sfx][p, t, :k].copy().view(np.float16))
+        payloads = []
+        if n_low > 0:
+            for s in range(job.stages):
+                payloads.append({
+                    "stage": s,
+                    "quantized": torch.from_numpy(f["codes" + sfx][p, t, s, :n_low].copy()),
+                    "scale": torch.tensor(f["qscale" + sfx][p, t, s]),
+                    "zero_point": torch.tensor(f["qzp" + sfx][p, t, s]),
+                    "residual_norm": float(f["qres" + sfx][p, t, s]),
+                })
+        return {"c_high_fp16": c_high,
+                "c_low_quant": {"payloads": payloads, "num_bits": job.bits, "num_stages": job.stages,
+                                "original_shape": torch.Size([n_low]), "original_dtype": "torch.float32"}}
 
     def _build(self, name):
         job = self._job
         dt, p = self._index[name]
         f = job._fetch()[dt]
-        info = f["info"][p]
-        r, k = int(info[2]), int(info[3])
-        n_low = r - k
         present = int(job.groups[dt].host["present"][p])
         out = OrderedDict()
         for t, task in enumerate(job.tasks):
             if not (present >> t) & 1:
                 continue
-            c_high = torch.from_numpy(f["chigh"][p, t, :k].copy().view(np.float16))
-            payloads = []
-            if n_low > 0:
-                for s in range(job.stages):
-                    payloads.append({
-                        "stage": s,
-                        "quantized": torch.from_numpy(f["codes"][p, t, s, :n_low].copy()),
-                        "scale": torch.tensor(f["qscale"][p, t, s]),
-                        "zero_point": torch.tensor(f["qzp"][p, t, s]),
-                        "residual_norm": float(f["qres"][p, t, s]),
-                    })
-            out[task] = {
-                "masked": {
-                    "c_high_fp16": c_high,
-                    "c_low_quant": {"payloads": payloads, "num_bits": job.bits, "num_stages": job.stages,
-                                    "original_shape": torch.Size([n_low]), "original_dtype": "torch.float32"},
-                },
-                "unmasked": None,
-            }
+            out[task] = {"masked": self._region(f, p, t, ""),
+                         "unmasked": self._region(f, p, t, "_n") if job.noise else None}
         return out
 
-    def raw_coefficients(self, name) -> np.ndarray:
+    def raw_coefficients(self, name, region: str = "masked") -> np.ndarray:
         """coef[t][j] before the fp16 / RTVQ round trip (first r columns valid)."""
         dt, p = self._index[name]
-        return self._job._fetch()[dt]["coef"][p]
+        return self._job._fetch()[dt]["coef" if region == "masked" else "coef_n"][p]
 
 
 class LazyBases(_LazyParamMap):
     """bases[param] = {"masked": {U_high, U_low, singular_values, k, mean, energy_retained, D, N}, "noise": None}.
     U_high / U_low / mean are written by the K5 kernel on first access."""
 
-    def meta(self, name) -> Dict:
+    def meta(self, name, region: str = "masked") -> Dict:
         job = self._job
         dt, p = self._index[name]
         f = job._fetch()[dt]
-        info = f["info"][p]
-        return {"k": int(info[3]), "r": int(info[2]), "D": int(f["dm"][p]), "N": int(info[1]),
-                "energy_retained": float(f["scal"][p, 0])}
+        sfx = "" if region == "masked" else "_n"
+        info = f["info" + sfx][p]
+        return {"k": int(info[3]), "r": int(info[2]), "D": int(f["dm" + sfx][p]), "N": int(info[1]),
+                "energy_retained": float(f["scal" + sfx][p, 0]), "solved": int(info[0]) == 0}
+
+    def _region(self, name, region):
+        job = self._job
+        dt, p = self._index[name]
+        f = job._fetch()[dt]
+        m = self.meta(name, region)
+        if not m["solved"]:
+            return None
+        sfx = "" if region == "masked" else "_n"
+        uh, ul, mn = (job._basis_tensors if region == "masked" else job._noise_basis_tensors)[name]
+        sv = torch.from_numpy(f["sv" + sfx][p, : m["r"]].copy()).to(job.device)
+        return {"U_high": uh, "U_low": ul, "singular_values": sv, "k": m["k"], "mean": mn,
+                "energy_retained": m["energy_retained"], "D": m["D"], "N": m["N"]}
 
     def _build(self, name):
         job = self._job
         job._materialize_bases()
-        dt, p = self._index[name]
-        f = job._fetch()[dt]
-        m = self.meta(name)
-        uh, ul, mn = job._basis_tensors[name]
-        sv = torch.from_numpy(f["sv"][p, : m["r"]].copy()).to(job.device)
-        return {"masked": {"U_high": uh, "U_low": ul, "singular_values": sv, "k": m["k"], "mean": mn,
-                           "energy_retained": m["energy_retained"], "D": m["D"], "N": m["N"]},
-                "noise": None}
+        return {"masked": self._region(name, "masked"),
+                "noise": self._region(name, "noise") if job.noise else None}
 
-    def right_vectors(self, name) -> np.ndarray:
+    def right_vectors(self, name, region: str = "masked") -> np.ndarray:
         """V[t][j] (fp64), the right singular vectors the coefficients were formed from."""
         dt, p = self._index[name]
-        return self._job._fetch()[dt]["V"][p]
+        return self._job._fetch()[dt]["V" if region == "masked" else "V_n"][p]
 
 
 _ERR_KEYS = ("absolute_error", "relative_error", "max_absolute_error", "mean_absolute_error", "original_norm",

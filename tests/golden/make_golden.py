@@ -114,6 +114,13 @@ PIPELINE_CASES = {
     "nomask_fp32_nocenter": dict(n=6, mask_p=None, cfg=dict(svd_fp16=False, svd_center=False,
                                                             svd_energy_threshold=0.8)),
     "iid_degenerate_nan": dict(n=8, mask_p=None, family="throughput", cfg=dict(svd_energy_threshold=0.95)),
+    # noise region (svd_include_noise): a second basis over the rows outside the combined mask
+    "majority_noise_uniform": dict(n=8, mask_p=0.5, cfg=dict(svd_mask_strategy="majority", svd_energy_threshold=0.9,
+                                                             svd_include_noise=True, svd_noise_shrink=0.5)),
+    "union_noise_cluster_3stage": dict(n=6, mask_p=0.3, cfg=dict(svd_mask_strategy="union", svd_weighting="cluster",
+                                                                 svd_cluster_k=2, svd_energy_threshold=0.85,
+                                                                 svd_rtvq_stages=3, svd_include_noise=True,
+                                                                 svd_noise_shrink=0.25)),
 }
 
 
@@ -146,7 +153,7 @@ def pipeline_case(name, spec):
         diag_json = json.load(open(os.path.join(art, "diagnostics.json")))
         cfg_json = json.load(open(os.path.join(art, "config.json")))
     # right singular vectors of the very matrices the pipeline decomposed (same function, same input)
-    vh = {}
+    vh, vh_noise = {}, {}
     combined = quiet(ref_masks.combine_masks, masks, strategy=cfg.svd_mask_strategy, verbose=False) if masks else {}
     for p, b in res["bases"].items():
         cols = []
@@ -158,6 +165,12 @@ def pipeline_case(name, spec):
         _, S, Vh = ref_basis.compute_svd(T)
         assert torch.equal(S, b["masked"]["singular_values"])
         vh[p] = Vh
+        if b.get("noise") is not None:
+            rest = [(fts[t][p] - base[p]).flatten()[~combined[p].flatten()] for t in tasks]
+            T, _ = ref_basis.stack_and_center(rest, cfg.svd_center)
+            _, S, Vh = ref_basis.compute_svd(T)
+            assert torch.equal(S, b["noise"]["singular_values"])
+            vh_noise[p] = Vh
     diag = res["diagnostics"]
     return {"tasks": tasks, "base": dict(base), "finetuned": {t: dict(fts[t]) for t in tasks},
             "masks": {t: dict(masks[t]) for t in tasks} if masks is not None else None,
@@ -165,7 +178,7 @@ def pipeline_case(name, spec):
             "merged_state_dict": res["merged_state_dict"], "bases": res["bases"], "compressed": res["compressed"],
             "diagnostics": json.loads(json.dumps(diag, default=lambda o: o.item() if hasattr(o, "item") else list(o))),
             "diagnostics_json": diag_json, "config_json": cfg_json, "files": files, "Vh": vh,
-            "combined_masks": combined}
+            "Vh_noise": vh_noise, "combined_masks": combined}
 
 
 def main():

@@ -53,7 +53,9 @@ def run_both(shapes, n_tasks: int, mask_p: Optional[float] = None, family: str =
     ref = R.run_reference_path(base, fts, masks, ref_cfg)
     ref["_base"] = base
     sign_ref = {p: b["Vh"] for p, b in ref["bases"].items()} if sign_align else None
-    res = merge_state_dicts(base, fts, masks, cfg, device, sign_ref=sign_ref, performance=perf,
+    sign_ref_noise = {p: b["Vh"] for p, b in ref["bases_noise"].items()} if sign_align else None
+    res = merge_state_dicts(base, fts, masks, cfg, device, sign_ref=sign_ref, sign_ref_noise=sign_ref_noise,
+                            performance=perf,
                             cluster_assignments=ref["cluster_assignments"] if cfg.svd_weighting == "cluster" else None)
     return ref, res, (base, fts, masks, tasks)
 
@@ -104,12 +106,19 @@ def compare_run(ref: Dict, res: Dict, check_diag: bool = True, tol_merged: Optio
     assert sorted(cm.keys()) == sorted(k for k in ref["combined_masks"] if k in job.shapes)
     for name, m in cm.items():
         assert torch.equal(m.cpu(), ref["combined_masks"][name]), f"combined mask differs: {name}"
-    for name, rb in ref["bases"].items():
+    regions = [(name, rb, ref["compressed"][name], "masked") for name, rb in ref["bases"].items()]
+    # noise region (svd_include_noise): the same checks on the basis / coefficients of the unmasked rows
+    ref_noise = ref.get("bases_noise") or {}
+    regions += [(name, rb, ref["compressed_noise"][name], "noise") for name, rb in ref_noise.items()]
+    if job.noise:
+        for name in ref["bases"]:
+            assert res["bases"].meta(name, "noise")["solved"] == (name in ref_noise), f"noise basis presence: {name}"
+    for name, rb, ref_comp, region in regions:
         report["params"] += 1
-        meta = res["bases"].meta(name)
+        meta = res["bases"].meta(name, region)
         S_ref = rb["singular_values"].numpy()
         dt, p = res["bases"]._index[name]
-        S_new = job._fetch()[dt]["sv"][p][: len(S_ref)]
+        S_new = job._fetch()[dt]["sv" if region == "masked" else "sv_n"][p][: len(S_ref)]
         assert meta["D"] == rb["D"] and meta["N"] == rb["N"]
         assert len(S_ref) == meta["r"]
         if S_ref[0] > 0:
@@ -128,13 +137,13 @@ def compare_run(ref: Dict, res: Dict, check_diag: bool = True, tol_merged: Optio
             dust.add(name)
         # coefficients / codes
         comp_new = res["compressed"][name]
-        raw = res["compressed"].raw_coefficients(name)
+        raw = res["compressed"].raw_coefficients(name, region)
         k = rb["k"]
         for ti, task in enumerate(job.tasks):
-            if task not in ref["compressed"][name] or ref["compressed"][name][task] is None:
+            if task not in ref_comp or ref_comp[task] is None:
                 continue
-            rc = ref["compressed"][name][task]
-            nc = comp_new[task]["masked"]
+            rc = ref_comp[task]
+            nc = comp_new[task]["masked" if region == "masked" else "unmasked"]
             has_raw = "c_high_fp32" in rc
             c_ref = torch.cat([rc["c_high_fp32"], rc["c_low_fp32"]]).numpy() if has_raw else np.zeros(0, np.float32)
             finite = np.isfinite(c_ref).all()
@@ -239,9 +248,16 @@ def golden_as_reference(case: Dict) -> Dict:
         bases[p] = d
     compressed = {p: {t: (a["masked"] if a.get("masked") is not None else None) for t, a in per.items()}
                   for p, per in case["compressed"].items()}
+    bases_noise, compressed_noise = {}, {}
+    for p, b in case["bases"].items():
+        if b.get("noise") is not None:
+            bases_noise[p] = dict(b["noise"], Vh=case["Vh_noise"][p])
+            compressed_noise[p] = {t: a["unmasked"] for t, a in case["compressed"][p].items()
+                                   if a.get("unmasked") is not None}
     merged = case["merged_state_dict"]
     deltas = {p: merged[p] - base[p] for p in case["bases"]}
     diag = case["diagnostics"]
     return {"merged_state_dict": merged, "merged_deltas": deltas, "bases": bases, "compressed": compressed,
+            "bases_noise": bases_noise, "compressed_noise": compressed_noise,
             "combined_masks": case["combined_masks"], "diagnostics": diag, "weights": diag["task_weights"],
             "cluster_assignments": diag.get("cluster_assignments"), "_base": base}

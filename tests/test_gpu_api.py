@@ -23,14 +23,15 @@ def _gold(name):
 
 # ---- the CUDA path against the real reference's outputs -------------------------------------------------
 @pytest.mark.parametrize("name", ["union_uniform", "majority_performance_3stage", "intersection_cluster",
-                                  "nomask_fp32_nocenter"])
+                                  "nomask_fp32_nocenter", "majority_noise_uniform", "union_noise_cluster_3stage"])
 def test_cuda_path_against_reference_golden(cuda_device, name):
     from svd_quantization_task_merging_b200.engine import merge_state_dicts
     case = _gold(name)
     cfg = SVDHybridConfig(tasks=case["tasks"], svd_max_rank=64, svd_store_artifacts=False, **case["config"])
     ref = parity.golden_as_reference(case)
     res = merge_state_dicts(case["base"], case["finetuned"], case["masks"], cfg, "cuda", sign_ref=case["Vh"],
-                            performance=case["performance"], cluster_assignments=ref["cluster_assignments"])
+                            sign_ref_noise=case.get("Vh_noise"), performance=case["performance"],
+                            cluster_assignments=ref["cluster_assignments"])
     rep = parity.compare_run(ref, res)
     print(name, rep)
     assert res["diagnostics"]["task_weights"] == ref["weights"]

@@ -198,3 +198,86 @@ def test_wide_path_cluster_and_fp32_basis(cuda_device):
                                   svd_cluster_k=2, svd_energy_threshold=0.9, svd_fp16=False)
     rep = parity.compare_run(ref, res)
     print(_summary(rep))
+
+
+# ---- noise region (svd_include_noise): second basis over the rows outside the combined mask ----------------
+@pytest.mark.parametrize("strategy,mask_p,shrink,weighting,n_tasks,fp16", [
+    ("majority", 0.5, 0.5, "uniform", 8, True), ("union", 0.3, 0.25, "performance", 8, True),
+    ("intersection", 0.9, 1.0, "cluster", 8, True), ("majority", 0.5, 0.5, "uniform", 5, False),
+    ("union", 0.2, 0.5, "uniform", 12, True)])
+def test_noise_region(cuda_device, strategy, mask_p, shrink, weighting, n_tasks, fp16):
+    """svd_include_noise (cli.py:336-351, basis.py:455-466, compress.py:91-107, merge.py:257-284): the unmasked
+    rows get their own basis, coefficients and codes, and shrink * reconstruction lands in the unmasked positions."""
+    kw = dict(svd_weighting=weighting)
+    if weighting == "cluster":
+        kw["svd_cluster_k"] = 2
+    if weighting == "performance":
+        kw["svd_weighting_temperature"] = 5.0
+    ref, res, _ = parity.run_both(parity.MEDIUM_SHAPES, n_tasks, mask_p=mask_p, svd_mask_strategy=strategy,
+                                  svd_energy_threshold=0.9, svd_include_noise=True, svd_noise_shrink=shrink,
+                                  svd_fp16=fp16, **kw)
+    assert ref["bases_noise"], "the case must exercise the noise region"
+    rep = parity.compare_run(ref, res)
+    print(_summary(rep))
+    assert rep["code_equal"] >= 0.9 * rep["code_total"]
+    # unmasked positions are no longer zero deltas
+    name = "blk.attn.weight"
+    m = ref["combined_masks"][name]
+    d = (res["merged_state_dict"][name].cpu() - ref["_base"][name])[~m]
+    assert d.abs().max() > 0
+
+
+def test_noise_region_edge_cases(cuda_device):
+    """Noise region of a parameter whose mask is all-True (no noise basis), whose mask is below
+    svd_min_mask_size (parameter skipped, no noise either), with a single unmasked element, and without a mask."""
+    tasks = synth.task_names(4)
+    shapes = {"alltrue": (64,), "small": (64,), "one_left": (64,), "nomask": (50,), "normal": (40, 40)}
+    base, fts = synth.make_checkpoints(shapes, tasks, family="parity", seed=5)
+    masks = {}
+    for i, t in enumerate(tasks):
+        g = torch.Generator().manual_seed(100 + i)
+        one = torch.ones(64, dtype=torch.bool)
+        small = torch.zeros(64, dtype=torch.bool)
+        small[:5] = True
+        left = torch.ones(64, dtype=torch.bool)
+        left[17] = False
+        masks[t] = {"alltrue": one, "small": small, "one_left": left, "normal": torch.rand(40, 40, generator=g) < 0.5}
+    ref_cfg, cfg = parity.make_cfgs(tasks, svd_mask_strategy="intersection", svd_energy_threshold=0.9,
+                                    svd_include_noise=True, svd_noise_shrink=0.5)
+    from oracle import svd_hybrid_ref as R
+    from svd_quantization_task_merging_b200.engine import merge_state_dicts
+    ref = R.run_reference_path(base, fts, masks, ref_cfg)
+    ref["_base"] = base
+    assert sorted(ref["bases_noise"]) == ["normal", "one_left"]
+    res = merge_state_dicts(base, fts, masks, cfg, "cuda", sign_ref={p: b["Vh"] for p, b in ref["bases"].items()},
+                            sign_ref_noise={p: b["Vh"] for p, b in ref["bases_noise"].items()})
+    rep = parity.compare_run(ref, res)
+    print(_summary(rep))
+    assert torch.equal(res["merged_state_dict"]["small"].cpu(), base["small"])
+    comp = res["compressed"]["alltrue"][tasks[0]]
+    assert comp["unmasked"] is None and comp["masked"] is not None
+    assert res["compressed"]["one_left"][tasks[0]]["unmasked"]["c_high_fp16"].numel() == 1
+
+
+def test_noise_region_wide_path(cuda_device):
+    shapes = {"blk.attn.weight": (300, 70), "blk.bias": (4099,), "ln.weight": (768,)}
+    ref, res, _ = parity.run_both(shapes, 20, mask_p=0.5, svd_mask_strategy="majority", svd_energy_threshold=0.9,
+                                  svd_include_noise=True, svd_noise_shrink=0.5)
+    assert ref["bases_noise"]
+    rep = parity.compare_run(ref, res)
+    print(_summary(rep))
+    assert rep["code_equal"] >= 0.9 * rep["code_total"]
+
+
+def test_noise_region_materialised_bases(cuda_device):
+    """bases[param]["noise"] in the reference layout (basis.py:455-466): U spans the same subspace."""
+    ref, res, _ = parity.run_both({"w": (120, 50), "b": (3000,)}, 8, mask_p=0.5, svd_mask_strategy="majority",
+                                  svd_energy_threshold=0.9, svd_include_noise=True)
+    for name, rb in ref["bases_noise"].items():
+        nb = res["bases"][name]["noise"]
+        assert nb["U_high"].shape == rb["U_high"].shape and nb["U_low"].shape == rb["U_low"].shape
+        assert nb["U_high"].dtype == rb["U_high"].dtype and nb["k"] == rb["k"] and nb["D"] == rb["D"]
+        assert parity.max_principal_sine(nb["U_high"].float(), rb["U_high"].float()) < 2e-3   # fp16 storage
+        assert torch.allclose(nb["mean"].cpu(), rb["mean"], atol=1e-7)
+        mb, rmb = res["bases"][name]["masked"], ref["bases"][name]
+        assert parity.max_principal_sine(mb["U_high"].float(), rmb["U_high"].float()) < 2e-3

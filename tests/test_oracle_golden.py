@@ -131,7 +131,8 @@ def _ref_cfg(case):
 
 
 @pytest.mark.parametrize("name", ["union_uniform", "majority_performance_3stage", "intersection_cluster",
-                                  "nomask_fp32_nocenter", "iid_degenerate_nan"])
+                                  "nomask_fp32_nocenter", "iid_degenerate_nan", "majority_noise_uniform",
+                                  "union_noise_cluster_3stage"])
 def test_pipeline_golden(name):
     """oracle.run_reference_path reproduces run_svd_hybrid_pipeline of the real reference.
     Same torch build -> same LAPACK -> equal to round-off; tolerances only cover a different host CPU
@@ -161,6 +162,22 @@ def test_pipeline_golden(name):
             if (sgn == 1).all():
                 for a, b in zip(gc["c_low_quant"]["payloads"], mc["c_low_quant"]["payloads"]):
                     assert (a["quantized"] == b["quantized"]).float().mean() >= 0.9
+        # noise region (svd_include_noise): same checks on the second basis / coefficient set
+        gn = gb.get("noise")
+        assert (gn is not None) == (p in res["bases_noise"]), p
+        if gn is not None:
+            mn = res["bases_noise"][p]
+            assert mn["k"] == gn["k"] and mn["D"] == gn["D"] and mn["N"] == gn["N"]
+            assert torch.allclose(mn["singular_values"], gn["singular_values"], rtol=1e-5, atol=1e-9)
+            assert mn["U_high"].shape == gn["U_high"].shape and mn["U_low"].shape == gn["U_low"].shape
+            sgn = torch.sign((mn["Vh"] * case["Vh_noise"][p]).sum(1))
+            sgn[sgn == 0] = 1
+            for t in case["tasks"]:
+                gc, mc = case["compressed"][p][t]["unmasked"], res["compressed_noise"][p][t]
+                assert torch.allclose(mc["c_high_fp32"] * sgn[:gn["k"]], gc["c_high_fp16"].float(), rtol=2e-3,
+                                      atol=1e-7)
+        else:
+            assert all(case["compressed"][p][t]["unmasked"] is None for t in case["tasks"])
     for p, gm in case["merged_state_dict"].items():
         mm = res["merged_state_dict"][p]
         assert mm.dtype == gm.dtype and mm.shape == gm.shape
@@ -185,11 +202,13 @@ def test_pipeline_golden(name):
         assert gd["summary"][key] == pytest.approx(md["summary"][key], rel=1e-9, nan_ok=True)
 
 
-def test_pipeline_golden_exact_when_same_host_numerics():
+@pytest.mark.parametrize("name", ["union_uniform", "majority_noise_uniform", "union_noise_cluster_3stage"])
+def test_pipeline_golden_exact_when_same_host_numerics(name):
     """On a host whose LAPACK takes the same code path, the oracle is bit-identical to the reference
     (same torch ops in the same order); on any other host the check above applies."""
-    case = load("pipeline_golden.pt")["union_uniform"]
-    res = R.run_reference_path(case["base"], case["finetuned"], case["masks"], _ref_cfg(case))
+    case = load("pipeline_golden.pt")[name]
+    res = R.run_reference_path(case["base"], case["finetuned"], case["masks"], _ref_cfg(case),
+                               assignments=case["diagnostics"].get("cluster_assignments"))
     p = next(iter(case["bases"]))
     if not torch.equal(res["bases"][p]["singular_values"], case["bases"][p]["masked"]["singular_values"]):
         pytest.skip("different LAPACK code path on this host; tolerance-based golden test covers it")
@@ -202,6 +221,12 @@ def test_pipeline_golden_exact_when_same_host_numerics():
             assert torch.equal(a["c_high_fp16"], b["c_high_fp16"])
             for x, y in zip(a["c_low_quant"]["payloads"], b["c_low_quant"]["payloads"]):
                 assert torch.equal(x["quantized"], y["quantized"]) and torch.equal(x["scale"], y["scale"])
+            a = case["compressed"][p][t]["unmasked"]
+            if a is not None:
+                b = res["compressed_noise"][p][t]
+                assert torch.equal(a["c_high_fp16"], b["c_high_fp16"])
+                for x, y in zip(a["c_low_quant"]["payloads"], b["c_low_quant"]["payloads"]):
+                    assert torch.equal(x["quantized"], y["quantized"]) and torch.equal(x["scale"], y["scale"])
     gd, md = case["diagnostics"], res["diagnostics"]
     for p, gp in gd["per_parameter"].items():
         for t, er in gp["reconstruction_errors"].items():
