@@ -3,7 +3,8 @@
 //
 //   k5_tile_offsets   exclusive scan of K1's per-tile masked counts (row offset of every tile)
 //   k5_write_basis    re-reads the inputs and writes U_high [Dm x k], U_low [Dm x (r-k)] (fp16 or
-//                     fp32) and mean [Dm x 1] COMPACTED to the masked rows, the layout of
+//                     fp32) and mean [Dm x 1] COMPACTED to the masked rows (staged through shared
+//                     memory so the stores are 16-byte coalesced), the layout of
 //                     construct_basis (src/svd_hybrid/basis.py:363-364,398-407) after
 //                     apply_mask_to_tensor (src/svd_hybrid/mask_loader.py:675-679)
 //   k_combine_masks   union / intersection / majority over torch.bool tensors
@@ -37,9 +38,35 @@ __global__ void __launch_bounds__(32) k5_tile_offsets(const uint32_t* count, con
 
 #endif  // SVDQ_DTYPE == 0
 
-template <typename T, int NT>
+// One CTA per tile.  Per 1024-element step the CTA scans the mask bits (row index of every kept element),
+// rebuilds the basis rows of its kept elements into a shared-memory image of the step's slice of U_high /
+// U_low / mean -- the kept rows of a step are consecutive rows of the artifacts -- and then copies the three
+// slices out with 16-byte coalesced stores (the smem image starts at the same offset modulo 16 bytes as the
+// global slice, so head / tail handling is a few scalar elements).
+template <typename OUT> struct OutCvt;
+template <> struct OutCvt<__half> { static __device__ __forceinline__ __half cvt(float v) { return __float2half_rn(v); } };
+template <> struct OutCvt<float> { static __device__ __forceinline__ float cvt(float v) { return v; } };
+
+template <typename OUT>
+__device__ __forceinline__ void k5_copy_out(OUT* __restrict__ dst, const OUT* __restrict__ src, int64_t g0, int n,
+                                            int tid) {
+    // dst + g0 .. + n  <-  src[0 .. n);  src is placed so that (src address) == (dst + g0 address) mod 16
+    constexpr int V = 16 / (int)sizeof(OUT);
+    const int head = min(n, (int)((V - (g0 % V)) % V));
+    if (tid < head) dst[g0 + tid] = src[tid];
+    const int nvec = (n - head) / V;
+    const uint4* s4 = reinterpret_cast<const uint4*>(src + head);
+    uint4* d4 = reinterpret_cast<uint4*>(dst + g0 + head);
+    for (int i = tid; i < nvec; i += kBlock) d4[i] = s4[i];
+    const int done = head + nvec * V;
+    if (tid < n - done) dst[g0 + done + tid] = src[done + tid];
+}
+
+template <typename T, int NT, typename OUT>
 __global__ void __launch_bounds__(kBlock) k5_write_basis(const K5Args a) {
     constexpr int NTP = (NT + 3) & ~3;
+    constexpr int V = 16 / (int)sizeof(OUT);
+    extern __shared__ __align__(16) unsigned char dyn[];
     __shared__ __align__(16) float sWT[NT][NTP];
     __shared__ const void* s_ptr[NT + 1];
     __shared__ uint32_t s_warp[kBlock / 32];
@@ -59,16 +86,28 @@ __global__ void __launch_bounds__(kBlock) k5_write_basis(const K5Args a) {
         sWT[j][t] = (t < NT) ? a.W[(int64_t)p * NT * NT + t * NT + j] : 0.0f;
     }
     __syncthreads();
+    uint32_t present_bits = 0;
+#pragma unroll
+    for (int t = 0; t < NT; ++t) present_bits |= (s_ptr[t + 1] != nullptr ? 1u : 0u) << t;
+    __syncthreads();
+    if (tid >= 1 && tid <= NT && s_ptr[tid] == nullptr) s_ptr[tid] = s_ptr[0];      // delta == 0, dropped below
+    __syncthreads();
     const uint32_t* packed = has_mask ? a.packed + a.pmask_off[p] : nullptr;
     const float n_f = (float)(n_active > 0 ? n_active : 1);
     float* mean_out = a.mean ? a.mean[p] : nullptr;
+    OUT* uh_out = reinterpret_cast<OUT*>(a.u_high[p]);
+    OUT* ul_out = reinterpret_cast<OUT*>(a.u_low[p]);
     int64_t row_base = a.tile_row_off[tile];
+    // smem image: [U_high slice | U_low slice | mean slice], each re-based per step (see k5_copy_out)
+    OUT* s_u = reinterpret_cast<OUT*>(dyn);
+    float* s_mean = reinterpret_cast<float*>(dyn + ((size_t)(kStep * NT + 3 * V) * sizeof(OUT) + 15) / 16 * 16);
 
     for (int64_t e0 = start; e0 < stop; e0 += kStep) {
         const int64_t e = e0 + (int64_t)tid * kVec;
         uint32_t bits = 0;
+        const bool full = e + kVec <= numel;
         if (e < stop) {
-            const uint32_t valid = (e + kVec <= numel) ? 0xFu : ((1u << (int)(numel - e)) - 1u);
+            const uint32_t valid = full ? 0xFu : ((1u << (int)(numel - e)) - 1u);
             if (has_mask) {
                 const uint32_t w = __ldg(packed + (e >> 5));
                 bits = ((a.invert ? ~w : w) >> (int)(e & 31)) & valid;
@@ -91,44 +130,61 @@ __global__ void __launch_bounds__(kBlock) k5_write_basis(const K5Args a) {
             if (w < warp) warp_off += v;
             step_total += v;
         }
-        __syncthreads();
-        int64_t row = row_base + warp_off + (incl - mine);
-        row_base += step_total;
-        if (bits == 0) continue;
+        int lr = (int)(warp_off + (incl - mine));                 // first row of this thread inside the step
+        const int64_t gh = row_base * k, gl = row_base * nlow, gm = row_base;
+        OUT* s_h = s_u + (gh % V);
+        OUT* s_l = s_u + ((gh % V) + (int64_t)step_total * k + V - 1) / V * V + (gl % V);
+        float* s_m = s_mean + (gm % 4);
 
-        float b[kVec], x[NT][kVec], mean[kVec];
+        if (bits != 0) {
+            float b[kVec], x[NT][kVec], mean[kVec];
+            if (full) {
+                Elem<T>::load4(s_ptr[0], e, b);
 #pragma unroll
-        for (int c = 0; c < kVec; ++c) {
-            b[c] = (e + c < numel) ? Elem<T>::load1(s_ptr[0], e + c) : 0.0f;
-            mean[c] = 0.0f;
-        }
+                for (int t = 0; t < NT; ++t) Elem<T>::load4(s_ptr[t + 1], e, x[t]);
+            } else {
 #pragma unroll
-        for (int t = 0; t < NT; ++t) {
-            const void* fp = s_ptr[t + 1];
-#pragma unroll
-            for (int c = 0; c < kVec; ++c) {
-                x[t][c] = (fp != nullptr && e + c < numel) ? Elem<T>::sub(Elem<T>::load1(fp, e + c), b[c]) : 0.0f;
-                mean[c] += x[t][c];
-            }
-        }
-#pragma unroll
-        for (int c = 0; c < kVec; ++c) mean[c] = a.center ? __fdiv_rn(mean[c], n_f) : 0.0f;
-#pragma unroll
-        for (int c = 0; c < kVec; ++c) {
-            if (!((bits >> c) & 1u)) continue;
-            if (mean_out) mean_out[row] = mean[c];
-            for (int j = 0; j < r; ++j) {
-                float u = 0.0f;
+                for (int c = 0; c < kVec; ++c) b[c] = (e + c < numel) ? Elem<T>::load1(s_ptr[0], e + c) : 0.0f;
 #pragma unroll
                 for (int t = 0; t < NT; ++t)
-                    u = fmaf((s_ptr[t + 1] != nullptr) ? x[t][c] - mean[c] : 0.0f, sWT[j][t], u);
-                void* dst = j < k ? a.u_high[p] : a.u_low[p];
-                const int64_t off = j < k ? row * k + j : row * nlow + (j - k);
-                if (a.fp16_basis) reinterpret_cast<__half*>(dst)[off] = __float2half_rn(u);
-                else reinterpret_cast<float*>(dst)[off] = u;
+#pragma unroll
+                    for (int c = 0; c < kVec; ++c)
+                        x[t][c] = (e + c < numel) ? Elem<T>::load1(s_ptr[t + 1], e + c) : 0.0f;
             }
-            ++row;
+#pragma unroll
+            for (int c = 0; c < kVec; ++c) mean[c] = 0.0f;
+#pragma unroll
+            for (int t = 0; t < NT; ++t)
+#pragma unroll
+                for (int c = 0; c < kVec; ++c) { x[t][c] = Elem<T>::sub(x[t][c], b[c]); mean[c] += x[t][c]; }
+#pragma unroll
+            for (int c = 0; c < kVec; ++c) mean[c] = a.center ? __fdiv_rn(mean[c], n_f) : 0.0f;
+#pragma unroll
+            for (int t = 0; t < NT; ++t)
+#pragma unroll
+                for (int c = 0; c < kVec; ++c) x[t][c] = ((present_bits >> t) & 1u) ? x[t][c] - mean[c] : 0.0f;
+#pragma unroll
+            for (int c = 0; c < kVec; ++c) {
+                if (!((bits >> c) & 1u)) continue;
+                if (mean_out) s_m[lr] = mean[c];
+#pragma unroll
+                for (int j = 0; j < NT; ++j) {
+                    if (j >= r) break;
+                    float u = 0.0f;
+#pragma unroll
+                    for (int t = 0; t < NT; ++t) u = fmaf(x[t][c], sWT[j][t], u);
+                    if (j < k) s_h[lr * k + j] = OutCvt<OUT>::cvt(u);
+                    else s_l[lr * nlow + (j - k)] = OutCvt<OUT>::cvt(u);
+                }
+                ++lr;
+            }
         }
+        __syncthreads();
+        k5_copy_out<OUT>(uh_out, s_h, gh, (int)step_total * k, tid);
+        k5_copy_out<OUT>(ul_out, s_l, gl, (int)step_total * nlow, tid);
+        if (mean_out) k5_copy_out<float>(mean_out, s_m, gm, (int)step_total, tid);
+        row_base += step_total;
+        __syncthreads();
     }
 }
 
@@ -154,18 +210,28 @@ __global__ void __launch_bounds__(kBlock) k_unpack_mask(const uint32_t* packed, 
 
 #endif  // SVDQ_DTYPE == 0
 
+template <typename T, int NT, typename OUT>
+static cudaError_t k5_go(const K5Args& a, int n_tiles, cudaStream_t st) {
+    constexpr int V = 16 / (int)sizeof(OUT);
+    const size_t dsm = ((size_t)(kStep * NT + 3 * V) * sizeof(OUT) + 15) / 16 * 16 + (kStep + 4) * sizeof(float);
+    cudaError_t e = cudaFuncSetAttribute(k5_write_basis<T, NT, OUT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)dsm);
+    if (e != cudaSuccess) return e;
+    k5_write_basis<T, NT, OUT><<<n_tiles, kBlock, dsm, st>>>(a);
+    return cudaGetLastError();
+}
+
 template <>
 cudaError_t k5_launch_dtype<SVDQ_DTYPE>(int nt, const K5Args& a, int n_tiles, cudaStream_t st) {
     using T = DTypeOf<SVDQ_DTYPE>::type;
     if (n_tiles <= 0) return cudaSuccess;
     switch (nt) {
-#define SVDQ_CASE(N) case N: k5_write_basis<T, N><<<n_tiles, kBlock, 0, st>>>(a); break;
+#define SVDQ_CASE(N) case N: return a.fp16_basis ? k5_go<T, N, __half>(a, n_tiles, st) : k5_go<T, N, float>(a, n_tiles, st);
         SVDQ_CASE(1) SVDQ_CASE(2) SVDQ_CASE(3) SVDQ_CASE(4) SVDQ_CASE(5) SVDQ_CASE(6) SVDQ_CASE(7) SVDQ_CASE(8)
         SVDQ_CASE(9) SVDQ_CASE(10) SVDQ_CASE(11) SVDQ_CASE(12) SVDQ_CASE(13) SVDQ_CASE(14) SVDQ_CASE(15) SVDQ_CASE(16)
 #undef SVDQ_CASE
         default: return cudaErrorInvalidValue;
     }
-    return cudaGetLastError();
 }
 
 #if SVDQ_DTYPE == 0

@@ -648,39 +648,57 @@ class MergeJob:
         cfg, N, te = self.cfg, self.N, self.tile_elems
         st = _native.stream_ptr()
         udt = torch.float16 if cfg.svd_fp16 else torch.float32
-        # name -> (U_high, U_low, mean) per region; "noise" only with svd_include_noise
-        self._basis_tensors: Dict[str, Tuple[torch.Tensor, torch.Tensor, Optional[torch.Tensor]]] = {}
-        self._noise_basis_tensors: Dict[str, Tuple[torch.Tensor, torch.Tensor, Optional[torch.Tensor]]] = {}
+        esz = 2 if cfg.svd_fp16 else 4
+        # (dtype, region) -> flat U_high / U_low / mean buffers + per-parameter element offsets; the per-parameter
+        # tensors handed out by basis_tensors() are views into them (one allocation instead of 3 P small ones)
+        self._basis_store: Dict[Tuple[torch.dtype, str], Dict] = {}
         with torch.cuda.device(self.device):
             for dt, g in self.groups.items():
                 t = g.t
                 P = len(g.names)
                 for reg in ((0, 1) if g.tn is not None else (0,)):
                     sfx, o = ("", g.t) if reg == 0 else ("_n", g.tn)
-                    store = self._basis_tensors if reg == 0 else self._noise_basis_tensors
-                    info, dm = fetched[dt]["info" + sfx], fetched[dt]["dm" + sfx]
-                    uh_ptr, ul_ptr, mn_ptr = np.zeros(P, np.int64), np.zeros(P, np.int64), np.zeros(P, np.int64)
-                    for p, name in enumerate(g.names):
-                        if info[p, 0] != 0:
-                            continue
-                        r, k, d = int(info[p, 2]), int(info[p, 3]), int(dm[p])
-                        uh = torch.zeros(d, k, dtype=udt, device=self.device)
-                        ul = torch.zeros(d, r - k, dtype=udt, device=self.device)
-                        mn = torch.zeros(d, 1, dtype=torch.float32, device=self.device) if cfg.svd_center else None
-                        store[name] = (uh, ul, mn)
-                        uh_ptr[p], ul_ptr[p] = uh.data_ptr(), ul.data_ptr()
-                        mn_ptr[p] = mn.data_ptr() if mn is not None else 0
-                    row_off = torch.zeros(max(g.n_tiles, 1), dtype=torch.int64, device=self.device)
-                    uh_d, ul_d, mn_d = _dev(uh_ptr, self.device), _dev(ul_ptr, self.device), _dev(mn_ptr, self.device)
+                    info, dm = fetched[dt]["info" + sfx], fetched[dt]["dm" + sfx].astype(np.int64)
+                    ok = info[:, 0] == 0
+                    r, k = info[:, 2].astype(np.int64), info[:, 3].astype(np.int64)
+                    al = 16 // esz                                    # slices start 16-byte aligned
+                    nh = np.where(ok, (dm * k + al - 1) // al * al, 0)
+                    nl = np.where(ok, (dm * (r - k) + al - 1) // al * al, 0)
+                    nm = np.where(ok, (dm + 3) // 4 * 4, 0)
+                    oh, ol, om = (np.concatenate([[0], np.cumsum(x)]).astype(np.int64) for x in (nh, nl, nm))
+                    uh = torch.empty(max(int(oh[-1]), 1), dtype=udt, device=self.device)
+                    ul = torch.empty(max(int(ol[-1]), 1), dtype=udt, device=self.device)
+                    mn = torch.empty(max(int(om[-1]), 1), dtype=torch.float32, device=self.device) \
+                        if cfg.svd_center else None
+                    uh_d = _dev(np.where(ok, uh.data_ptr() + oh[:-1] * esz, 0).astype(np.int64), self.device)
+                    ul_d = _dev(np.where(ok, ul.data_ptr() + ol[:-1] * esz, 0).astype(np.int64), self.device)
+                    mn_d = _dev(np.where(ok, mn.data_ptr() + om[:-1] * 4, 0).astype(np.int64), self.device) \
+                        if mn is not None else None
+                    row_off = torch.empty(max(g.n_tiles, 1), dtype=torch.int64, device=self.device)
                     _native.call("svdq_basis_offsets", P, reg, te, _ptr(t["count"]), _ptr(t["tile_begin"]),
                                  _ptr(t["numel"]), _ptr(row_off), st)
                     _native.call("svdq_write_basis", _FLOAT_DTYPES[g.dtype], N, int(bool(cfg.svd_fp16)),
                                  int(bool(cfg.svd_center)), reg, g.n_tiles, te, _ptr(t["tptr"]), _ptr(t["numel"]),
                                  _ptr(t["tile_param"]), _ptr(t["tile_local"]), _ptr(t["pm_off"]), _ptr(t["has_mask"]),
                                  _ptr(t["packed"]), _ptr(o["info"]), _ptr(o["W"]), _ptr(row_off), _ptr(uh_d),
-                                 _ptr(ul_d), _ptr(mn_d) if cfg.svd_center else None, st)
+                                 _ptr(ul_d), _ptr(mn_d), st)
                     g.keep.extend([row_off, uh_d, ul_d, mn_d])
+                    self._basis_store[(dt, "masked" if reg == 0 else "noise")] = dict(
+                        uh=uh, ul=ul, mn=mn, oh=oh, ol=ol, om=om, dm=dm, r=r, k=k, ok=ok)
         self._bases_done = True
+
+    def basis_tensors(self, dt: torch.dtype, p: int, region: str = "masked"):
+        """(U_high [D x k], U_low [D x (r-k)], mean [D x 1] | None) of parameter p of dtype group dt."""
+        self._materialize_bases()
+        st = self._basis_store[(dt, region)]
+        if not st["ok"][p]:
+            return None
+        d, r, k = int(st["dm"][p]), int(st["r"][p]), int(st["k"][p])
+        oh, ol, om = int(st["oh"][p]), int(st["ol"][p]), int(st["om"][p])
+        uh = st["uh"][oh: oh + d * k].view(d, k)
+        ul = st["ul"][ol: ol + d * (r - k)].view(d, r - k)
+        mn = st["mn"][om: om + d].view(d, 1) if st["mn"] is not None else None
+        return uh, ul, mn
 
     def combined_masks(self) -> Dict[str, torch.Tensor]:
         """Combined tall masks as torch.bool tensors (what combine_masks returns)."""

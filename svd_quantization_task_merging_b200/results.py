@@ -110,7 +110,7 @@ class LazyBases(_LazyParamMap):
         if not m["solved"]:
             return None
         sfx = "" if region == "masked" else "_n"
-        uh, ul, mn = (job._basis_tensors if region == "masked" else job._noise_basis_tensors)[name]
+        uh, ul, mn = job.basis_tensors(dt, p, region)
         sv = torch.from_numpy(f["sv" + sfx][p, : m["r"]].copy()).to(job.device)
         return {"U_high": uh, "U_low": ul, "singular_values": sv, "k": m["k"], "mean": mn,
                 "energy_retained": m["energy_retained"], "D": m["D"], "N": m["N"]}

@@ -193,7 +193,7 @@ def _write_case(tmp, case):
     return ck, md
 
 
-@pytest.mark.parametrize("name", ["union_uniform", "intersection_cluster"])
+@pytest.mark.parametrize("name", ["union_uniform", "intersection_cluster", "majority_noise_uniform"])
 def test_pipeline_on_disk_writes_reference_layout(cuda_device, tmp_path, name, monkeypatch):
     from src.svd_hybrid.cli import run_svd_hybrid_pipeline
     monkeypatch.setenv("SVDQ_CLUSTER_BACKEND", "sklearn")      # label-exact parity with the reference's k-means
@@ -220,7 +220,21 @@ def test_pipeline_on_disk_writes_reference_layout(cuda_device, tmp_path, name, m
         for key in ("U_high", "U_low", "singular_values", "mean"):
             assert nb[key].shape == g[key].shape and nb[key].dtype == g[key].dtype and nb[key].device.type == "cpu"
         assert nb["k"] == g["k"] and nb["D"] == g["D"] and nb["N"] == g["N"]
+        # noise region artifacts (storage.py:92-104,166-170): present exactly where the reference wrote them
+        assert ("noise" in art["bases"][p]) == (gb.get("noise") is not None), p
+        if gb.get("noise") is not None:
+            nn, gn = art["bases"][p]["noise"], gb["noise"]
+            assert list(nn.keys()) == list(gn.keys())
+            for key in ("U_high", "U_low", "singular_values", "mean"):
+                assert nn[key].shape == gn[key].shape and nn[key].dtype == gn[key].dtype
+            assert nn["k"] == gn["k"] and nn["D"] == gn["D"] and nn["N"] == gn["N"]
         for t in case["tasks"]:
+            gu = case["compressed"][p][t].get("unmasked")
+            assert ("unmasked" in art["compressed"][p][t]) == (gu is not None)
+            if gu is not None:
+                au = art["compressed"][p][t]["unmasked"]
+                assert au["c_high_fp16"].shape == gu["c_high_fp16"].shape
+                assert au["c_low_quant"]["original_shape"] == gu["c_low_quant"]["original_shape"]
             a, b = art["compressed"][p][t]["masked"], case["compressed"][p][t]["masked"]
             assert a["c_high_fp16"].dtype == torch.float16 and a["c_high_fp16"].shape == b["c_high_fp16"].shape
             qa, qb = a["c_low_quant"], b["c_low_quant"]
