@@ -170,7 +170,8 @@ int svdq_param_requantize(int n_tasks, int64_t n_params, int rtvq_bits, int rtvq
  *           compute_reconstruction_error / compute_parameter_diagnostics
  *           (src/svd_hybrid/diagnostics.py:72-231).
  * out: [P] table of fp32 output tensors (merged = base + delta; parameters without a basis get
- *      a copy of base).  diag_partials: [n_tiles][5][NT] fp32 (may be NULL when diag == 0).
+ *      a copy of base).  diag_partials: [n_tiles][4][NT] fp32 (sum e^2, sum |e|, sum rec^2, max |e| per task;
+ *      may be NULL when diag == 0).
  * noise_*: outputs of a second svdq_param_solve over gram_noise / dm_noise (svd_include_noise): the unmasked
  *      positions then receive noise_shrink * (U_noise cbar_noise + mean) instead of 0 (merge.py:257-284,
  *      mask_loader.py:757-760).  All NULL = no noise region.  The diagnostics stay those of the masked region.
@@ -186,9 +187,10 @@ int svdq_reconstruct_merge(int dtype, int n_tasks, int fp16_basis, int diag, int
 
 /* diagnostics finalisation: out [P][NT][6] fp64 = absolute_error, relative_error,
  * max_absolute_error, mean_absolute_error, original_norm, reconstructed_norm
- * (src/svd_hybrid/diagnostics.py:110-117) */
+ * (src/svd_hybrid/diagnostics.py:110-117).  original_norm^2 is read off the diagonal of gram_masked
+ * (the masked task vector's squared norm, already reduced in fp64 by svdq_gram_reduce). */
 int svdq_diag_finalize(int n_tasks, int64_t n_params, const float* diag_partials, const int64_t* tile_begin,
-                       const int64_t* dm, const int32_t* info, double* out, void* stream);
+                       const int64_t* dm, const int32_t* info, const double* gram_masked, double* out, void* stream);
 
 /*
  * K5 — materialise the bases in the reference artifact layout

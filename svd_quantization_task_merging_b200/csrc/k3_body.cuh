@@ -8,7 +8,7 @@
 
 namespace svdq {
 
-constexpr int kDiagRows = 5;      // sum e^2, sum |e|, sum rec^2, sum orig^2, max |e|
+constexpr int kDiagRows = 4;      // sum e^2, sum |e|, sum rec^2, max |e|  (sum orig^2 = diagonal of K1's masked Gram)
 
 // Second coefficient set of a parameter: the basis of the elements OUTSIDE the combined mask (svd_include_noise,
 // src/svd_hybrid/basis.py:455-466); its reconstruction is scaled by svd_noise_shrink (merge.py:257-284) and
@@ -190,19 +190,20 @@ __device__ __forceinline__ void k3_step(const float (&b)[kVec], float (&x)[NT][k
         res[c] = b[c] + (m ? val : other);
     }
     if (DIAG) {
+        // elements that count: inside the combined mask and inside the tensor (one mask word for all tasks)
+        const int64_t left = numel - e;
+        const uint32_t mb = bits & (left >= (int64_t)kVec ? 0xFu : ((1u << (int)(left > 0 ? left : 0)) - 1u));
 #pragma unroll
         for (int t = 0; t < NT; ++t) {
             if (!((present_bits >> t) & 1u)) continue;
 #pragma unroll
             for (int c = 0; c < kVec; ++c) {
-                const bool m = ((bits >> c) & 1u) && (e + c < numel);
-                if (m) {
+                if ((mb >> c) & 1u) {
                     const float er = orig[t][c] - rec[t][c];
                     dacc[0 * NT + t] = fmaf(er, er, dacc[0 * NT + t]);
                     dacc[1 * NT + t] += fabsf(er);
                     dacc[2 * NT + t] = fmaf(rec[t][c], rec[t][c], dacc[2 * NT + t]);
-                    dacc[3 * NT + t] = fmaf(orig[t][c], orig[t][c], dacc[3 * NT + t]);
-                    dacc[4 * NT + t] = fmaxf(dacc[4 * NT + t], fabsf(er));
+                    dacc[3 * NT + t] = fmaxf(dacc[3 * NT + t], fabsf(er));
                 }
             }
         }

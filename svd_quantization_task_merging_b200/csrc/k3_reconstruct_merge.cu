@@ -147,7 +147,7 @@ __global__ void __launch_bounds__(kBlock, (NT <= 8 && !DIAG) ? 2 : 1) k3_reconst
             for (int q = 0; q < kRows / (kBlock / 32); ++q) {
                 const int rr = warp * (kRows / (kBlock / 32)) + q;
                 if (r0 + rr < NR) {
-                    const bool is_max = (r0 + rr) >= 4 * NT;
+                    const bool is_max = (r0 + rr) >= 3 * NT;
                     float s = 0.0f;
 #pragma unroll
                     for (int c = 0; c < kBlock / 32; ++c) {
@@ -174,14 +174,15 @@ __global__ void __launch_bounds__(32) k3_diag_finalize(const K3DiagArgs a) {
     const int p = blockIdx.x, t = threadIdx.x;
     if (t >= a.nt) return;
     const int NT = a.nt, NR = kDiagRows * NT;
-    double se = 0.0, sa = 0.0, sr = 0.0, so = 0.0;
+    double se = 0.0, sa = 0.0, sr = 0.0;
     float mx = 0.0f;
     for (int64_t tl = a.tile_begin[p]; tl < a.tile_begin[p + 1]; ++tl) {
         const float* d = a.diag + tl * NR;
-        se += (double)d[0 * NT + t]; sa += (double)d[1 * NT + t];
-        sr += (double)d[2 * NT + t]; so += (double)d[3 * NT + t];
-        mx = fmaxf(mx, d[4 * NT + t]);
+        se += (double)d[0 * NT + t]; sa += (double)d[1 * NT + t]; sr += (double)d[2 * NT + t];
+        mx = fmaxf(mx, d[3 * NT + t]);
     }
+    // ||orig_t||^2 over the masked rows is the diagonal of the (uncentred) masked Gram K1 already reduced in fp64
+    const double so = a.gram_masked[((int64_t)p * NT + t) * NT + t];
     double* o = a.out + ((int64_t)p * NT + t) * 6;
     const bool solved = a.info[(int64_t)p * 8] == kSolved;
     const double dm = (double)a.dm[p];

@@ -253,9 +253,8 @@ __global__ void __launch_bounds__(kBlock) k6_reconstruct_merge(const K3Args a, c
                         float* d1 = dyn + (size_t)(1 * N + t) * kBlock + tid;
                         float* d2 = dyn + (size_t)(2 * N + t) * kBlock + tid;
                         float* d3 = dyn + (size_t)(3 * N + t) * kBlock + tid;
-                        float* d4 = dyn + (size_t)(4 * N + t) * kBlock + tid;
                         *d0 = fmaf(er, er, *d0); *d1 += fabsf(er); *d2 = fmaf(rec[c], rec[c], *d2);
-                        *d3 = fmaf(x[c], x[c], *d3); *d4 = fmaxf(*d4, fabsf(er));
+                        *d3 = fmaxf(*d3, fabsf(er));
                     }
                 }
             }
@@ -269,7 +268,7 @@ __global__ void __launch_bounds__(kBlock) k6_reconstruct_merge(const K3Args a, c
         const int NR = kDiagRows * N;
         float* dout = a.diag + (int64_t)tile * NR;
         for (int row = warp; row < NR; row += kBlock / 32) {       // one warp reduces one row, fixed order
-            const bool is_max = row >= 4 * N;
+            const bool is_max = row >= 3 * N;
             float s = 0.0f;
             for (int c = 0; c < kBlock / 32; ++c) {
                 const float v = dyn[(size_t)row * kBlock + lane + 32 * c];

@@ -306,12 +306,13 @@ int svdq_reconstruct_merge(int dtype, int n_tasks, int fp16_basis, int diag, int
 }
 
 int svdq_diag_finalize(int n_tasks, int64_t n_params, const float* diag_partials, const int64_t* tile_begin,
-                       const int64_t* dm, const int32_t* info, double* out, void* stream) {
+                       const int64_t* dm, const int32_t* info, const double* gram_masked, double* out, void* stream) {
     REQUIRE(n_tasks >= 1 && n_tasks <= SVDQ_MAX_TASKS, "n_tasks must be in [1, 32]");
     REQUIRE(n_params >= 0 && n_params < (1ll << 31), "n_params");
     if (n_params == 0) return 0;
-    REQUIRE(diag_partials && tile_begin && dm && info && out, "null pointer");
+    REQUIRE(diag_partials && tile_begin && dm && info && gram_masked && out, "null pointer");
     svdq::K3DiagArgs a;
+    a.gram_masked = gram_masked;
     a.diag = diag_partials; a.tile_begin = tile_begin; a.dm = dm; a.info = info; a.out = out; a.nt = n_tasks;
     return finish(__func__, svdq::k3_diag_launch(a, (int)n_params, (cudaStream_t)stream));
 }

@@ -75,7 +75,7 @@ struct K3Args {
     const float* scal;            // [P][4]
     const float* chat;            // [P][NT*NT]  chat[t][j] (DIAG)
     float* const* out;            // [P] merged fp32 tensors
-    float* diag;                  // [n_tiles][5][NT] partials (DIAG)
+    float* diag;                  // [n_tiles][4][NT] partials (DIAG): sum e^2, sum |e|, sum rec^2, max |e|
     int tile_elems;
     int center;
     // noise region (svd_include_noise): second solve over the rows outside the mask; all null = off
@@ -88,7 +88,8 @@ struct K3Args {
 };
 
 struct K3DiagArgs {
-    const float* diag;            // [n_tiles][5][NT]
+    const float* diag;            // [n_tiles][4][NT]
+    const double* gram_masked;    // [P][NT*NT]: its diagonal = sum orig^2 over the masked rows
     const int64_t* tile_begin;    // [P+1]
     const int64_t* dm;            // [P]
     const int32_t* info;          // [P][8]

@@ -313,7 +313,7 @@ class MergeJob:
             gram_masked=z(P, N * N, dtype=f64), gram_all=z(P, N * N, dtype=f64) if self.cluster_mode else None,
             dm=z(P, dtype=i64), **solve_outputs(),
             out=torch.empty(out_total, dtype=f32, device=dev),
-            diag=z(max(n_tiles, 1) * 5 * N) if self.want_diag else None,
+            diag=z(max(n_tiles, 1) * 4 * N) if self.want_diag else None,
             diag_out=z(P, N, 6, dtype=f64) if self.want_diag else None,
         )
         # noise region: its own Gram, row count and solve outputs (same layout as the masked region's)
@@ -558,7 +558,7 @@ class MergeJob:
                 for g in self.groups.values():
                     t = g.t
                     _native.call("svdq_diag_finalize", N, len(g.names), _ptr(t["diag"]), _ptr(t["tile_begin"]),
-                                 _ptr(t["dm"]), _ptr(t["info"]), _ptr(t["diag_out"]), st)
+                                 _ptr(t["dm"]), _ptr(t["info"]), _ptr(t["gram_masked"]), _ptr(t["diag_out"]), st)
             mark("end")
         self._events = ev
         self._ran = True
