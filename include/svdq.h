@@ -141,7 +141,7 @@ int svdq_param_average(int n_tasks, int64_t n_params, const uint32_t* present, c
                        float* gvec, float* scal, void* stream);
 
 /*
- * K7 — exact projection on the STORED basis for selected (small) parameters, n_tasks <= 8.
+ * K7 — exact projection on the STORED basis for selected (small) parameters, n_tasks <= 32.
  * Replaces project_to_basis / compress_single_task (src/svd_hybrid/compress.py:6-56) literally: the basis row is
  * rebuilt, rounded to fp16 when fp16_basis (the cast of src/svd_hybrid/cli.py:355-361 precedes the projection in
  * the reference) and contracted with (tau_t - mean) over the masked rows.  sel_tile_param / sel_tile_local list

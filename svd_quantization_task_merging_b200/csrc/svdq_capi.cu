@@ -238,7 +238,7 @@ int svdq_project_exact(int dtype, int n_tasks, int fp16_basis, int center, int r
                        const void* const* tensors, const int64_t* numel, const int32_t* sel_tile_param,
                        const int32_t* sel_tile_local, const int64_t* pmask_off, const uint8_t* has_mask,
                        const uint32_t* packed, const int32_t* info, const float* W, float* proj, void* stream) {
-    REQUIRE(n_tasks >= 1 && n_tasks <= 8, "exact projection supports n_tasks in [1, 8]");
+    REQUIRE(n_tasks >= 1 && n_tasks <= SVDQ_MAX_TASKS, "n_tasks must be in [1, 32]");
     REQUIRE(dtype >= 0 && dtype <= 2, "dtype");
     REQUIRE(tile_elems > 0 && tile_elems % svdq::kStep == 0, "tile_elems must be a positive multiple of 1024");
     REQUIRE(n_sel_tiles >= 0 && n_sel_tiles < (1ll << 31), "n_sel_tiles");

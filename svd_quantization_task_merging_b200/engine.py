@@ -163,11 +163,11 @@ class MergeJob:
         # coefficients: "closed" = Sigma V^T for every parameter; "exact" = re-project every parameter on the stored
         # (fp16) basis like the reference does (one more read of the inputs); "auto" = exact for parameters of at
         # most EXACT_MAX_NUMEL elements, where the closed form's 2.4e-4/sqrt(Dm) deviation can flip an fp16 value or
-        # an RTVQ code, closed form above (deviation below LAPACK's own round-off).  Needs fp16 bases and N <= 8.
+        # an RTVQ code, closed form above (deviation below LAPACK's own round-off).  Only meaningful with fp16 bases.
         self.projection = projection or os.environ.get("SVDQ_PROJECTION", "auto")
         if self.projection not in ("closed", "auto", "exact"):
             raise ValueError(f"projection must be closed | auto | exact, got {self.projection}")
-        if not config.svd_fp16 or self.N > 8:
+        if not config.svd_fp16:
             self.projection = "closed"
         self.stages = int(config.svd_rtvq_stages)
         self.bits = int(config.svd_low_bits)
