@@ -34,6 +34,8 @@ WORKLOADS = {
     "vit-b-16-majority": ("ViT-B-16", 8, "majority", 0.5, "performance", 3),
     "vit-b-32-union": ("ViT-B-32", 8, "union", 0.3, "uniform", 2),
     "toy": ("toy", 8, "union", 0.5, "uniform", 2),
+    # configs[3]-style stress (not a bench line): 20 task vectors take the blocked-Gram wide path
+    "vit-l-14-20tasks": ("ViT-L-14", 20, "union", 0.3, "uniform", 2),
 }
 
 

@@ -74,13 +74,15 @@ int svdq_tv_mask_gram(int dtype, int n_tasks, int mask_strategy, int full, int64
  * svdq_mask_pack combines the N tall masks once (same reference lines as K1's mask part) into the packed
  * mask + per-tile counts; svdq_tv_gram_premasked then accumulates the Gram of a SUBSET of <= 16 tasks
  * (tensors = [P][n_tasks+1] table of that subset) under that pre-combined mask.  The caller runs it for
- * pairs of task blocks and assembles the N x N Gram.  svdq_param_solve, svdq_reconstruct_merge and
+ * pairs of task blocks and assembles the N x N Gram.  mask_mode selects the rows that enter the Gram: 0 = inside
+ * the combined mask, 1 = all rows (whole-model Gram of cluster weighting), 2 = outside the mask (noise region);
+ * gram is one block [n_tiles][n(n+1)/2] per launch.  svdq_param_solve, svdq_reconstruct_merge and
  * svdq_diag_finalize accept n_tasks <= 32 directly.
  */
 int svdq_mask_pack(int n_tasks, int mask_strategy, int64_t n_tiles, int tile_elems, const uint8_t* const* masks,
                    const int64_t* numel, const int32_t* tile_param, const int32_t* tile_local,
                    const int64_t* pmask_off, uint32_t* packed, uint32_t* count, void* stream);
-int svdq_tv_gram_premasked(int dtype, int n_tasks, int full, int64_t n_tiles, int tile_elems,
+int svdq_tv_gram_premasked(int dtype, int n_tasks, int mask_mode, int64_t n_tiles, int tile_elems,
                            const void* const* tensors, const int64_t* numel, const int32_t* tile_param,
                            const int32_t* tile_local, const int64_t* pmask_off, const uint8_t* has_mask,
                            const uint32_t* packed, float* gram, uint32_t* count, void* stream);

@@ -59,9 +59,15 @@ __global__ void __launch_bounds__(kBlock, (NT <= 8 && !FULL) ? 2 : 1) k1_tv_mask
     const uint32_t* packed_in = (has_mask && premasked) ? a.packed_in + a.pmask_off[p] : nullptr;
 
     const bool comp = a.second_complement != 0;   // FULL: second block = Gram of the UNMASKED elements (noise region)
-    float2 acc2[G];
+    // more than 10 tasks: the packed (float2) accumulators would not fit the register file -> plain fp32
+    // accumulators and scalar FMAs (FULL is not offered there: the callers run a second launch in mask_mode 1 / 2)
+    constexpr bool kScalarAcc = NT > 10 && !FULL;
+    float2 acc2[kScalarAcc ? 1 : G];
+    float acc1[kScalarAcc ? G : 1];
 #pragma unroll
-    for (int i = 0; i < G; ++i) acc2[i] = make_float2(0.0f, 0.0f);
+    for (int i = 0; i < (kScalarAcc ? 1 : G); ++i) acc2[i] = make_float2(0.0f, 0.0f);
+#pragma unroll
+    for (int i = 0; i < (kScalarAcc ? G : 1); ++i) acc1[i] = 0.0f;
     uint32_t cnt = 0;
 
     for (int64_t e0 = start; e0 < stop; e0 += kStep) {          // uniform trip count per CTA
@@ -120,7 +126,9 @@ __global__ void __launch_bounds__(kBlock, (NT <= 8 && !FULL) ? 2 : 1) k1_tv_mask
         if (active) {
             const uint32_t valid = full ? 0xFu : ((1u << (int)(numel - e)) - 1u);
             if (premasked) {
-                bits = (mw[0] >> (int)(e & 31)) & valid;
+                // mask_mode 0: rows inside the combined mask; 1: all rows; 2: rows outside the mask
+                const uint32_t w = a.mask_mode == 1 ? 0xffffffffu : (a.mask_mode == 2 ? (has_mask ? ~mw[0] : 0u) : mw[0]);
+                bits = (w >> (int)(e & 31)) & valid;
             } else if (has_mask) {
                 uint32_t votes = 0;                              // 4 byte lanes, one per element
 #pragma unroll
@@ -145,7 +153,7 @@ __global__ void __launch_bounds__(kBlock, (NT <= 8 && !FULL) ? 2 : 1) k1_tv_mask
 
         // packed 2-wide FMAs (fma.rn.f32x2): FULL pairs the masked Gram with the all-element Gram of the
         // same (i, j) -- or, with second_complement, with the Gram of the unmasked elements; otherwise two consecutive elements share one instruction
-        if (FULL) {
+        if constexpr (FULL) {
 #pragma unroll
             for (int c = 0; c < kVec; ++c) {
                 const bool m = (bits >> c) & 1u;
@@ -157,6 +165,19 @@ __global__ void __launch_bounds__(kBlock, (NT <= 8 && !FULL) ? 2 : 1) k1_tv_mask
 #pragma unroll
                     for (int j = i; j < NT; ++j)
                         acc2[tri_index(i, j, NT)] = __ffma2_rn(v[i], v[j], acc2[tri_index(i, j, NT)]);
+            }
+        } else if constexpr (kScalarAcc) {
+#pragma unroll
+            for (int c = 0; c < kVec; ++c) {
+                const bool m = (bits >> c) & 1u;
+                float v[NT];
+#pragma unroll
+                for (int t = 0; t < NT; ++t) v[t] = m ? d[t][c] : 0.0f;
+#pragma unroll
+                for (int i = 0; i < NT; ++i)
+#pragma unroll
+                    for (int j = i; j < NT; ++j)
+                        acc1[tri_index(i, j, NT)] = fmaf(v[i], v[j], acc1[tri_index(i, j, NT)]);
             }
         } else {
 #pragma unroll
@@ -178,7 +199,8 @@ __global__ void __launch_bounds__(kBlock, (NT <= 8 && !FULL) ? 2 : 1) k1_tv_mask
     float acc[NACC];
 #pragma unroll
     for (int i = 0; i < G; ++i) {
-        if (FULL) { acc[i] = acc2[i].x; acc[G + i] = acc2[i].y; }
+        if constexpr (FULL) { acc[i] = acc2[i].x; acc[G + i] = acc2[i].y; }
+        else if constexpr (kScalarAcc) acc[i] = acc1[i];
         else acc[i] = acc2[i].x + acc2[i].y;
     }
     // ---- CTA reduction in a fixed order: kRows accumulator rows per round through smem ----------

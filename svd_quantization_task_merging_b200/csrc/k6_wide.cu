@@ -88,40 +88,28 @@ cudaError_t k6_mask_pack_launch(const K6MaskArgs& a, int n_tiles, cudaStream_t s
 }
 #endif  // SVDQ_DTYPE == 0
 
-// two elements per thread
-constexpr int kWVec = 2;
+// four elements per thread (two packed pairs)
+constexpr int kWVec = 4;
 constexpr int kWStep = kBlock * kWVec;
 
-template <typename T> struct Elem2;
-template <> struct Elem2<float> {
-    static __device__ __forceinline__ void load(const void* p, int64_t e, bool full, int64_t numel, float (&o)[2]) {
-        const float* q = reinterpret_cast<const float*>(p);
-        if (full) { const float2 v = __ldg(reinterpret_cast<const float2*>(q + e)); o[0] = v.x; o[1] = v.y; }
-        else { o[0] = e < numel ? __ldg(q + e) : 0.0f; o[1] = e + 1 < numel ? __ldg(q + e + 1) : 0.0f; }
-    }
-};
-template <> struct Elem2<__nv_bfloat16> {
-    static __device__ __forceinline__ void load(const void* p, int64_t e, bool full, int64_t numel, float (&o)[2]) {
-        const __nv_bfloat16* q = reinterpret_cast<const __nv_bfloat16*>(p);
-        o[0] = e < numel ? __bfloat162float(q[e]) : 0.0f;
-        o[1] = e + 1 < numel ? __bfloat162float(q[e + 1]) : 0.0f;
-    }
-};
-template <> struct Elem2<__half> {
-    static __device__ __forceinline__ void load(const void* p, int64_t e, bool full, int64_t numel, float (&o)[2]) {
-        const __half* q = reinterpret_cast<const __half*>(p);
-        o[0] = e < numel ? __half2float(q[e]) : 0.0f;
-        o[1] = e + 1 < numel ? __half2float(q[e + 1]) : 0.0f;
+template <typename T> struct Elem2 {
+    static __device__ __forceinline__ void load(const void* p, int64_t e, bool full, int64_t numel, float (&o)[kWVec]) {
+        if (full) Elem<T>::load4(p, e, o);
+        else {
+#pragma unroll
+            for (int c = 0; c < kWVec; ++c) o[c] = (e + c < numel) ? Elem<T>::load1(p, e + c) : 0.0f;
+        }
     }
 };
 
 // RP: compile-time bound on the number of basis columns (24 or 32)
-// NOISE (svd_include_noise): a second coefficient set for the rows outside the combined mask; every element
-// picks the set of its own region (index 0 = masked rows, 1 = the rest), so the two elements of a thread may
-// read different rows of sW -- the region stride is padded by 4 floats to keep the two 16-byte reads on
-// different banks.
+// NOISE (svd_include_noise): a second coefficient set for the rows outside the combined mask.  Every element
+// belongs to exactly one region, so the task value is split into (masked part, unmasked part) -- one of them is
+// zero -- and both parts are contracted with their own W into the SAME accumulators (uniform broadcast reads
+// of W, no per-element select in the inner loop); the column sums, cbar and tails are picked per element.
 template <typename T, int RP, bool FP16B, bool DIAG, bool NOISE>
-__global__ void __launch_bounds__(kBlock) k6_reconstruct_merge(const K3Args a, const int n_tasks) {
+__global__ void __launch_bounds__(kBlock, (RP <= 24 && !NOISE) ? 2 : 1) k6_reconstruct_merge(const K3Args a,
+                                                                                             const int n_tasks) {
     extern __shared__ __align__(16) float dyn[];                  // DIAG: [5 * n_tasks][kBlock] accumulators
     constexpr int NREG = NOISE ? 2 : 1;
     constexpr int kRegStride = kMaxTasks * RP + 4;
@@ -172,56 +160,98 @@ __global__ void __launch_bounds__(kBlock) k6_reconstruct_merge(const K3Args a, c
     float* outp = a.out[p];
     const float n_f = (float)(n_active > 0 ? n_active : 1);
 
+    constexpr int kH = kWVec / 2;
     for (int64_t e0 = start; e0 < stop; e0 += kWStep) {
         const int64_t e = e0 + (int64_t)tid * kWVec;
         if (e >= stop) continue;
         const bool full = e + kWVec <= numel;
         float b[kWVec];
         Elem2<T>::load(s_ptr[0], e, full, numel, b);
-        float res[kWVec] = {b[0], b[1]};
+        float res[kWVec];
+#pragma unroll
+        for (int c = 0; c < kWVec; ++c) res[c] = b[c];
         if (status == kSolved) {
-            float u[RP][kWVec];
+            float2 u[RP][kH];                                    // basis-row accumulators, packed element pairs
 #pragma unroll
-            for (int j = 0; j < RP; ++j) { u[j][0] = 0.0f; u[j][1] = 0.0f; }
-            float mean[kWVec] = {0.0f, 0.0f};
-            uint32_t bits = 0x3u;
-            if (has_mask) bits = (__ldg(packed + (e >> 5)) >> (int)(e & 31)) & 0x3u;
-            // region of each of the thread's two elements (0 = masked rows)
-            const int g0 = (NOISE && !(bits & 1u)) ? NREG - 1 : 0, g1 = (NOISE && !(bits & 2u)) ? NREG - 1 : 0;
-            for (int t = 0; t < N; ++t) {                        // stream the tasks once
-                const void* fp = s_ptr[t + 1];
-                if (fp == nullptr) continue;
-                float f[kWVec];
-                Elem2<T>::load(fp, e, full, numel, f);
-                const float x0 = Elem<T>::sub(f[0], b[0]), x1 = Elem<T>::sub(f[1], b[1]);
-                mean[0] += x0; mean[1] += x1;
+            for (int j = 0; j < RP; ++j)
 #pragma unroll
-                for (int j = 0; j < RP; j += 4) {
-                    const float4 w = *reinterpret_cast<const float4*>(&SW(g0, t, j));
-                    const float4 v = NOISE ? *reinterpret_cast<const float4*>(&SW(g1, t, j)) : w;
-                    u[j + 0][0] = fmaf(x0, w.x, u[j + 0][0]); u[j + 0][1] = fmaf(x1, v.x, u[j + 0][1]);
-                    u[j + 1][0] = fmaf(x0, w.y, u[j + 1][0]); u[j + 1][1] = fmaf(x1, v.y, u[j + 1][1]);
-                    u[j + 2][0] = fmaf(x0, w.z, u[j + 2][0]); u[j + 2][1] = fmaf(x1, v.z, u[j + 2][1]);
-                    u[j + 3][0] = fmaf(x0, w.w, u[j + 3][0]); u[j + 3][1] = fmaf(x1, v.w, u[j + 3][1]);
+                for (int h = 0; h < kH; ++h) u[j][h] = make_float2(0.0f, 0.0f);
+            float mean[kWVec];
+#pragma unroll
+            for (int c = 0; c < kWVec; ++c) mean[c] = 0.0f;
+            uint32_t bits = (1u << kWVec) - 1u;
+            if (has_mask) bits = (__ldg(packed + (e >> 5)) >> (int)(e & 31)) & ((1u << kWVec) - 1u);
+            // stream the tasks once, kUT at a time: their loads are issued back to back before any use (a task that
+            // lacks the parameter, or t >= N, reads the base tensor -> zero delta; its W row is zero / unused)
+            constexpr int kUT = 4;
+            for (int t0 = 0; t0 < N; t0 += kUT) {
+                float f[kUT][kWVec];
+#pragma unroll
+                for (int q = 0; q < kUT; ++q) {
+                    const void* fp = (t0 + q < N) ? s_ptr[t0 + q + 1] : nullptr;
+                    Elem2<T>::load(fp ? fp : s_ptr[0], e, full, numel, f[q]);
+                }
+#pragma unroll
+                for (int q = 0; q < kUT; ++q) {
+                    const int t = t0 + q;                        // sW rows t >= N are zero
+                    float2 xm[kH], xn[NOISE ? kH : 1];
+#pragma unroll
+                    for (int h = 0; h < kH; ++h) {
+                        const float x0 = Elem<T>::sub(f[q][2 * h], b[2 * h]);
+                        const float x1 = Elem<T>::sub(f[q][2 * h + 1], b[2 * h + 1]);
+                        mean[2 * h] += x0; mean[2 * h + 1] += x1;
+                        if (NOISE) {
+                            const bool m0 = (bits >> (2 * h)) & 1u, m1 = (bits >> (2 * h + 1)) & 1u;
+                            xm[h] = make_float2(m0 ? x0 : 0.0f, m1 ? x1 : 0.0f);
+                            xn[h] = make_float2(m0 ? 0.0f : x0, m1 ? 0.0f : x1);
+                        } else xm[h] = make_float2(x0, x1);
+                    }
+#pragma unroll
+                    for (int j = 0; j < RP; j += 4) {
+                        const float4 w = *reinterpret_cast<const float4*>(&SW(0, t, j));
+                        const float wv[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+                        for (int z = 0; z < 4; ++z) {
+                            const float2 w2 = make_float2(wv[z], wv[z]);
+#pragma unroll
+                            for (int h = 0; h < kH; ++h) u[j + z][h] = __ffma2_rn(xm[h], w2, u[j + z][h]);
+                        }
+                        if (NOISE) {
+                            const float4 v = *reinterpret_cast<const float4*>(&SW(NREG - 1, t, j));
+                            const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                            for (int z = 0; z < 4; ++z) {
+                                const float2 v2 = make_float2(vv[z], vv[z]);
+#pragma unroll
+                                for (int h = 0; h < kH; ++h) u[j + z][h] = __ffma2_rn(xn[h], v2, u[j + z][h]);
+                            }
+                        }
+                    }
                 }
             }
 #pragma unroll
             for (int c = 0; c < kWVec; ++c) mean[c] = a.center ? __fdiv_rn(mean[c], n_f) : 0.0f;
             // u = (tau - mean) W = tau W - mean * colsum(W); fp16 round trip; contract with cbar
-            float acc[kWVec] = {0.0f, 0.0f};
-            const int gsel[kWVec] = {g0, g1};
-            const int rsel[kWVec] = {g0 ? r_n : r, g1 ? r_n : r};
+            float acc[kWVec];
+            int gsel[kWVec], rsel[kWVec];
+#pragma unroll
+            for (int c = 0; c < kWVec; ++c) {
+                acc[c] = 0.0f;
+                gsel[c] = (NOISE && !((bits >> c) & 1u)) ? NREG - 1 : 0;
+                rsel[c] = gsel[c] ? r_n : r;
+            }
 #pragma unroll
             for (int j = 0; j < RP; ++j) {
 #pragma unroll
                 for (int c = 0; c < kWVec; ++c) {
+                    float& uc = (c & 1) ? u[j][c >> 1].y : u[j][c >> 1].x;
                     if (j < rsel[c]) {
-                        float v = fmaf(-mean[c], sSW[gsel[c]][j], u[j][c]);
+                        float v = fmaf(-mean[c], sSW[gsel[c]][j], uc);
                         if (FP16B) v = round_fp16(v);
-                        u[j][c] = v;
+                        uc = v;
                         acc[c] = fmaf(v, sCbar[gsel[c]][j], acc[c]);
                     } else {
-                        u[j][c] = 0.0f;
+                        uc = 0.0f;
                     }
                 }
             }
@@ -238,29 +268,38 @@ __global__ void __launch_bounds__(kBlock) k6_reconstruct_merge(const K3Args a, c
                     if (fp == nullptr) continue;
                     float f[kWVec];
                     Elem2<T>::load(fp, e, full, numel, f);
-                    const float x[kWVec] = {Elem<T>::sub(f[0], b[0]), Elem<T>::sub(f[1], b[1])};
-                    float rec[kWVec] = {0.0f, 0.0f};
+                    float2 rec2[kH];
+#pragma unroll
+                    for (int h = 0; h < kH; ++h) rec2[h] = make_float2(0.0f, 0.0f);
 #pragma unroll
                     for (int j = 0; j < RP; ++j) {
                         const float ch = sChat[t][j];
-                        rec[0] = fmaf(u[j][0], ch, rec[0]); rec[1] = fmaf(u[j][1], ch, rec[1]);
+                        const float2 ch2 = make_float2(ch, ch);
+#pragma unroll
+                        for (int h = 0; h < kH; ++h) rec2[h] = __ffma2_rn(u[j][h], ch2, rec2[h]);
                     }
+                    float* d0 = dyn + (size_t)(0 * N + t) * kBlock + tid;
+                    float* d1 = dyn + (size_t)(1 * N + t) * kBlock + tid;
+                    float* d2 = dyn + (size_t)(2 * N + t) * kBlock + tid;
+                    float* d3 = dyn + (size_t)(3 * N + t) * kBlock + tid;
+                    float se = *d0, sa = *d1, sr = *d2, mx = *d3;
 #pragma unroll
                     for (int c = 0; c < kWVec; ++c) {
                         if (!(((bits >> c) & 1u) && e + c < numel)) continue;
-                        const float er = x[c] - rec[c];
-                        float* d0 = dyn + (size_t)(0 * N + t) * kBlock + tid;
-                        float* d1 = dyn + (size_t)(1 * N + t) * kBlock + tid;
-                        float* d2 = dyn + (size_t)(2 * N + t) * kBlock + tid;
-                        float* d3 = dyn + (size_t)(3 * N + t) * kBlock + tid;
-                        *d0 = fmaf(er, er, *d0); *d1 += fabsf(er); *d2 = fmaf(rec[c], rec[c], *d2);
-                        *d3 = fmaxf(*d3, fabsf(er));
+                        const float rc = (c & 1) ? rec2[c >> 1].y : rec2[c >> 1].x;
+                        const float er = Elem<T>::sub(f[c], b[c]) - rc;
+                        se = fmaf(er, er, se); sa += fabsf(er); sr = fmaf(rc, rc, sr); mx = fmaxf(mx, fabsf(er));
                     }
+                    *d0 = se; *d1 = sa; *d2 = sr; *d3 = mx;
                 }
             }
         }
-        if (full) *reinterpret_cast<float2*>(outp + e) = make_float2(res[0], res[1]);
-        else if (e < numel) outp[e] = res[0];
+        if (full) stg_stream_f4(outp + e, make_float4(res[0], res[1], res[2], res[3]));
+        else {
+#pragma unroll
+            for (int c = 0; c < kWVec; ++c)
+                if (e + c < numel) outp[e + c] = res[c];
+        }
     }
 
     if (DIAG) {

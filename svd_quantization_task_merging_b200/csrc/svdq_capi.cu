@@ -126,7 +126,7 @@ int svdq_tv_mask_gram(int dtype, int n_tasks, int mask_strategy, int full, int64
     a.tensors = tensors; a.masks = masks; a.numel = numel; a.tile_param = tile_param; a.tile_local = tile_local;
     a.pmask_off = pmask_off; a.packed = packed; a.gram = gram; a.count = count; a.tile_elems = tile_elems;
     a.strategy = mask_strategy;
-    a.packed_in = nullptr; a.has_mask_in = nullptr; a.second_complement = full == 2;
+    a.packed_in = nullptr; a.has_mask_in = nullptr; a.second_complement = full == 2; a.mask_mode = 0;
     REQUIRE(full >= 0 && full <= 2, "full must be 0 (masked), 1 (+ all elements) or 2 (+ complement)");
     return finish(__func__, k1_launch(dtype, n_tasks, a, (int)n_tiles, full != 0, (cudaStream_t)stream));
 }
@@ -147,7 +147,7 @@ int svdq_mask_pack(int n_tasks, int mask_strategy, int64_t n_tiles, int tile_ele
     return finish(__func__, svdq::k6_mask_pack_launch(a, (int)n_tiles, (cudaStream_t)stream));
 }
 
-int svdq_tv_gram_premasked(int dtype, int n_tasks, int full, int64_t n_tiles, int tile_elems,
+int svdq_tv_gram_premasked(int dtype, int n_tasks, int mask_mode, int64_t n_tiles, int tile_elems,
                            const void* const* tensors, const int64_t* numel, const int32_t* tile_param,
                            const int32_t* tile_local, const int64_t* pmask_off, const uint8_t* has_mask,
                            const uint32_t* packed, float* gram, uint32_t* count, void* stream) {
@@ -161,8 +161,9 @@ int svdq_tv_gram_premasked(int dtype, int n_tasks, int full, int64_t n_tiles, in
     svdq::K1Args a;
     a.tensors = tensors; a.masks = nullptr; a.numel = numel; a.tile_param = tile_param; a.tile_local = tile_local;
     a.pmask_off = pmask_off; a.packed = nullptr; a.gram = gram; a.count = count; a.tile_elems = tile_elems;
-    a.strategy = 0; a.packed_in = packed; a.has_mask_in = has_mask; a.second_complement = full == 2;
-    REQUIRE(full >= 0 && full <= 2, "full must be 0 (masked), 1 (+ all elements) or 2 (+ complement)");
+    a.strategy = 0; a.packed_in = packed; a.has_mask_in = has_mask; a.second_complement = 0; a.mask_mode = mask_mode;
+    REQUIRE(mask_mode >= 0 && mask_mode <= 2, "mask_mode must be 0 (masked rows), 1 (all rows) or 2 (unmasked rows)");
+    const int full = 0;
     // always the direct-load kernel: the staged variant combines the task masks itself
     cudaError_t e;
     switch (dtype) {

@@ -25,6 +25,8 @@ struct K1Args {
     // FULL only: 0 = second block is the Gram over ALL elements, 1 = over the elements OUTSIDE the combined mask
     // (the noise region of svd_include_noise; all = masked + complement is then formed by k2_gram_reduce)
     int second_complement;
+    // pre-combined mask mode only: 0 = rows inside the combined mask, 1 = all rows, 2 = rows outside the mask
+    int mask_mode;
 };
 
 struct K2ReduceArgs {

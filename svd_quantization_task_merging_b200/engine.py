@@ -343,9 +343,10 @@ class MergeJob:
                     sub_ptr = np.concatenate([tptr[:, :1], tptr[:, 1 + idx]], axis=1)
                     gl = nl * (nl + 1) // 2
                     g.sub.append(dict(idx=torch.from_numpy(idx).to(dev), n=nl, tptr=_dev(sub_ptr, dev),
-                                      gram=z(max(n_tiles, 1) * full * gl), gm=z(P, nl * nl, dtype=f64),
-                                      ga=z(P, nl * nl, dtype=f64) if self.cluster_mode else None,
-                                      gn=z(P, nl * nl, dtype=f64) if self.noise else None))
+                                      gram=z(max(n_tiles, 1) * gl), gm=z(P, nl * nl, dtype=f64),
+                                      g2=z(P, nl * nl, dtype=f64) if (self.cluster_mode or self.noise) else None))
+            g.t["dm_scratch"] = z(P, dtype=i64)
+            g.t["count_scratch"] = z(max(n_tiles, 1), dtype=i32)
         optr = np.asarray([g.t["out"].data_ptr() + 4 * o for o in out_off], np.int64)
         g.t["optr"] = _dev(optr, dev)
         def sign_table(ref):
@@ -460,21 +461,31 @@ class MergeJob:
                     gm_full = t["gram_masked"].view(P, N, N)
                     ga_full = t["gram_all"].view(P, N, N) if self.cluster_mode else None
                     gn_full = g.tn["gram"].view(P, N, N) if self.noise else None
+                    second = 2 if self.noise else (1 if self.cluster_mode else 0)   # rows of the second Gram
                     for sub in g.sub:
-                        _native.call("svdq_tv_gram_premasked", _FLOAT_DTYPES[g.dtype], sub["n"], full, g.n_tiles, te,
-                                     _ptr(sub["tptr"]), _ptr(t["numel"]), _ptr(t["tile_param"]), _ptr(t["tile_local"]),
-                                     _ptr(t["pm_off"]), _ptr(t["has_mask"]), _ptr(t["packed"]), _ptr(sub["gram"]),
-                                     _ptr(t["count"]), st)
-                        _native.call("svdq_gram_reduce", sub["n"], full, P, mms, _ptr(sub["gram"]), _ptr(t["count"]),
-                                     _ptr(t["tile_begin"]), _ptr(t["numel"]), _ptr(t["has_mask"]), _ptr(sub["gm"]),
-                                     _ptr(sub["ga"]), _ptr(t["dm"]), _ptr(sub["gn"]),
-                                     _ptr(g.tn["dm"]) if self.noise else None, st)
+                        for mode, dst, cnt, dm_out in ((0, sub["gm"], t["count"], t["dm"]),
+                                                       (second, sub["g2"], t["count_scratch"], t["dm_scratch"])):
+                            if dst is None:
+                                continue
+                            _native.call("svdq_tv_gram_premasked", _FLOAT_DTYPES[g.dtype], sub["n"], mode, g.n_tiles,
+                                         te, _ptr(sub["tptr"]), _ptr(t["numel"]), _ptr(t["tile_param"]),
+                                         _ptr(t["tile_local"]), _ptr(t["pm_off"]), _ptr(t["has_mask"]),
+                                         _ptr(t["packed"]), _ptr(sub["gram"]), _ptr(cnt), st)
+                            _native.call("svdq_gram_reduce", sub["n"], 0, P, mms, _ptr(sub["gram"]), _ptr(cnt),
+                                         _ptr(t["tile_begin"]), None, None, _ptr(dst), None, _ptr(dm_out), None, None,
+                                         st)
                         ix = sub["idx"]
                         gm_full[:, ix[:, None], ix[None, :]] = sub["gm"].view(P, sub["n"], sub["n"])
-                        if ga_full is not None:
-                            ga_full[:, ix[:, None], ix[None, :]] = sub["ga"].view(P, sub["n"], sub["n"])
-                        if gn_full is not None:
-                            gn_full[:, ix[:, None], ix[None, :]] = sub["gn"].view(P, sub["n"], sub["n"])
+                        if sub["g2"] is not None:
+                            g2 = sub["g2"].view(P, sub["n"], sub["n"])
+                            if gn_full is not None:
+                                gn_full[:, ix[:, None], ix[None, :]] = g2
+                            if ga_full is not None:       # all = masked + complement (noise mode) or the all-rows Gram
+                                ga_full[:, ix[:, None], ix[None, :]] = (g2 + sub["gm"].view_as(g2)) if self.noise else g2
+                    if self.noise:
+                        # rows of the noise region (same rule as svdq_gram_reduce's dm_noise)
+                        on = (t["has_mask"] != 0) & (t["dm"] >= mms) & (t["dm"] > 0)
+                        g.tn["dm"].copy_(torch.where(on, t["numel"] - t["dm"], torch.zeros_like(t["dm"])))
                 mark("k1")
             max_rank = int(cfg.svd_max_rank) if cfg.svd_max_rank is not None else 0
 
