@@ -88,36 +88,62 @@ cudaError_t k6_mask_pack_launch(const K6MaskArgs& a, int n_tiles, cudaStream_t s
 }
 #endif  // SVDQ_DTYPE == 0
 
-// four elements per thread (two packed pairs)
-constexpr int kWVec = 4;
+// ---- pass 2 for 17..32 task vectors ------------------------------------------------------------------------
+// Two elements per thread.  All (N+1) loads of a step are issued back to back, the centred task vectors stay in
+// registers as PAIRS OF TASKS (x_2q, x_2q+1), and every basis-row entry u_dj = sum_t x_dt W[t][j] is a chain of
+// packed FMAs over task pairs: the second operand (W[2q][j], W[2q+1][j]) is one aligned 64-bit word of shared
+// memory, so no register moves are needed to build packed operands (with two ELEMENTS per FMA every W entry had
+// to be duplicated first: 21 % of the instructions of the previous version).  Even / odd partial sums are
+// added at the end.  NTMAX (24 or 32) bounds the unrolled loops; tasks t >= N read nothing and count as zero.
+constexpr int kWVec = 2;
 constexpr int kWStep = kBlock * kWVec;
 
-template <typename T> struct Elem2 {
-    static __device__ __forceinline__ void load(const void* p, int64_t e, bool full, int64_t numel, float (&o)[kWVec]) {
-        if (full) Elem<T>::load4(p, e, o);
-        else {
-#pragma unroll
-            for (int c = 0; c < kWVec; ++c) o[c] = (e + c < numel) ? Elem<T>::load1(p, e + c) : 0.0f;
-        }
+template <typename T> struct Elem2;
+template <> struct Elem2<float> {
+    static __device__ __forceinline__ void load(const void* p, int64_t e, bool full, int64_t numel, float (&o)[2]) {
+        const float* q = reinterpret_cast<const float*>(p);
+        if (full) {
+            float2 v;
+            asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(q + e));
+            o[0] = v.x; o[1] = v.y;
+        } else { o[0] = e < numel ? __ldg(q + e) : 0.0f; o[1] = e + 1 < numel ? __ldg(q + e + 1) : 0.0f; }
+    }
+};
+template <> struct Elem2<__nv_bfloat16> {
+    static __device__ __forceinline__ void load(const void* p, int64_t e, bool full, int64_t numel, float (&o)[2]) {
+        const __nv_bfloat16* q = reinterpret_cast<const __nv_bfloat16*>(p);
+        if (full) {
+            const uint32_t v = __ldg(reinterpret_cast<const uint32_t*>(q + e));
+            o[0] = __uint_as_float(v << 16); o[1] = __uint_as_float(v & 0xffff0000u);
+        } else { o[0] = e < numel ? __bfloat162float(q[e]) : 0.0f; o[1] = e + 1 < numel ? __bfloat162float(q[e + 1]) : 0.0f; }
+    }
+};
+template <> struct Elem2<__half> {
+    static __device__ __forceinline__ void load(const void* p, int64_t e, bool full, int64_t numel, float (&o)[2]) {
+        const __half* q = reinterpret_cast<const __half*>(p);
+        if (full) {
+            const uint32_t v = __ldg(reinterpret_cast<const uint32_t*>(q + e));
+            const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&v));
+            o[0] = f.x; o[1] = f.y;
+        } else { o[0] = e < numel ? __half2float(q[e]) : 0.0f; o[1] = e + 1 < numel ? __half2float(q[e + 1]) : 0.0f; }
     }
 };
 
-// RP: compile-time bound on the number of basis columns (24 or 32)
-// NOISE (svd_include_noise): a second coefficient set for the rows outside the combined mask.  Every element
-// belongs to exactly one region, so the task value is split into (masked part, unmasked part) -- one of them is
-// zero -- and both parts are contracted with their own W into the SAME accumulators (uniform broadcast reads
-// of W, no per-element select in the inner loop); the column sums, cbar and tails are picked per element.
-template <typename T, int RP, bool FP16B, bool DIAG, bool NOISE>
-__global__ void __launch_bounds__(kBlock, (RP <= 24 && !NOISE) ? 2 : 1) k6_reconstruct_merge(const K3Args a,
-                                                                                             const int n_tasks) {
-    extern __shared__ __align__(16) float dyn[];                  // DIAG: [5 * n_tasks][kBlock] accumulators
+// NOISE (svd_include_noise): a second coefficient set for the rows outside the combined mask; an element picks the
+// set of its own region (0 = masked rows, 1 = the rest) simply by the base address of its W / cbar reads.
+template <typename T, int NTMAX, bool FP16B, bool DIAG, bool NOISE>
+__global__ void __launch_bounds__(kBlock, (NTMAX <= 24 && !DIAG) ? 2 : 1) k6_reconstruct_merge(const K3Args a,
+                                                                                               const int n_tasks) {
+    extern __shared__ __align__(16) float dyn[];                  // DIAG: [4 * n_tasks][kBlock] accumulators
     constexpr int NREG = NOISE ? 2 : 1;
-    constexpr int kRegStride = kMaxTasks * RP + 4;
-    __shared__ __align__(16) float sWf[NREG * kRegStride];        // sW(g, t, j) = W_g[t][j]
-    __shared__ float sChat[DIAG ? kMaxTasks : 1][RP];
-    __shared__ float sCbar[NREG][RP], sSW[NREG][RP];
-    __shared__ const void* s_ptr[kMaxTasks + 1];
-#define SW(g, t, j) sWf[(g) * kRegStride + (t) * RP + (j)]
+    constexpr int TP = NTMAX / 2;                                 // task pairs
+    constexpr int kRegStride = NTMAX * TP + 2;                    // float2 units; +2: regions on different banks
+    __shared__ __align__(16) float2 sW2[NREG * kRegStride];       // W2(g, j, q) = (W_g[2q][j], W_g[2q+1][j])
+    __shared__ __align__(16) float2 sChat2[DIAG ? NTMAX : 1][TP]; // (chat[2q][j], chat[2q+1][j])
+    __shared__ float sCbar[NREG][NTMAX];
+    __shared__ const void* s_ptr[NTMAX + 1];
+    __shared__ uint32_t s_present;
+#define W2(g, j, q) sW2[(g) * kRegStride + (j) * TP + (q)]
     const int N = n_tasks;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tile = blockIdx.x;
@@ -133,173 +159,174 @@ __global__ void __launch_bounds__(kBlock, (RP <= 24 && !NOISE) ? 2 : 1) k6_recon
     const bool noise_on = NOISE && status == kSolved && a.info_n[(int64_t)p * 8 + 0] == kSolved;
     const int r_n = noise_on ? a.info_n[(int64_t)p * 8 + 4] : 0;
     const float tail_n = noise_on ? a.scal_n[(int64_t)p * 4 + 1] : 0.0f;
-    if (tid <= N) s_ptr[tid] = a.tensors[(int64_t)p * (N + 1) + tid];
-    for (int i = tid; i < kMaxTasks * RP; i += kBlock) {
-        const int t = i / RP, j = i % RP;
-        const bool ok = t < N && j < N;
-        SW(0, t, j) = ok ? a.W[(int64_t)p * N * N + t * N + j] : 0.0f;
-        if (NOISE) SW(NREG - 1, t, j) = (ok && noise_on) ? a.W_n[(int64_t)p * N * N + t * N + j] : 0.0f;
-        if (DIAG) sChat[t][j] = ok ? a.chat[(int64_t)p * N * N + t * N + j] : 0.0f;
+    const int r_loop = NOISE ? max(r, r_n) : r;
+    if (tid <= NTMAX) s_ptr[tid] = tid <= N ? a.tensors[(int64_t)p * (N + 1) + tid] : nullptr;
+    for (int i = tid; i < NTMAX * TP; i += kBlock) {
+        const int j = i / TP, q = i % TP;
+        const int t0 = 2 * q, t1 = 2 * q + 1;
+        auto at = [&](const float* M, int t) { return (t < N && j < N) ? M[(int64_t)p * N * N + t * N + j] : 0.0f; };
+        W2(0, j, q) = make_float2(at(a.W, t0), at(a.W, t1));
+        if (NOISE) W2(NREG - 1, j, q) = noise_on ? make_float2(at(a.W_n, t0), at(a.W_n, t1)) : make_float2(0.0f, 0.0f);
+        if (DIAG) sChat2[j][q] = make_float2(at(a.chat, t0), at(a.chat, t1));
     }
-    if (tid < RP) {
+    if (tid < NTMAX) {
         sCbar[0][tid] = tid < N ? a.cbar[(int64_t)p * N + tid] : 0.0f;
         if (NOISE) sCbar[NREG - 1][tid] = (tid < N && noise_on) ? a.cbar_n[(int64_t)p * N + tid] : 0.0f;
     }
     if (DIAG) for (int i = tid; i < kDiagRows * N * kBlock; i += kBlock) dyn[i] = 0.0f;
     __syncthreads();
-    if (tid < RP) {                                               // column sums of W over the active tasks
-#pragma unroll
-        for (int g = 0; g < NREG; ++g) {
-            float s = 0.0f;
-            for (int t = 0; t < N; ++t) if (s_ptr[t + 1] != nullptr) s += SW(g, t, tid);
-            sSW[g][tid] = s;
-        }
+    if (tid == 0) {
+        uint32_t pb = 0;
+        for (int t = 0; t < N; ++t) pb |= (s_ptr[t + 1] != nullptr ? 1u : 0u) << t;
+        s_present = pb;
     }
+    __syncthreads();
+    const uint32_t present_bits = s_present;
+    // a task that lacks the parameter (or t >= N) reads the base tensor: zero delta, dropped again after centring
+    if (tid >= 1 && tid <= NTMAX && s_ptr[tid] == nullptr) s_ptr[tid] = s_ptr[0];
     __syncthreads();
     const uint32_t* packed = has_mask ? a.packed + a.pmask_off[p] : nullptr;
     float* outp = a.out[p];
     const float n_f = (float)(n_active > 0 ? n_active : 1);
 
-    constexpr int kH = kWVec / 2;
     for (int64_t e0 = start; e0 < stop; e0 += kWStep) {
         const int64_t e = e0 + (int64_t)tid * kWVec;
         if (e >= stop) continue;
         const bool full = e + kWVec <= numel;
         float b[kWVec];
         Elem2<T>::load(s_ptr[0], e, full, numel, b);
-        float res[kWVec];
-#pragma unroll
-        for (int c = 0; c < kWVec; ++c) res[c] = b[c];
+        float res[kWVec] = {b[0], b[1]};
         if (status == kSolved) {
-            float2 u[RP][kH];                                    // basis-row accumulators, packed element pairs
+            // ---- all loads of the step back to back ----------------------------------------------------------
+            float2 xp[TP][kWVec];                                // xp[q][c] = (x_2q, x_2q+1) of element c
 #pragma unroll
-            for (int j = 0; j < RP; ++j)
+            for (int q = 0; q < TP; ++q) {
+                float f0[kWVec] = {b[0], b[1]}, f1[kWVec] = {b[0], b[1]};
+                if (2 * q < N) Elem2<T>::load(s_ptr[2 * q + 1], e, full, numel, f0);
+                if (2 * q + 1 < N) Elem2<T>::load(s_ptr[2 * q + 2], e, full, numel, f1);
 #pragma unroll
-                for (int h = 0; h < kH; ++h) u[j][h] = make_float2(0.0f, 0.0f);
-            float mean[kWVec];
-#pragma unroll
-            for (int c = 0; c < kWVec; ++c) mean[c] = 0.0f;
-            uint32_t bits = (1u << kWVec) - 1u;
-            if (has_mask) bits = (__ldg(packed + (e >> 5)) >> (int)(e & 31)) & ((1u << kWVec) - 1u);
-            // stream the tasks once, kUT at a time: their loads are issued back to back before any use (a task that
-            // lacks the parameter, or t >= N, reads the base tensor -> zero delta; its W row is zero / unused)
-            constexpr int kUT = 4;
-            for (int t0 = 0; t0 < N; t0 += kUT) {
-                float f[kUT][kWVec];
-#pragma unroll
-                for (int q = 0; q < kUT; ++q) {
-                    const void* fp = (t0 + q < N) ? s_ptr[t0 + q + 1] : nullptr;
-                    Elem2<T>::load(fp ? fp : s_ptr[0], e, full, numel, f[q]);
-                }
-#pragma unroll
-                for (int q = 0; q < kUT; ++q) {
-                    const int t = t0 + q;                        // sW rows t >= N are zero
-                    float2 xm[kH], xn[NOISE ? kH : 1];
-#pragma unroll
-                    for (int h = 0; h < kH; ++h) {
-                        const float x0 = Elem<T>::sub(f[q][2 * h], b[2 * h]);
-                        const float x1 = Elem<T>::sub(f[q][2 * h + 1], b[2 * h + 1]);
-                        mean[2 * h] += x0; mean[2 * h + 1] += x1;
-                        if (NOISE) {
-                            const bool m0 = (bits >> (2 * h)) & 1u, m1 = (bits >> (2 * h + 1)) & 1u;
-                            xm[h] = make_float2(m0 ? x0 : 0.0f, m1 ? x1 : 0.0f);
-                            xn[h] = make_float2(m0 ? 0.0f : x0, m1 ? 0.0f : x1);
-                        } else xm[h] = make_float2(x0, x1);
-                    }
-#pragma unroll
-                    for (int j = 0; j < RP; j += 4) {
-                        const float4 w = *reinterpret_cast<const float4*>(&SW(0, t, j));
-                        const float wv[4] = {w.x, w.y, w.z, w.w};
-#pragma unroll
-                        for (int z = 0; z < 4; ++z) {
-                            const float2 w2 = make_float2(wv[z], wv[z]);
-#pragma unroll
-                            for (int h = 0; h < kH; ++h) u[j + z][h] = __ffma2_rn(xm[h], w2, u[j + z][h]);
-                        }
-                        if (NOISE) {
-                            const float4 v = *reinterpret_cast<const float4*>(&SW(NREG - 1, t, j));
-                            const float vv[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-                            for (int z = 0; z < 4; ++z) {
-                                const float2 v2 = make_float2(vv[z], vv[z]);
-#pragma unroll
-                                for (int h = 0; h < kH; ++h) u[j + z][h] = __ffma2_rn(xn[h], v2, u[j + z][h]);
-                            }
-                        }
-                    }
-                }
+                for (int c = 0; c < kWVec; ++c) xp[q][c] = make_float2(f0[c], f1[c]);
             }
+            uint32_t bits = 0x3u;
+            if (has_mask) bits = (__ldg(packed + (e >> 5)) >> (int)(e & 31)) & 0x3u;
+            // ---- task vectors, mean over the active tasks (summed in task order), centring --------------------
+            float mean[kWVec] = {0.0f, 0.0f};
 #pragma unroll
-            for (int c = 0; c < kWVec; ++c) mean[c] = a.center ? __fdiv_rn(mean[c], n_f) : 0.0f;
-            // u = (tau - mean) W = tau W - mean * colsum(W); fp16 round trip; contract with cbar
-            float acc[kWVec];
-            int gsel[kWVec], rsel[kWVec];
-#pragma unroll
-            for (int c = 0; c < kWVec; ++c) {
-                acc[c] = 0.0f;
-                gsel[c] = (NOISE && !((bits >> c) & 1u)) ? NREG - 1 : 0;
-                rsel[c] = gsel[c] ? r_n : r;
-            }
-#pragma unroll
-            for (int j = 0; j < RP; ++j) {
+            for (int q = 0; q < TP; ++q)
 #pragma unroll
                 for (int c = 0; c < kWVec; ++c) {
-                    float& uc = (c & 1) ? u[j][c >> 1].y : u[j][c >> 1].x;
-                    if (j < rsel[c]) {
-                        float v = fmaf(-mean[c], sSW[gsel[c]][j], uc);
-                        if (FP16B) v = round_fp16(v);
-                        uc = v;
-                        acc[c] = fmaf(v, sCbar[gsel[c]][j], acc[c]);
-                    } else {
-                        uc = 0.0f;
+                    xp[q][c].x = Elem<T>::sub(xp[q][c].x, b[c]);
+                    xp[q][c].y = Elem<T>::sub(xp[q][c].y, b[c]);
+                    mean[c] += xp[q][c].x;
+                    mean[c] += xp[q][c].y;
+                }
+#pragma unroll
+            for (int c = 0; c < kWVec; ++c) mean[c] = a.center ? __fdiv_rn(mean[c], n_f) : 0.0f;
+#pragma unroll
+            for (int q = 0; q < TP; ++q)
+#pragma unroll
+                for (int c = 0; c < kWVec; ++c) {
+                    xp[q][c].x = ((present_bits >> (2 * q)) & 1u) ? xp[q][c].x - mean[c] : 0.0f;
+                    xp[q][c].y = ((present_bits >> (2 * q + 1)) & 1u) ? xp[q][c].y - mean[c] : 0.0f;
+                }
+            // ---- basis rows column by column, contraction with cbar (and chat for the diagnostics) -----------
+            const float2* wbase[kWVec];
+            const float* cbase[kWVec];
+#pragma unroll
+            for (int c = 0; c < kWVec; ++c) {
+                const int g = (NOISE && !((bits >> c) & 1u)) ? NREG - 1 : 0;
+                wbase[c] = sW2 + g * kRegStride;
+                cbase[c] = sCbar[g];
+            }
+            float acc[kWVec] = {0.0f, 0.0f};
+            float2 rec2[DIAG ? TP : 1][kWVec];
+            if (DIAG) {
+#pragma unroll
+                for (int q = 0; q < TP; ++q)
+#pragma unroll
+                    for (int c = 0; c < kWVec; ++c) rec2[q][c] = make_float2(0.0f, 0.0f);
+            }
+#pragma unroll
+            for (int j0 = 0; j0 < NTMAX; j0 += 2) {              // two columns at a time: four independent FMA chains
+                if (j0 >= r_loop) break;
+                float u[2][kWVec];
+                float2 s2[2][kWVec];
+#pragma unroll
+                for (int z = 0; z < 2; ++z)
+#pragma unroll
+                    for (int c = 0; c < kWVec; ++c) s2[z][c] = make_float2(0.0f, 0.0f);
+#pragma unroll
+                for (int q = 0; q < TP; q += 2) {
+#pragma unroll
+                    for (int z = 0; z < 2; ++z)
+#pragma unroll
+                        for (int c = 0; c < kWVec; ++c) {
+                            const float4 w = *reinterpret_cast<const float4*>(wbase[c] + (j0 + z) * TP + q);
+                            s2[z][c] = __ffma2_rn(xp[q][c], make_float2(w.x, w.y), s2[z][c]);
+                            s2[z][c] = __ffma2_rn(xp[q + 1][c], make_float2(w.z, w.w), s2[z][c]);
+                        }
+                }
+#pragma unroll
+                for (int z = 0; z < 2; ++z) {
+#pragma unroll
+                    for (int c = 0; c < kWVec; ++c) u[z][c] = s2[z][c].x + s2[z][c].y;
+                    if (FP16B) {
+                        const float2 h = __half22float2(__float22half2_rn(make_float2(u[z][0], u[z][1])));
+                        u[z][0] = h.x; u[z][1] = h.y;
+                    }
+                }
+#pragma unroll
+                for (int z = 0; z < 2; ++z) {
+                    // a column at or beyond r_loop has zero W and zero cbar / chat entries: contributes exactly 0
+                    const int j = j0 + z;
+#pragma unroll
+                    for (int c = 0; c < kWVec; ++c) acc[c] = fmaf(u[z][c], cbase[c][j], acc[c]);
+                    if (DIAG) {
+#pragma unroll
+                        for (int c = 0; c < kWVec; ++c) {
+                            const float2 ud = make_float2(u[z][c], u[z][c]);
+#pragma unroll
+                            for (int q = 0; q < TP; ++q) rec2[q][c] = __ffma2_rn(ud, sChat2[j][q], rec2[q][c]);
+                        }
                     }
                 }
             }
 #pragma unroll
             for (int c = 0; c < kWVec; ++c) {
                 const bool m = (bits >> c) & 1u;
-                float val = (acc[c] + mean[c]) + (gsel[c] ? tail_n : tail_add);
+                float val = (acc[c] + mean[c]) + ((NOISE && !m) ? tail_n : tail_add);
                 if (NOISE && !m) val = noise_on ? __fmul_rn(val, a.noise_shrink) : 0.0f;
                 res[c] = b[c] + ((m || NOISE) ? val : 0.0f);
             }
             if (DIAG) {
-                for (int t = 0; t < N; ++t) {
-                    const void* fp = s_ptr[t + 1];
-                    if (fp == nullptr) continue;
-                    float f[kWVec];
-                    Elem2<T>::load(fp, e, full, numel, f);
-                    float2 rec2[kH];
+                // the diagnostics compare with the UNCENTRED masked task vector: re-read it (L2 hit)
 #pragma unroll
-                    for (int h = 0; h < kH; ++h) rec2[h] = make_float2(0.0f, 0.0f);
+                for (int q = 0; q < TP; ++q) {
 #pragma unroll
-                    for (int j = 0; j < RP; ++j) {
-                        const float ch = sChat[t][j];
-                        const float2 ch2 = make_float2(ch, ch);
+                    for (int z = 0; z < 2; ++z) {
+                        const int t = 2 * q + z;
+                        if (t >= N || !((present_bits >> t) & 1u)) continue;
+                        float f[kWVec];
+                        Elem2<T>::load(s_ptr[t + 1], e, full, numel, f);
+                        float* d0 = dyn + (size_t)(0 * N + t) * kBlock + tid;
+                        float* d1 = dyn + (size_t)(1 * N + t) * kBlock + tid;
+                        float* d2 = dyn + (size_t)(2 * N + t) * kBlock + tid;
+                        float* d3 = dyn + (size_t)(3 * N + t) * kBlock + tid;
+                        float se = *d0, sa = *d1, sr = *d2, mx = *d3;
 #pragma unroll
-                        for (int h = 0; h < kH; ++h) rec2[h] = __ffma2_rn(u[j][h], ch2, rec2[h]);
+                        for (int c = 0; c < kWVec; ++c) {
+                            if (!(((bits >> c) & 1u) && e + c < numel)) continue;
+                            const float rc = z ? rec2[q][c].y : rec2[q][c].x;
+                            const float er = Elem<T>::sub(f[c], b[c]) - rc;
+                            se = fmaf(er, er, se); sa += fabsf(er); sr = fmaf(rc, rc, sr); mx = fmaxf(mx, fabsf(er));
+                        }
+                        *d0 = se; *d1 = sa; *d2 = sr; *d3 = mx;
                     }
-                    float* d0 = dyn + (size_t)(0 * N + t) * kBlock + tid;
-                    float* d1 = dyn + (size_t)(1 * N + t) * kBlock + tid;
-                    float* d2 = dyn + (size_t)(2 * N + t) * kBlock + tid;
-                    float* d3 = dyn + (size_t)(3 * N + t) * kBlock + tid;
-                    float se = *d0, sa = *d1, sr = *d2, mx = *d3;
-#pragma unroll
-                    for (int c = 0; c < kWVec; ++c) {
-                        if (!(((bits >> c) & 1u) && e + c < numel)) continue;
-                        const float rc = (c & 1) ? rec2[c >> 1].y : rec2[c >> 1].x;
-                        const float er = Elem<T>::sub(f[c], b[c]) - rc;
-                        se = fmaf(er, er, se); sa += fabsf(er); sr = fmaf(rc, rc, sr); mx = fmaxf(mx, fabsf(er));
-                    }
-                    *d0 = se; *d1 = sa; *d2 = sr; *d3 = mx;
                 }
             }
         }
-        if (full) stg_stream_f4(outp + e, make_float4(res[0], res[1], res[2], res[3]));
-        else {
-#pragma unroll
-            for (int c = 0; c < kWVec; ++c)
-                if (e + c < numel) outp[e + c] = res[c];
-        }
+        if (full) stg_stream_f2(outp + e, make_float2(res[0], res[1]));
+        else if (e < numel) outp[e] = res[0];
     }
 
     if (DIAG) {
@@ -320,6 +347,7 @@ __global__ void __launch_bounds__(kBlock, (RP <= 24 && !NOISE) ? 2 : 1) k6_recon
             if (lane == 0) dout[row] = s;
         }
     }
+#undef W2
 }
 
 template <typename T, int RP>
@@ -358,5 +386,4 @@ cudaError_t k6_merge_launch_dtype<SVDQ_DTYPE>(int n_tasks, const K3Args& a, int 
     return launch_wide<T, 32>(a, n_tasks, n_tiles, fp16b, diag, st);
 }
 
-#undef SW
 }  // namespace svdq

@@ -41,6 +41,9 @@ __device__ __forceinline__ void stg_stream_f4(float* p, float4 v) {
     asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};"
                  :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
+__device__ __forceinline__ void stg_stream_f2(float* p, float2 v) {
+    asm volatile("st.global.cs.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(v.x), "f"(v.y) : "memory");
+}
 
 // ---- element type adapters ------------------------------------------------------------------
 // load4: four consecutive elements starting at element index e of tensor p (vector path needs
