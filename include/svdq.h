@@ -17,7 +17,7 @@
  *   - dtype codes: 0 = float32, 1 = bfloat16, 2 = float16 (dtype of base / fine-tuned tensors).
  *   - mask strategy codes: 0 = union, 1 = intersection, 2 = majority (votes >= 0.5 * n_present).
  *   - NT = n_tasks is the stride of every per-task array; n_tasks <= 16 for svdq_tv_mask_gram /
- *     svdq_gram_reduce / svdq_write_basis, <= 32 everywhere else (see "wide path" below).
+ *     svdq_write_basis (and svdq_gram_reduce with a second Gram block), <= 32 everywhere else (see "wide path").
  *   - "tile" = tile_elems consecutive elements of one parameter (tile_elems % 1024 == 0);
  *     tiles are numbered parameter by parameter: tile_begin[p] .. tile_begin[p+1]-1.
  *   - tensor pointer tables: tensors[p*(NT+1) + 0] = base, [.. + 1 + t] = fine-tuned tensor of
@@ -82,6 +82,14 @@ int svdq_tv_mask_gram(int dtype, int n_tasks, int mask_strategy, int full, int64
 int svdq_mask_pack(int n_tasks, int mask_strategy, int64_t n_tiles, int tile_elems, const uint8_t* const* masks,
                    const int64_t* numel, const int32_t* tile_param, const int32_t* tile_local,
                    const int64_t* pmask_off, uint32_t* packed, uint32_t* count, void* stream);
+/* Single-pass Gram of ALL n_tasks <= 32 task vectors under the pre-combined mask: the inputs are read once,
+ * staged through shared memory, and the 8x8 task blocks of the Gram are spread over the warps of a persistent CTA.
+ * gram: [n_tiles][n(n+1)/2]; tile_elems must be a multiple of 1536; svdq_gram_reduce (full = 0) reduces it for
+ * n_tasks <= 32.  Same reference lines as svdq_tv_mask_gram. */
+int svdq_gram_staged(int dtype, int n_tasks, int mask_mode, int64_t n_tiles, int tile_elems,
+                     const void* const* tensors, const int64_t* numel, const int32_t* tile_param,
+                     const int32_t* tile_local, const int64_t* pmask_off, const uint8_t* has_mask,
+                     const uint32_t* packed, float* gram, void* stream);
 int svdq_tv_gram_premasked(int dtype, int n_tasks, int mask_mode, int64_t n_tiles, int tile_elems,
                            const void* const* tensors, const int64_t* numel, const int32_t* tile_param,
                            const int32_t* tile_local, const int64_t* pmask_off, const uint8_t* has_mask,

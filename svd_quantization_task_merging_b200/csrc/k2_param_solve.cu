@@ -15,7 +15,7 @@ __global__ void __launch_bounds__(kBlock) k2_gram_reduce(const K2ReduceArgs a) {
     const int p = blockIdx.x, tid = threadIdx.x;
     const int NT = a.nt, G = tri_count(NT), NACC = a.full ? 2 * G : G;
     const int64_t t0 = a.tile_begin[p], t1 = a.tile_begin[p + 1];
-    __shared__ double s_part[kBlock / 32][2 * tri_count(16)];
+    __shared__ double s_part[kBlock / 32][tri_count(kMaxTasks)];   // 528 >= 2 * tri_count(16): FULL needs nt <= 16
     __shared__ unsigned long long s_cnt[kBlock / 32];
     const int lane = tid & 31, warp = tid >> 5;
 
@@ -175,7 +175,7 @@ cudaError_t k2_average_launch(const K2SolveArgs& a, int n_params, cudaStream_t s
 
 cudaError_t k2_reduce_launch(const K2ReduceArgs& a, int n_params, cudaStream_t st) {
     if (n_params <= 0) return cudaSuccess;
-    if (a.nt < 1 || a.nt > 16) return cudaErrorInvalidValue;
+    if (a.nt < 1 || a.nt > kMaxTasks || (a.full && a.nt > 16)) return cudaErrorInvalidValue;
     k2_gram_reduce<<<n_params, kBlock, 0, st>>>(a);
     return cudaGetLastError();
 }

@@ -152,6 +152,8 @@ class MergeJob:
         if config.svd_mask_strategy not in _native.STRATEGY_CODE:
             raise ValueError(f"Unknown mask strategy: {config.svd_mask_strategy}")
         self.tile_elems = int(tile_elems)
+        if self.wide and self.tile_elems % 3072 != 0:
+            self.tile_elems = 12288                      # the staged wide Gram walks tiles in chunks of 512 / 768
         self.want_diag = config.svd_eval_reconstruction if diagnostics is None else bool(diagnostics)
         self.materialize = bool(materialize_bases)
         self.sign_ref = sign_ref
@@ -333,20 +335,8 @@ class MergeJob:
                 sl = (np.arange(n_sel, dtype=np.int64) - np.repeat(sel_begin[:-1], sel_tiles)).astype(np.int32)
                 g.sel = dict(n=n_sel, begin=_dev(sel_begin, dev), param=_dev(sp, dev), local=_dev(sl, dev),
                              proj=z(max(n_sel, 1) * N * N))
-        g.sub = []
         if self.wide:
-            blocks = [list(range(b, min(b + 8, N))) for b in range(0, N, 8)]
-            for bi in range(len(blocks)):
-                for bj in range(bi + 1, len(blocks)):
-                    idx = np.asarray(blocks[bi] + blocks[bj], np.int64)
-                    nl = len(idx)
-                    sub_ptr = np.concatenate([tptr[:, :1], tptr[:, 1 + idx]], axis=1)
-                    gl = nl * (nl + 1) // 2
-                    g.sub.append(dict(idx=torch.from_numpy(idx).to(dev), n=nl, tptr=_dev(sub_ptr, dev),
-                                      gram=z(max(n_tiles, 1) * gl), gm=z(P, nl * nl, dtype=f64),
-                                      g2=z(P, nl * nl, dtype=f64) if (self.cluster_mode or self.noise) else None))
             g.t["dm_scratch"] = z(P, dtype=i64)
-            g.t["count_scratch"] = z(max(n_tiles, 1), dtype=i32)
         optr = np.asarray([g.t["out"].data_ptr() + 4 * o for o in out_off], np.int64)
         g.t["optr"] = _dev(optr, dev)
         def sign_table(ref):
@@ -451,38 +441,29 @@ class MergeJob:
                                  _ptr(t["tile_begin"]), _ptr(t["numel"]), _ptr(t["has_mask"]), _ptr(t["gram_masked"]),
                                  _ptr(t["gram_all"]), _ptr(t["dm"]), _ptr(tn.get("gram")), _ptr(tn.get("dm")), st)
             else:
-                # 17..32 tasks: combine the masks once, then one Gram launch per pair of 8-task blocks
+                # 17..32 tasks: combine the masks once, then the single-pass staged Gram (K8)
                 for g in self.groups.values():
                     t = g.t
                     P = len(g.names)
                     _native.call("svdq_mask_pack", N, strat, g.n_tiles, te, _ptr(t["mptr"]), _ptr(t["numel"]),
                                  _ptr(t["tile_param"]), _ptr(t["tile_local"]), _ptr(t["pm_off"]), _ptr(t["packed"]),
                                  _ptr(t["count"]), st)
-                    gm_full = t["gram_masked"].view(P, N, N)
-                    ga_full = t["gram_all"].view(P, N, N) if self.cluster_mode else None
-                    gn_full = g.tn["gram"].view(P, N, N) if self.noise else None
-                    second = 2 if self.noise else (1 if self.cluster_mode else 0)   # rows of the second Gram
-                    for sub in g.sub:
-                        for mode, dst, cnt, dm_out in ((0, sub["gm"], t["count"], t["dm"]),
-                                                       (second, sub["g2"], t["count_scratch"], t["dm_scratch"])):
-                            if dst is None:
-                                continue
-                            _native.call("svdq_tv_gram_premasked", _FLOAT_DTYPES[g.dtype], sub["n"], mode, g.n_tiles,
-                                         te, _ptr(sub["tptr"]), _ptr(t["numel"]), _ptr(t["tile_param"]),
-                                         _ptr(t["tile_local"]), _ptr(t["pm_off"]), _ptr(t["has_mask"]),
-                                         _ptr(t["packed"]), _ptr(sub["gram"]), _ptr(cnt), st)
-                            _native.call("svdq_gram_reduce", sub["n"], 0, P, mms, _ptr(sub["gram"]), _ptr(cnt),
-                                         _ptr(t["tile_begin"]), None, None, _ptr(dst), None, _ptr(dm_out), None, None,
-                                         st)
-                        ix = sub["idx"]
-                        gm_full[:, ix[:, None], ix[None, :]] = sub["gm"].view(P, sub["n"], sub["n"])
-                        if sub["g2"] is not None:
-                            g2 = sub["g2"].view(P, sub["n"], sub["n"])
-                            if gn_full is not None:
-                                gn_full[:, ix[:, None], ix[None, :]] = g2
-                            if ga_full is not None:       # all = masked + complement (noise mode) or the all-rows Gram
-                                ga_full[:, ix[:, None], ix[None, :]] = (g2 + sub["gm"].view_as(g2)) if self.noise else g2
+                    # one staged launch per Gram: rows inside the mask, then (cluster weighting / noise region)
+                    # all rows or the rows outside the mask
+                    second = 2 if self.noise else (1 if self.cluster_mode else 0)
+                    dst2 = g.tn["gram"] if self.noise else t["gram_all"]
+                    launches = [(0, t["gram_masked"], t["dm"])]
+                    if second:
+                        launches.append((second, dst2, t["dm_scratch"]))
+                    for mode, dst, dm_out in launches:
+                        _native.call("svdq_gram_staged", _FLOAT_DTYPES[g.dtype], N, mode, g.n_tiles, te,
+                                     _ptr(t["tptr"]), _ptr(t["numel"]), _ptr(t["tile_param"]), _ptr(t["tile_local"]),
+                                     _ptr(t["pm_off"]), _ptr(t["has_mask"]), _ptr(t["packed"]), _ptr(t["gram"]), st)
+                        _native.call("svdq_gram_reduce", N, 0, P, mms, _ptr(t["gram"]), _ptr(t["count"]),
+                                     _ptr(t["tile_begin"]), None, None, _ptr(dst), None, _ptr(dm_out), None, None, st)
                     if self.noise:
+                        if self.cluster_mode:            # all rows = masked + unmasked
+                            torch.add(t["gram_masked"], g.tn["gram"], out=t["gram_all"])
                         # rows of the noise region (same rule as svdq_gram_reduce's dm_noise)
                         on = (t["has_mask"] != 0) & (t["dm"] >= mms) & (t["dm"] > 0)
                         g.tn["dm"].copy_(torch.where(on, t["numel"] - t["dm"], torch.zeros_like(t["dm"])))
