@@ -36,6 +36,7 @@ WORKLOADS = {
     "toy": ("toy", 8, "union", 0.5, "uniform", 2),
     # configs[3]-style stress (not a bench line): 20 task vectors take the blocked-Gram wide path
     "vit-l-14-20tasks": ("ViT-L-14", 20, "union", 0.3, "uniform", 2),
+    "vit-l-14-14tasks": ("ViT-L-14", 14, "majority", 0.5, "uniform", 2),
 }
 
 
