@@ -72,12 +72,11 @@ int svdq_tv_mask_gram(int dtype, int n_tasks, int mask_strategy, int full, int64
 /*
  * Wide path, 17..32 task vectors (the Gram accumulators of that many tasks do not fit one thread):
  * svdq_mask_pack combines the N tall masks once (same reference lines as K1's mask part) into the packed
- * mask + per-tile counts; svdq_tv_gram_premasked then accumulates the Gram of a SUBSET of <= 16 tasks
- * (tensors = [P][n_tasks+1] table of that subset) under that pre-combined mask.  The caller runs it for
- * pairs of task blocks and assembles the N x N Gram.  mask_mode selects the rows that enter the Gram: 0 = inside
- * the combined mask, 1 = all rows (whole-model Gram of cluster weighting), 2 = outside the mask (noise region);
- * gram is one block [n_tiles][n(n+1)/2] per launch.  svdq_param_solve, svdq_reconstruct_merge and
- * svdq_diag_finalize accept n_tasks <= 32 directly.
+ * mask + per-tile counts; svdq_gram_staged then accumulates the Gram of all N tasks under that mask in one
+ * pass over the inputs.  mask_mode selects the rows that enter the Gram: 0 = inside the combined mask, 1 = all
+ * rows (whole-model Gram of cluster weighting), 2 = outside the mask (noise region).  svdq_gram_reduce
+ * (full = 0), svdq_param_solve, svdq_project_exact, svdq_reconstruct_merge and svdq_diag_finalize accept
+ * n_tasks <= 32 directly.
  */
 int svdq_mask_pack(int n_tasks, int mask_strategy, int64_t n_tiles, int tile_elems, const uint8_t* const* masks,
                    const int64_t* numel, const int32_t* tile_param, const int32_t* tile_local,
@@ -90,10 +89,6 @@ int svdq_gram_staged(int dtype, int n_tasks, int mask_mode, int64_t n_tiles, int
                      const void* const* tensors, const int64_t* numel, const int32_t* tile_param,
                      const int32_t* tile_local, const int64_t* pmask_off, const uint8_t* has_mask,
                      const uint32_t* packed, float* gram, void* stream);
-int svdq_tv_gram_premasked(int dtype, int n_tasks, int mask_mode, int64_t n_tiles, int tile_elems,
-                           const void* const* tensors, const int64_t* numel, const int32_t* tile_param,
-                           const int32_t* tile_local, const int64_t* pmask_off, const uint8_t* has_mask,
-                           const uint32_t* packed, float* gram, uint32_t* count, void* stream);
 
 /*
  * K2a — fixed-order fp64 reduction of K1's tile partials per parameter.

@@ -27,7 +27,6 @@ _SIGNATURES = {
     "svdq_k4_scratch_bytes": (C.c_int64, []),
     "svdq_tv_mask_gram": (C.c_int, [_i32, _i32, _i32, _i32, _i64, _i32] + [_vp] * 10),
     "svdq_mask_pack": (C.c_int, [_i32, _i32, _i64, _i32] + [_vp] * 8),
-    "svdq_tv_gram_premasked": (C.c_int, [_i32, _i32, _i32, _i64, _i32] + [_vp] * 10),
     "svdq_gram_staged": (C.c_int, [_i32, _i32, _i32, _i64, _i32] + [_vp] * 9),
     "svdq_gram_reduce": (C.c_int, [_i32, _i32, _i64, _i32] + [_vp] * 11),
     "svdq_param_solve": (C.c_int, [_i32, _i64, _i32, _f32, _i32, _i32, _i32, _i32] + [_vp] * 22),

@@ -49,18 +49,16 @@ __global__ void __launch_bounds__(kBlock, (NT <= 8 && !FULL) ? 2 : 1) k1_tv_mask
     int n_present = 0;
 #pragma unroll
     for (int t = 0; t < NT; ++t) n_present += s_mask[t] != nullptr;
-    const bool premasked = a.packed_in != nullptr;           // combined mask already packed (wide mode)
-    const bool has_mask = premasked ? (a.has_mask_in[p] != 0) : (n_present > 0);
+    const bool has_mask = n_present > 0;
     const bool all_masks = n_present == NT;
     // per-byte vote thresholds: union >= 1, intersection >= n_present, majority 2*votes >= n_present
     const uint32_t thr_bytes = 0x01010101u * (uint32_t)(a.strategy == kUnion ? 1 : n_present);
     const bool majority = a.strategy == kMajority;
-    uint32_t* packed = (has_mask && !premasked) ? a.packed + a.pmask_off[p] : nullptr;
-    const uint32_t* packed_in = (has_mask && premasked) ? a.packed_in + a.pmask_off[p] : nullptr;
+    uint32_t* packed = has_mask ? a.packed + a.pmask_off[p] : nullptr;
 
     const bool comp = a.second_complement != 0;   // FULL: second block = Gram of the UNMASKED elements (noise region)
     // more than 10 tasks: the packed (float2) accumulators would not fit the register file -> plain fp32
-    // accumulators and scalar FMAs (FULL is not offered there: the callers run a second launch in mask_mode 1 / 2)
+    // accumulators and scalar FMAs (FULL above 10 tasks falls back to the packed accumulators and spills)
     constexpr bool kScalarAcc = NT > 10 && !FULL;
     float2 acc2[kScalarAcc ? 1 : G];
     float acc1[kScalarAcc ? G : 1];
@@ -85,8 +83,6 @@ __global__ void __launch_bounds__(kBlock, (NT <= 8 && !FULL) ? 2 : 1) k1_tv_mask
             if (all_masks) {
 #pragma unroll
                 for (int t = 0; t < NT; ++t) mw[t] = ldg_stream_u32(s_mask[t] + e);
-            } else if (premasked) {
-                mw[0] = has_mask ? __ldg(packed_in + (e >> 5)) : 0xffffffffu;
             } else if (has_mask) {
 #pragma unroll
                 for (int t = 0; t < NT; ++t) mw[t] = s_mask[t] ? ldg_stream_u32(s_mask[t] + e) : 0u;
@@ -105,7 +101,6 @@ __global__ void __launch_bounds__(kBlock, (NT <= 8 && !FULL) ? 2 : 1) k1_tv_mask
                         if (e + c < numel) mw[t] |= (uint32_t)__ldg(s_mask[t] + e + c) << (8 * c);
                 }
             }
-            if (premasked) mw[0] = has_mask ? __ldg(packed_in + (e >> 5)) : 0xffffffffu;
         } else {
 #pragma unroll
             for (int c = 0; c < kVec; ++c) b[c] = 0.0f;
@@ -125,11 +120,7 @@ __global__ void __launch_bounds__(kBlock, (NT <= 8 && !FULL) ? 2 : 1) k1_tv_mask
         uint32_t bits = 0;                                       // 4 combined-mask bits of this thread
         if (active) {
             const uint32_t valid = full ? 0xFu : ((1u << (int)(numel - e)) - 1u);
-            if (premasked) {
-                // mask_mode 0: rows inside the combined mask; 1: all rows; 2: rows outside the mask
-                const uint32_t w = a.mask_mode == 1 ? 0xffffffffu : (a.mask_mode == 2 ? (has_mask ? ~mw[0] : 0u) : mw[0]);
-                bits = (w >> (int)(e & 31)) & valid;
-            } else if (has_mask) {
+            if (has_mask) {
                 uint32_t votes = 0;                              // 4 byte lanes, one per element
 #pragma unroll
                 for (int t = 0; t < NT; ++t) votes += __vminu4(mw[t], 0x01010101u);
@@ -143,7 +134,7 @@ __global__ void __launch_bounds__(kBlock, (NT <= 8 && !FULL) ? 2 : 1) k1_tv_mask
         }
         cnt += __popc(bits);
 
-        if (has_mask && !premasked) {   // eight lanes share one 32-bit word of the packed combined mask
+        if (has_mask) {                 // eight lanes share one 32-bit word of the packed combined mask
             uint32_t w = bits << ((lane & 7) * 4);
             w |= __shfl_xor_sync(0xffffffffu, w, 1);
             w |= __shfl_xor_sync(0xffffffffu, w, 2);

@@ -1,13 +1,12 @@
 // K6 — "wide" path for 17..32 task vectors (configs[3]: 20 tasks), where the N(N+1)/2 Gram
 // accumulators no longer fit one thread's registers:
 //   k6_mask_pack            combines the N tall masks once (runtime N) -> packed mask + per-tile counts;
-//                           the Gram is then accumulated by k1_tv_mask_gram<., NT <= 16> launches over
-//                           task-subset pairs in pre-combined-mask mode, all seeing this same mask
-//   k6_reconstruct_merge    pass 2 with a runtime number of tasks: basis-row accumulators for all
-//                           r <= 32 columns live in registers (two elements per thread), the tasks are
-//                           streamed once; optional fused diagnostics accumulate in shared memory
-// Same reference lines as K1 / K3.  Bound: HBM for the mask pass; pass 2 is shared-memory/FMA-bound at
-// N = 20 (N*r = 400 FMAs per element) -- see DESIGN.md.
+//                           the Gram is then accumulated by k8_gram_staged under this mask
+//   k6_reconstruct_merge    pass 2 with a runtime number of tasks (two elements per thread, the centred
+//                           task vectors in registers as pairs of tasks); optional fused diagnostics
+//                           accumulate in shared memory
+// Same reference lines as K1 / K3.  Bound: HBM for the mask pass; pass 2 is issue-bound at N = 20
+// (N*r = 400 FMAs per element) -- see DESIGN.md.
 #include "svdq_kernels.h"
 #include "k3_body.cuh"
 

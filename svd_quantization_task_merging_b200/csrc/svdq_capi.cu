@@ -147,33 +147,6 @@ int svdq_mask_pack(int n_tasks, int mask_strategy, int64_t n_tiles, int tile_ele
     return finish(__func__, svdq::k6_mask_pack_launch(a, (int)n_tiles, (cudaStream_t)stream));
 }
 
-int svdq_tv_gram_premasked(int dtype, int n_tasks, int mask_mode, int64_t n_tiles, int tile_elems,
-                           const void* const* tensors, const int64_t* numel, const int32_t* tile_param,
-                           const int32_t* tile_local, const int64_t* pmask_off, const uint8_t* has_mask,
-                           const uint32_t* packed, float* gram, uint32_t* count, void* stream) {
-    REQUIRE(n_tasks >= 1 && n_tasks <= SVDQ_MAX_STREAM_TASKS, "n_tasks must be in [1, 16]");
-    REQUIRE(dtype >= 0 && dtype <= 2, "dtype");
-    REQUIRE(tile_elems > 0 && tile_elems % svdq::kStep == 0, "tile_elems must be a positive multiple of 1024");
-    REQUIRE(n_tiles >= 0 && n_tiles < (1ll << 31), "n_tiles");
-    if (n_tiles == 0) return 0;
-    REQUIRE(tensors && numel && tile_param && tile_local && pmask_off && has_mask && packed && gram && count,
-            "null pointer");
-    svdq::K1Args a;
-    a.tensors = tensors; a.masks = nullptr; a.numel = numel; a.tile_param = tile_param; a.tile_local = tile_local;
-    a.pmask_off = pmask_off; a.packed = nullptr; a.gram = gram; a.count = count; a.tile_elems = tile_elems;
-    a.strategy = 0; a.packed_in = packed; a.has_mask_in = has_mask; a.second_complement = 0; a.mask_mode = mask_mode;
-    REQUIRE(mask_mode >= 0 && mask_mode <= 2, "mask_mode must be 0 (masked rows), 1 (all rows) or 2 (unmasked rows)");
-    const int full = 0;
-    // always the direct-load kernel: the staged variant combines the task masks itself
-    cudaError_t e;
-    switch (dtype) {
-        case svdq::kF32:  e = svdq::k1_launch_dtype<svdq::kF32>(n_tasks, a, (int)n_tiles, full != 0, (cudaStream_t)stream); break;
-        case svdq::kBF16: e = svdq::k1_launch_dtype<svdq::kBF16>(n_tasks, a, (int)n_tiles, full != 0, (cudaStream_t)stream); break;
-        default:          e = svdq::k1_launch_dtype<svdq::kF16>(n_tasks, a, (int)n_tiles, full != 0, (cudaStream_t)stream); break;
-    }
-    return finish(__func__, e);
-}
-
 int svdq_gram_staged(int dtype, int n_tasks, int mask_mode, int64_t n_tiles, int tile_elems,
                      const void* const* tensors, const int64_t* numel, const int32_t* tile_param,
                      const int32_t* tile_local, const int64_t* pmask_off, const uint8_t* has_mask,

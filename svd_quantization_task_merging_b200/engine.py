@@ -32,7 +32,7 @@ from .svd_hybrid.weighting import compute_weights, effective_merge_weights
 
 TILE_ELEMS = 16384          # elements per tile (multiple of 1024); fixes the reduction order
 MAX_STREAM_TASKS = 16      # register-resident Gram (one K1 launch)
-MAX_TASKS = 32             # wide path: Gram over pairs of 8-task blocks, runtime-N pass 2
+MAX_TASKS = 32             # wide path: mask pack + single-pass staged Gram (K8) + runtime-N pass 2 (K6)
 EXACT_MAX_NUMEL = 262144   # projection="auto": parameters up to this size are re-projected on the stored basis
 _FLOAT_DTYPES = {torch.float32: 0, torch.bfloat16: 1, torch.float16: 2}
 _ALIGN = {torch.float32: 16, torch.bfloat16: 16, torch.float16: 16}   # 16 B: TMA bulk-copy source alignment
