@@ -16,8 +16,8 @@
  *     thread-local message for the last non-zero return.
  *   - dtype codes: 0 = float32, 1 = bfloat16, 2 = float16 (dtype of base / fine-tuned tensors).
  *   - mask strategy codes: 0 = union, 1 = intersection, 2 = majority (votes >= 0.5 * n_present).
- *   - NT = n_tasks is the stride of every per-task array; n_tasks <= 16 for svdq_tv_mask_gram /
- *     svdq_write_basis (and svdq_gram_reduce with a second Gram block), <= 32 everywhere else (see "wide path").
+ *   - NT = n_tasks is the stride of every per-task array; n_tasks <= 16 for svdq_tv_mask_gram (and for
+ *     svdq_gram_reduce with a second Gram block), <= 32 everywhere else (see "wide path").
  *   - "tile" = tile_elems consecutive elements of one parameter (tile_elems % 1024 == 0);
  *     tiles are numbered parameter by parameter: tile_begin[p] .. tile_begin[p+1]-1.
  *   - tensor pointer tables: tensors[p*(NT+1) + 0] = base, [.. + 1 + t] = fine-tuned tensor of

@@ -62,8 +62,12 @@ __device__ __forceinline__ void k5_copy_out(OUT* __restrict__ dst, const OUT* __
     if (tid < n - done) dst[g0 + done + tid] = src[done + tid];
 }
 
-template <typename T, int NT, typename OUT>
+// NT bounds the unrolled task loops (n = a.n_tasks <= NT tasks are real); VEC elements per thread and step: 4 up to
+// 16 tasks, 2 above (the task values of a thread's elements stay in registers).
+template <typename T, int NT, typename OUT, int VEC>
 __global__ void __launch_bounds__(kBlock) k5_write_basis(const K5Args a) {
+    constexpr int kStepV = kBlock * VEC;
+    const int n = a.n_tasks;
     constexpr int NTP = (NT + 3) & ~3;
     constexpr int V = 16 / (int)sizeof(OUT);
     extern __shared__ __align__(16) unsigned char dyn[];
@@ -80,10 +84,10 @@ __global__ void __launch_bounds__(kBlock) k5_write_basis(const K5Args a) {
     const int64_t start = (int64_t)a.tile_local[tile] * a.tile_elems;
     const int64_t stop = min(start + (int64_t)a.tile_elems, numel);
     const bool has_mask = a.has_mask[p] != 0;
-    if (tid <= NT) s_ptr[tid] = a.tensors[(int64_t)p * (NT + 1) + tid];
+    if (tid <= NT) s_ptr[tid] = tid <= n ? a.tensors[(int64_t)p * (n + 1) + tid] : nullptr;
     for (int i = tid; i < NT * NTP; i += kBlock) {
         const int j = i / NTP, t = i % NTP;
-        sWT[j][t] = (t < NT) ? a.W[(int64_t)p * NT * NT + t * NT + j] : 0.0f;
+        sWT[j][t] = (t < n && j < n) ? a.W[(int64_t)p * n * n + t * n + j] : 0.0f;
     }
     __syncthreads();
     uint32_t present_bits = 0;
@@ -100,14 +104,14 @@ __global__ void __launch_bounds__(kBlock) k5_write_basis(const K5Args a) {
     int64_t row_base = a.tile_row_off[tile];
     // smem image: [U_high slice | U_low slice | mean slice], each re-based per step (see k5_copy_out)
     OUT* s_u = reinterpret_cast<OUT*>(dyn);
-    float* s_mean = reinterpret_cast<float*>(dyn + ((size_t)(kStep * NT + 3 * V) * sizeof(OUT) + 15) / 16 * 16);
+    float* s_mean = reinterpret_cast<float*>(dyn + ((size_t)(kStepV * NT + 3 * V) * sizeof(OUT) + 15) / 16 * 16);
 
-    for (int64_t e0 = start; e0 < stop; e0 += kStep) {
-        const int64_t e = e0 + (int64_t)tid * kVec;
+    for (int64_t e0 = start; e0 < stop; e0 += kStepV) {
+        const int64_t e = e0 + (int64_t)tid * VEC;
         uint32_t bits = 0;
-        const bool full = e + kVec <= numel;
+        const bool full = e + VEC <= numel;
         if (e < stop) {
-            const uint32_t valid = full ? 0xFu : ((1u << (int)(numel - e)) - 1u);
+            const uint32_t valid = full ? ((1u << VEC) - 1u) : ((1u << (int)(numel - e)) - 1u);
             if (has_mask) {
                 const uint32_t w = __ldg(packed + (e >> 5));
                 bits = ((a.invert ? ~w : w) >> (int)(e & 31)) & valid;
@@ -137,34 +141,37 @@ __global__ void __launch_bounds__(kBlock) k5_write_basis(const K5Args a) {
         float* s_m = s_mean + (gm % 4);
 
         if (bits != 0) {
-            float b[kVec], x[NT][kVec], mean[kVec];
-            if (full) {
-                Elem<T>::load4(s_ptr[0], e, b);
+            float b[VEC], x[NT][VEC], mean[VEC];
+            if constexpr (VEC == 4) {
+                if (full) {
+                    Elem<T>::load4(s_ptr[0], e, b);
 #pragma unroll
-                for (int t = 0; t < NT; ++t) Elem<T>::load4(s_ptr[t + 1], e, x[t]);
-            } else {
+                    for (int t = 0; t < NT; ++t) Elem<T>::load4(s_ptr[t + 1], e, x[t]);
+                }
+            }
+            if (VEC != 4 || !full) {
 #pragma unroll
-                for (int c = 0; c < kVec; ++c) b[c] = (e + c < numel) ? Elem<T>::load1(s_ptr[0], e + c) : 0.0f;
+                for (int c = 0; c < VEC; ++c) b[c] = (e + c < numel) ? Elem<T>::load1(s_ptr[0], e + c) : 0.0f;
 #pragma unroll
                 for (int t = 0; t < NT; ++t)
 #pragma unroll
-                    for (int c = 0; c < kVec; ++c)
+                    for (int c = 0; c < VEC; ++c)
                         x[t][c] = (e + c < numel) ? Elem<T>::load1(s_ptr[t + 1], e + c) : 0.0f;
             }
 #pragma unroll
-            for (int c = 0; c < kVec; ++c) mean[c] = 0.0f;
+            for (int c = 0; c < VEC; ++c) mean[c] = 0.0f;
 #pragma unroll
             for (int t = 0; t < NT; ++t)
 #pragma unroll
-                for (int c = 0; c < kVec; ++c) { x[t][c] = Elem<T>::sub(x[t][c], b[c]); mean[c] += x[t][c]; }
+                for (int c = 0; c < VEC; ++c) { x[t][c] = Elem<T>::sub(x[t][c], b[c]); mean[c] += x[t][c]; }
 #pragma unroll
-            for (int c = 0; c < kVec; ++c) mean[c] = a.center ? __fdiv_rn(mean[c], n_f) : 0.0f;
+            for (int c = 0; c < VEC; ++c) mean[c] = a.center ? __fdiv_rn(mean[c], n_f) : 0.0f;
 #pragma unroll
             for (int t = 0; t < NT; ++t)
 #pragma unroll
-                for (int c = 0; c < kVec; ++c) x[t][c] = ((present_bits >> t) & 1u) ? x[t][c] - mean[c] : 0.0f;
+                for (int c = 0; c < VEC; ++c) x[t][c] = ((present_bits >> t) & 1u) ? x[t][c] - mean[c] : 0.0f;
 #pragma unroll
-            for (int c = 0; c < kVec; ++c) {
+            for (int c = 0; c < VEC; ++c) {
                 if (!((bits >> c) & 1u)) continue;
                 if (mean_out) s_m[lr] = mean[c];
 #pragma unroll
@@ -210,14 +217,15 @@ __global__ void __launch_bounds__(kBlock) k_unpack_mask(const uint32_t* packed, 
 
 #endif  // SVDQ_DTYPE == 0
 
-template <typename T, int NT, typename OUT>
+template <typename T, int NT, typename OUT, int VEC>
 static cudaError_t k5_go(const K5Args& a, int n_tiles, cudaStream_t st) {
     constexpr int V = 16 / (int)sizeof(OUT);
-    const size_t dsm = ((size_t)(kStep * NT + 3 * V) * sizeof(OUT) + 15) / 16 * 16 + (kStep + 4) * sizeof(float);
-    cudaError_t e = cudaFuncSetAttribute(k5_write_basis<T, NT, OUT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)dsm);
+    constexpr int kStepV = kBlock * VEC;
+    const size_t dsm = ((size_t)(kStepV * NT + 3 * V) * sizeof(OUT) + 15) / 16 * 16 + (kStepV + 4) * sizeof(float);
+    cudaError_t e = cudaFuncSetAttribute(k5_write_basis<T, NT, OUT, VEC>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm);
     if (e != cudaSuccess) return e;
-    k5_write_basis<T, NT, OUT><<<n_tiles, kBlock, dsm, st>>>(a);
+    k5_write_basis<T, NT, OUT, VEC><<<n_tiles, kBlock, dsm, st>>>(a);
     return cudaGetLastError();
 }
 
@@ -225,13 +233,19 @@ template <>
 cudaError_t k5_launch_dtype<SVDQ_DTYPE>(int nt, const K5Args& a, int n_tiles, cudaStream_t st) {
     using T = DTypeOf<SVDQ_DTYPE>::type;
     if (n_tiles <= 0) return cudaSuccess;
+    if (a.tile_elems % (kBlock * 4) != 0) return cudaErrorInvalidValue;
     switch (nt) {
-#define SVDQ_CASE(N) case N: return a.fp16_basis ? k5_go<T, N, __half>(a, n_tiles, st) : k5_go<T, N, float>(a, n_tiles, st);
+#define SVDQ_CASE(N) \
+    case N: return a.fp16_basis ? k5_go<T, N, __half, 4>(a, n_tiles, st) : k5_go<T, N, float, 4>(a, n_tiles, st);
         SVDQ_CASE(1) SVDQ_CASE(2) SVDQ_CASE(3) SVDQ_CASE(4) SVDQ_CASE(5) SVDQ_CASE(6) SVDQ_CASE(7) SVDQ_CASE(8)
         SVDQ_CASE(9) SVDQ_CASE(10) SVDQ_CASE(11) SVDQ_CASE(12) SVDQ_CASE(13) SVDQ_CASE(14) SVDQ_CASE(15) SVDQ_CASE(16)
 #undef SVDQ_CASE
-        default: return cudaErrorInvalidValue;
+        default: break;
     }
+    if (nt < 1 || nt > kMaxTasks) return cudaErrorInvalidValue;
+    // 17..32 tasks: runtime task count under a compile-time bound, two elements per thread
+    if (nt <= 24) return a.fp16_basis ? k5_go<T, 24, __half, 2>(a, n_tiles, st) : k5_go<T, 24, float, 2>(a, n_tiles, st);
+    return a.fp16_basis ? k5_go<T, 32, __half, 2>(a, n_tiles, st) : k5_go<T, 32, float, 2>(a, n_tiles, st);
 }
 
 #if SVDQ_DTYPE == 0

@@ -333,7 +333,7 @@ int svdq_write_basis(int dtype, int n_tasks, int fp16_basis, int center, int reg
                      const int32_t* tile_local, const int64_t* pmask_off, const uint8_t* has_mask,
                      const uint32_t* packed, const int32_t* info, const float* W, const int64_t* tile_row_off,
                      void* const* u_high, void* const* u_low, float* const* mean, void* stream) {
-    REQUIRE(n_tasks >= 1 && n_tasks <= SVDQ_MAX_STREAM_TASKS, "n_tasks must be in [1, 16]");
+    REQUIRE(n_tasks >= 1 && n_tasks <= SVDQ_MAX_TASKS, "n_tasks must be in [1, 32]");
     REQUIRE(dtype >= 0 && dtype <= 2, "dtype");
     REQUIRE(tile_elems > 0 && tile_elems % svdq::kStep == 0, "tile_elems must be a positive multiple of 1024");
     REQUIRE(n_tiles >= 0 && n_tiles < (1ll << 31), "n_tiles");
@@ -344,7 +344,7 @@ int svdq_write_basis(int dtype, int n_tasks, int fp16_basis, int center, int reg
     a.tensors = tensors; a.numel = numel; a.tile_param = tile_param; a.tile_local = tile_local;
     a.pmask_off = pmask_off; a.has_mask = has_mask; a.packed = packed; a.info = info; a.W = W;
     a.tile_row_off = tile_row_off; a.u_high = u_high; a.u_low = u_low; a.mean = mean; a.tile_elems = tile_elems;
-    a.center = center; a.fp16_basis = fp16_basis; a.invert = region == 1;
+    a.center = center; a.fp16_basis = fp16_basis; a.invert = region == 1; a.n_tasks = n_tasks;
     REQUIRE(region == 0 || region == 1, "region must be 0 (masked rows) or 1 (rows outside the mask)");
     return finish(__func__, k5_launch(dtype, n_tasks, a, (int)n_tiles, (cudaStream_t)stream));
 }

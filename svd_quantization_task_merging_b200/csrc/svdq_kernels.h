@@ -162,6 +162,7 @@ struct K5Args {
     int center;
     int fp16_basis;
     int invert;                   // 1 = rows outside the combined mask (noise basis, basis.py:455-466)
+    int n_tasks;                  // stride of the per-task tables (<= the kernel's compile-time task bound)
 };
 
 // launchers (one translation unit per kernel family; K1/K3/K5 additionally one per dtype)

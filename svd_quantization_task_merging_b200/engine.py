@@ -633,9 +633,6 @@ class MergeJob:
         """K5: U_high / U_low / mean compacted to the masked rows, in the artifact dtype."""
         if self._bases_done:
             return
-        if self.wide:
-            raise NotImplementedError("materialising U_high / U_low for more than 16 task vectors is not part of "
-                                      "this build (K5 is register-tiled for N <= 16)")
         fetched = self._fetch()
         cfg, N, te = self.cfg, self.N, self.tile_elems
         st = _native.stream_ptr()

@@ -281,3 +281,18 @@ def test_noise_region_materialised_bases(cuda_device):
         assert torch.allclose(nb["mean"].cpu(), rb["mean"], atol=1e-7)
         mb, rmb = res["bases"][name]["masked"], ref["bases"][name]
         assert parity.max_principal_sine(mb["U_high"].float(), rmb["U_high"].float()) < 2e-3
+
+
+def test_wide_path_materialised_bases(cuda_device):
+    """U_high / U_low / mean in the reference layout for 20 task vectors (K5 with a runtime task count), incl.
+    the noise basis: same subspaces and means as the oracle's LAPACK bases."""
+    ref, res, _ = parity.run_both({"w": (130, 60), "b": (3001,)}, 20, mask_p=0.5, svd_mask_strategy="majority",
+                                  svd_energy_threshold=0.9, svd_include_noise=True)
+    for region, ref_bases in (("masked", ref["bases"]), ("noise", ref["bases_noise"])):
+        assert ref_bases
+        for name, rb in ref_bases.items():
+            nb = res["bases"][name][region]
+            assert nb["U_high"].shape == rb["U_high"].shape and nb["U_low"].shape == rb["U_low"].shape
+            assert nb["U_high"].dtype == rb["U_high"].dtype and nb["k"] == rb["k"] and nb["D"] == rb["D"]
+            assert parity.max_principal_sine(nb["U_high"].float(), rb["U_high"].float()) < 2e-3   # fp16 storage
+            assert torch.allclose(nb["mean"].cpu(), rb["mean"], atol=1e-7)
