@@ -587,9 +587,6 @@ class MergeJob:
             self._fetched = out
         return self._fetched
 
-    def merged_deltas_device(self) -> Dict[str, torch.Tensor]:
-        raise NotImplementedError
-
     def merged_state_dict(self, to_host: bool = False) -> "OrderedDict[str, torch.Tensor]":
         """merged = base + delta for every base key, in base key order (merge.py:483-494)."""
         if not self._ran:
