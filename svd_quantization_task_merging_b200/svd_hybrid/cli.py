@@ -14,7 +14,7 @@ import torch
 from .config import SVDHybridConfig
 from .diagnostics import compression_statistics_from_sizes, print_detailed_compression_report, print_diagnostics_summary
 from .mask_loader import load_task_masks
-from .storage import save_all_artifacts, save_merged_model
+from .storage import save_all_artifacts, save_combined_masks, save_merged_model
 from .task_vector_loader import get_task_checkpoint_paths, load_checkpoint
 
 
@@ -68,6 +68,11 @@ def run_svd_hybrid_pipeline(config: SVDHybridConfig, verbose: bool = True) -> Di
 
     if config.svd_store_artifacts:                                                     # cli.py:727-735
         save_all_artifacts(bases, compressed, diagnostics, config, config.artifact_dir)
+        # additive to the reference layout: the combined tall masks, without which a masked run cannot be re-merged
+        # from its artifacts (the reference's reload passes no masks, reload.py:204, and fails on the scatter)
+        cm = job.combined_masks()
+        if cm:
+            save_combined_masks(cm, config.artifact_dir)
     save_merged_model(merged, config.output_dir)                                       # cli.py:740
     os.makedirs(config.output_dir, exist_ok=True)
     with open(os.path.join(config.output_dir, "weights.json"), "w") as f:

@@ -1,7 +1,8 @@
 """Rebuild a merged model from stored artifacts.  Mirror of src/svd_hybrid/reload.py:60-267.
 
-Masks are not part of the reference's artifact layout, so -- exactly as in the reference -- only
-unmasked runs reload faithfully (reload.py:204)."""
+Masks are not part of the reference's artifact layout (reload.py:204 passes none, so the reference can only
+re-merge unmasked runs).  This build writes the combined masks as one additive file (storage.save_combined_masks)
+and uses it here when present; artifacts written by the reference reload exactly as they do there."""
 import argparse
 import os
 from typing import Dict
@@ -9,7 +10,7 @@ from typing import Dict
 import torch
 
 from .merge import apply_merged_deltas, merge_all_parameters
-from .storage import load_all_artifacts
+from .storage import load_all_artifacts, load_combined_masks
 from .task_vector_loader import load_checkpoint
 from .weighting import compute_uniform_weights
 
@@ -21,8 +22,9 @@ def _merge_from_artifacts(artifact_dir: str, device: str):
     weights = diag["task_weights"] if "task_weights" in diag else compute_uniform_weights(tasks)
     shapes = {p: torch.Size(d["original_shape"]) for p, d in diag.get("per_parameter", {}).items()
               if d.get("original_shape") is not None}
-    deltas = merge_all_parameters(art["compressed"], art["bases"], {}, weights, shapes, art["config"], device=device,
-                                  verbose=False)
+    masks = load_combined_masks(artifact_dir, device=device)
+    deltas = merge_all_parameters(art["compressed"], art["bases"], masks, weights, shapes, art["config"],
+                                  device=device, verbose=False)
     return art, deltas
 
 

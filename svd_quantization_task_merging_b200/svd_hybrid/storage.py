@@ -134,6 +134,32 @@ def load_all_artifacts(artifact_dir: str, device: str = "cpu") -> Dict[str, Any]
     return {"bases": bases, "compressed": compressed, "diagnostics": diagnostics, "config": config}
 
 
+def save_combined_masks(masks: Dict[str, torch.Tensor], output_dir: str, filename: str = "combined_masks.pt"):
+    """Not part of the reference layout (it stores no masks): one extra file next to config.json, bit-packed
+    (numpy packbits, little bit order) with the shapes, that lets reload re-merge masked runs."""
+    import numpy as np
+    os.makedirs(output_dir, exist_ok=True)
+    packed = {name: {"shape": list(m.shape),
+                     "bits": torch.from_numpy(np.packbits(m.detach().cpu().numpy().reshape(-1), bitorder="little"))}
+              for name, m in masks.items()}
+    torch.save(packed, os.path.join(output_dir, filename))
+
+
+def load_combined_masks(artifact_dir: str, device: str = "cpu", filename: str = "combined_masks.pt"
+                        ) -> Dict[str, torch.Tensor]:
+    """{} when the artifacts hold no masks (unmasked run, or artifacts written by the reference)."""
+    import numpy as np
+    path = os.path.join(artifact_dir, filename)
+    if not os.path.exists(path):
+        return {}
+    out = {}
+    for name, rec in torch.load(path, map_location="cpu", weights_only=False).items():
+        n = int(np.prod(rec["shape"])) if len(rec["shape"]) else 1
+        bits = np.unpackbits(rec["bits"].numpy(), count=n, bitorder="little").astype(bool)
+        out[name] = torch.from_numpy(bits).view(rec["shape"]).to(device)
+    return out
+
+
 def save_merged_model(merged_state_dict: Dict[str, torch.Tensor], output_dir: str, filename: str = "merged_state_dict.pt"):
     os.makedirs(output_dir, exist_ok=True)
     torch.save({k: (v.cpu() if torch.is_tensor(v) else v) for k, v in merged_state_dict.items()},

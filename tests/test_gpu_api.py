@@ -208,7 +208,8 @@ def test_pipeline_on_disk_writes_reference_layout(cuda_device, tmp_path, name, m
     assert list(res.keys()) == ["merged_state_dict", "diagnostics", "bases", "compressed"]
     files = sorted(os.path.relpath(os.path.join(r, f), tmp_path) for r, _, fs in os.walk(tmp_path) for f in fs
                    if os.path.relpath(r, tmp_path).split(os.sep)[0] in ("out", "art"))
-    assert files == case["files"]                        # exactly the files the reference wrote
+    extra = {os.path.join("art", "combined_masks.pt")} if case["masks"] is not None else set()
+    assert set(files) == set(case["files"]) | extra     # the files the reference wrote (+ the additive mask file)
     art = load_all_artifacts(str(tmp_path / "art"))
     gold_diag = case["diagnostics_json"]
     assert set(art["diagnostics"].keys()) == set(gold_diag.keys())
@@ -249,6 +250,42 @@ def test_pipeline_on_disk_writes_reference_layout(cuda_device, tmp_path, name, m
         d_ref = m - case["base"][p]
         assert parity.rel_l2(merged[p] - case["base"][p], d_ref) < 5e-2     # no sign hint: RTVQ-noise level
     assert json.load(open(tmp_path / "out" / "weights.json")) == case["diagnostics"]["task_weights"]
+
+
+def test_pipeline_on_disk_20_tasks_with_artifacts(cuda_device, tmp_path):
+    """The reference's default settings (store artifacts + diagnostics) on a 20-task merge: the wide path writes
+    bases / coefficients / diagnostics / merged model in the same layout, and the reload path re-merges them."""
+    from src.svd_hybrid.cli import run_svd_hybrid_pipeline
+    from src.svd_hybrid.reload import reconstruct_from_artifacts
+    from svd_quantization_task_merging_b200 import synth
+    shapes = {"a.weight": (96, 40), "a.bias": (1500,), "ln.weight": (257,)}
+    tasks = synth.task_names(20)
+    base, fts = synth.make_checkpoints(shapes, tasks, family="parity", seed=11)
+    masks = synth.make_masks(shapes, tasks, 0.5, seed=12)
+    case = {"base": base, "finetuned": fts, "masks": masks, "tasks": tasks}
+    ck, md = _write_case(tmp_path, case)
+    cfg = SVDHybridConfig(tasks=tasks, checkpoint_dir=str(ck), base_model_path=str(tmp_path / "base.pt"),
+                          mask_dir=str(md), svd_mask_strategy="majority", svd_store_artifacts=True,
+                          svd_eval_reconstruction=True, output_dir=str(tmp_path / "out"),
+                          artifact_dir=str(tmp_path / "art"), device="cuda")
+    res = run_svd_hybrid_pipeline(cfg, verbose=False)
+    for p in shapes:
+        assert os.path.exists(tmp_path / "art" / "basis" / f"{p}.pt")
+        assert os.path.exists(tmp_path / "art" / "coeffs" / f"{p}.pt")
+        b = torch.load(tmp_path / "art" / "basis" / f"{p}.pt", weights_only=False)["masked"]
+        assert b["U_high"].shape == (b["D"], b["k"]) and b["U_low"].shape[1] == b["singular_values"].numel() - b["k"]
+        assert b["N"] == 20 and b["U_high"].dtype == torch.float16
+    assert set(res["diagnostics"]["per_parameter"]) == set(shapes)
+    # oracle on the same inputs: merged weights at RTVQ-noise level (no sign hint through the file interface)
+    ref = R.run_reference_path(base, fts, masks, R.RefConfig(tasks=tasks, svd_mask_strategy="majority"))
+    for p in shapes:
+        d_ref = ref["merged_state_dict"][p] - base[p]
+        assert parity.rel_l2(res["merged_state_dict"][p].cpu() - base[p], d_ref) < 5e-2
+    # reload re-merges the masked run from the artifacts (uses the additive combined_masks.pt)
+    out = reconstruct_from_artifacts(str(tmp_path / "art"), str(tmp_path / "base.pt"), str(tmp_path / "re.pt"), "cpu")
+    assert set(out["merged_state_dict"]) == set(base)
+    for p in shapes:
+        assert torch.allclose(out["merged_state_dict"][p], res["merged_state_dict"][p].cpu(), rtol=1e-4, atol=1e-6), p
 
 
 def test_reload_from_artifacts_unmasked(cuda_device, tmp_path):
