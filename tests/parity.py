@@ -135,6 +135,12 @@ def compare_run(ref: Dict, res: Dict, check_diag: bool = True, tol_merged: Optio
         # by LAPACK round-off dust, so NaN-ness of this parameter is not reproducible.
         if job.cfg.svd_center and 0 < meta["r"] - meta["k"] <= 2 and meta["r"] == meta["N"]:
             dust.add(name)
+        # A low-energy block of exactly 2 coefficients with more than one RTVQ stage: after stage 0 the two residuals
+        # are mathematically EQUAL (codes 0 and 2^b-1: x - deq = (scale*lo - round(scale*lo)) / scale for both), so
+        # the stage-1 range is pure round-off of the coefficients -- exactly 0 (scale = inf -> NaN, rtvq.py:17) or a
+        # few ulps -- in the reference as well.  Which one is not reproducible from coefficients that differ by 1e-7.
+        if job.stages > 1 and meta["r"] - meta["k"] == 2:
+            dust.add(name)
         # coefficients / codes
         comp_new = res["compressed"][name]
         raw = res["compressed"].raw_coefficients(name, region)
@@ -197,7 +203,7 @@ def compare_run(ref: Dict, res: Dict, check_diag: bool = True, tol_merged: Optio
     report["dust_params"] = sorted(dust)
     flipped = flipped | dust
     if check_diag and ref["diagnostics"].get("per_parameter") is not None and "per_parameter" in res["diagnostics"]:
-        compare_diagnostics(ref["diagnostics"], res["diagnostics"], flipped=flipped)
+        compare_diagnostics(ref["diagnostics"], res["diagnostics"], flipped=flipped, dust=dust)
     return report
 
 
@@ -205,7 +211,7 @@ def _base_of(ref, name):
     return ref["_base"][name].float()
 
 
-def compare_diagnostics(d_ref: Dict, d_new: Dict, tol_exact: float = TOL_DIAG, flipped=()):
+def compare_diagnostics(d_ref: Dict, d_new: Dict, tol_exact: float = TOL_DIAG, flipped=(), dust=()):
     """Diagnostics floats agree to TOL_DIAG for every parameter whose stored artifacts (fp16 c_high, RTVQ
     codes) are identical to the oracle's; a parameter with a one-step flip is itself a different (equally
     valid) quantisation, so its error figures are only compared at the quantisation-noise level."""
@@ -217,6 +223,8 @@ def compare_diagnostics(d_ref: Dict, d_new: Dict, tol_exact: float = TOL_DIAG, f
         assert int(pn["masked_size"]) == int(pr["masked_size"]) and int(pn["unmasked_size"]) == int(pr["unmasked_size"])
         assert pn["basis"]["k"] == pr["basis"]["k"] and pn["basis"]["D"] == pr["basis"]["D"]
         assert pn["compression_ratios"] == pr["compression_ratios"], name
+        if name in dust:
+            continue                      # NaN-ness of its error figures is decided by round-off (see compare_run)
         for task, er in pr["reconstruction_errors"].items():
             en = pn["reconstruction_errors"][task]
             for key, v in er.items():
@@ -231,6 +239,8 @@ def compare_diagnostics(d_ref: Dict, d_new: Dict, tol_exact: float = TOL_DIAG, f
                     assert abs(w - v) <= tol * abs(v) + floor + 1e-12, f"{name}/{task}/{key}: {w} vs {v}"
     tol = 5e-2 if flipped else tol_exact
     for key, v in d_ref["summary"].items():
+        if dust and key == "average_reconstruction_error":
+            continue
         w = d_new["summary"][key]
         if isinstance(v, float) and np.isnan(v):
             assert np.isnan(w)

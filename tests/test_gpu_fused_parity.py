@@ -296,3 +296,16 @@ def test_wide_path_materialised_bases(cuda_device):
             assert nb["U_high"].dtype == rb["U_high"].dtype and nb["k"] == rb["k"] and nb["D"] == rb["D"]
             assert parity.max_principal_sine(nb["U_high"].float(), rb["U_high"].float()) < 2e-3   # fp16 storage
             assert torch.allclose(nb["mean"].cpu(), rb["mean"], atol=1e-7)
+
+
+@pytest.mark.parametrize("n_tasks", [1, 2, 3, 9, 16, 17])
+@pytest.mark.parametrize("mask_p", [None, 0.5])
+def test_task_count_sweep_with_tiny_parameters(cuda_device, n_tasks, mask_p):
+    """Task counts at the seams of the kernel families (1, 2, 3; 9 and 16 on the direct kernels; 17 on the wide
+    path) with a parameter of fewer elements than tasks (thin SVD with r = D < N) and one below svd_min_mask_size."""
+    shapes = {"a.weight": (64, 33), "b": (700,), "c": (5,)}
+    ref, res, _ = parity.run_both(shapes, n_tasks, mask_p=mask_p, svd_mask_strategy="majority",
+                                  svd_energy_threshold=0.9)
+    rep = parity.compare_run(ref, res)
+    print(_summary(rep), rep["dust_params"])
+    assert rep["chigh_equal"] >= 0.9 * rep["chigh_total"]
