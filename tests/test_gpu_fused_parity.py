@@ -309,3 +309,32 @@ def test_task_count_sweep_with_tiny_parameters(cuda_device, n_tasks, mask_p):
     rep = parity.compare_run(ref, res)
     print(_summary(rep), rep["dust_params"])
     assert rep["chigh_equal"] >= 0.9 * rep["chigh_total"]
+
+
+@pytest.mark.parametrize("dtype,n_tasks", [(torch.bfloat16, 20), (torch.float16, 20), (torch.bfloat16, 12),
+                                           (torch.float16, 32)])
+def test_half_precision_inputs_beyond_8_tasks(cuda_device, dtype, n_tasks):
+    """bf16 / fp16 checkpoints through the direct (9..16 tasks) and wide (17..32 tasks) kernel families, with masks
+    and a materialised basis; the oracle runs on the dtype-rounded deltas in fp32 (the reference's SVD rejects
+    half-precision inputs on CPU)."""
+    from oracle import svd_hybrid_ref as R
+    from svd_quantization_task_merging_b200.engine import merge_state_dicts
+    tasks = synth.task_names(n_tasks)
+    shapes = {"w": (256, 130), "b": (4099,), "ln": (300,)}
+    base, fts = synth.make_checkpoints(shapes, tasks, family="parity", seed=21, dtype=dtype)
+    masks = synth.make_masks(shapes, tasks, 0.5, seed=22)
+    ref_cfg, cfg = parity.make_cfgs(tasks, svd_energy_threshold=0.9, svd_mask_strategy="majority")
+    base32 = {k: v.float() for k, v in base.items()}
+    fts32 = {t: {k: base32[k] + (fts[t][k] - base[k]).float() for k in base} for t in tasks}
+    ref = R.run_reference_path(base32, fts32, masks, ref_cfg)
+    res = merge_state_dicts(base, fts, masks, cfg, "cuda", sign_ref={p: b["Vh"] for p, b in ref["bases"].items()})
+    for name, b in ref["bases"].items():
+        assert res["bases"].meta(name)["k"] == b["k"], name
+        nb = res["bases"][name]["masked"]
+        assert nb["U_high"].shape == b["U_high"].shape
+        assert parity.max_principal_sine(nb["U_high"].float(), b["U_high"].float()) < 2e-3
+    for name in base:
+        d_ref = ref["merged_deltas"][name]
+        d_new = res["merged_state_dict"][name].cpu() - base32[name]
+        assert res["merged_state_dict"][name].dtype == torch.float32
+        assert parity.rel_l2(d_new, d_ref) < 2e-3, name
