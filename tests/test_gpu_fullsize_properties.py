@@ -56,6 +56,47 @@ def test_vit_b_32_full_model_properties(cuda_device):
         assert all(torch.equal(part[n], ma[n]) for n in mine)
 
 
+def test_vit_b_32_twenty_tasks_wide_path_properties(cuda_device):
+    """configs[3] style at full ViT-B-32 size: 20 tasks take the wide path (mask pack, staged single-pass Gram,
+    runtime-N pass 2).  Determinism, bit-exact masks, untouched elements, sharded == unsharded, and the singular
+    values of the largest parameters against an independent fp64 torch.linalg.svdvals of the masked, centred
+    task matrix built with torch ops on the GPU."""
+    from svd_quantization_task_merging_b200.engine import MergeJob
+    shapes, tasks, base, fts, masks = _inputs("ViT-B-32", 20, 0.3)
+    cfg = SVDHybridConfig(tasks=tasks, svd_energy_threshold=0.9, svd_mask_strategy="majority",
+                          svd_store_artifacts=False, svd_eval_reconstruction=False)
+    a = MergeJob(base, fts, masks, cfg, "cuda").run()
+    assert a.wide
+    b = MergeJob(base, fts, masks, cfg, "cuda").run()
+    ma, mb = a.merged_state_dict(), b.merged_state_dict()
+    assert all(torch.equal(ma[k], mb[k]) for k in ma)                                  # determinism
+    fa = a._fetch()[torch.float32]
+    cm = a.combined_masks()
+    names = a.groups[torch.float32].names
+    big = sorted(range(len(names)), key=lambda i: -int(np.prod(shapes[names[i]])))[:3]
+    for i, k in enumerate(names):
+        votes = torch.stack([masks[t][k] for t in tasks]).sum(0)
+        maj = 2 * votes >= len(tasks)
+        assert torch.equal(cm[k], maj), k
+        assert int(fa["dm"][i]) == int(maj.sum())
+        assert torch.equal(ma[k][~maj], base[k][~maj]), k
+        assert torch.isfinite(ma[k]).all(), k
+        if i in big:
+            T = torch.stack([(fts[t][k] - base[k])[maj] for t in tasks], 1).double()
+            T = T - T.mean(1, keepdim=True)
+            S = torch.linalg.svdvals(T).cpu().numpy()
+            r = int(fa["info"][i, 2])
+            assert r == 20
+            got = fa["sv"][i][:r]
+            ok = np.abs(got - S[:r]) <= np.maximum(2e-6 * S[0], 2e-9 * S[0] ** 2 / np.maximum(S[:r], 1e-30)) + \
+                (S[:r] <= 1e-5 * S[0]) * 1e-4 * S[0]
+            assert ok.all(), (k, got, S[:r])
+    owner = sharding.lpt_partition({k: int(np.prod(v)) * 21 for k, v in shapes.items()}, 8)
+    mine = [n for n, r in owner.items() if r == 3]
+    part = MergeJob(base, fts, masks, cfg, "cuda", param_filter=mine).run().merged_state_dict()
+    assert all(torch.equal(part[n], ma[n]) for n in mine)
+
+
 def test_all_true_masks_equal_no_masks_and_scale_equivariance(cuda_device):
     """ViT-B-16 shapes (configs[1] sizes), 8 tasks, 4-bit x 3 stages."""
     from svd_quantization_task_merging_b200.engine import MergeJob
