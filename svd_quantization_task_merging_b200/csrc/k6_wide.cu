@@ -93,7 +93,7 @@ cudaError_t k6_mask_pack_launch(const K6MaskArgs& a, int n_tiles, cudaStream_t s
 // packed FMAs over task pairs: the second operand (W[2q][j], W[2q+1][j]) is one aligned 64-bit word of shared
 // memory, so no register moves are needed to build packed operands (with two ELEMENTS per FMA every W entry had
 // to be duplicated first: 21 % of the instructions of the previous version).  Even / odd partial sums are
-// added at the end.  NTMAX (24 or 32) bounds the unrolled loops; tasks t >= N read nothing and count as zero.
+// added at the end.  NTMAX (20, 24 or 32) bounds the unrolled loops; tasks t >= N read nothing and count as zero.
 constexpr int kWVec = 2;
 constexpr int kWStep = kBlock * kWVec;
 
@@ -381,6 +381,7 @@ cudaError_t k6_merge_launch_dtype<SVDQ_DTYPE>(int n_tasks, const K3Args& a, int 
     using T = DTypeOf<SVDQ_DTYPE>::type;
     if (n_tiles <= 0) return cudaSuccess;
     if (n_tasks < 1 || n_tasks > kMaxTasks) return cudaErrorInvalidValue;
+    if (n_tasks <= 20) return launch_wide<T, 20>(a, n_tasks, n_tiles, fp16b, diag, st);   // the standard 20-task merge
     if (n_tasks <= 24) return launch_wide<T, 24>(a, n_tasks, n_tiles, fp16b, diag, st);
     return launch_wide<T, 32>(a, n_tasks, n_tiles, fp16b, diag, st);
 }
