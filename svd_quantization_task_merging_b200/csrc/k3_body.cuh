@@ -23,56 +23,57 @@ template <int NT> struct K3NoiseSet {
     bool on = false;
 };
 
-// x: in = fine-tuned values, scratch afterwards.  res: out = merged values.
-template <typename T, int NT, bool FP16B, bool DIAG, bool NOISE = false>
-__device__ __forceinline__ void k3_step(const float (&b)[kVec], float (&x)[NT][kVec], const uint32_t pword,
+// x: in = fine-tuned values, scratch afterwards.  res: out = merged values.  VEC = elements per thread and call
+// (4; 2 for the kernel with fused diagnostics, whose 4*NT running reductions otherwise cap it at 8 warps per SM).
+template <typename T, int NT, bool FP16B, bool DIAG, bool NOISE = false, int VEC = kVec>
+__device__ __forceinline__ void k3_step(const float (&b)[VEC], float (&x)[NT][VEC], const uint32_t pword,
                                         const int64_t e, const int64_t numel, const int r, const uint32_t present_bits,
                                         const int center, const float n_f, const float tail_add,
                                         const float (*sWT)[(NT + 3) & ~3], const float (*sChatT)[(NT + 3) & ~3],
-                                        const float* sCbar, const float* sG, float (&res)[kVec],
+                                        const float* sCbar, const float* sG, float (&res)[VEC],
                                         float (&dacc)[DIAG ? kDiagRows * NT : 1],
                                         const K3NoiseSet<NT>& ns = K3NoiseSet<NT>()) {
     struct { int center; } a{center};
-    float mean[kVec];
+    float mean[VEC];
 #pragma unroll
-    for (int c = 0; c < kVec; ++c) mean[c] = 0.0f;
+    for (int c = 0; c < VEC; ++c) mean[c] = 0.0f;
 #pragma unroll
     for (int t = 0; t < NT; ++t)
 #pragma unroll
-        for (int c = 0; c < kVec; ++c) {
+        for (int c = 0; c < VEC; ++c) {
             x[t][c] = Elem<T>::sub(x[t][c], b[c]);
             mean[c] += x[t][c];
         }
-    const uint32_t bits = (pword >> (int)(e & 31)) & 0xFu;
+    const uint32_t bits = (pword >> (int)(e & 31)) & ((1u << VEC) - 1u);
 
-    float orig[DIAG ? NT : 1][kVec];
+    float orig[DIAG ? NT : 1][VEC];
     if (DIAG) {
 #pragma unroll
         for (int t = 0; t < NT; ++t)
 #pragma unroll
-            for (int c = 0; c < kVec; ++c) orig[t][c] = x[t][c];
+            for (int c = 0; c < VEC; ++c) orig[t][c] = x[t][c];
     }
     // mean over the active tasks = sum / n (basis.py:109); n a power of two: multiply by 1/n, exactly the same
     const int n_i = (int)n_f;
     const bool pow2 = (n_i & (n_i - 1)) == 0;
     const float inv_n = __fdiv_rn(1.0f, n_f);
 #pragma unroll
-    for (int c = 0; c < kVec; ++c) mean[c] = a.center ? (pow2 ? mean[c] * inv_n : __fdiv_rn(mean[c], n_f)) : 0.0f;
+    for (int c = 0; c < VEC; ++c) mean[c] = a.center ? (pow2 ? mean[c] * inv_n : __fdiv_rn(mean[c], n_f)) : 0.0f;
     if (present_bits == ((1u << NT) - 1u)) {
 #pragma unroll
         for (int t = 0; t < NT; ++t)
 #pragma unroll
-            for (int c = 0; c < kVec; ++c) x[t][c] = x[t][c] - mean[c];
+            for (int c = 0; c < VEC; ++c) x[t][c] = x[t][c] - mean[c];
     } else {
 #pragma unroll
         for (int t = 0; t < NT; ++t)
 #pragma unroll
-            for (int c = 0; c < kVec; ++c) x[t][c] = ((present_bits >> t) & 1u) ? x[t][c] - mean[c] : 0.0f;
+            for (int c = 0; c < VEC; ++c) x[t][c] = ((present_bits >> t) & 1u) ? x[t][c] - mean[c] : 0.0f;
     }
 
     // The two tall-skinny contractions run as packed 2-wide FMAs (fma.rn.f32x2): elements (0,1) and (2,3)
     // of the thread share an instruction; the fp16 round trip of the basis row uses the packed converts.
-    constexpr int kH = kVec / 2;
+    constexpr int kH = VEC / 2;
     float2 x2[NT][kH];
 #pragma unroll
     for (int t = 0; t < NT; ++t)
@@ -128,12 +129,12 @@ __device__ __forceinline__ void k3_step(const float (&b)[kVec], float (&x)[NT][k
             for (int h = 0; h < kH; ++h) acc2[h] = __ffma2_rn(x2[t][h], g2, acc2[h]);
         }
     }
-    float acc[kVec];
+    float acc[VEC];
 #pragma unroll
     for (int h = 0; h < kH; ++h) { acc[2 * h] = acc2[h].x; acc[2 * h + 1] = acc2[h].y; }
     // noise region: the same centred task vectors contracted with the second (unmasked-rows) coefficient set;
     // every element belongs to exactly one region, the select happens at the store
-    float accn[NOISE ? kVec : 1];
+    float accn[NOISE ? VEC : 1];
     if (NOISE) {
         float2 an2[kH];
 #pragma unroll
@@ -174,7 +175,7 @@ __device__ __forceinline__ void k3_step(const float (&b)[kVec], float (&x)[NT][k
 #pragma unroll
         for (int h = 0; h < kH; ++h) { accn[2 * h] = an2[h].x; accn[2 * h + 1] = an2[h].y; }
     }
-    float rec[DIAG ? NT : 1][kVec];
+    float rec[DIAG ? NT : 1][VEC];
     if (DIAG) {
 #pragma unroll
         for (int t = 0; t < NT; ++t)
@@ -182,7 +183,7 @@ __device__ __forceinline__ void k3_step(const float (&b)[kVec], float (&x)[NT][k
             for (int h = 0; h < kH; ++h) { rec[t][2 * h] = rec2[t][h].x; rec[t][2 * h + 1] = rec2[t][h].y; }
     }
 #pragma unroll
-    for (int c = 0; c < kVec; ++c) {
+    for (int c = 0; c < VEC; ++c) {
         const bool m = (bits >> c) & 1u;
         const float val = (acc[c] + mean[c]) + tail_add;
         float other = 0.0f;
@@ -192,12 +193,12 @@ __device__ __forceinline__ void k3_step(const float (&b)[kVec], float (&x)[NT][k
     if (DIAG) {
         // elements that count: inside the combined mask and inside the tensor (one mask word for all tasks)
         const int64_t left = numel - e;
-        const uint32_t mb = bits & (left >= (int64_t)kVec ? 0xFu : ((1u << (int)(left > 0 ? left : 0)) - 1u));
+        const uint32_t mb = bits & (left >= (int64_t)VEC ? ((1u << VEC) - 1u) : ((1u << (int)(left > 0 ? left : 0)) - 1u));
 #pragma unroll
         for (int t = 0; t < NT; ++t) {
             if (!((present_bits >> t) & 1u)) continue;
 #pragma unroll
-            for (int c = 0; c < kVec; ++c) {
+            for (int c = 0; c < VEC; ++c) {
                 if ((mb >> c) & 1u) {
                     const float er = orig[t][c] - rec[t][c];
                     dacc[0 * NT + t] = fmaf(er, er, dacc[0 * NT + t]);

@@ -22,8 +22,14 @@ namespace svdq {
 
 
 
+// VEC = elements per thread and step: 4, or 2 for the variant with fused diagnostics up to 8 tasks -- its 4*NT running
+// reductions per thread fit 128 registers only with two elements in flight, which buys a second resident CTA.
+template <int NT, bool DIAG> struct K3Vec { static constexpr int value = (DIAG && NT <= 8) ? 2 : 4; };
+
 template <typename T, int NT, bool FP16B, bool DIAG, bool NOISE>
-__global__ void __launch_bounds__(kBlock, (NT <= 8 && !DIAG) ? 2 : 1) k3_reconstruct_merge(const K3Args a) {
+__global__ void __launch_bounds__(kBlock, (NT <= 8) ? 2 : 1) k3_reconstruct_merge(const K3Args a) {
+    constexpr int VEC = K3Vec<NT, DIAG>::value;
+    constexpr int kStepV = kBlock * VEC;
     constexpr int NTP = (NT + 3) & ~3;
     __shared__ __align__(16) float sWT[NT][NTP];        // sWT[j][t] = W[t][j]
     __shared__ __align__(16) float sChatT[DIAG ? NT : 1][NTP];   // sChatT[j][t] = chat[t][j]
@@ -87,47 +93,60 @@ __global__ void __launch_bounds__(kBlock, (NT <= 8 && !DIAG) ? 2 : 1) k3_reconst
     if (tid >= 1 && tid <= NT && s_ptr[tid] == nullptr) s_ptr[tid] = s_ptr[0];
     __syncthreads();
 
-    for (int64_t e0 = start; e0 < stop; e0 += kStep) {
-        const int64_t e = e0 + (int64_t)tid * kVec;
+    for (int64_t e0 = start; e0 < stop; e0 += kStepV) {
+        const int64_t e = e0 + (int64_t)tid * VEC;
         if (e >= stop) continue;
-        const bool full = e + kVec <= numel;
-        float b[kVec];
-        float res[kVec];
+        const bool full = e + VEC <= numel;
+        float b[VEC];
+        float res[VEC];
         if (status != kSolved) {
             // parameter without a basis (mask below svd_min_mask_size / no data): merged = base
-            if (full) Elem<T>::load4(s_ptr[0], e, b);
-            else {
+            if constexpr (VEC == 4) {
+                if (full) Elem<T>::load4(s_ptr[0], e, b);
+                else {
 #pragma unroll
-                for (int c = 0; c < kVec; ++c) b[c] = (e + c < numel) ? Elem<T>::load1(s_ptr[0], e + c) : 0.0f;
-            }
+                    for (int c = 0; c < VEC; ++c) b[c] = (e + c < numel) ? Elem<T>::load1(s_ptr[0], e + c) : 0.0f;
+                }
+            } else ElemPair<T>::load(s_ptr[0], e, full, numel, b);
 #pragma unroll
-            for (int c = 0; c < kVec; ++c) res[c] = b[c];
+            for (int c = 0; c < VEC; ++c) res[c] = b[c];
         } else {
             // ---- phase 1: all loads of the step back to back ----------------------------------------
-            float x[NT][kVec];                   // fine-tuned values -> task vectors -> centred task vectors
+            float x[NT][VEC];                    // fine-tuned values -> task vectors -> centred task vectors
             uint32_t pword = 0xffffffffu;
-            if (full) {
-                Elem<T>::load4(s_ptr[0], e, b);
+            if constexpr (VEC == 4) {
+                if (full) {
+                    Elem<T>::load4(s_ptr[0], e, b);
 #pragma unroll
-                for (int t = 0; t < NT; ++t) Elem<T>::load4(s_ptr[t + 1], e, x[t]);
+                    for (int t = 0; t < NT; ++t) Elem<T>::load4(s_ptr[t + 1], e, x[t]);
+                } else {
+#pragma unroll
+                    for (int c = 0; c < VEC; ++c) b[c] = (e + c < numel) ? Elem<T>::load1(s_ptr[0], e + c) : 0.0f;
+#pragma unroll
+                    for (int t = 0; t < NT; ++t)
+#pragma unroll
+                        for (int c = 0; c < VEC; ++c)
+                            x[t][c] = (e + c < numel) ? Elem<T>::load1(s_ptr[t + 1], e + c) : 0.0f;
+                }
             } else {
+                ElemPair<T>::load(s_ptr[0], e, full, numel, b);
 #pragma unroll
-                for (int c = 0; c < kVec; ++c) b[c] = (e + c < numel) ? Elem<T>::load1(s_ptr[0], e + c) : 0.0f;
-#pragma unroll
-                for (int t = 0; t < NT; ++t)
-#pragma unroll
-                    for (int c = 0; c < kVec; ++c)
-                        x[t][c] = (e + c < numel) ? Elem<T>::load1(s_ptr[t + 1], e + c) : 0.0f;
+                for (int t = 0; t < NT; ++t) ElemPair<T>::load(s_ptr[t + 1], e, full, numel, x[t]);
             }
             if (has_mask) pword = __ldg(packed + (e >> 5));
-            k3_step<T, NT, FP16B, DIAG, NOISE>(b, x, pword, e, numel, r, present_bits, a.center, n_f, tail_add, sWT,
-                                               sChatT, sCbar, sG, res, dacc, ns);
+            k3_step<T, NT, FP16B, DIAG, NOISE, VEC>(b, x, pword, e, numel, r, present_bits, a.center, n_f, tail_add,
+                                                    sWT, sChatT, sCbar, sG, res, dacc, ns);
         }
-        if (full) stg_stream_f4(outp + e, make_float4(res[0], res[1], res[2], res[3]));
-        else {
+        if constexpr (VEC == 4) {
+            if (full) stg_stream_f4(outp + e, make_float4(res[0], res[1], res[2], res[3]));
+            else {
 #pragma unroll
-            for (int c = 0; c < kVec; ++c)
-                if (e + c < numel) outp[e + c] = res[c];
+                for (int c = 0; c < VEC; ++c)
+                    if (e + c < numel) outp[e + c] = res[c];
+            }
+        } else {
+            if (full) stg_stream_f2(outp + e, make_float2(res[0], res[1]));
+            else if (e < numel) outp[e] = res[0];
         }
     }
 

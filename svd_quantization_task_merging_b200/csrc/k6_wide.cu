@@ -97,36 +97,7 @@ cudaError_t k6_mask_pack_launch(const K6MaskArgs& a, int n_tiles, cudaStream_t s
 constexpr int kWVec = 2;
 constexpr int kWStep = kBlock * kWVec;
 
-template <typename T> struct Elem2;
-template <> struct Elem2<float> {
-    static __device__ __forceinline__ void load(const void* p, int64_t e, bool full, int64_t numel, float (&o)[2]) {
-        const float* q = reinterpret_cast<const float*>(p);
-        if (full) {
-            float2 v;
-            asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(q + e));
-            o[0] = v.x; o[1] = v.y;
-        } else { o[0] = e < numel ? __ldg(q + e) : 0.0f; o[1] = e + 1 < numel ? __ldg(q + e + 1) : 0.0f; }
-    }
-};
-template <> struct Elem2<__nv_bfloat16> {
-    static __device__ __forceinline__ void load(const void* p, int64_t e, bool full, int64_t numel, float (&o)[2]) {
-        const __nv_bfloat16* q = reinterpret_cast<const __nv_bfloat16*>(p);
-        if (full) {
-            const uint32_t v = __ldg(reinterpret_cast<const uint32_t*>(q + e));
-            o[0] = __uint_as_float(v << 16); o[1] = __uint_as_float(v & 0xffff0000u);
-        } else { o[0] = e < numel ? __bfloat162float(q[e]) : 0.0f; o[1] = e + 1 < numel ? __bfloat162float(q[e + 1]) : 0.0f; }
-    }
-};
-template <> struct Elem2<__half> {
-    static __device__ __forceinline__ void load(const void* p, int64_t e, bool full, int64_t numel, float (&o)[2]) {
-        const __half* q = reinterpret_cast<const __half*>(p);
-        if (full) {
-            const uint32_t v = __ldg(reinterpret_cast<const uint32_t*>(q + e));
-            const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&v));
-            o[0] = f.x; o[1] = f.y;
-        } else { o[0] = e < numel ? __half2float(q[e]) : 0.0f; o[1] = e + 1 < numel ? __half2float(q[e + 1]) : 0.0f; }
-    }
-};
+template <typename T> using Elem2 = ElemPair<T>;
 
 // NOISE (svd_include_noise): a second coefficient set for the rows outside the combined mask; an element picks the
 // set of its own region (0 = masked rows, 1 = the rest) simply by the base address of its W / cbar reads.

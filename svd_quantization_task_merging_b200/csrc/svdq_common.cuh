@@ -93,6 +93,39 @@ template <> struct Elem<__half> {
 };
 
 // round-trip through fp16 (the reference stores bases as .half() and upcasts again)
+// two consecutive elements starting at an EVEN element index e (8- / 4-byte aligned vector access when `full`)
+template <typename T> struct ElemPair;
+template <> struct ElemPair<float> {
+    static __device__ __forceinline__ void load(const void* p, int64_t e, bool full, int64_t numel, float (&o)[2]) {
+        const float* q = reinterpret_cast<const float*>(p);
+        if (full) {
+            float2 v;
+            asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(q + e));
+            o[0] = v.x; o[1] = v.y;
+        } else { o[0] = e < numel ? __ldg(q + e) : 0.0f; o[1] = e + 1 < numel ? __ldg(q + e + 1) : 0.0f; }
+    }
+};
+template <> struct ElemPair<__nv_bfloat16> {
+    static __device__ __forceinline__ void load(const void* p, int64_t e, bool full, int64_t numel, float (&o)[2]) {
+        const __nv_bfloat16* q = reinterpret_cast<const __nv_bfloat16*>(p);
+        if (full) {
+            const uint32_t v = __ldg(reinterpret_cast<const uint32_t*>(q + e));
+            o[0] = __uint_as_float(v << 16); o[1] = __uint_as_float(v & 0xffff0000u);
+        } else { o[0] = e < numel ? __bfloat162float(q[e]) : 0.0f; o[1] = e + 1 < numel ? __bfloat162float(q[e + 1]) : 0.0f; }
+    }
+};
+template <> struct ElemPair<__half> {
+    static __device__ __forceinline__ void load(const void* p, int64_t e, bool full, int64_t numel, float (&o)[2]) {
+        const __half* q = reinterpret_cast<const __half*>(p);
+        if (full) {
+            const uint32_t v = __ldg(reinterpret_cast<const uint32_t*>(q + e));
+            const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&v));
+            o[0] = f.x; o[1] = f.y;
+        } else { o[0] = e < numel ? __half2float(q[e]) : 0.0f; o[1] = e + 1 < numel ? __half2float(q[e + 1]) : 0.0f; }
+    }
+};
+
+
 __device__ __forceinline__ float round_fp16(float x) { return __half2float(__float2half_rn(x)); }
 
 }  // namespace svdq
