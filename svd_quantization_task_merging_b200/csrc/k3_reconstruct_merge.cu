@@ -22,12 +22,13 @@ namespace svdq {
 
 
 
-// VEC = elements per thread and step: 4, or 2 for the variant with fused diagnostics up to 8 tasks -- its 4*NT running
-// reductions per thread fit 128 registers only with two elements in flight, which buys a second resident CTA.
-template <int NT, bool DIAG> struct K3Vec { static constexpr int value = (DIAG && NT <= 8) ? 2 : 4; };
+// VEC = elements per thread and step: 4 up to 8 tasks; 2 with fused diagnostics (4*NT running reductions per thread)
+// and above 8 tasks (NT x VEC task values per thread), where two elements in flight keep the register count low
+// enough for more resident warps.
+template <int NT, bool DIAG> struct K3Vec { static constexpr int value = (DIAG || NT > 8) ? 2 : 4; };
 
 template <typename T, int NT, bool FP16B, bool DIAG, bool NOISE>
-__global__ void __launch_bounds__(kBlock, (NT <= 8) ? 2 : 1) k3_reconstruct_merge(const K3Args a) {
+__global__ void __launch_bounds__(kBlock, (NT <= 8 || !DIAG) ? 2 : 1) k3_reconstruct_merge(const K3Args a) {
     constexpr int VEC = K3Vec<NT, DIAG>::value;
     constexpr int kStepV = kBlock * VEC;
     constexpr int NTP = (NT + 3) & ~3;
