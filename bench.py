@@ -21,6 +21,8 @@ import sys
 import threading
 import time
 
+import numpy as np
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
@@ -242,15 +244,19 @@ def run_ours(args):
     secondary = None
     if args.secondary and world == 1:
         def timed(fn, n):
+            # median of per-call device times after two warm-up calls (the first calls pay cudaMalloc)
+            fn()
             fn()
             torch.cuda.synchronize(dev)
-            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a0.record()
+            times = []
             for _ in range(n):
+                a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a0.record()
                 fn()
-            a1.record()
-            torch.cuda.synchronize(dev)
-            return a0.elapsed_time(a1) / n
+                a1.record()
+                torch.cuda.synchronize(dev)
+                times.append(a0.elapsed_time(a1))
+            return float(np.median(times))
         jd = MergeJob(base, fts, masks, cfg, str(dev), performance=perf, diagnostics=True)
         ms_diag = timed(jd.run, 5)
         del jd
