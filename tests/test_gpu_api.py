@@ -305,22 +305,24 @@ def test_reload_from_artifacts_unmasked(cuda_device, tmp_path):
 
 
 # ---- world-size invariance of the parameter-sharded path -----------------------------------------------------
-@pytest.mark.parametrize("weighting", ["uniform", "cluster"])
-def test_sharded_results_bit_identical_for_any_world_size(cuda_device, weighting):
+@pytest.mark.parametrize("weighting,noise,n_tasks", [("uniform", False, 8), ("cluster", False, 8), ("cluster", True, 8),
+                                                     ("uniform", False, 20)])
+def test_sharded_results_bit_identical_for_any_world_size(cuda_device, weighting, noise, n_tasks):
     """Parameters are independent units: processing the shards of world size 2/4/8 (logical ranks, one
     after the other on this GPU) must reproduce the single-rank result bit for bit."""
     from svd_quantization_task_merging_b200.engine import MergeJob
-    tasks = synth.task_names(8)
+    tasks = synth.task_names(n_tasks)
     shapes = dict(parity.MEDIUM_SHAPES)
     shapes.update({f"extra{i}.weight": (64 + i, 33) for i in range(9)})
     base, fts = synth.make_checkpoints(shapes, tasks, family="parity", seed=31)
     masks = synth.make_masks(shapes, tasks, 0.6, seed=32)
-    cfg = SVDHybridConfig(tasks=tasks, svd_energy_threshold=0.9, svd_weighting=weighting, svd_store_artifacts=False)
+    cfg = SVDHybridConfig(tasks=tasks, svd_energy_threshold=0.9, svd_weighting=weighting, svd_store_artifacts=False,
+                          svd_include_noise=noise)
     full = MergeJob(base, fts, masks, cfg, "cuda").run()
     merged_full = full.merged_state_dict()
     diag_full = full.results()["diagnostics"]["per_parameter"]
     gram = torch.from_numpy(full.whole_model_gram).cuda().view(-1) if weighting == "cluster" else None
-    cost = {k: int(np.prod(v)) * 9 for k, v in shapes.items()}
+    cost = {k: int(np.prod(v)) * (n_tasks + 1) for k, v in shapes.items()}
     for world in (2, 4, 8):
         owner = sharding.lpt_partition(cost, world)
         seen = set()
@@ -334,7 +336,9 @@ def test_sharded_results_bit_identical_for_any_world_size(cuda_device, weighting
             assert sorted(part.keys()) == sorted(mine)
             d = job.results()["diagnostics"]["per_parameter"]
             for n in mine:
-                assert torch.equal(part[n], merged_full[n]), (world, rank, n)
+                # bit patterns, so that NaNs (degenerate few-row noise regions quantise to NaN like in the reference)
+                # count as equal
+                assert torch.equal(part[n].view(torch.int32), merged_full[n].view(torch.int32)), (world, rank, n)
                 if n in diag_full:
                     assert d[n] == diag_full[n], (world, rank, n)
             seen.update(mine)
