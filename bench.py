@@ -129,6 +129,13 @@ def cpu_baseline(workload: str, steps: int = 1, warmup: int = 0):
     import torch
     from oracle import svd_hybrid_ref as R
     from svd_quantization_task_merging_b200 import synth
+    # all the host threads this process may use (torchrun exports OMP_NUM_THREADS=1 to its workers)
+    try:
+        n_host = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n_host = os.cpu_count() or 1
+    if torch.get_num_threads() < n_host:
+        torch.set_num_threads(n_host)
     cfg, tasks, model, p = _make_cfg(workload)
     shapes_all = synth.model_shapes(model)
     names = _cpu_sample_names(shapes_all, model)
