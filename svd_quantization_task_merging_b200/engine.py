@@ -381,8 +381,6 @@ class MergeJob:
         for g in self.groups.values():
             s = g.t["gram_all"].sum(dim=0)
             tot = s if tot is None else tot + s
-        if self.gram_reduce_hook is not None:       # multi-GPU: sum the per-rank Grams (sharding.allreduce_gram)
-            tot = self.gram_reduce_hook(tot)
         if self._side is None:
             self._side = torch.cuda.Stream(device=self.device)
             self._gram_host = torch.empty(self.N * self.N, dtype=torch.float64, pin_memory=True)
@@ -390,6 +388,8 @@ class MergeJob:
         ready.record()
         self._side.wait_event(ready)
         with torch.cuda.stream(self._side):
+            if self.gram_reduce_hook is not None:   # multi-GPU: sum the per-rank Grams (sharding.allreduce_gram);
+                tot = self.gram_reduce_hook(tot)    # on the side stream, so the solve does not wait for the collective
             self._gram_host.copy_(tot, non_blocking=True)
             self._gram_done = torch.cuda.Event()
             self._gram_done.record()
