@@ -35,38 +35,57 @@ __global__ void __launch_bounds__(kBlock) k6_mask_pack(const K6MaskArgs a) {
     const bool majority = a.strategy == kMajority;
     uint32_t* packed = has_mask ? a.packed + a.pmask_off[p] : nullptr;
     uint32_t cnt = 0;
-    for (int64_t e0 = start; e0 < stop; e0 += kStep) {
-        const int64_t e = e0 + (int64_t)tid * kVec;
+    // 16 elements (one 128-bit mask load per task) per thread and step, eight tasks' loads in flight
+    constexpr int kMV = 16;
+    for (int64_t e0 = start; e0 < stop; e0 += (int64_t)kBlock * kMV) {
+        const int64_t e = e0 + (int64_t)tid * kMV;
         uint32_t bits = 0;
         if (e < stop) {
-            const bool full = e + kVec <= numel;
-            const uint32_t valid = full ? 0xFu : ((1u << (int)(numel - e)) - 1u);
+            const bool full = e + kMV <= numel;
+            const uint32_t valid = full ? 0xFFFFu : ((1u << (int)(numel - e)) - 1u);
             if (has_mask) {
-                uint32_t votes = 0;
-                for (int t = 0; t < a.n_tasks; ++t) {
-                    const uint8_t* mp = s_mask[t];
-                    if (mp == nullptr) continue;
-                    uint32_t w = 0;
-                    if (full) w = ldg_stream_u32(mp + e);
-                    else
-                        for (int c = 0; c < kVec; ++c)
-                            if (e + c < numel) w |= (uint32_t)__ldg(mp + e + c) << (8 * c);
-                    votes += __vminu4(w, 0x01010101u);
+                uint32_t votes[4] = {0u, 0u, 0u, 0u};
+                constexpr int kUT = 8;
+                for (int t0 = 0; t0 < a.n_tasks; t0 += kUT) {
+                    uint4 w[kUT];
+#pragma unroll
+                    for (int q = 0; q < kUT; ++q) {
+                        const uint8_t* mp = (t0 + q < a.n_tasks) ? s_mask[t0 + q] : nullptr;
+                        w[q] = make_uint4(0u, 0u, 0u, 0u);
+                        if (mp == nullptr) continue;
+                        if (full) {
+                            asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+                                         : "=r"(w[q].x), "=r"(w[q].y), "=r"(w[q].z), "=r"(w[q].w) : "l"(mp + e));
+                        } else {
+                            uint32_t ww[4] = {0u, 0u, 0u, 0u};
+                            for (int c = 0; c < kMV; ++c)
+                                if (e + c < numel) ww[c >> 2] |= (uint32_t)__ldg(mp + e + c) << (8 * (c & 3));
+                            w[q] = make_uint4(ww[0], ww[1], ww[2], ww[3]);
+                        }
+                    }
+#pragma unroll
+                    for (int q = 0; q < kUT; ++q) {
+                        votes[0] += __vminu4(w[q].x, 0x01010101u); votes[1] += __vminu4(w[q].y, 0x01010101u);
+                        votes[2] += __vminu4(w[q].z, 0x01010101u); votes[3] += __vminu4(w[q].w, 0x01010101u);
+                    }
                 }
-                if (majority) votes += votes;
-                const uint32_t ge = __vcmpgeu4(votes, thr_bytes);
-                bits = (((ge >> 7) & 1u) | ((ge >> 14) & 2u) | ((ge >> 21) & 4u) | ((ge >> 28) & 8u)) & valid;
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    uint32_t v = votes[g];
+                    if (majority) v += v;
+                    const uint32_t ge = __vcmpgeu4(v, thr_bytes);
+                    bits |= (((ge >> 7) & 1u) | ((ge >> 14) & 2u) | ((ge >> 21) & 4u) | ((ge >> 28) & 8u)) << (4 * g);
+                }
+                bits &= valid;
             } else {
                 bits = valid;
             }
         }
         cnt += __popc(bits);
-        if (has_mask) {
-            uint32_t w = bits << ((lane & 7) * 4);
+        if (has_mask) {                                  // two lanes share one 32-bit word of the packed mask
+            uint32_t w = bits << ((lane & 1) * 16);
             w |= __shfl_xor_sync(0xffffffffu, w, 1);
-            w |= __shfl_xor_sync(0xffffffffu, w, 2);
-            w |= __shfl_xor_sync(0xffffffffu, w, 4);
-            if ((lane & 7) == 0 && e < stop) packed[e >> 5] = w;
+            if ((lane & 1) == 0 && e < stop) packed[e >> 5] = w;
         }
     }
     cnt = __reduce_add_sync(0xffffffffu, cnt);
