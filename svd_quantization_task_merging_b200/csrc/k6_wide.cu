@@ -227,6 +227,7 @@ __global__ void __launch_bounds__(kBlock, (NTMAX <= 24 && !DIAG) ? 2 : 1) k6_rec
                 wbase[c] = sW2 + g * kRegStride;
                 cbase[c] = sCbar[g];
             }
+            constexpr int kJB = (NTMAX % 4 == 0 && !DIAG) ? 4 : 2;
             float acc[kWVec] = {0.0f, 0.0f};
             float2 rec2[DIAG ? TP : 1][kWVec];
             if (DIAG) {
@@ -236,18 +237,18 @@ __global__ void __launch_bounds__(kBlock, (NTMAX <= 24 && !DIAG) ? 2 : 1) k6_rec
                     for (int c = 0; c < kWVec; ++c) rec2[q][c] = make_float2(0.0f, 0.0f);
             }
 #pragma unroll
-            for (int j0 = 0; j0 < NTMAX; j0 += 2) {              // two columns at a time: four independent FMA chains
+            for (int j0 = 0; j0 < NTMAX; j0 += kJB) {            // kJB columns at a time: 2 * kJB independent FMA chains
                 if (j0 >= r_loop) break;
-                float u[2][kWVec];
-                float2 s2[2][kWVec];
+                float u[kJB][kWVec];
+                float2 s2[kJB][kWVec];
 #pragma unroll
-                for (int z = 0; z < 2; ++z)
+                for (int z = 0; z < kJB; ++z)
 #pragma unroll
                     for (int c = 0; c < kWVec; ++c) s2[z][c] = make_float2(0.0f, 0.0f);
 #pragma unroll
                 for (int q = 0; q < TP; q += 2) {
 #pragma unroll
-                    for (int z = 0; z < 2; ++z)
+                    for (int z = 0; z < kJB; ++z)
 #pragma unroll
                         for (int c = 0; c < kWVec; ++c) {
                             const float4 w = *reinterpret_cast<const float4*>(wbase[c] + (j0 + z) * TP + q);
@@ -256,7 +257,7 @@ __global__ void __launch_bounds__(kBlock, (NTMAX <= 24 && !DIAG) ? 2 : 1) k6_rec
                         }
                 }
 #pragma unroll
-                for (int z = 0; z < 2; ++z) {
+                for (int z = 0; z < kJB; ++z) {
 #pragma unroll
                     for (int c = 0; c < kWVec; ++c) u[z][c] = s2[z][c].x + s2[z][c].y;
                     if (FP16B) {
@@ -265,7 +266,7 @@ __global__ void __launch_bounds__(kBlock, (NTMAX <= 24 && !DIAG) ? 2 : 1) k6_rec
                     }
                 }
 #pragma unroll
-                for (int z = 0; z < 2; ++z) {
+                for (int z = 0; z < kJB; ++z) {
                     // a column at or beyond r_loop has zero W and zero cbar / chat entries: contributes exactly 0
                     const int j = j0 + z;
 #pragma unroll
