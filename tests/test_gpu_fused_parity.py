@@ -338,3 +338,19 @@ def test_half_precision_inputs_beyond_8_tasks(cuda_device, dtype, n_tasks):
         d_new = res["merged_state_dict"][name].cpu() - base32[name]
         assert res["merged_state_dict"][name].dtype == torch.float32
         assert parity.rel_l2(d_new, d_ref) < 2e-3, name
+
+
+@pytest.mark.parametrize("kw", [dict(svd_max_rank=2), dict(svd_max_rank=None), dict(svd_min_mask_size=2000),
+                                dict(svd_energy_threshold=1.0), dict(svd_energy_threshold=0.5),
+                                dict(svd_center=False, svd_max_rank=3), dict(svd_low_bits=1, svd_rtvq_stages=4),
+                                dict(svd_low_bits=8, svd_rtvq_stages=8)])
+def test_config_corner_values(cuda_device, kw):
+    """Rank cap, no cap, a mask-size gate that skips parameters, energy thresholds at the ends of (0, 1], and the
+    extreme quantiser settings (select_rank basis.py:199-211, gate cli.py:332, rtvq.py:39-82)."""
+    ref, res, _ = parity.run_both(parity.MEDIUM_SHAPES, 8, mask_p=0.5, svd_mask_strategy="majority", **kw)
+    rep = parity.compare_run(ref, res)
+    print(_summary(rep), rep["dust_params"])
+    if "svd_max_rank" in kw and kw["svd_max_rank"] is not None:
+        assert all(res["bases"].meta(n)["k"] <= kw["svd_max_rank"] for n in ref["bases"])
+    if "svd_min_mask_size" in kw:
+        assert set(ref["bases"]) < set(parity.MEDIUM_SHAPES)          # some parameters were skipped in both
