@@ -638,6 +638,7 @@ class MergeJob:
         # (dtype, region) -> flat U_high / U_low / mean buffers + per-parameter element offsets; the per-parameter
         # tensors handed out by basis_tensors() are views into them (one allocation instead of 3 P small ones)
         self._basis_store: Dict[Tuple[torch.dtype, str], Dict] = {}
+        self._basis_aux: List[tuple] = []
         with torch.cuda.device(self.device):
             for dt, g in self.groups.items():
                 t = g.t
@@ -668,7 +669,7 @@ class MergeJob:
                                  _ptr(t["tile_param"]), _ptr(t["tile_local"]), _ptr(t["pm_off"]), _ptr(t["has_mask"]),
                                  _ptr(t["packed"]), _ptr(o["info"]), _ptr(o["W"]), _ptr(row_off), _ptr(uh_d),
                                  _ptr(ul_d), _ptr(mn_d), st)
-                    g.keep.extend([row_off, uh_d, ul_d, mn_d])
+                    self._basis_aux.append((row_off, uh_d, ul_d, mn_d))      # alive until the next materialisation
                     self._basis_store[(dt, "masked" if reg == 0 else "noise")] = dict(
                         uh=uh, ul=ul, mn=mn, oh=oh, ol=ol, om=om, dm=dm, r=r, k=k, ok=ok)
         self._bases_done = True
