@@ -70,6 +70,20 @@ int svdq_tv_mask_gram(int dtype, int n_tasks, int mask_strategy, int full, int64
                       uint32_t* packed, float* gram, uint32_t* count, void* stream);
 
 /*
+ * K1 with BIT-packed task masks: identical to svdq_tv_mask_gram except that every non-NULL entry of mask_bits
+ * points to ceil(numel/8) bytes (padded to a multiple of 16, 16-byte aligned) holding element 8k+i in bit i of
+ * byte k.  For inputs staged from host memory (load_task_masks, src/svd_hybrid/mask_loader.py:238-330, yields
+ * host torch.bool tensors): the masks then cross PCIe at one bit per element.  svdq_host_pack_mask is the
+ * matching host-side encoder (src/dst are HOST pointers; pure re-encoding of one mask, no combination -- the
+ * vote of combine_masks stays on the device).
+ */
+int svdq_tv_mask_gram_bits(int dtype, int n_tasks, int mask_strategy, int full, int64_t n_tiles, int tile_elems,
+                           const void* const* tensors, const uint8_t* const* mask_bits, const int64_t* numel,
+                           const int32_t* tile_param, const int32_t* tile_local, const int64_t* pmask_off,
+                           uint32_t* packed, float* gram, uint32_t* count, void* stream);
+int svdq_host_pack_mask(const uint8_t* src_host, int64_t n, uint8_t* dst_host, int n_threads);
+
+/*
  * Wide path, 17..32 task vectors (the Gram accumulators of that many tasks do not fit one thread):
  * svdq_mask_pack combines the N tall masks once (same reference lines as K1's mask part) into the packed
  * mask + per-tile counts; svdq_gram_staged then accumulates the Gram of all N tasks under that mask in one

@@ -26,6 +26,8 @@ _SIGNATURES = {
     "svdq_last_error": (C.c_char_p, []),
     "svdq_k4_scratch_bytes": (C.c_int64, []),
     "svdq_tv_mask_gram": (C.c_int, [_i32, _i32, _i32, _i32, _i64, _i32] + [_vp] * 10),
+    "svdq_tv_mask_gram_bits": (C.c_int, [_i32, _i32, _i32, _i32, _i64, _i32] + [_vp] * 10),
+    "svdq_host_pack_mask": (C.c_int, [_vp, _i64, _vp, _i32]),
     "svdq_mask_pack": (C.c_int, [_i32, _i32, _i64, _i32] + [_vp] * 8),
     "svdq_gram_staged": (C.c_int, [_i32, _i32, _i32, _i64, _i32] + [_vp] * 9),
     "svdq_gram_reduce": (C.c_int, [_i32, _i32, _i64, _i32] + [_vp] * 11),

@@ -51,6 +51,7 @@ __global__ void __launch_bounds__(kBlock, (NT <= 8 && !FULL) ? 2 : 1) k1_tv_mask
     for (int t = 0; t < NT; ++t) n_present += s_mask[t] != nullptr;
     const bool has_mask = n_present > 0;
     const bool all_masks = n_present == NT;
+    const bool mask_bits = a.mask_bits != 0;
     // per-byte vote thresholds: union >= 1, intersection >= n_present, majority 2*votes >= n_present
     const uint32_t thr_bytes = 0x01010101u * (uint32_t)(a.strategy == kUnion ? 1 : n_present);
     const bool majority = a.strategy == kMajority;
@@ -80,7 +81,12 @@ __global__ void __launch_bounds__(kBlock, (NT <= 8 && !FULL) ? 2 : 1) k1_tv_mask
             Elem<T>::load4(s_ptr[0], e, b);
 #pragma unroll
             for (int t = 0; t < NT; ++t) Elem<T>::load4(s_ptr[t + 1], e, f[t]);
-            if (all_masks) {
+            if (mask_bits) {                                     // bit-packed task masks (host-staged inputs)
+#pragma unroll
+                for (int t = 0; t < NT; ++t)
+                    mw[t] = s_mask[t] ? nibble_to_bytes((__ldg(reinterpret_cast<const uint32_t*>(s_mask[t]) + (e >> 5))
+                                                         >> (int)(e & 31)) & 0xFu) : 0u;
+            } else if (all_masks) {
 #pragma unroll
                 for (int t = 0; t < NT; ++t) mw[t] = ldg_stream_u32(s_mask[t] + e);
             } else if (has_mask) {
@@ -95,7 +101,10 @@ __global__ void __launch_bounds__(kBlock, (NT <= 8 && !FULL) ? 2 : 1) k1_tv_mask
 #pragma unroll
                 for (int c = 0; c < kVec; ++c) f[t][c] = (e + c < numel) ? Elem<T>::load1(s_ptr[t + 1], e + c) : 0.0f;
                 mw[t] = 0;
-                if (s_mask[t] != nullptr) {
+                if (s_mask[t] != nullptr && mask_bits) {         // bits past numel are cut by `valid` below
+                    mw[t] = nibble_to_bytes((__ldg(reinterpret_cast<const uint32_t*>(s_mask[t]) + (e >> 5))
+                                             >> (int)(e & 31)) & 0xFu);
+                } else if (s_mask[t] != nullptr) {
 #pragma unroll
                     for (int c = 0; c < kVec; ++c)
                         if (e + c < numel) mw[t] |= (uint32_t)__ldg(s_mask[t] + e + c) << (8 * c);

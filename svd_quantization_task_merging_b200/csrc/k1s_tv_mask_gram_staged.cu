@@ -82,7 +82,8 @@ __global__ void __launch_bounds__(kBlock + 32, 1) k1s_tv_mask_gram(const K1Args 
         PipeState ps;
         const bool is_tensor = lane <= NT;
         const bool is_mask = lane > NT && lane <= 2 * NT;
-        const int my_bytes = is_tensor ? kTensorBytes : kStep;
+        const int kMaskChunk = a.mask_bits ? kStep / 8 : kStep;          // bytes of one task's mask per chunk
+        const int my_bytes = is_tensor ? kTensorBytes : kMaskChunk;
         const int my_off = is_tensor ? lane * kTensorBytes : kMaskOff + (lane - NT - 1) * kStep;
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
             const int p = a.tile_param[tile];
@@ -98,6 +99,7 @@ __global__ void __launch_bounds__(kBlock + 32, 1) k1s_tv_mask_gram(const K1Args 
             }
             const int n_present = __popc(__ballot_sync(0xffffffffu, is_mask && my_ptr != nullptr));
             const int64_t my_esize = is_tensor ? (int64_t)sizeof(T) : 1;
+            const bool bits_in = a.mask_bits != 0;
             for (int64_t e0 = start; e0 < stop; e0 += kStep) {
                 if (lane == 0) mbar_wait(&empty[ps.stage], ps.phase ^ 1u);
                 __syncwarp();
@@ -105,10 +107,12 @@ __global__ void __launch_bounds__(kBlock + 32, 1) k1s_tv_mask_gram(const K1Args 
                 if (e0 + kStep <= numel) {
                     if (lane == 0) {
                         s_direct[ps.stage] = 0;
-                        mbar_arrive_expect_tx(&full[ps.stage], (uint32_t)((NT + 1) * kTensorBytes + n_present * kStep));
+                        mbar_arrive_expect_tx(&full[ps.stage], (uint32_t)((NT + 1) * kTensorBytes + n_present * kMaskChunk));
                     }
                     __syncwarp();
-                    if (my_ptr != nullptr) bulk_g2s(sb + my_off, my_ptr + e0 * my_esize, my_bytes, &full[ps.stage]);
+                    if (my_ptr != nullptr)
+                        bulk_g2s(sb + my_off, my_ptr + ((!is_tensor && bits_in) ? e0 / 8 : e0 * my_esize), my_bytes,
+                                 &full[ps.stage]);
                 } else if (lane == 0) {
                     s_direct[ps.stage] = 1;          // tail chunk: consumers load it themselves
                     mbar_arrive(&full[ps.stage]);
@@ -143,6 +147,7 @@ __global__ void __launch_bounds__(kBlock + 32, 1) k1s_tv_mask_gram(const K1Args 
         uint32_t* packed = has_mask ? a.packed + a.pmask_off[p] : nullptr;
 
         const bool comp = a.second_complement != 0;
+        const bool mask_bits = a.mask_bits != 0;
         float2 acc2[G];
 #pragma unroll
         for (int i = 0; i < G; ++i) acc2[i] = make_float2(0.0f, 0.0f);
@@ -161,14 +166,23 @@ __global__ void __launch_bounds__(kBlock + 32, 1) k1s_tv_mask_gram(const K1Args 
 #pragma unroll
                 for (int t = 0; t < NT; ++t) SmemElem<T>::load4(sb + (t + 1) * kTensorBytes, tid, f[t]);
 #pragma unroll
-                for (int t = 0; t < NT; ++t)
-                    mw[t] = (s_mask[t] != nullptr) ? *reinterpret_cast<const uint32_t*>(sb + kMaskOff + t * kStep + tid * 4) : 0u;
+                for (int t = 0; t < NT; ++t) {
+                    if (s_mask[t] == nullptr) mw[t] = 0u;
+                    else if (!mask_bits) mw[t] = *reinterpret_cast<const uint32_t*>(sb + kMaskOff + t * kStep + tid * 4);
+                    else mw[t] = nibble_to_bytes((*reinterpret_cast<const uint32_t*>(sb + kMaskOff + t * kStep + (tid >> 3) * 4)
+                                                  >> ((tid & 7) * 4)) & 0xFu);
+                }
             } else if (active && fullv) {
                 Elem<T>::load4(s_ptr[0], e, b);
 #pragma unroll
                 for (int t = 0; t < NT; ++t) Elem<T>::load4(s_ptr[t + 1], e, f[t]);
 #pragma unroll
-                for (int t = 0; t < NT; ++t) mw[t] = s_mask[t] ? ldg_stream_u32(s_mask[t] + e) : 0u;
+                for (int t = 0; t < NT; ++t) {
+                    if (s_mask[t] == nullptr) mw[t] = 0u;
+                    else if (!mask_bits) mw[t] = ldg_stream_u32(s_mask[t] + e);
+                    else mw[t] = nibble_to_bytes((__ldg(reinterpret_cast<const uint32_t*>(s_mask[t]) + (e >> 5))
+                                                  >> (int)(e & 31)) & 0xFu);
+                }
             } else if (active) {
 #pragma unroll
                 for (int c = 0; c < kVec; ++c) b[c] = (e + c < numel) ? Elem<T>::load1(s_ptr[0], e + c) : 0.0f;
@@ -177,7 +191,10 @@ __global__ void __launch_bounds__(kBlock + 32, 1) k1s_tv_mask_gram(const K1Args 
 #pragma unroll
                     for (int c = 0; c < kVec; ++c) f[t][c] = (e + c < numel) ? Elem<T>::load1(s_ptr[t + 1], e + c) : 0.0f;
                     mw[t] = 0;
-                    if (s_mask[t] != nullptr) {
+                    if (s_mask[t] != nullptr && mask_bits) {
+                        mw[t] = nibble_to_bytes((__ldg(reinterpret_cast<const uint32_t*>(s_mask[t]) + (e >> 5))
+                                                 >> (int)(e & 31)) & 0xFu);       // bits past numel are cut by `valid`
+                    } else if (s_mask[t] != nullptr) {
 #pragma unroll
                         for (int c = 0; c < kVec; ++c)
                             if (e + c < numel) mw[t] |= (uint32_t)__ldg(s_mask[t] + e + c) << (8 * c);

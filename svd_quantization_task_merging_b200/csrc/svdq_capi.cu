@@ -3,6 +3,8 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <thread>
+#include <vector>
 
 #include "../../include/svdq.h"
 #include "svdq_kernels.h"
@@ -110,10 +112,10 @@ const char* svdq_last_error(void) { return g_err; }
 
 int64_t svdq_k4_scratch_bytes(void) { return (int64_t)sizeof(svdq::K4Stats) * svdq::kK4MaxGrid; }
 
-int svdq_tv_mask_gram(int dtype, int n_tasks, int mask_strategy, int full, int64_t n_tiles, int tile_elems,
-                      const void* const* tensors, const uint8_t* const* masks, const int64_t* numel,
-                      const int32_t* tile_param, const int32_t* tile_local, const int64_t* pmask_off,
-                      uint32_t* packed, float* gram, uint32_t* count, void* stream) {
+static int tv_mask_gram_impl(const char* fn_name, int mask_bits, int dtype, int n_tasks, int mask_strategy, int full,
+                             int64_t n_tiles, int tile_elems, const void* const* tensors, const uint8_t* const* masks,
+                             const int64_t* numel, const int32_t* tile_param, const int32_t* tile_local,
+                             const int64_t* pmask_off, uint32_t* packed, float* gram, uint32_t* count, void* stream) {
     REQUIRE(n_tasks >= 1 && n_tasks <= SVDQ_MAX_STREAM_TASKS, "n_tasks must be in [1, 16]");
     REQUIRE(dtype >= 0 && dtype <= 2, "dtype");
     REQUIRE(mask_strategy >= 0 && mask_strategy <= 2, "Unknown mask strategy");
@@ -127,8 +129,55 @@ int svdq_tv_mask_gram(int dtype, int n_tasks, int mask_strategy, int full, int64
     a.pmask_off = pmask_off; a.packed = packed; a.gram = gram; a.count = count; a.tile_elems = tile_elems;
     a.strategy = mask_strategy;
     a.packed_in = nullptr; a.has_mask_in = nullptr; a.second_complement = full == 2; a.mask_mode = 0;
+    a.mask_bits = mask_bits;
     REQUIRE(full >= 0 && full <= 2, "full must be 0 (masked), 1 (+ all elements) or 2 (+ complement)");
-    return finish(__func__, k1_launch(dtype, n_tasks, a, (int)n_tiles, full != 0, (cudaStream_t)stream));
+    return finish(fn_name, k1_launch(dtype, n_tasks, a, (int)n_tiles, full != 0, (cudaStream_t)stream));
+}
+
+int svdq_tv_mask_gram(int dtype, int n_tasks, int mask_strategy, int full, int64_t n_tiles, int tile_elems,
+                      const void* const* tensors, const uint8_t* const* masks, const int64_t* numel,
+                      const int32_t* tile_param, const int32_t* tile_local, const int64_t* pmask_off,
+                      uint32_t* packed, float* gram, uint32_t* count, void* stream) {
+    return tv_mask_gram_impl(__func__, 0, dtype, n_tasks, mask_strategy, full, n_tiles, tile_elems, tensors, masks, numel,
+                             tile_param, tile_local, pmask_off, packed, gram, count, stream);
+}
+
+int svdq_tv_mask_gram_bits(int dtype, int n_tasks, int mask_strategy, int full, int64_t n_tiles, int tile_elems,
+                           const void* const* tensors, const uint8_t* const* mask_bits, const int64_t* numel,
+                           const int32_t* tile_param, const int32_t* tile_local, const int64_t* pmask_off,
+                           uint32_t* packed, float* gram, uint32_t* count, void* stream) {
+    return tv_mask_gram_impl(__func__, 1, dtype, n_tasks, mask_strategy, full, n_tiles, tile_elems, tensors, mask_bits,
+                             numel, tile_param, tile_local, pmask_off, packed, gram, count, stream);
+}
+
+// Host-side transfer encoding of one task mask: torch.bool bytes -> bits (element 8k+i = bit i of byte k).  Eight
+// input bytes become one output byte with one multiply; the range is split across n_threads host threads.
+int svdq_host_pack_mask(const uint8_t* src, int64_t n, uint8_t* dst, int n_threads) {
+    REQUIRE(n >= 0 && (n == 0 || (src && dst)), "null pointer");
+    REQUIRE(n_threads >= 1 && n_threads <= 256, "n_threads must be in [1, 256]");
+    const int64_t n_out = (n + 7) / 8;
+    auto work = [src, dst, n](int64_t lo, int64_t hi) {          // output bytes [lo, hi)
+        for (int64_t k = lo; k < hi; ++k) {
+            const int64_t e = k * 8;
+            uint64_t x = 0;
+            if (e + 8 <= n) memcpy(&x, src + e, 8);
+            else memcpy(&x, src + e, (size_t)(n - e));
+            // any non-zero byte counts as set (torch.bool storage is 0/1, be safe): fold every bit of a byte into bit 0
+            x |= x >> 4; x |= x >> 2; x |= x >> 1;
+            x &= 0x0101010101010101ull;
+            dst[k] = (uint8_t)((x * 0x0102040810204080ull) >> 56);
+        }
+    };
+    const int64_t per = ((n_out + n_threads - 1) / n_threads + 63) & ~(int64_t)63;
+    if (n_threads == 1 || n_out < (1 << 16)) { work(0, n_out); return 0; }
+    std::vector<std::thread> pool;
+    for (int t = 0; t < n_threads; ++t) {
+        const int64_t lo = (int64_t)t * per, hi = lo + per < n_out ? lo + per : n_out;
+        if (lo >= hi) break;
+        pool.emplace_back(work, lo, hi);
+    }
+    for (auto& th : pool) th.join();
+    return 0;
 }
 
 int svdq_mask_pack(int n_tasks, int mask_strategy, int64_t n_tiles, int tile_elems, const uint8_t* const* masks,
@@ -162,6 +211,7 @@ int svdq_gram_staged(int dtype, int n_tasks, int mask_mode, int64_t n_tiles, int
     a.tensors = tensors; a.masks = nullptr; a.numel = numel; a.tile_param = tile_param; a.tile_local = tile_local;
     a.pmask_off = pmask_off; a.packed = nullptr; a.gram = gram; a.count = nullptr; a.tile_elems = tile_elems;
     a.strategy = 0; a.packed_in = packed; a.has_mask_in = has_mask; a.second_complement = 0; a.mask_mode = mask_mode;
+    a.mask_bits = 0;
     cudaError_t e;
     switch (dtype) {
         case svdq::kF32:  e = svdq::k8_launch_dtype<svdq::kF32>(n_tasks, a, (int)n_tiles, sm_count(), (cudaStream_t)stream); break;

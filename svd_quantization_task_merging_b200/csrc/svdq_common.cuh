@@ -126,6 +126,8 @@ template <> struct ElemPair<__half> {
 };
 
 
+// four mask bits (bit c = element c) -> four 0/1 bytes in the lanes of a 32-bit word (the layout torch.bool gives)
+__device__ __forceinline__ uint32_t nibble_to_bytes(uint32_t nib) { return (nib * 0x00204081u) & 0x01010101u; }
 __device__ __forceinline__ float round_fp16(float x) { return __half2float(__float2half_rn(x)); }
 
 }  // namespace svdq

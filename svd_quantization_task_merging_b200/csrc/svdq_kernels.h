@@ -27,6 +27,9 @@ struct K1Args {
     int second_complement;
     // pre-combined mask mode only: 0 = rows inside the combined mask, 1 = all rows, 2 = rows outside the mask
     int mask_mode;
+    // 1 = the task masks are BIT-packed (element 8k+i = bit i of byte k; what svdq_host_pack_mask writes), so that
+    // masks staged from the host cross PCIe at 1/8 of the bytes; 0 = torch.bool storage, one byte per element
+    int mask_bits;
 };
 
 struct K2ReduceArgs {

@@ -74,6 +74,8 @@ def pack_state_dict(sd: Mapping[str, torch.Tensor], pin: bool = False, align_ele
     if len(dtypes) != 1:
         raise ValueError("pack_state_dict needs a single dtype per state dict")
     dtype = next(iter(dtypes))
+    if dtype == torch.bool:
+        align_elems = max(align_elems, 128)      # masks: rows stay 16-byte aligned after the host-side bit pack
     offs, n = {}, 0
     for k, v in sd.items():
         offs[k] = n
@@ -100,6 +102,89 @@ def _to_device_state_dict(sd: Mapping[str, torch.Tensor], device) -> Mapping[str
         out.flat, out.offsets = flat, sd.offsets
         return out
     return sd
+
+
+@dataclass
+class _PackedBits:
+    """One task mask as it sits on the device after a host-side bit pack: ``bits`` = ceil(numel/8) bytes."""
+    shape: torch.Size
+    bits: torch.Tensor
+
+
+_PIN_STAGING: Dict[str, object] = {"buf": None, "event": None}
+
+
+def _pinned_staging(nbytes: int) -> torch.Tensor:
+    """Process-wide pinned staging buffer for the bit-packed masks (grow-only; a previous upload out of it is
+    waited for before it is overwritten)."""
+    ev = _PIN_STAGING["event"]
+    if ev is not None:
+        ev.synchronize()
+        _PIN_STAGING["event"] = None
+    buf = _PIN_STAGING["buf"]
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(nbytes + nbytes // 8, dtype=torch.uint8).pin_memory()
+        _PIN_STAGING["buf"] = buf
+    return buf
+
+
+def _upload_mask_bits(task_masks: Sequence[Optional[Mapping[str, torch.Tensor]]], device
+                      ) -> Tuple[List[Optional[Dict[str, _PackedBits]]], int]:
+    """HOST torch.bool masks -> bits on the host (svdq_host_pack_mask, all host threads; runs while the tensors'
+    host->device copies are in flight) -> one upload of numel/8 bytes per task.  A pure transfer encoding: the
+    masks are combined on the device (K1) exactly as with byte masks."""
+    n_threads = max(1, min(16, len(os.sched_getaffinity(0))))
+    plan, total = [], 0
+    for m in task_masks:
+        if m is None:
+            plan.append(None)
+            continue
+        whole = (isinstance(m, PackedStateDict) and m.flat.dtype == torch.bool and m.flat.is_contiguous()
+                 and all(o % 128 == 0 for o in m.offsets.values()))
+        if whole:                                             # one call for the whole flat buffer
+            entry = dict(whole=True, base=total, offs={k: o // 8 for k, o in m.offsets.items()})
+            total += (m.flat.numel() + 7) // 8
+        else:
+            offs = {}
+            entry = dict(whole=False, base=total, offs=offs)
+            for k, v in m.items():
+                offs[k] = total - entry["base"]
+                total += ((v.numel() + 7) // 8 + 15) // 16 * 16
+        total = (total + 16 + 15) // 16 * 16                  # K1's last partial vector reads a whole 32-bit word
+        plan.append(entry)
+    stage = _pinned_staging(max(total, 16))
+    base_ptr = stage.data_ptr()
+    keep = []
+    for m, entry in zip(task_masks, plan):
+        if m is None:
+            continue
+        if entry["whole"]:
+            _native.call("svdq_host_pack_mask", m.flat.data_ptr(), m.flat.numel(), base_ptr + entry["base"], n_threads)
+        else:
+            for k, v in m.items():
+                v = v.detach()
+                if v.dtype != torch.bool:
+                    v = v.bool()
+                v = v.contiguous()
+                keep.append(v)
+                _native.call("svdq_host_pack_mask", v.data_ptr(), v.numel(), base_ptr + entry["base"] + entry["offs"][k],
+                             n_threads)
+    dev_bits = torch.empty(max(total, 16), dtype=torch.uint8, device=device)
+    dev_bits.copy_(stage[: dev_bits.numel()], non_blocking=True)
+    ev = torch.cuda.Event()
+    ev.record()
+    _PIN_STAGING["event"] = ev
+    out: List[Optional[Dict[str, _PackedBits]]] = []
+    for m, entry in zip(task_masks, plan):
+        if m is None:
+            out.append(None)
+            continue
+        d = {}
+        for k, v in m.items():
+            o = entry["base"] + entry["offs"][k]
+            d[k] = _PackedBits(v.shape, dev_bits[o: o + (v.numel() + 7) // 8])
+        out.append(d)
+    return out, total
 
 
 @dataclass
@@ -199,15 +284,23 @@ class MergeJob:
             for v in sd.values():
                 if v.device != dev:
                     self.h2d_bytes += v.numel() * v.element_size()
-        masks_d: List[Optional[Mapping[str, torch.Tensor]]] = []
-        for t in self.tasks:
-            m = task_masks.get(t) if task_masks else None
-            if m is not None:
-                for v in m.values():
-                    if v.device != dev:
-                        self.h2d_bytes += v.numel() * v.element_size()
-                m = _to_device_state_dict(m, dev)
-            masks_d.append(m)
+        masks_h = [(task_masks.get(t) if task_masks else None) for t in self.tasks]
+        # masks that all sit in host memory (what load_task_masks yields) cross PCIe bit-packed: 1/8 of the bytes
+        self.mask_bits = (not self.wide and any(m is not None for m in masks_h) and
+                          all(torch.is_tensor(v) and v.device.type == "cpu" for m in masks_h if m is not None
+                              for v in m.values()))
+        masks_d: List[Optional[Mapping[str, object]]] = []
+        if self.mask_bits:
+            masks_d, nbytes = _upload_mask_bits(masks_h, dev)
+            self.h2d_bytes += nbytes
+        else:
+            for m in masks_h:
+                if m is not None:
+                    for v in m.values():
+                        if v.device != dev:
+                            self.h2d_bytes += v.numel() * v.element_size()
+                    m = _to_device_state_dict(m, dev)
+                masks_d.append(m)
 
         self.base_keys = list(base.keys())
         self.base_ref = base
@@ -248,6 +341,9 @@ class MergeJob:
                 if mk.shape != b.shape:
                     mrow = [None] * self.N       # cli.py:330: a mask of the wrong shape is not used
                     break
+                if isinstance(mk, _PackedBits):
+                    mrow[i] = mk.bits
+                    continue
                 if mk.dtype != torch.bool:
                     mk = mk.bool()
                 mrow[i] = _aligned_flat(mk, dev, 16)
@@ -429,7 +525,8 @@ class MergeJob:
             if not self.wide:
                 for g in self.groups.values():
                     t = g.t
-                    _native.call("svdq_tv_mask_gram", _FLOAT_DTYPES[g.dtype], N, strat, full, g.n_tiles, te,
+                    _native.call("svdq_tv_mask_gram_bits" if self.mask_bits else "svdq_tv_mask_gram",
+                                 _FLOAT_DTYPES[g.dtype], N, strat, full, g.n_tiles, te,
                                  _ptr(t["tptr"]), _ptr(t["mptr"]), _ptr(t["numel"]), _ptr(t["tile_param"]),
                                  _ptr(t["tile_local"]), _ptr(t["pm_off"]), _ptr(t["packed"]), _ptr(t["gram"]),
                                  _ptr(t["count"]), st)

@@ -55,6 +55,23 @@ def test_invalid_arguments_are_value_errors_without_touching_the_gpu():
     assert lib.svdq_unpack_mask(None, 0, None, None) == 0
 
 
+def test_host_mask_packer_matches_numpy_packbits():
+    """svdq_host_pack_mask is the host-side transfer encoding of one task mask (element 8k+i -> bit i of byte k)."""
+    import numpy as np
+    lib = _native.load()
+    rng = np.random.default_rng(7)
+    for n, threads in [(0, 1), (1, 1), (7, 1), (8, 2), (1023, 1), (70_001, 3), (1 << 20, 4), ((1 << 20) + 5, 16)]:
+        src = (rng.random(n) < 0.3).astype(np.uint8)
+        if n > 10:
+            src[3] = 255                                    # any non-zero byte is a set bit
+        dst = np.zeros((n + 7) // 8, np.uint8)
+        rc = lib.svdq_host_pack_mask(src.ctypes.data if n else None, n, dst.ctypes.data if n else None, threads)
+        assert rc == 0
+        assert np.array_equal(dst, np.packbits(src != 0, bitorder="little")), (n, threads)
+    assert lib.svdq_host_pack_mask(None, 8, None, 1) < 0
+    assert lib.svdq_host_pack_mask(None, 0, None, 0) < 0
+
+
 def test_product_path_fails_loudly_without_cuda():
     import torch
     if torch.cuda.is_available():

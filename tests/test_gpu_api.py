@@ -343,3 +343,49 @@ def test_sharded_results_bit_identical_for_any_world_size(cuda_device, weighting
                     assert d[n] == diag_full[n], (world, rank, n)
             seen.update(mine)
         assert seen == set(shapes)
+
+
+# ---- host masks travel bit-packed; device masks stay torch.bool bytes: same results, bit for bit ---------------
+@pytest.mark.parametrize("strategy,n_tasks,dtype,noise", [("union", 3, torch.float32, False),
+                                                          ("majority", 8, torch.float32, True),
+                                                          ("intersection", 8, torch.bfloat16, False),
+                                                          ("majority", 12, torch.float32, False),
+                                                          ("union", 16, torch.float16, False)])
+def test_host_bit_packed_masks_equal_device_byte_masks(cuda_device, strategy, n_tasks, dtype, noise):
+    from svd_quantization_task_merging_b200.engine import MergeJob, pack_state_dict
+    tasks = synth.task_names(n_tasks)
+    shapes = dict(parity.MEDIUM_SHAPES)
+    shapes.update({"odd.weight": (1031, 7), "tiny.bias": (5,), "chunk.weight": (1024, 3), "word.weight": (33,)})
+    base, fts = synth.make_checkpoints(shapes, tasks, family="parity", seed=51)
+    base = {k: v.to(dtype) for k, v in base.items()}
+    fts = {t: {k: v.to(dtype) for k, v in sd.items()} for t, sd in fts.items()}
+    masks = synth.make_masks(shapes, tasks, 0.55, seed=52)
+    del masks[tasks[0]]["odd.weight"]                         # a task without a mask for one parameter
+    masks[tasks[1]]["tiny.bias"] = torch.ones(6, dtype=torch.bool)        # wrong shape: parameter runs unmasked
+    masks[tasks[-1]] = {k: v.to(torch.uint8) * 3 for k, v in masks[tasks[-1]].items()}   # non-bool mask dtype
+    cfg = SVDHybridConfig(tasks=tasks, svd_energy_threshold=0.9, svd_mask_strategy=strategy, svd_store_artifacts=False,
+                          svd_include_noise=noise, svd_weighting="cluster")
+    variants = {
+        "device_bytes": {t: {k: v.cuda() for k, v in m.items()} for t, m in masks.items()},
+        "host_dicts": masks,
+        "host_packed": {t: (pack_state_dict(m, pin=True) if m and len({v.dtype for v in m.values()}) == 1 else m)
+                        for t, m in masks.items()},
+    }
+    results = {}
+    for tag, mk in variants.items():
+        job = MergeJob(base, fts, mk, cfg, "cuda")
+        assert job.mask_bits == (tag != "device_bytes")
+        job.run()
+        results[tag] = (job.merged_state_dict(), job.combined_masks(), job.results()["diagnostics"]["per_parameter"])
+    ref_m, ref_c, ref_d = results["device_bytes"]
+    itype = torch.int32 if dtype == torch.float32 else torch.int16
+    for tag in ("host_dicts", "host_packed"):
+        m, c, d = results[tag]
+        assert sorted(c.keys()) == sorted(ref_c.keys())
+        for k in ref_c:
+            assert torch.equal(c[k], ref_c[k]), (tag, k)
+        for k in ref_m:
+            assert torch.equal(m[k].view(itype), ref_m[k].view(itype)), (tag, k)
+        # through json so that NaNs (few-task degenerate blocks quantise to NaN like in the reference) compare equal
+        canon = lambda x: json.dumps(x, sort_keys=True, default=lambda o: o.item() if hasattr(o, "item") else str(o))
+        assert canon(d) == canon(ref_d), tag
