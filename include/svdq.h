@@ -72,7 +72,7 @@ int svdq_tv_mask_gram(int dtype, int n_tasks, int mask_strategy, int full, int64
 /*
  * K1 with BIT-packed task masks: identical to svdq_tv_mask_gram except that every non-NULL entry of mask_bits
  * points to ceil(numel/8) bytes (padded to a multiple of 16, 16-byte aligned) holding element 8k+i in bit i of
- * byte k.  For inputs staged from host memory (load_task_masks, src/svd_hybrid/mask_loader.py:238-330, yields
+ * byte k.  For inputs staged from host memory (load_task_masks, src/svd_hybrid/mask_loader.py:242-409, yields
  * host torch.bool tensors): the masks then cross PCIe at one bit per element.  svdq_host_pack_mask is the
  * matching host-side encoder (src/dst are HOST pointers; pure re-encoding of one mask, no combination -- the
  * vote of combine_masks stays on the device).
