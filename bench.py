@@ -39,7 +39,12 @@ WORKLOADS = {
     # configs[3]-style stress (not a bench line): 20 task vectors take the blocked-Gram wide path
     "vit-l-14-20tasks": ("ViT-L-14", 20, "union", 0.3, "uniform", 2),
     "vit-l-14-14tasks": ("ViT-L-14", 14, "majority", 0.5, "uniform", 2),
+    # configs[4] capacity stress: one rank's shard of the 8-way LPT partition of Llama-3-8B (bf16 task vectors, no
+    # masks); under torchrun with 8 ranks every rank takes its own shard = the whole model
+    "llama-3-8b-shard": ("Llama-3-8B", 8, "union", None, "uniform", 2),
 }
+# workload extras: input dtype, logical world size of the parameter partition the shard is taken from
+WORKLOAD_EXTRA = {"llama-3-8b-shard": {"dtype": "bfloat16", "shard_world": 8}}
 
 
 def _measured_peak():
@@ -120,7 +125,11 @@ def _cpu_sample_names(shapes, model):
     if model == "toy":
         return list(shapes.keys())
     prefs = tuple(f"transformer.resblocks.{i}." for i in range(4))
-    return [k for k in shapes if k.startswith(prefs)]
+    names = [k for k in shapes if k.startswith(prefs)]
+    if names:
+        return names
+    # other models: the attention projections and norms of the first decoder layer (Llama-3-8B: 41.9 M params)
+    return [k for k in shapes if k.startswith("model.layers.0.") and ".mlp." not in k]
 
 
 def cpu_baseline(workload: str, steps: int = 1, warmup: int = 0):
@@ -140,8 +149,9 @@ def cpu_baseline(workload: str, steps: int = 1, warmup: int = 0):
     shapes_all = synth.model_shapes(model)
     names = _cpu_sample_names(shapes_all, model)
     shapes = {k: shapes_all[k] for k in names}
-    base, fts = synth.make_checkpoints(shapes, tasks, family="parity", seed=1234)
-    masks = synth.make_masks(shapes, tasks, p, seed=4321)
+    in_dtype = getattr(torch, WORKLOAD_EXTRA.get(workload, {}).get("dtype", "float32"))
+    base, fts = synth.make_checkpoints(shapes, tasks, family="parity", seed=1234, dtype=in_dtype)
+    masks = synth.make_masks(shapes, tasks, p, seed=4321) if p is not None else None
     perf = synth.performance_table(tasks) if cfg.svd_weighting == "performance" else None
     rcfg = R.RefConfig(tasks=tasks, svd_energy_threshold=cfg.svd_energy_threshold, svd_max_rank=cfg.svd_max_rank,
                        svd_center=cfg.svd_center, svd_fp16=cfg.svd_fp16, svd_low_bits=cfg.svd_low_bits,
@@ -161,7 +171,7 @@ def cpu_baseline(workload: str, steps: int = 1, warmup: int = 0):
     dt = (time.perf_counter() - t0) / max(steps, 1)
     return {"value": n_params / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
             "sample": f"{model} {len(names)} tensors ({n_params / 1e6:.1f} M params: "
-                      f"{'first four transformer blocks' if model != 'toy' else 'whole toy model'}), {len(tasks)} tasks, "
+                      f"{'whole toy model' if model == 'toy' else 'first four transformer blocks' if model.startswith('ViT') else 'attention + norms of the first decoder layer'}), {len(tasks)} tasks, "
                       f"oracle/svd_hybrid_ref.py (torch-eager CPU restatement of the reference path; its full-feature "
                       f"k-means excluded), {dt:.2f} s per pass"}, dt, n_params
 
@@ -220,11 +230,22 @@ def run_ours(args):
 
     cfg, tasks, model, p = _make_cfg(args.workload)
     shapes = synth.model_shapes(model)
-    n_params = synth.total_params(shapes)
     N = len(tasks)
+    extra = WORKLOAD_EXTRA.get(args.workload, {})
+    in_dtype = getattr(torch, extra.get("dtype", "float32"))
+    shard_note = ""
+    if extra.get("shard_world"):
+        from svd_quantization_task_merging_b200 import sharding
+        sw = extra["shard_world"]
+        owner = sharding.lpt_partition({k: int(np.prod(v)) * (N + 1) for k, v in shapes.items()}, sw)
+        mine = (args.shard_rank + rank) % sw
+        shapes = type(shapes)((k, v) for k, v in shapes.items() if owner[k] == mine)
+        shard_note = f"; shard {mine} of the {sw}-way LPT partition per rank"
+    n_params = synth.total_params(shapes)
     # synthetic random-init checkpoints, resident in HBM before the timed region
-    base, fts = synth.make_checkpoints(shapes, tasks, family="parity", seed=1234 + rank, device=str(dev))
-    masks = synth.make_masks(shapes, tasks, p, seed=4321 + rank, device=str(dev))
+    base, fts = synth.make_checkpoints(shapes, tasks, family="parity", seed=1234 + rank, device=str(dev),
+                                       dtype=in_dtype)
+    masks = synth.make_masks(shapes, tasks, p, seed=4321 + rank, device=str(dev)) if p is not None else None
     perf = synth.performance_table(tasks) if cfg.svd_weighting == "performance" else None
     job = MergeJob(base, fts, masks, cfg, str(dev), performance=perf, diagnostics=False)
     launches_per_step = job.gpu_launches
@@ -264,7 +285,12 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_ms = float(t.item())
     ms_per_step = total_ms / args.steps
-    value = n_params * world / (ms_per_step * 1e-3)
+    n_total = n_params * world
+    if world > 1 and extra.get("shard_world"):            # shards differ in size: sum the ranks' parameter counts
+        c = torch.tensor([n_params], dtype=torch.int64, device=dev)
+        dist.all_reduce(c)
+        n_total = int(c.item())
+    value = n_total / (ms_per_step * 1e-3)
 
     # secondary figures: the same merge with the per-task reconstruction diagnostics fused into
     # pass 2, and with the bases (U_high / U_low fp16, mean) materialised in the artifact layout
@@ -313,10 +339,10 @@ def run_ours(args):
         solved_all = [solved]
 
     # roofline of the dominant kernel (algorithmic bytes per element x elements per launch / measured time)
-    n_masked_params = n_params
-    has_masks = True
-    bytes_k1 = n_params * ((N + 1) * 4 + (N if has_masks else 0) + 1 / 8)
-    bytes_k3 = n_params * ((N + 1) * 4 + 1 / 8 + 4)
+    has_masks = masks is not None
+    es = torch.empty(0, dtype=in_dtype).element_size()
+    bytes_k1 = n_params * ((N + 1) * es + (N + 1 / 8 if has_masks else 0))
+    bytes_k3 = n_params * ((N + 1) * es + (1 / 8 if has_masks else 0) + 4)
     peak, peak_src = _measured_peak()
     k1_ms, k3_ms, k2_ms = (k_times[k] / args.steps for k in ("k1", "k3", "k2"))
     dom = "k1_tv_mask_gram" if k1_ms >= k3_ms else "k3_reconstruct_merge"
@@ -344,7 +370,8 @@ def run_ours(args):
         from svd_quantization_task_merging_b200.engine import merge_state_dicts
         h_base = pack_state_dict({k: v.cpu() for k, v in base.items()}, pin=True)
         h_fts = {t: pack_state_dict({k: v.cpu() for k, v in fts[t].items()}, pin=True) for t in tasks}
-        h_masks = {t: pack_state_dict({k: v.cpu() for k, v in masks[t].items()}, pin=True) for t in tasks}
+        h_masks = ({t: pack_state_dict({k: v.cpu() for k, v in masks[t].items()}, pin=True) for t in tasks}
+                   if masks is not None else None)
         del job, base, fts, masks
         torch.cuda.empty_cache()
         h2d = d2h = 0
@@ -363,7 +390,7 @@ def run_ours(args):
         tt = torch.tensor([dt], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        e2e = {"value": n_params * world / float(tt.item()), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+        e2e = {"value": n_total / float(tt.item()), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(d2h), "ms_per_step": float(tt.item()) * 1e3, "steps": e_steps}
 
     if rank == 0:
@@ -373,12 +400,16 @@ def run_ours(args):
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": f"{args.workload}: {model} image encoder ({len(shapes)} tensors, "
-                                       f"{n_params} params) x {N} random-init task vectors (decaying spectrum), "
-                                       f"{cfg.svd_mask_strategy} tall masks (Bernoulli {p}), {cfg.svd_weighting} "
+                "config": {"workload": f"{args.workload}: {model} {'image encoder' if model.startswith('ViT') else 'weights'} "
+                                       f"({len(shapes)} tensors, "
+                                       f"{n_params} params, {str(in_dtype).split('.')[-1]}) x {N} random-init task vectors "
+                                       f"(decaying spectrum), "
+                                       + (f"{cfg.svd_mask_strategy} tall masks (Bernoulli {p}), " if has_masks else "no masks, ")
+                                       + f"{cfg.svd_weighting} "
                                        f"weighting, energy {cfg.svd_energy_threshold}, {cfg.svd_low_bits}-bit x "
-                                       f"{cfg.svd_rtvq_stages}-stage RTVQ, fp16 bases; per-GPU copy of the workload",
-                           "l2": "inputs (13.4 GB per step) are larger than the 126 MB L2; no flush needed",
+                                       f"{cfg.svd_rtvq_stages}-stage RTVQ, fp16 bases; "
+                                       + ("per-GPU copy of the workload" if not shard_note else shard_note[2:]),
+                           "l2": f"inputs ({bytes_k1 / 1e9:.1f} GB per step) are larger than the 126 MB L2; no flush needed",
                            "diagnostics_fused": False, "artifacts_materialised": False,
                            "parallelism": f"parameter-independent, {world} GPU(s), no data-path collective"},
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
@@ -396,6 +427,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="vit-l-14-cluster", choices=sorted(WORKLOADS))
+    ap.add_argument("--shard-rank", type=int, default=0, help="which shard rank 0 takes (sharded workloads)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--secondary", action="store_true", help="also time the fused-diagnostics and artifact variants")

@@ -111,8 +111,12 @@ int svdq_gram_staged(int dtype, int n_tasks, int mask_mode, int64_t n_tiles, int
  * count, non-zero only where the reference builds a noise basis (src/svd_hybrid/cli.py:330-338,
  * src/svd_hybrid/basis.py:455-466): the parameter has a mask, the masked count passes min_mask_size, and
  * at least one element is unmasked.  numel / has_mask / gram_noise / dm_noise may be NULL otherwise.
+ * gram is CONSUMED: parameters with >= 512 tiles are reduced in two levels (64 tile ranges over 64 CTAs, then the
+ * range sums in order) and the fp64 range sums overwrite the head of each range; count is left intact
+ * (svdq_basis_offsets reads it).  The split depends only on the parameter's own tile count, so results do not
+ * depend on how parameters are sharded.
  */
-int svdq_gram_reduce(int n_tasks, int full, int64_t n_params, int min_mask_size, const float* gram,
+int svdq_gram_reduce(int n_tasks, int full, int64_t n_params, int min_mask_size, float* gram,
                      const uint32_t* count, const int64_t* tile_begin, const int64_t* numel, const uint8_t* has_mask,
                      double* gram_masked, double* gram_all, int64_t* dm, double* gram_noise, int64_t* dm_noise,
                      void* stream);

@@ -11,19 +11,89 @@
 namespace svdq {
 
 
-__global__ void __launch_bounds__(kBlock) k2_gram_reduce(const K2ReduceArgs a) {
+// Parameters with many tiles (Llama-sized: lm_head has 32,064 tiles of 16,384 elements) are reduced in two levels so
+// that more than one SM works on them: k2_gram_partial sums kRedSplit contiguous tile ranges per parameter and
+// leaves each range's fp64 partial in place of the range's first two tiles; k2_gram_reduce adds the partials in
+// range order.  The split depends only on the parameter's own tile count: the summation order -- and so every bit
+// of the result -- is independent of how parameters are sharded over ranks.
+constexpr int kRedSplit = 64;
+constexpr int kRedSplitMin = 512;        // tiles; below that one CTA reduces the parameter directly
+constexpr int kRedMaxBig = 1024;         // parameters scanned per blockIdx.y (bounds the shared list of big ones)
+
+__device__ __forceinline__ void red_split(int64_t T, int64_t& L, int& ns) {
+    L = (T + kRedSplit - 1) / kRedSplit;          // >= 8 tiles per range; the last range takes the remainder
+    ns = (int)(T / L);
+}
+
+__global__ void __launch_bounds__(kBlock) k2_gram_partial(const K2ReduceArgs a, float* gram_rw, const int n_params) {
+    const int s = blockIdx.x, tid = threadIdx.x;
+    const int NT = a.nt, G = tri_count(NT), NACC = a.full ? 2 * G : G;
+    __shared__ double s_part[kBlock / 32][tri_count(kMaxTasks)];
+    __shared__ int s_big[kRedMaxBig];
+    __shared__ int s_nbig;
+    const int lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_nbig = 0;
+    __syncthreads();
+    const int p_lo = blockIdx.y * kRedMaxBig, p_hi = min(n_params, p_lo + kRedMaxBig);
+    for (int p = p_lo + tid; p < p_hi; p += kBlock)
+        if (a.tile_begin[p + 1] - a.tile_begin[p] >= kRedSplitMin) s_big[atomicAdd(&s_nbig, 1)] = p;
+    __syncthreads();
+    const int nbig = s_nbig;
+    for (int b = 0; b < nbig; ++b) {               // order of the list is irrelevant: parameters are independent
+        const int p = s_big[b];
+        const int64_t t0 = a.tile_begin[p], t1 = a.tile_begin[p + 1];
+        int64_t L;
+        int ns;
+        red_split(t1 - t0, L, ns);
+        if (s >= ns) continue;                     // uniform per CTA
+        const int64_t b0 = t0 + (int64_t)s * L, b1 = (s == ns - 1) ? t1 : b0 + L;
+        for (int r = lane; r < NACC; r += 32) {
+            double acc = 0.0;
+            for (int64_t t = b0 + warp; t < b1; t += kBlock / 32) acc += (double)a.gram[t * NACC + r];
+            s_part[warp][r] = acc;
+        }
+        __syncthreads();                           // every read of the range is done before its head is overwritten
+        for (int r = tid; r < NACC; r += kBlock) {
+            double m = 0.0;
+            for (int w = 0; w < kBlock / 32; ++w) m += s_part[w][r];
+            gram_rw[b0 * NACC + 2 * r] = __int_as_float(__double2loint(m));
+            gram_rw[b0 * NACC + 2 * r + 1] = __int_as_float(__double2hiint(m));
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(kBlock) k2_gram_reduce(const K2ReduceArgs a, const int n_big) {
     const int p = blockIdx.x, tid = threadIdx.x;
     const int NT = a.nt, G = tri_count(NT), NACC = a.full ? 2 * G : G;
     const int64_t t0 = a.tile_begin[p], t1 = a.tile_begin[p + 1];
     __shared__ double s_part[kBlock / 32][tri_count(kMaxTasks)];   // 528 >= 2 * tri_count(16): FULL needs nt <= 16
     __shared__ unsigned long long s_cnt[kBlock / 32];
     const int lane = tid & 31, warp = tid >> 5;
+    const bool two_level = n_big >= 0 && t1 - t0 >= kRedSplitMin;
 
-    // each warp owns tiles warp, warp+8, ...; inside a warp lane l owns accumulator rows l, l+32, ...
-    for (int r = lane; r < NACC; r += 32) {
-        double s = 0.0;
-        for (int64_t t = t0 + warp; t < t1; t += kBlock / 32) s += (double)a.gram[t * NACC + r];
-        s_part[warp][r] = s;
+    if (two_level) {
+        // partials of k2_gram_partial, added in range order; rows spread over the threads, warp 0's slot holds them
+        int64_t L;
+        int ns;
+        red_split(t1 - t0, L, ns);
+        for (int r = tid; r < NACC; r += kBlock) {
+            double acc = 0.0;
+            for (int s = 0; s < ns; ++s) {
+                const float* q = a.gram + (t0 + (int64_t)s * L) * NACC + 2 * r;
+                acc += __hiloint2double(__float_as_int(q[1]), __float_as_int(q[0]));
+            }
+            s_part[0][r] = acc;
+        }
+        for (int r = tid; r < NACC; r += kBlock)
+            for (int w = 1; w < kBlock / 32; ++w) s_part[w][r] = 0.0;
+    } else {
+        // each warp owns tiles warp, warp+8, ...; inside a warp lane l owns accumulator rows l, l+32, ...
+        for (int r = lane; r < NACC; r += 32) {
+            double s = 0.0;
+            for (int64_t t = t0 + warp; t < t1; t += kBlock / 32) s += (double)a.gram[t * NACC + r];
+            s_part[warp][r] = s;
+        }
     }
     unsigned long long c = 0;
     for (int64_t t = t0 + tid; t < t1; t += kBlock) c += a.count[t];
@@ -176,7 +246,9 @@ cudaError_t k2_average_launch(const K2SolveArgs& a, int n_params, cudaStream_t s
 cudaError_t k2_reduce_launch(const K2ReduceArgs& a, int n_params, cudaStream_t st) {
     if (n_params <= 0) return cudaSuccess;
     if (a.nt < 1 || a.nt > kMaxTasks || (a.full && a.nt > 16)) return cudaErrorInvalidValue;
-    k2_gram_reduce<<<n_params, kBlock, 0, st>>>(a);
+    const dim3 grid(kRedSplit, (n_params + kRedMaxBig - 1) / kRedMaxBig);
+    k2_gram_partial<<<grid, kBlock, 0, st>>>(a, const_cast<float*>(a.gram), n_params);
+    k2_gram_reduce<<<n_params, kBlock, 0, st>>>(a, 0);
     return cudaGetLastError();
 }
 

@@ -221,7 +221,7 @@ int svdq_gram_staged(int dtype, int n_tasks, int mask_mode, int64_t n_tiles, int
     return finish(__func__, e);
 }
 
-int svdq_gram_reduce(int n_tasks, int full, int64_t n_params, int min_mask_size, const float* gram,
+int svdq_gram_reduce(int n_tasks, int full, int64_t n_params, int min_mask_size, float* gram,
                      const uint32_t* count, const int64_t* tile_begin, const int64_t* numel, const uint8_t* has_mask,
                      double* gram_masked, double* gram_all, int64_t* dm, double* gram_noise, int64_t* dm_noise,
                      void* stream) {

@@ -661,7 +661,9 @@ class MergeJob:
         ng = len(self.groups)
         any_exact = any(g.sel is not None for g in self.groups.values())
         nreg = 2 if self.noise else 1
-        return ng * (3 + nreg + (1 if self.want_diag else 0) + (nreg if (self.cluster_mode or any_exact) else 0)
+        # every svdq_gram_reduce is two launches (k2_gram_partial + k2_gram_reduce)
+        n_reduce = 1 + (1 if self.wide and (self.cluster_mode or self.noise) else 0)
+        return ng * (3 + n_reduce + nreg + (1 if self.want_diag else 0) + (nreg if (self.cluster_mode or any_exact) else 0)
                      + (2 * nreg if any_exact else 0))
 
     def event_times_ms(self) -> Dict[str, float]:

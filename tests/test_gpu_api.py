@@ -389,3 +389,49 @@ def test_host_bit_packed_masks_equal_device_byte_masks(cuda_device, strategy, n_
         # through json so that NaNs (few-task degenerate blocks quantise to NaN like in the reference) compare equal
         canon = lambda x: json.dumps(x, sort_keys=True, default=lambda o: o.item() if hasattr(o, "item") else str(o))
         assert canon(d) == canon(ref_d), tag
+
+
+# ---- two-level Gram reduction of parameters with >= 512 tiles --------------------------------------------------
+@pytest.mark.parametrize("weighting,noise", [("uniform", False), ("cluster", False), ("uniform", True)])
+def test_two_level_gram_reduction_of_many_tile_parameters(cuda_device, weighting, noise):
+    """tile_elems = 1024 makes 512+ tiles cheap: 511 tiles (one level), 512 (64 ranges of 8), 513 (57 ranges of 9),
+    684 and 2000 tiles.  The reduced Grams / counts match an fp64 torch Gram of the masked task vectors, and a job
+    that owns only some of the parameters reproduces them bit for bit."""
+    from svd_quantization_task_merging_b200.engine import MergeJob
+    tasks = synth.task_names(8)
+    shapes = {"t511.weight": (511 * 1024 - 3,), "t512.weight": (512, 1024), "t513.weight": (512 * 1024 + 1,),
+              "t684.weight": (700_000,), "t2000.weight": (2000, 1024), "small.weight": (300, 7)}
+    base, fts = synth.make_checkpoints(shapes, tasks, family="parity", seed=61, device="cuda")
+    masks = synth.make_masks(shapes, tasks, 0.5, seed=62, device="cuda")
+    cfg = SVDHybridConfig(tasks=tasks, svd_energy_threshold=0.9, svd_mask_strategy="majority", svd_weighting=weighting,
+                          svd_store_artifacts=False, svd_include_noise=noise)
+    job = MergeJob(base, fts, masks, cfg, "cuda", tile_elems=1024).run()
+    g = job.groups[torch.float32]
+    got = g.t["gram_masked"].view(-1, 8, 8).clone()
+    got_n = g.tn["gram"].view(-1, 8, 8).clone() if noise else None
+    dm = g.t["dm"].clone()
+    for i, k in enumerate(g.names):
+        maj = (2 * torch.stack([masks[t][k] for t in tasks]).sum(0) >= 8).view(-1)
+        T = torch.stack([(fts[t][k] - base[k]).view(-1) for t in tasks], 1).double()
+        ref = T[maj].T @ T[maj]
+        assert int(dm[i]) == int(maj.sum())
+        assert (got[i] - ref).abs().max() <= 2e-6 * ref.abs().max(), k
+        if noise:
+            ref_n = T[~maj].T @ T[~maj]
+            assert (got_n[i] - ref_n).abs().max() <= 2e-6 * ref_n.abs().max(), k
+    if weighting == "cluster":
+        T_all = torch.cat([torch.stack([(fts[t][k] - base[k]).view(-1) for t in tasks], 1).double() for k in g.names])
+        whole = torch.from_numpy(job.whole_model_gram).cuda()
+        ref = T_all.T @ T_all
+        assert (whole - ref).abs().max() <= 2e-6 * ref.abs().max()
+    merged = job.merged_state_dict()
+    part = MergeJob(base, fts, masks, cfg, "cuda", tile_elems=1024, param_filter=["t513.weight", "t2000.weight"])
+    if weighting == "cluster":
+        gram = torch.from_numpy(job.whole_model_gram).cuda().view(-1)
+        part.gram_reduce_hook = lambda g_local: gram.clone()
+    part.run()
+    gp = part.groups[torch.float32]
+    for i, k in enumerate(gp.names):
+        j = g.names.index(k)
+        assert torch.equal(gp.t["gram_masked"].view(-1, 8, 8)[i], got[j]), k
+        assert torch.equal(part.merged_state_dict()[k].view(torch.int32), merged[k].view(torch.int32)), k

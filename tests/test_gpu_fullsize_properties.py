@@ -97,6 +97,67 @@ def test_vit_b_32_twenty_tasks_wide_path_properties(cuda_device):
     assert all(torch.equal(part[n], ma[n]) for n in mine)
 
 
+def test_llama_3_8b_shard_bf16_capacity(cuda_device):
+    """configs[4]: Llama-3-8B-shaped bf16 task vectors, parameter-sharded 8 ways.  Rank 0's shard of the LPT
+    partition (lm_head: one 525,336,576-element parameter, 1.0 B parameters in all) on one GPU: the partition is
+    balanced without row-splitting, the run is deterministic and finite, the spectrum of the 525 M x 8 task matrix
+    matches an independent fp64 Gram eigensolve, and with uniform weights the merged delta is the mean task vector
+    up to the coefficient quantisation (the centred coefficients average to zero)."""
+    from svd_quantization_task_merging_b200.engine import MergeJob
+    if torch.cuda.get_device_properties(0).total_memory < 100e9:
+        pytest.skip("needs ~80 GB of HBM")
+    shapes_all = synth.model_shapes("Llama-3-8B")
+    assert synth.total_params(shapes_all) == 8_030_261_248
+    cost = {k: int(np.prod(v)) * 9 for k, v in shapes_all.items()}
+    owner = sharding.lpt_partition(cost, 8)
+    assert sharding.partition_balance(cost, owner, 8) < 1.01
+    shapes = {k: v for k, v in shapes_all.items() if owner[k] == 0}
+    assert "lm_head.weight" in shapes and 0.99e9 < synth.total_params(shapes) < 1.02e9
+    tasks = synth.task_names(8)
+    base, fts = synth.make_checkpoints(shapes, tasks, family="parity", seed=77, device="cuda", dtype=torch.bfloat16)
+    torch.cuda.empty_cache()
+    cfg = SVDHybridConfig(tasks=tasks, svd_energy_threshold=0.9, svd_store_artifacts=False, svd_eval_reconstruction=False)
+    a = MergeJob(base, fts, None, cfg, "cuda", diagnostics=False).run()
+    ma = {k: v.clone() for k, v in a.merged_state_dict().items()}
+    fa = a._fetch()[torch.bfloat16]
+    names = a.groups[torch.bfloat16].names
+    del a
+    torch.cuda.empty_cache()
+    b = MergeJob(base, fts, None, cfg, "cuda", diagnostics=False).run()
+    mb = b.merged_state_dict()
+    assert all(torch.equal(ma[k].view(torch.int32), mb[k].view(torch.int32)) for k in ma)      # determinism
+    del b, mb
+    torch.cuda.empty_cache()
+    assert (fa["info"][:, 0] == 0).all() and len(names) == len(shapes)
+    i = names.index("lm_head.weight")
+    # independent spectrum: bf16 task vectors (ft - base rounded to bf16, task_vector_loader.py:103-145), centred
+    # in fp64, Gram accumulated in fp64 over row chunks
+    k = "lm_head.weight"
+    G = torch.zeros(8, 8, dtype=torch.float64, device="cuda")
+    mean_delta_sq = 0.0
+    err_sq = 0.0
+    flat_m, flat_b = ma[k].view(-1), base[k].view(-1)
+    step = 1 << 24
+    for lo in range(0, flat_b.numel(), step):
+        T = torch.stack([(fts[t][k].view(-1)[lo: lo + step] - flat_b[lo: lo + step]) for t in tasks], 1).double()
+        mean = T.mean(1)
+        Tc = T - mean[:, None]
+        G += Tc.T @ Tc
+        got = flat_m[lo: lo + step].double() - flat_b[lo: lo + step].double()
+        mean_delta_sq += float((mean ** 2).sum())
+        err_sq += float(((got - mean) ** 2).sum())
+        assert torch.isfinite(got).all()
+    S = torch.linalg.eigvalsh(G).clamp_min(0).sqrt().flip(0).cpu().numpy()
+    r = int(fa["info"][i, 2])
+    assert r == 8
+    got_s = fa["sv"][i][:r]
+    ok = np.abs(got_s - S[:r]) <= np.maximum(2e-6 * S[0], 2e-9 * S[0] ** 2 / np.maximum(S[:r], 1e-30)) + \
+        (S[:r] <= 1e-5 * S[0]) * 1e-4 * S[0]
+    assert ok.all(), (got_s, S[:r])
+    # merged - base = mean task vector + U cbar, and cbar ~ 0: the deviation is quantisation noise of the coefficients
+    assert err_sq ** 0.5 <= 0.05 * (float(np.sum(S ** 2)) / 8) ** 0.5 + 1e-3 * mean_delta_sq ** 0.5, (err_sq, mean_delta_sq)
+
+
 def test_all_true_masks_equal_no_masks_and_scale_equivariance(cuda_device):
     """ViT-B-16 shapes (configs[1] sizes), 8 tasks, 4-bit x 3 stages."""
     from svd_quantization_task_merging_b200.engine import MergeJob
