@@ -123,9 +123,7 @@ __global__ void __launch_bounds__(kBlock, (NT <= 8 && !FULL) ? 2 : 1) k1_tv_mask
         // ---- phase 2: task vectors, combined mask ------------------------------------------------
         float d[NT][kVec];
 #pragma unroll
-        for (int t = 0; t < NT; ++t)
-#pragma unroll
-            for (int c = 0; c < kVec; ++c) d[t][c] = Elem<T>::sub(f[t][c], b[c]);
+        for (int t = 0; t < NT; ++t) Elem<T>::template subv<kVec>(f[t], b, d[t]);
         uint32_t bits = 0;                                       // 4 combined-mask bits of this thread
         if (active) {
             const uint32_t valid = full ? 0xFu : ((1u << (int)(numel - e)) - 1u);

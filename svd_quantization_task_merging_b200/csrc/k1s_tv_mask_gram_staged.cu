@@ -217,9 +217,7 @@ __global__ void __launch_bounds__(kBlock + 32, 1) k1s_tv_mask_gram(const K1Args 
 
             float d[NT][kVec];
 #pragma unroll
-            for (int t = 0; t < NT; ++t)
-#pragma unroll
-                for (int c = 0; c < kVec; ++c) d[t][c] = Elem<T>::sub(f[t][c], b[c]);
+            for (int t = 0; t < NT; ++t) Elem<T>::template subv<kVec>(f[t], b, d[t]);
             uint32_t bits = 0;
             if (active) {
                 const uint32_t valid = fullv ? 0xFu : ((1u << (int)(numel - e)) - 1u);

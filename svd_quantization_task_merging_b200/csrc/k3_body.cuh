@@ -38,12 +38,11 @@ __device__ __forceinline__ void k3_step(const float (&b)[VEC], float (&x)[NT][VE
 #pragma unroll
     for (int c = 0; c < VEC; ++c) mean[c] = 0.0f;
 #pragma unroll
-    for (int t = 0; t < NT; ++t)
+    for (int t = 0; t < NT; ++t) {
+        Elem<T>::template subv<VEC>(x[t], b, x[t]);
 #pragma unroll
-        for (int c = 0; c < VEC; ++c) {
-            x[t][c] = Elem<T>::sub(x[t][c], b[c]);
-            mean[c] += x[t][c];
-        }
+        for (int c = 0; c < VEC; ++c) mean[c] += x[t][c];
+    }
     const uint32_t bits = (pword >> (int)(e & 31)) & ((1u << VEC) - 1u);
 
     float orig[DIAG ? NT : 1][VEC];

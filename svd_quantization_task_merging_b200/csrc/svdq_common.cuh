@@ -60,6 +60,10 @@ template <> struct Elem<float> {
     }
     // delta = finetuned - base in the tensors' own dtype (task_vector_loader.py:142)
     static __device__ __forceinline__ float sub(float f, float b) { return __fsub_rn(f, b); }
+    template <int V> static __device__ __forceinline__ void subv(const float (&f)[V], const float (&b)[V], float (&d)[V]) {
+#pragma unroll
+        for (int c = 0; c < V; ++c) d[c] = __fsub_rn(f[c], b[c]);
+    }
 };
 
 template <> struct Elem<__nv_bfloat16> {
@@ -75,6 +79,18 @@ template <> struct Elem<__nv_bfloat16> {
     static __device__ __forceinline__ float sub(float f, float b) {
         return __bfloat162float(__float2bfloat16_rn(__fsub_rn(f, b)));
     }
+    // V (even) differences at once: the same fp32 subtract + round-to-nearest-even to bf16 as sub(), with the packed
+    // convert (one F2FP on the ALU pipe per pair instead of two F2F on the quarter-rate XU pipe)
+    template <int V> static __device__ __forceinline__ void subv(const float (&f)[V], const float (&b)[V], float (&d)[V]) {
+        static_assert(V % 2 == 0, "pairs");
+#pragma unroll
+        for (int c = 0; c < V; c += 2) {
+            const __nv_bfloat162 r = __floats2bfloat162_rn(__fsub_rn(f[c], b[c]), __fsub_rn(f[c + 1], b[c + 1]));
+            const uint32_t w = *reinterpret_cast<const uint32_t*>(&r);
+            d[c] = __uint_as_float(w << 16);
+            d[c + 1] = __uint_as_float(w & 0xffff0000u);
+        }
+    }
 };
 
 template <> struct Elem<__half> {
@@ -89,6 +105,15 @@ template <> struct Elem<__half> {
     }
     static __device__ __forceinline__ float sub(float f, float b) {
         return __half2float(__float2half_rn(__fsub_rn(f, b)));
+    }
+    template <int V> static __device__ __forceinline__ void subv(const float (&f)[V], const float (&b)[V], float (&d)[V]) {
+        static_assert(V % 2 == 0, "pairs");
+#pragma unroll
+        for (int c = 0; c < V; c += 2) {
+            const float2 r = __half22float2(__floats2half2_rn(__fsub_rn(f[c], b[c]), __fsub_rn(f[c + 1], b[c + 1])));
+            d[c] = r.x;
+            d[c + 1] = r.y;
+        }
     }
 };
 
