@@ -152,6 +152,13 @@ def cpu_baseline(workload: str, steps: int = 1, warmup: int = 0):
     in_dtype = getattr(torch, WORKLOAD_EXTRA.get(workload, {}).get("dtype", "float32"))
     base, fts = synth.make_checkpoints(shapes, tasks, family="parity", seed=1234, dtype=in_dtype)
     masks = synth.make_masks(shapes, tasks, p, seed=4321) if p is not None else None
+    upcast = ""
+    if in_dtype != torch.float32:
+        # torch.linalg.svd has no 16-bit CPU kernel, so the reference cannot run these inputs as they are: it gets
+        # the fp32 stand-in with identical task vectors, base32 = base, ft32 = base + bf16(ft - base)
+        fts = {t: {k: base[k].float() + (v - base[k]).float() for k, v in sd.items()} for t, sd in fts.items()}
+        base = {k: v.float() for k, v in base.items()}
+        upcast = f", {str(in_dtype).split('.')[-1]} task vectors upcast to fp32"
     perf = synth.performance_table(tasks) if cfg.svd_weighting == "performance" else None
     rcfg = R.RefConfig(tasks=tasks, svd_energy_threshold=cfg.svd_energy_threshold, svd_max_rank=cfg.svd_max_rank,
                        svd_center=cfg.svd_center, svd_fp16=cfg.svd_fp16, svd_low_bits=cfg.svd_low_bits,
@@ -171,7 +178,7 @@ def cpu_baseline(workload: str, steps: int = 1, warmup: int = 0):
     dt = (time.perf_counter() - t0) / max(steps, 1)
     return {"value": n_params / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
             "sample": f"{model} {len(names)} tensors ({n_params / 1e6:.1f} M params: "
-                      f"{'whole toy model' if model == 'toy' else 'first four transformer blocks' if model.startswith('ViT') else 'attention + norms of the first decoder layer'}), {len(tasks)} tasks, "
+                      f"{'whole toy model' if model == 'toy' else 'first four transformer blocks' if model.startswith('ViT') else 'attention + norms of the first decoder layer'}), {len(tasks)} tasks{upcast}, "
                       f"oracle/svd_hybrid_ref.py (torch-eager CPU restatement of the reference path; its full-feature "
                       f"k-means excluded), {dt:.2f} s per pass"}, dt, n_params
 
@@ -185,7 +192,8 @@ def run_reference_arm(args):
     line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": dt * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{args.workload}: {model} x {len(tasks)} tasks, {cfg.svd_mask_strategy} masks, "
+            "config": {"workload": f"{args.workload}: {model} x {len(tasks)} tasks, "
+                                   f"{cfg.svd_mask_strategy + ' masks' if p is not None else 'no masks'}, "
                                    f"{cfg.svd_weighting} weighting, {cfg.svd_low_bits}-bit x {cfg.svd_rtvq_stages} RTVQ"
                                    f" (bounded CPU sample per step)"},
             "cpu_baseline": base,
