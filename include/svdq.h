@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define SVDQ_ABI_VERSION 2
+#define SVDQ_ABI_VERSION 3   /* 3: svdq_tv_mask_gram_bits, svdq_host_pack_mask; svdq_gram_reduce consumes its gram argument */
 #define SVDQ_MAX_STREAM_TASKS 16
 #define SVDQ_MAX_TASKS 32
 #define SVDQ_MAX_STAGES 8
