@@ -133,7 +133,8 @@ def _upload_mask_bits(task_masks: Sequence[Optional[Mapping[str, torch.Tensor]]]
     """HOST torch.bool masks -> bits on the host (svdq_host_pack_mask, all host threads; runs while the tensors'
     host->device copies are in flight) -> one upload of numel/8 bytes per task.  A pure transfer encoding: the
     masks are combined on the device (K1) exactly as with byte masks."""
-    n_threads = max(1, min(16, len(os.sched_getaffinity(0))))
+    # host threads for the re-encoding: this process's CPUs, shared with the other ranks of the node under torchrun
+    n_threads = max(1, min(16, len(os.sched_getaffinity(0)) // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))))
     plan, total = [], 0
     for m in task_masks:
         if m is None:
