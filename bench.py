@@ -191,7 +191,7 @@ def run_reference_arm(args):
     cfg, tasks, model, p = _make_cfg(args.workload)
     line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": dt * 1e3, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "scaling": "weak" if (WORKLOAD_EXTRA.get(args.workload, {}).get("shard_world") or args.replicas) else "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"{args.workload}: {model} x {len(tasks)} tasks, "
                                    f"{cfg.svd_mask_strategy + ' masks' if p is not None else 'no masks'}, "
                                    f"{cfg.svd_weighting} weighting, {cfg.svd_low_bits}-bit x {cfg.svd_rtvq_stages} RTVQ"
@@ -222,7 +222,7 @@ def _bind_to_gpu_numa_node(gpu_index: int):
 def run_ours(args):
     import torch
     import torch.distributed as dist
-    from svd_quantization_task_merging_b200 import _native, synth
+    from svd_quantization_task_merging_b200 import _native, sharding, synth
     from svd_quantization_task_merging_b200.engine import MergeJob, pack_state_dict
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -237,27 +237,68 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
 
     cfg, tasks, model, p = _make_cfg(args.workload)
-    shapes = synth.model_shapes(model)
+    shapes_all = synth.model_shapes(model)
     N = len(tasks)
     extra = WORKLOAD_EXTRA.get(args.workload, {})
     in_dtype = getattr(torch, extra.get("dtype", "float32"))
-    shard_note = ""
+    cost = {k: int(np.prod(v)) * (N + 1) for k, v in shapes_all.items()}
+    # How the N ranks split the work (north_star: "the model is partitioned per parameter across the GPUs"):
+    #   strong  : ONE model, LPT-partitioned over the ranks; every rank holds, uploads and merges only its shard
+    #   shard   : weak scaling of a capacity workload: rank r merges shard r of a fixed 8-way partition (Llama-3-8B:
+    #             8 ranks = the whole 8.03 B-parameter model)
+    #   replicas: weak scaling, every rank merges its own copy of the model (round-1 behaviour; --replicas)
     if extra.get("shard_world"):
-        from svd_quantization_task_merging_b200 import sharding
-        sw = extra["shard_world"]
-        owner = sharding.lpt_partition({k: int(np.prod(v)) * (N + 1) for k, v in shapes.items()}, sw)
+        mode, sw = "shard", extra["shard_world"]
+        owner = sharding.lpt_partition(cost, sw)
         mine = (args.shard_rank + rank) % sw
-        shapes = type(shapes)((k, v) for k, v in shapes.items() if owner[k] == mine)
-        shard_note = f"; shard {mine} of the {sw}-way LPT partition per rank"
+        shard_note = f"shard {mine} of the {sw}-way LPT partition per rank"
+    elif args.replicas or world == 1:
+        mode, owner, mine = ("replicas" if world > 1 else "single"), {k: 0 for k in shapes_all}, 0
+        shard_note = "per-GPU copy of the workload" if world > 1 else "whole model on one GPU"
+    else:
+        mode, mine = "strong", rank
+        owner = sharding.lpt_partition(cost, world)
+        shard_note = f"ONE model LPT-partitioned by parameter over {world} ranks (strong scaling)"
+    shapes = type(shapes_all)((k, v) for k, v in shapes_all.items() if owner[k] == mine)
     n_params = synth.total_params(shapes)
-    # synthetic random-init checkpoints, resident in HBM before the timed region
-    base, fts = synth.make_checkpoints(shapes, tasks, family="parity", seed=1234 + rank, device=str(dev),
-                                       dtype=in_dtype)
-    masks = synth.make_masks(shapes, tasks, p, seed=4321 + rank, device=str(dev)) if p is not None else None
+    # synthetic random-init checkpoints, resident in HBM before the timed region.  Every tensor has its own random
+    # stream (per_tensor), so a rank that generates only its shard holds exactly the tensors of the whole model.
+    seed = 1234 + (rank if mode == "replicas" else 0)
+    gen = dict(family=args.family, seed=seed, device=str(dev), dtype=in_dtype, per_tensor=True)
+    base, fts = synth.make_checkpoints(shapes, tasks, **gen)
+    masks = synth.make_masks(shapes, tasks, p, seed=4321 + seed, device=str(dev), per_tensor=True) if p is not None else None
     perf = synth.performance_table(tasks) if cfg.svd_weighting == "performance" else None
     job = MergeJob(base, fts, masks, cfg, str(dev), performance=perf, diagnostics=False)
+    collectives = []
+    if mode == "strong" and job.cluster_mode:
+        job.gram_reduce_hook = sharding.allreduce_gram          # N x N fp64 whole-model Gram, on the job's side stream
+        collectives.append("all_reduce(8x8 fp64 whole-model Gram)")
     launches_per_step = job.gpu_launches
     torch.cuda.synchronize(dev)
+
+    # per-parameter records (rank, k, energy, masked size) of all ranks: one flat all-gather per step (device side)
+    rec_gather = None
+    if mode == "strong":
+        by_rank = [sum(1 for q in owner.values() if q == r) for r in range(world)]
+        pmax = max(by_rank)
+        rec_out = torch.empty(world * pmax, 16, dtype=torch.float64, device=dev)
+        rec_buf = torch.zeros(pmax, 16, dtype=torch.float64, device=dev)
+        collectives.append("all_gather_into_tensor(per-parameter records, fp64 [P,16])")
+
+        def rec_gather():
+            o = 0
+            for g in job.groups.values():
+                P = len(g.names)
+                rec_buf[o: o + P, :8] = g.t["info"]
+                rec_buf[o: o + P, 8] = g.t["dm"]
+                rec_buf[o: o + P, 9:13] = g.t["scal"]
+                o += P
+            dist.all_gather_into_tensor(rec_out, rec_buf)
+
+    def step(record_events=False):
+        job.run(record_events=record_events)
+        if rec_gather is not None:
+            rec_gather()
 
     def barrier():
         torch.cuda.synchronize(dev)
@@ -269,7 +310,7 @@ def run_ours(args):
     if rank == 0:
         sampler.start()
     for _ in range(args.warmup):
-        job.run()
+        step()
     barrier()
     t_begin = time.perf_counter()
     k_times = {"k1": 0.0, "k2": 0.0, "k3": 0.0}
@@ -277,7 +318,7 @@ def run_ours(args):
     jobs_events = []
     ev0.record()
     for _ in range(args.steps):
-        job.run(record_events=True)
+        step(record_events=True)
         jobs_events.append(job._events)
     ev1.record()
     barrier()
@@ -293,17 +334,22 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_ms = float(t.item())
     ms_per_step = total_ms / args.steps
-    n_total = n_params * world
-    if world > 1 and extra.get("shard_world"):            # shards differ in size: sum the ranks' parameter counts
+    # parameters merged per step by all ranks together
+    if world > 1:
         c = torch.tensor([n_params], dtype=torch.int64, device=dev)
-        dist.all_reduce(c)
-        n_total = int(c.item())
+        gathered_n = [torch.zeros_like(c) for _ in range(world)]
+        dist.all_gather(gathered_n, c)
+        params_per_rank = [int(x.item()) for x in gathered_n]
+    else:
+        params_per_rank = [n_params]
+    n_total = sum(params_per_rank)
     value = n_total / (ms_per_step * 1e-3)
 
     # secondary figures: the same merge with the per-task reconstruction diagnostics fused into
-    # pass 2, and with the bases (U_high / U_low fp16, mean) materialised in the artifact layout
+    # pass 2 (the reference's default svd_eval_reconstruction=True), and with the bases (U_high / U_low fp16,
+    # mean) materialised in the artifact layout
     secondary = None
-    if args.secondary and world == 1:
+    if world == 1 and not args.no_secondary:
         def timed(fn, n):
             # median of per-call device times after two warm-up calls (the first calls pay cudaMalloc)
             fn()
@@ -335,7 +381,6 @@ def run_ours(args):
                      "with_artifacts": {"ms_per_step": ms_per_step + ms_art,
                                         "value": n_params / ((ms_per_step + ms_art) * 1e-3)}}
 
-    # NCCL is used only to gather diagnostics scalars (parameters are independent: no data-path collective)
     fetched = job._fetch()
     solved = sum(int((f["info"][:, 0] == 0).sum()) for f in fetched.values())
     if world > 1:
@@ -346,7 +391,57 @@ def run_ours(args):
     else:
         solved_all = [solved]
 
-    # roofline of the dominant kernel (algorithmic bytes per element x elements per launch / measured time)
+    # strong scaling extras (outside the timed region): the optional all-gather of the merged shards over NVLink
+    # (one padded all_gather_into_tensor), and a bit-identity check of the sharded result against ONE GPU merging
+    # the whole model (rank 0 regenerates the full model; per-tensor streams make the shards identical)
+    sharded = None
+    if mode == "strong":
+        sizes = [0] * world
+        flat = next(iter(job.groups.values())).t["out"] if len(job.groups) == 1 else \
+            torch.cat([g.t["out"] for g in job.groups.values()])
+        sz = torch.tensor([flat.numel()], dtype=torch.int64, device=dev)
+        gsz = [torch.zeros_like(sz) for _ in range(world)]
+        dist.all_gather(gsz, sz)
+        sizes = [int(x.item()) for x in gsz]
+        allm = sharding.gather_merged(flat, sizes)          # warm-up
+        barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        for _ in range(3):
+            allm = sharding.gather_merged(flat, sizes)
+        g1.record()
+        barrier()
+        tg = torch.tensor([g0.elapsed_time(g1) / 3], dtype=torch.float64, device=dev)
+        dist.all_reduce(tg, op=dist.ReduceOp.MAX)
+        equal, assign_equal, checked = None, None, 0
+        assign = [job.cluster_assignments]
+        if rank == 0:
+            b_all, f_all = synth.make_checkpoints(shapes_all, tasks, **gen)
+            m_all = synth.make_masks(shapes_all, tasks, p, seed=4321 + seed, device=str(dev), per_tensor=True) \
+                if p is not None else None
+            one = MergeJob(b_all, f_all, m_all, cfg, str(dev), performance=perf, diagnostics=False).run()
+            ref = one.merged_state_dict()
+            equal = True
+            for r in range(world):
+                names_r = sorted(k for k in shapes_all if owner[k] == r)
+                off = 0
+                for k in names_r:          # arena layout of rank r: sorted names, 64-element aligned
+                    n = int(np.prod(shapes_all[k]))
+                    got = allm[r, off: off + n].view(shapes_all[k])
+                    equal = equal and bool(torch.equal(got, ref[k]))
+                    checked += 1
+                    off += (n + 63) // 64 * 64
+            assign_equal = one.cluster_assignments == job.cluster_assignments
+            del b_all, f_all, m_all, one, ref
+        del allm
+        torch.cuda.empty_cache()
+        barrier()
+        sharded = {"gather_merged_ms": float(tg.item()), "gather_merged_bytes_per_rank": int(max(sizes)) * 4 * world,
+                   "equals_single_gpu_bitwise": equal, "tensors_compared": checked,
+                   "cluster_assignments_equal": assign_equal}
+
+    # roofline of the dominant kernel (algorithmic bytes per element x elements per launch / measured time);
+    # this rank's launch processes this rank's elements
     has_masks = masks is not None
     es = torch.empty(0, dtype=in_dtype).element_size()
     bytes_k1 = n_params * ((N + 1) * es + (N + 1 / 8 if has_masks else 0))
@@ -358,19 +453,20 @@ def run_ours(args):
     achieved = dom_bytes / (dom_ms * 1e-3) / 1e9
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tpath):
+    if os.path.exists(tpath) and world == 1:
         try:
             traffic = json.load(open(tpath)).get(dom)
         except Exception:
             traffic = None
+    whole_bytes = (bytes_k1 + bytes_k3) / n_params * n_total        # all ranks' algorithmic bytes per step
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": dom_bytes, "launch_ms": dom_ms,
                 "kernels_ms_per_step": {"k1_tv_mask_gram": k1_ms, "k2_reduce+cluster+solve": k2_ms,
                                         "k3_reconstruct_merge": k3_ms},
-                "whole_path": {"algorithmic_bytes_per_step": bytes_k1 + bytes_k3,
-                               "achieved": (bytes_k1 + bytes_k3) / (ms_per_step * 1e-3) / 1e9,
-                               "frac": (bytes_k1 + bytes_k3) / (ms_per_step * 1e-3) / 1e9 / peak}}
+                "whole_path": {"algorithmic_bytes_per_step": whole_bytes,
+                               "achieved": whole_bytes / (ms_per_step * 1e-3) / 1e9,
+                               "frac": whole_bytes / (ms_per_step * 1e-3) / 1e9 / (peak * world)}}
 
     # end to end through the public API with HOST buffers: H2D of every input + D2H of the merged model per step
     e2e = None
@@ -384,45 +480,59 @@ def run_ours(args):
         torch.cuda.empty_cache()
         h2d = d2h = 0
         e_steps = max(1, min(args.steps, 3))
-        merge_state_dicts(h_base, h_fts, h_masks, cfg, str(dev), performance=perf, diagnostics=False, to_host="reuse")
+
+        def e2e_call():
+            if mode == "strong":      # public sharded API: per-rank shard upload, Gram all-reduce, flat record gather
+                return sharding.merge_state_dicts_sharded(h_base, h_fts, h_masks, cfg, str(dev), owner=owner,
+                                                          performance=perf, diagnostics=False, to_host="reuse")
+            return merge_state_dicts(h_base, h_fts, h_masks, cfg, str(dev), performance=perf, diagnostics=False,
+                                     to_host="reuse")
+        e2e_call()
         barrier()
         t0 = time.perf_counter()
         for _ in range(e_steps):
-            r = merge_state_dicts(h_base, h_fts, h_masks, cfg, str(dev), performance=perf, diagnostics=False,
-                                  to_host="reuse")
+            r = e2e_call()
             h2d = r["job"].h2d_bytes
             d2h = sum(g.t["out"].numel() * 4 for g in r["job"].groups.values())
             del r
         barrier()
         dt = (time.perf_counter() - t0) / e_steps
         tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+        hb = torch.tensor([h2d, d2h], dtype=torch.int64, device=dev)
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        e2e = {"value": n_total / float(tt.item()), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
-               "d2h_bytes_per_step": int(d2h), "ms_per_step": float(tt.item()) * 1e3, "steps": e_steps}
+            dist.all_reduce(hb)
+        e2e = {"value": n_total / float(tt.item()), "unit": UNIT, "h2d_bytes_per_step": int(hb[0].item()),
+               "d2h_bytes_per_step": int(hb[1].item()), "ms_per_step": float(tt.item()) * 1e3, "steps": e_steps,
+               "bytes_are": "summed over all ranks"}
 
     if rank == 0:
         cpu = None
         if world == 1 and not args.no_cpu:
             cpu, _, _ = cpu_baseline(args.workload, steps=1, warmup=0)
+        dt_name = {"float32": "f32", "bfloat16": "bf16", "float16": "f16"}[str(in_dtype).split(".")[-1]]
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+                "scaling": "weak" if mode in ("shard", "replicas") else "strong",
+                "vs_baseline": None, "dtype": dt_name, "data": "synthetic",
                 "config": {"workload": f"{args.workload}: {model} {'image encoder' if model.startswith('ViT') else 'weights'} "
-                                       f"({len(shapes)} tensors, "
-                                       f"{n_params} params, {str(in_dtype).split('.')[-1]}) x {N} random-init task vectors "
-                                       f"(decaying spectrum), "
+                                       f"({len(shapes_all)} tensors, {synth.total_params(shapes_all)} params, "
+                                       f"{str(in_dtype).split('.')[-1]}) x {N} random-init task vectors "
+                                       f"({'decaying spectrum' if args.family == 'parity' else 'iid'}), "
                                        + (f"{cfg.svd_mask_strategy} tall masks (Bernoulli {p}), " if has_masks else "no masks, ")
                                        + f"{cfg.svd_weighting} "
                                        f"weighting, energy {cfg.svd_energy_threshold}, {cfg.svd_low_bits}-bit x "
-                                       f"{cfg.svd_rtvq_stages}-stage RTVQ, fp16 bases; "
-                                       + ("per-GPU copy of the workload" if not shard_note else shard_note[2:]),
-                           "l2": f"inputs ({bytes_k1 / 1e9:.1f} GB per step) are larger than the 126 MB L2; no flush needed",
+                                       f"{cfg.svd_rtvq_stages}-stage RTVQ, fp16 bases; " + shard_note,
+                           "l2": f"inputs ({bytes_k1 / 1e9:.1f} GB per rank and step) "
+                                 + ("are larger than the 126 MB L2; no flush needed" if bytes_k1 > 4e8 else
+                                    "-- see DESIGN.md section 7 on L2 residency at high rank counts"),
                            "diagnostics_fused": False, "artifacts_materialised": False,
-                           "parallelism": f"parameter-independent, {world} GPU(s), no data-path collective"},
+                           "cluster_backend": "kmeans (reference procedure, svdq_host_kmeans)",
+                           "parallelism": f"{mode}: {world} GPU(s), parameter-sharded, no data-path collective; "
+                                          f"collectives per step: {collectives if collectives else 'none'}"},
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
-                "gpu_launches": launches_per_step * args.steps, "params_with_basis_per_rank": solved_all,
-                "secondary": secondary}
+                "gpu_launches": launches_per_step * args.steps, "params_per_rank": params_per_rank,
+                "params_with_basis_per_rank": solved_all, "sharded": sharded, "secondary": secondary}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -438,7 +548,12 @@ def main():
     ap.add_argument("--shard-rank", type=int, default=0, help="which shard rank 0 takes (sharded workloads)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--secondary", action="store_true", help="also time the fused-diagnostics and artifact variants")
+    ap.add_argument("--secondary", action="store_true", help="(default at 1 GPU) time the fused-diagnostics and artifact variants")
+    ap.add_argument("--no-secondary", action="store_true")
+    ap.add_argument("--replicas", action="store_true",
+                    help="N > 1: weak scaling with one model copy per GPU instead of one model sharded over the GPUs")
+    ap.add_argument("--family", default="parity", choices=["parity", "throughput"],
+                    help="synthetic input family (SURVEY 8d): decaying spectrum | iid")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

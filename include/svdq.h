@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define SVDQ_ABI_VERSION 3   /* 3: svdq_tv_mask_gram_bits, svdq_host_pack_mask; svdq_gram_reduce consumes its gram argument */
+#define SVDQ_ABI_VERSION 4   /* 4: svdq_host_kmeans, per-cluster svdq_param_average; 3: svdq_tv_mask_gram_bits, svdq_host_pack_mask */
 #define SVDQ_MAX_STREAM_TASKS 16
 #define SVDQ_MAX_TASKS 32
 #define SVDQ_MAX_STAGES 8
@@ -82,6 +82,20 @@ int svdq_tv_mask_gram_bits(int dtype, int n_tasks, int mask_strategy, int full, 
                            const int32_t* tile_param, const int32_t* tile_local, const int64_t* pmask_off,
                            uint32_t* packed, float* gram, uint32_t* count, void* stream);
 int svdq_host_pack_mask(const uint8_t* src_host, int64_t n, uint8_t* dst_host, int n_threads);
+
+/*
+ * Host-side k-means of cluster weighting (all pointers are HOST pointers; no CUDA call).
+ * Replaces: compute_kmeans_clustering (src/svd_hybrid/clustering.py:123-156), i.e. the call
+ *           sklearn.cluster.KMeans(n_clusters=k, random_state=seed, n_init=n_init).fit_predict(features)
+ *           that cluster_tasks (clustering.py:198-245, from cli.py:530) makes with seed 42, n_init 10.
+ * features_host: row-major [n x d] float32 (the engine passes an isometric n x n embedding of the whole-model
+ * task Gram that K1 accumulates, rows = tasks in sorted-name order like clustering.py:87).  The procedure is
+ * scikit-learn 1.9's, step by step (numpy RandomState stream, k-means++ with 2 + int(log k) local trials,
+ * float32 Lloyd iterations, max_iter / tol stopping rules, first-best-wins selection over the n_init runs), so
+ * labels_host [n] equals sklearn's labels_, not just its partition.  inertia_host (optional) = inertia_.
+ */
+int svdq_host_kmeans(const float* features_host, int n, int d, int k, uint32_t seed, int n_init, int max_iter,
+                     double tol, int32_t* labels_host, double* inertia_host);
 
 /*
  * Wide path, 17..32 task vectors (the Gram accumulators of that many tasks do not fit one thread):
@@ -137,7 +151,7 @@ int svdq_gram_reduce(int n_tasks, int full, int64_t n_params, int min_mask_size,
  * Outputs (per parameter, stride NT; S = rtvq_stages):
  *   info [P][8] int32  : status (0 solved, 1 skipped: mask below min_mask_size, 2 empty),
  *                        n_active, r = min(Dm, n_active), k, r_eff, 0, 0, 0
- *   sv [P][NT] fp32 singular values; scal [P][4] = energy_retained, tail_add, 0, 0
+ *   sv [P][NT] fp32 singular values; scal [P][4] = energy_retained, tail_add, mean_scale, 0
  *   coef [P][NT][NT] raw coefficients coef[t][j]; chigh [P][NT][NT] fp16 bits (j < k)
  *   codes [P][NT][S][NT] uint8 (i < r-k); qscale/qzp/qres [P][NT][S]
  *   chat [P][NT][NT] coefficients after fp16 / RTVQ round trip; cbar [P][NT] weighted average
@@ -156,11 +170,18 @@ int svdq_param_solve(int n_tasks, int64_t n_params, int center, float energy_thr
  * K2c — weighted average only: svdq_param_solve called with weights == NULL stops after the
  * coefficients / RTVQ / W; this entry point then forms cbar, gvec and scal[1] once the task weights
  * are known (cluster weighting derives them from the whole-model Gram on the host meanwhile).
- * Replaces dequantize_and_average (src/svd_hybrid/merge.py:89-141) and the weight folding of
- * merge_with_clustering (merge.py:586-626).
+ * Replaces dequantize_and_average (src/svd_hybrid/merge.py:89-141) and merge_with_clustering
+ * (merge.py:586-626) + merge_cluster_results (src/svd_hybrid/clustering.py:374-425).
+ * cluster_of / cluster_omega (both NULL = no clustering): cluster_of[t] in [0, NT) is the cluster index of task
+ * position t, cluster_omega[c] the cross-cluster weight (softmax of the mean member weight, renormalised over the
+ * clusters).  Per parameter the member weights are renormalised over the members of each cluster that HAVE the
+ * parameter; a cluster none of whose members has it contributes zeros, mean included, exactly like the
+ * reference (merge.py:289-290): scal[2] receives the resulting factor on the mean (1 otherwise), which
+ * svdq_reconstruct_merge applies.
  */
 int svdq_param_average(int n_tasks, int64_t n_params, const uint32_t* present, const double* weights,
-                       const int32_t* avg_order, const int32_t* info, const float* chat, const float* W, float* cbar,
+                       const int32_t* avg_order, const int32_t* cluster_of, const double* cluster_omega,
+                       const int32_t* info, const float* chat, const float* W, float* cbar,
                        float* gvec, float* scal, void* stream);
 
 /*

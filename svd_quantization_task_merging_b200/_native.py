@@ -12,7 +12,7 @@ from typing import Optional
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libsvdq.so")
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 DTYPE_CODE = {"float32": 0, "bfloat16": 1, "float16": 2}
 STRATEGY_CODE = {"union": 0, "intersection": 1, "majority": 2}
@@ -28,11 +28,12 @@ _SIGNATURES = {
     "svdq_tv_mask_gram": (C.c_int, [_i32, _i32, _i32, _i32, _i64, _i32] + [_vp] * 10),
     "svdq_tv_mask_gram_bits": (C.c_int, [_i32, _i32, _i32, _i32, _i64, _i32] + [_vp] * 10),
     "svdq_host_pack_mask": (C.c_int, [_vp, _i64, _vp, _i32]),
+    "svdq_host_kmeans": (C.c_int, [_vp, _i32, _i32, _i32, C.c_uint32, _i32, _i32, C.c_double, _vp, _vp]),
     "svdq_mask_pack": (C.c_int, [_i32, _i32, _i64, _i32] + [_vp] * 8),
     "svdq_gram_staged": (C.c_int, [_i32, _i32, _i32, _i64, _i32] + [_vp] * 9),
     "svdq_gram_reduce": (C.c_int, [_i32, _i32, _i64, _i32] + [_vp] * 11),
     "svdq_param_solve": (C.c_int, [_i32, _i64, _i32, _f32, _i32, _i32, _i32, _i32] + [_vp] * 22),
-    "svdq_param_average": (C.c_int, [_i32, _i64] + [_vp] * 10),
+    "svdq_param_average": (C.c_int, [_i32, _i64] + [_vp] * 12),
     "svdq_project_exact": (C.c_int, [_i32, _i32, _i32, _i32, _i32, _i64, _i32] + [_vp] * 11),
     "svdq_param_requantize": (C.c_int, [_i32, _i64, _i32, _i32] + [_vp] * 12),
     "svdq_reconstruct_merge": (C.c_int, [_i32, _i32, _i32, _i32, _i32, _i64, _i32] + [_vp] * 20 + [_f32, _vp]),

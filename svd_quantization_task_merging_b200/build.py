@@ -32,7 +32,7 @@ UNITS: List[Tuple[str, object]] = (
     + [("k6_wide.cu", d) for d in (0, 1, 2)]
     + [("k7_project_exact.cu", d) for d in (0, 1, 2)]
     + [("k8_gram_staged.cu", d) for d in (0, 1, 2)]
-    + [("k2_param_solve.cu", None), ("k4_rtvq_large.cu", None), ("svdq_capi.cu", None)]
+    + [("k2_param_solve.cu", None), ("k4_rtvq_large.cu", None), ("svdq_capi.cu", None), ("host_kmeans.cpp", None)]
 )
 HEADERS = ["svdq_common.cuh", "svdq_kernels.h", "k2_core.h", "k3_body.cuh", "stage_pipe.cuh", os.path.join("..", "..", "include", "svdq.h")]
 
@@ -45,13 +45,30 @@ def _digest(paths: List[str], extra: str) -> str:
     return h.hexdigest()
 
 
+def _includes(path: str, seen=None) -> List[str]:
+    """The file and every in-tree header it includes with quotes, transitively (the unit's real dependencies: a
+    change to one header rebuilds only the units that see it)."""
+    import re
+    seen = seen if seen is not None else []
+    path = os.path.normpath(path)
+    if path in seen or not os.path.exists(path):
+        return seen
+    seen.append(path)
+    with open(path) as f:
+        for inc in re.findall(r'^\s*#\s*include\s+"([^"]+)"', f.read(), flags=re.M):
+            _includes(os.path.join(os.path.dirname(path), inc), seen)
+    return seen
+
+
 def _compile(unit: Tuple[str, object], verbose: bool) -> str:
     src, dt = unit
     stem = os.path.splitext(src)[0] + ("" if dt is None else f"_dt{dt}")
     obj = os.path.join(OBJDIR, stem + ".o")
     stamp = obj + ".sha"
-    deps = [os.path.join(CSRC, src)] + [os.path.normpath(os.path.join(CSRC, h)) for h in HEADERS]
+    deps = sorted(_includes(os.path.join(CSRC, src)))
     flags = COMMON + ([] if dt is None else [f"-DSVDQ_DTYPE={dt}"])
+    if src.endswith(".cpp"):                       # host-only unit: keep float32 arithmetic un-fused
+        flags = flags + ["-Xcompiler", "-ffp-contract=off"]
     want = _digest(deps, " ".join(flags))
     if os.path.exists(obj) and os.path.exists(stamp) and open(stamp).read() == want:
         return obj

@@ -210,6 +210,9 @@ struct SolveIn {
                               //      average_param runs later
     const int32_t* avg_order; // [NT] task positions in sorted-name order (merge.py:89)
     const double* sign_ref;   // [NT*NT] optional Vh_ref[j][t] (test-only sign alignment) or null
+    const int32_t* cluster_of = nullptr;  // [NT] cluster index (0 .. NT-1) of each task position, or null: no clustering
+    const double* omega = nullptr;        // [NT] cross-cluster weight by cluster index (softmax of the cluster scores,
+                                          //      renormalised: clustering.py:399-423); used only with cluster_of
 };
 
 struct SolveOut {             // all strides are NT (= cfg.n_tasks); S = cfg.stages
@@ -359,21 +362,44 @@ SVDQ_HD void average_param(const SolveConfig& cfg, const SolveIn& in, const Solv
     const int NT = cfg.n_tasks;
     if (out.info[0] != kSolved) return;
     const int r = out.info[2], r_eff = out.info[4];
-    double wsum = 0.0;
-    for (int o = 0; o < NT; ++o) {
-        const int t = in.avg_order[o];
-        if (in.present >> t & 1u) wsum += in.weights[t];
+    // Without clustering: weights renormalised over the tasks that have the parameter (merge.py:121-123).
+    // With clustering (merge_with_clustering, merge.py:586-626): the member weights are renormalised over the
+    // members of each cluster that have the parameter, every cluster's reconstruction (U c_c + mean) enters the
+    // cross-cluster average with omega[c], and a cluster WITHOUT any such member contributes zeros -- mean
+    // included (merge.py:289-290 via dequantize_and_average returning None).  All of it is linear, so it is one
+    // average with w_eff[t] = omega[c(t)] w[t] / wsum_c and the mean scaled by sum of omega over the non-empty
+    // clusters (= 1 unless a whole cluster lacks the parameter).
+    double wsum = 0.0, mean_scale = 1.0;
+    double wsum_c[kCoreMaxTasks];
+    if (in.cluster_of == nullptr) {
+        for (int o = 0; o < NT; ++o) {
+            const int t = in.avg_order[o];
+            if (in.present >> t & 1u) wsum += in.weights[t];
+        }
+    } else {
+        for (int c = 0; c < NT; ++c) wsum_c[c] = 0.0;
+        bool any[kCoreMaxTasks];
+        for (int c = 0; c < NT; ++c) any[c] = false;
+        for (int o = 0; o < NT; ++o) {
+            const int t = in.avg_order[o];
+            if (in.present >> t & 1u) { wsum_c[in.cluster_of[t]] += in.weights[t]; any[in.cluster_of[t]] = true; }
+        }
+        mean_scale = 0.0;
+        for (int c = 0; c < NT; ++c) if (any[c]) mean_scale += in.omega[c];
     }
     for (int j = ln.lane; j < r; j += ln.nl) {
         float acc = 0.0f;
         for (int o = 0; o < NT; ++o) {
             const int t = in.avg_order[o];
             if (!(in.present >> t & 1u)) continue;
-            const float w = (float)(in.weights[t] / wsum);
+            const float w = in.cluster_of == nullptr
+                                ? (float)(in.weights[t] / wsum)
+                                : (float)(in.omega[in.cluster_of[t]] * (in.weights[t] / wsum_c[in.cluster_of[t]]));
             acc = f_add(acc, f_mul(out.chat[t * NT + j], w));
         }
         out.cbar[j] = acc;
     }
+    if (ln.lane == 0) out.scal[2] = (float)mean_scale;
     ln.sync();
     if (ln.lane == 0) {
         float tail = 0.0f;

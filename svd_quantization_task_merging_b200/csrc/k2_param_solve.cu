@@ -183,6 +183,8 @@ __global__ void __launch_bounds__(32) k2_param_average(const K2SolveArgs a) {
     in.present = a.present[p];
     in.weights = a.weights;
     in.avg_order = a.avg_order;
+    in.cluster_of = a.cluster_of;
+    in.omega = a.omega;
     in.sign_ref = nullptr;
     SolveOut out = {};
     out.info = a.info + (int64_t)p * 8;

@@ -19,6 +19,7 @@ template <int NT> struct K3NoiseSet {
     const float* sG = nullptr;
     int r = 0;
     float tail_add = 0.0f;
+    float mean_scale = 1.0f;
     float shrink = 1.0f;
     bool on = false;
 };
@@ -29,6 +30,7 @@ template <typename T, int NT, bool FP16B, bool DIAG, bool NOISE = false, int VEC
 __device__ __forceinline__ void k3_step(const float (&b)[VEC], float (&x)[NT][VEC], const uint32_t pword,
                                         const int64_t e, const int64_t numel, const int r, const uint32_t present_bits,
                                         const int center, const float n_f, const float tail_add,
+                                        const float mean_scale,
                                         const float (*sWT)[(NT + 3) & ~3], const float (*sChatT)[(NT + 3) & ~3],
                                         const float* sCbar, const float* sG, float (&res)[VEC],
                                         float (&dacc)[DIAG ? kDiagRows * NT : 1],
@@ -184,9 +186,11 @@ __device__ __forceinline__ void k3_step(const float (&b)[VEC], float (&x)[NT][VE
 #pragma unroll
     for (int c = 0; c < VEC; ++c) {
         const bool m = (bits >> c) & 1u;
-        const float val = (acc[c] + mean[c]) + tail_add;
+        // mean_scale is 1 except under cluster weighting when a whole cluster lacks the parameter (that cluster
+        // contributes zeros, mean included: merge.py:289-290); fma(mean, 1, acc) rounds exactly like acc + mean
+        const float val = fmaf(mean[c], mean_scale, acc[c]) + tail_add;
         float other = 0.0f;
-        if (NOISE) other = ns.on ? __fmul_rn((accn[c] + mean[c]) + ns.tail_add, ns.shrink) : 0.0f;
+        if (NOISE) other = ns.on ? __fmul_rn(fmaf(mean[c], ns.mean_scale, accn[c]) + ns.tail_add, ns.shrink) : 0.0f;
         res[c] = b[c] + (m ? val : other);
     }
     if (DIAG) {

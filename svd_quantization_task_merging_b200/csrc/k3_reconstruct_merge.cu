@@ -51,6 +51,7 @@ __global__ void __launch_bounds__(kBlock, (NT <= 8 || !DIAG) ? 2 : 1) k3_reconst
     // diagnostics still walk all r columns so that a NaN coefficient shows up exactly as in the reference
     const int r = a.info[(int64_t)p * 8 + (DIAG ? 2 : 4)];
     const float tail_add = a.scal[(int64_t)p * 4 + 1];
+    const float mean_scale = a.scal[(int64_t)p * 4 + 2];
     const bool has_mask = a.has_mask[p] != 0;
 
     if (tid <= NT) s_ptr[tid] = a.tensors[(int64_t)p * (NT + 1) + tid];
@@ -65,6 +66,7 @@ __global__ void __launch_bounds__(kBlock, (NT <= 8 || !DIAG) ? 2 : 1) k3_reconst
         ns.on = status == kSolved && a.info_n[(int64_t)p * 8 + 0] == kSolved;
         ns.r = a.info_n[(int64_t)p * 8 + 4];
         ns.tail_add = a.scal_n[(int64_t)p * 4 + 1];
+        ns.mean_scale = a.scal_n[(int64_t)p * 4 + 2];
         ns.shrink = a.noise_shrink;
         ns.sWT = sWTn; ns.sCbar = sCbarN; ns.sG = sGn;
         for (int i = tid; i < NT * NTP; i += kBlock) {
@@ -135,7 +137,7 @@ __global__ void __launch_bounds__(kBlock, (NT <= 8 || !DIAG) ? 2 : 1) k3_reconst
                 for (int t = 0; t < NT; ++t) ElemPair<T>::load(s_ptr[t + 1], e, full, numel, x[t]);
             }
             if (has_mask) pword = __ldg(packed + (e >> 5));
-            k3_step<T, NT, FP16B, DIAG, NOISE, VEC>(b, x, pword, e, numel, r, present_bits, a.center, n_f, tail_add,
+            k3_step<T, NT, FP16B, DIAG, NOISE, VEC>(b, x, pword, e, numel, r, present_bits, a.center, n_f, tail_add, mean_scale,
                                                     sWT, sChatT, sCbar, sG, res, dacc, ns);
         }
         if constexpr (VEC == 4) {

@@ -155,6 +155,7 @@ __global__ void __launch_bounds__(kK3Consumers + 32, 1) k3s_reconstruct_merge(co
     // diagnostics still walk all r columns so that a NaN coefficient shows up exactly as in the reference
     const int r = a.info[(int64_t)p * 8 + (false ? 2 : 4)];
         const float tail_add = a.scal[(int64_t)p * 4 + 1];
+        const float mean_scale = a.scal[(int64_t)p * 4 + 2];
         const bool has_mask = a.has_mask[p] != 0;
         const uint32_t* packed = has_mask ? a.packed + a.pmask_off[p] : nullptr;
         const bool mask_in_ring = has_mask && ((reinterpret_cast<uintptr_t>(packed) & 15u) == 0);
@@ -210,7 +211,7 @@ __global__ void __launch_bounds__(kK3Consumers + 32, 1) k3s_reconstruct_merge(co
 #pragma unroll
                 for (int c = 0; c < kVec; ++c) res[c] = b[c];
             } else {
-                k3_step<T, NT, FP16B, false>(b, x, pword, e, numel, r, present_bits, a.center, n_f, tail_add, sWT, sChatT,
+                k3_step<T, NT, FP16B, false>(b, x, pword, e, numel, r, present_bits, a.center, n_f, tail_add, mean_scale, sWT, sChatT,
                                              sCbar, sG, res, dacc);
             }
             if (fullv) stg_stream_f4(outp + e, make_float4(res[0], res[1], res[2], res[3]));

@@ -144,10 +144,12 @@ __global__ void __launch_bounds__(kBlock, (NTMAX <= 24 && !DIAG) ? 2 : 1) k6_rec
     const int n_active = a.info[(int64_t)p * 8 + 1];
     const int r = a.info[(int64_t)p * 8 + (DIAG ? 2 : 4)];
     const float tail_add = a.scal[(int64_t)p * 4 + 1];
+    const float mean_scale = a.scal[(int64_t)p * 4 + 2];
     const bool has_mask = a.has_mask[p] != 0;
     const bool noise_on = NOISE && status == kSolved && a.info_n[(int64_t)p * 8 + 0] == kSolved;
     const int r_n = noise_on ? a.info_n[(int64_t)p * 8 + 4] : 0;
     const float tail_n = noise_on ? a.scal_n[(int64_t)p * 4 + 1] : 0.0f;
+    const float mean_scale_n = noise_on ? a.scal_n[(int64_t)p * 4 + 2] : 1.0f;
     const int r_loop = NOISE ? max(r, r_n) : r;
     if (tid <= NTMAX) s_ptr[tid] = tid <= N ? a.tensors[(int64_t)p * (N + 1) + tid] : nullptr;
     for (int i = tid; i < NTMAX * TP; i += kBlock) {
@@ -284,7 +286,7 @@ __global__ void __launch_bounds__(kBlock, (NTMAX <= 24 && !DIAG) ? 2 : 1) k6_rec
 #pragma unroll
             for (int c = 0; c < kWVec; ++c) {
                 const bool m = (bits >> c) & 1u;
-                float val = (acc[c] + mean[c]) + ((NOISE && !m) ? tail_n : tail_add);
+                float val = fmaf(mean[c], (NOISE && !m) ? mean_scale_n : mean_scale, acc[c]) + ((NOISE && !m) ? tail_n : tail_add);
                 if (NOISE && !m) val = noise_on ? __fmul_rn(val, a.noise_shrink) : 0.0f;
                 res[c] = b[c] + ((m || NOISE) ? val : 0.0f);
             }

@@ -180,6 +180,17 @@ int svdq_host_pack_mask(const uint8_t* src, int64_t n, uint8_t* dst, int n_threa
     return 0;
 }
 
+extern "C" int svdq_host_kmeans_impl(const float*, int, int, int, uint32_t, int, int, double, int32_t*, double*);
+
+int svdq_host_kmeans(const float* features, int n, int d, int k, uint32_t seed, int n_init, int max_iter, double tol,
+                     int32_t* labels, double* inertia) {
+    REQUIRE(features && labels, "null pointer");
+    REQUIRE(n >= 1 && d >= 1 && n <= 4096 && d <= 65536, "feature matrix shape");
+    REQUIRE(k >= 1 && k <= n, "Invalid k for the number of samples");      // clustering.py:147-148
+    REQUIRE(n_init >= 1 && max_iter >= 1 && tol >= 0.0, "n_init / max_iter / tol");
+    return svdq_host_kmeans_impl(features, n, d, k, seed, n_init, max_iter, tol, labels, inertia);
+}
+
 int svdq_mask_pack(int n_tasks, int mask_strategy, int64_t n_tiles, int tile_elems, const uint8_t* const* masks,
                    const int64_t* numel, const int32_t* tile_param, const int32_t* tile_local,
                    const int64_t* pmask_off, uint32_t* packed, uint32_t* count, void* stream) {
@@ -257,7 +268,7 @@ int svdq_param_solve(int n_tasks, int64_t n_params, int center, float energy_thr
     REQUIRE(gram_masked && dm && has_mask && present && avg_order, "null input pointer");
     REQUIRE(info && sv && scal && coef && chigh && codes && qscale && qzp && qres && chat && cbar && W && gvec && V,
             "null output pointer");
-    svdq::K2SolveArgs a;
+    svdq::K2SolveArgs a = {};
     a.cfg.n_tasks = n_tasks; a.cfg.center = center; a.cfg.energy_threshold = energy_threshold;
     a.cfg.max_rank = max_rank; a.cfg.min_mask_size = min_mask_size; a.cfg.bits = rtvq_bits; a.cfg.stages = rtvq_stages;
     a.gram_masked = gram_masked; a.dm = dm; a.has_mask = has_mask; a.present = present; a.weights = weights;
@@ -268,7 +279,8 @@ int svdq_param_solve(int n_tasks, int64_t n_params, int center, float energy_thr
 }
 
 int svdq_param_average(int n_tasks, int64_t n_params, const uint32_t* present, const double* weights,
-                       const int32_t* avg_order, const int32_t* info, const float* chat, const float* W, float* cbar,
+                       const int32_t* avg_order, const int32_t* cluster_of, const double* cluster_omega,
+                       const int32_t* info, const float* chat, const float* W, float* cbar,
                        float* gvec, float* scal, void* stream) {
     REQUIRE(n_tasks >= 1 && n_tasks <= SVDQ_MAX_TASKS, "n_tasks must be in [1, 32]");
     REQUIRE(n_params >= 0 && n_params < (1ll << 31), "n_params");
@@ -276,7 +288,9 @@ int svdq_param_average(int n_tasks, int64_t n_params, const uint32_t* present, c
     REQUIRE(present && weights && avg_order && info && chat && W && cbar && gvec && scal, "null pointer");
     svdq::K2SolveArgs a = {};
     a.cfg.n_tasks = n_tasks;
+    REQUIRE((cluster_of == nullptr) == (cluster_omega == nullptr), "cluster_of and cluster_omega go together");
     a.present = present; a.weights = weights; a.avg_order = avg_order;
+    a.cluster_of = cluster_of; a.omega = cluster_omega;
     a.info = const_cast<int32_t*>(info); a.chat = const_cast<float*>(chat); a.W = const_cast<float*>(W);
     a.cbar = cbar; a.gvec = gvec; a.scal = scal;
     return finish(__func__, svdq::k2_average_launch(a, (int)n_params, (cudaStream_t)stream));

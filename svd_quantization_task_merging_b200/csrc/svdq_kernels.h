@@ -59,6 +59,8 @@ struct K2SolveArgs {
     const uint32_t* present;      // [P]
     const double* weights;        // [NT]
     const int32_t* avg_order;     // [NT]
+    const int32_t* cluster_of;    // [NT] cluster index per task position, or null (svdq_param_average only)
+    const double* omega;          // [NT] cross-cluster weights by cluster index (with cluster_of)
     const double* sign_ref;       // [P][NT*NT] or null
     // outputs, strides per parameter as in SolveOut
     int32_t* info; float* sv; float* scal; float* coef; uint16_t* chigh; uint8_t* codes;

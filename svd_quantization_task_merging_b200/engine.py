@@ -28,7 +28,7 @@ import numpy as np
 import torch
 
 from . import _native
-from .svd_hybrid.weighting import compute_weights, effective_merge_weights
+from .svd_hybrid.weighting import cluster_omega, compute_weights
 
 TILE_ELEMS = 16384          # elements per tile (multiple of 1024); fixes the reduction order
 MAX_STREAM_TASKS = 16      # register-resident Gram (one K1 launch)
@@ -93,15 +93,61 @@ def pack_state_dict(sd: Mapping[str, torch.Tensor], pin: bool = False, align_ele
     return out
 
 
-def _to_device_state_dict(sd: Mapping[str, torch.Tensor], device) -> Mapping[str, torch.Tensor]:
-    """Host -> device move of a state dict (one copy when it is packed)."""
-    if isinstance(sd, PackedStateDict) and sd.flat.device != device:
-        flat = sd.flat.to(device, non_blocking=True)
-        out = PackedStateDict((k, flat[o: o + v.numel()].view(v.shape)) for (k, v), o in
-                              zip(sd.items(), sd.offsets.values()))
-        out.flat, out.offsets = flat, sd.offsets
-        return out
-    return sd
+def _to_device_state_dict(sd: Mapping[str, torch.Tensor], device, wanted=None) -> Tuple[Mapping[str, torch.Tensor], int]:
+    """Host -> device move of a state dict -> (device state dict, bytes copied).
+
+    A packed state dict moves with one copy.  With ``wanted`` (this rank's shard of a parameter-sharded merge)
+    only those tensors are copied, into one device arena: neighbouring wanted tensors of a packed state dict
+    travel as one copy, the rest one copy each -- nothing of another rank's shard crosses PCIe or occupies HBM."""
+    if wanted is None:
+        if isinstance(sd, PackedStateDict) and sd.flat.device != device:
+            flat = sd.flat.to(device, non_blocking=True)
+            out = PackedStateDict((k, flat[o: o + v.numel()].view(v.shape)) for (k, v), o in
+                                  zip(sd.items(), sd.offsets.values()))
+            out.flat, out.offsets = flat, sd.offsets
+            return out, flat.numel() * flat.element_size()
+        return sd, sum(v.numel() * v.element_size() for v in sd.values() if torch.is_tensor(v) and v.device != device)
+    keys = [k for k in sd.keys() if k in wanted and torch.is_tensor(sd[k])]
+    host = [k for k in keys if sd[k].device != device]
+    out: Dict[str, torch.Tensor] = {k: sd[k] for k in keys if sd[k].device == device}
+    if not host:
+        return out, 0
+    dtypes = {sd[k].dtype for k in host}
+    if len(dtypes) != 1:                                  # mixed dtypes: one copy per tensor
+        for k in host:
+            out[k] = sd[k].to(device, non_blocking=True)
+        return out, sum(sd[k].numel() * sd[k].element_size() for k in host)
+    dtype = next(iter(dtypes))
+    al = 128 if dtype == torch.bool else 64
+    packed = isinstance(sd, PackedStateDict) and sd.flat.dtype == dtype
+    if packed:
+        host.sort(key=lambda k: sd.offsets[k])
+    # runs of tensors that are neighbours in the packed host buffer (same padding rule as pack_state_dict)
+    runs, total = [], 0
+    for k in host:
+        n = sd[k].numel()
+        span = (n + al - 1) // al * al
+        if packed and runs and runs[-1]["src_end"] == sd.offsets[k]:
+            r = runs[-1]
+            r["keys"].append((k, total, n))
+            r["src_end"] += span
+            r["valid"] = (total - r["dst"]) + n
+        else:
+            runs.append(dict(keys=[(k, total, n)], dst=total, valid=n,
+                             src=sd.offsets[k] if packed else None, src_end=(sd.offsets[k] + span) if packed else None))
+        total += span
+    arena = torch.empty(max(total, 1), dtype=dtype, device=device)
+    nbytes = 0
+    for r in runs:
+        if packed:
+            arena[r["dst"]: r["dst"] + r["valid"]].copy_(sd.flat[r["src"]: r["src"] + r["valid"]], non_blocking=True)
+        else:
+            k, o, n = r["keys"][0]
+            arena[o: o + n].copy_(sd[k].detach().reshape(-1), non_blocking=True)
+        nbytes += r["valid"] * arena.element_size()
+        for k, o, n in r["keys"]:
+            out[k] = arena[o: o + n].view(sd[k].shape)
+    return out, nbytes
 
 
 @dataclass
@@ -128,13 +174,15 @@ def _pinned_staging(nbytes: int) -> torch.Tensor:
     return buf
 
 
-def _upload_mask_bits(task_masks: Sequence[Optional[Mapping[str, torch.Tensor]]], device
+def _upload_mask_bits(task_masks: Sequence[Optional[Mapping[str, torch.Tensor]]], device, wanted=None
                       ) -> Tuple[List[Optional[Dict[str, _PackedBits]]], int]:
     """HOST torch.bool masks -> bits on the host (svdq_host_pack_mask, all host threads; runs while the tensors'
     host->device copies are in flight) -> one upload of numel/8 bytes per task.  A pure transfer encoding: the
     masks are combined on the device (K1) exactly as with byte masks."""
     # host threads for the re-encoding: this process's CPUs, shared with the other ranks of the node under torchrun
     n_threads = max(1, min(16, len(os.sched_getaffinity(0)) // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))))
+    if wanted is not None:                                    # this rank's shard only
+        task_masks = [None if m is None else {k: v for k, v in m.items() if k in wanted} for m in task_masks]
     plan, total = [], 0
     for m in task_masks:
         if m is None:
@@ -247,7 +295,7 @@ class MergeJob:
         self.performance = performance
         self.fixed_assignments = cluster_assignments
         self.cluster_mode = config.svd_weighting == "cluster"
-        self.cluster_backend = cluster_backend or os.environ.get("SVDQ_CLUSTER_BACKEND", "exact")
+        self.cluster_backend = cluster_backend or os.environ.get("SVDQ_CLUSTER_BACKEND", "kmeans")
         # coefficients: "closed" = Sigma V^T for every parameter; "exact" = re-project every parameter on the stored
         # (fp16) basis like the reference does (one more read of the inputs); "auto" = exact for parameters of at
         # most EXACT_MAX_NUMEL elements, where the closed form's 2.4e-4/sqrt(Dm) deviation can flip an fp16 value or
@@ -278,13 +326,19 @@ class MergeJob:
     # ------------------------------------------------------------------------------------------
     def _stage_inputs(self, base, finetuned, task_masks, param_filter):
         dev = self.device
-        base_d = _to_device_state_dict(base, dev)
-        fts_d = [(_to_device_state_dict(finetuned[t], dev) if t in finetuned else {}) for t in self.tasks]
+        wanted = set(param_filter) if param_filter is not None else None
+        # with a parameter filter (this rank's shard) only the owned tensors cross PCIe and occupy HBM
         self.h2d_bytes = 0
-        for sd in [base] + [finetuned[t] for t in self.tasks if t in finetuned]:
-            for v in sd.values():
-                if v.device != dev:
-                    self.h2d_bytes += v.numel() * v.element_size()
+        base_d, nb = _to_device_state_dict(base, dev, wanted)
+        self.h2d_bytes += nb
+        fts_d = []
+        for t in self.tasks:
+            if t in finetuned:
+                sd, nb = _to_device_state_dict(finetuned[t], dev, wanted)
+                self.h2d_bytes += nb
+            else:
+                sd = {}
+            fts_d.append(sd)
         masks_h = [(task_masks.get(t) if task_masks else None) for t in self.tasks]
         # masks that all sit in host memory (what load_task_masks yields) cross PCIe bit-packed: 1/8 of the bytes
         self.mask_bits = (not self.wide and any(m is not None for m in masks_h) and
@@ -292,15 +346,13 @@ class MergeJob:
                               for v in m.values()))
         masks_d: List[Optional[Mapping[str, object]]] = []
         if self.mask_bits:
-            masks_d, nbytes = _upload_mask_bits(masks_h, dev)
+            masks_d, nbytes = _upload_mask_bits(masks_h, dev, wanted)
             self.h2d_bytes += nbytes
         else:
             for m in masks_h:
                 if m is not None:
-                    for v in m.values():
-                        if v.device != dev:
-                            self.h2d_bytes += v.numel() * v.element_size()
-                    m = _to_device_state_dict(m, dev)
+                    m, nb = _to_device_state_dict(m, dev, wanted)
+                    self.h2d_bytes += nb
                 masks_d.append(m)
 
         self.base_keys = list(base.keys())
@@ -311,12 +363,11 @@ class MergeJob:
         self._tensors: Dict[str, List[Optional[torch.Tensor]]] = {}
         self._masks: Dict[str, List[Optional[torch.Tensor]]] = {}
         self.shapes: Dict[str, torch.Size] = {}
-        wanted = set(param_filter) if param_filter is not None else None
         for name in sorted(base.keys()):
-            b = base_d[name]
             if wanted is not None and name not in wanted:
                 self.filtered_out.add(name)          # another rank's shard: not returned by this job
                 continue
+            b = base_d[name] if name in base_d else base[name]
             if not torch.is_tensor(b) or b.dtype not in _FLOAT_DTYPES or b.numel() == 0:
                 self.passthrough.append(name)
                 continue
@@ -463,10 +514,19 @@ class MergeJob:
                                            performance_file=getattr(cfg, "performance_file", None),
                                            temperature=cfg.svd_weighting_temperature,
                                            cluster_assignments=self.cluster_assignments)
-        eff = effective_merge_weights(self.tasks, self.weights,
-                                      self.cluster_assignments if self.cluster_mode else None)
-        w = np.asarray([eff[t] for t in self.tasks], np.float64)
+        w = np.asarray([self.weights.get(t, 1.0) for t in self.tasks], np.float64)
         order = np.asarray(sorted(range(self.N), key=lambda i: self.tasks[i]), np.int32)
+        self._cluster_tables = (None, None)
+        if self.cluster_mode and self.cluster_assignments:
+            # merge_with_clustering (merge.py:586-626): member weights renormalised inside each cluster PER PARAMETER
+            # over the members that have it (K2 average_param), clusters averaged with omega
+            om = cluster_omega(self.weights, self.cluster_assignments)
+            ids = sorted(om.keys())
+            index = {c: i for i, c in enumerate(ids)}
+            cl = np.asarray([index[self.cluster_assignments[t]] for t in self.tasks], np.int32)
+            omega = np.zeros(self.N, np.float64)
+            omega[: len(ids)] = [om[c] for c in ids]
+            self._cluster_tables = (_dev(cl, self.device), _dev(omega, self.device))
         return _dev(w, self.device), _dev(order, self.device)
 
     def _cluster_begin(self):
@@ -474,10 +534,10 @@ class MergeJob:
         k-means round trip overlaps the per-parameter solve on the main stream."""
         if self.fixed_assignments is not None:
             return
-        tot = None
+        # a rank whose shard is empty (more ranks than parameters) still joins the all-reduce with zeros
+        tot = torch.zeros(self.N * self.N, dtype=torch.float64, device=self.device)
         for g in self.groups.values():
-            s = g.t["gram_all"].sum(dim=0)
-            tot = s if tot is None else tot + s
+            tot = tot + g.t["gram_all"].sum(dim=0)
         if self._side is None:
             self._side = torch.cuda.Stream(device=self.device)
             self._gram_host = torch.empty(self.N * self.N, dtype=torch.float64, pin_memory=True)
@@ -609,9 +669,10 @@ class MergeJob:
             def average(w_dev, order_dev):
                 for g in self.groups.values():
                     for _, _, _, _, o in regions(g):
+                        cl_dev, om_dev = self._cluster_tables
                         _native.call("svdq_param_average", N, len(g.names), _ptr(g.t["present"]), _ptr(w_dev),
-                                     _ptr(order_dev), _ptr(o["info"]), _ptr(o["chat"]), _ptr(o["W"]), _ptr(o["cbar"]),
-                                     _ptr(o["gvec"]), _ptr(o["scal"]), st)
+                                     _ptr(order_dev), _ptr(cl_dev), _ptr(om_dev), _ptr(o["info"]), _ptr(o["chat"]),
+                                     _ptr(o["W"]), _ptr(o["cbar"]), _ptr(o["gvec"]), _ptr(o["scal"]), st)
 
             any_exact = any(g.sel is not None for g in self.groups.values())
             if self.cluster_mode:

@@ -131,37 +131,71 @@ _ERR_KEYS = ("absolute_error", "relative_error", "max_absolute_error", "mean_abs
              "reconstructed_norm")
 
 
-def build_diagnostics(job, index) -> Dict:
-    """diagnostics.py:234-321 schema from the fused K3 reductions."""
-    cfg = job.cfg
+REC_HEAD = 16      # status, n_active, r, k, dm, has_mask, present, numel, energy_retained, ndim, shape[0..5]
+REC_MAX_DIMS = 6
+
+
+def record_width(n_tasks: int) -> int:
+    return REC_HEAD + 6 * n_tasks
+
+
+def pack_records(job, index) -> Tuple[list, np.ndarray]:
+    """Per-parameter records of the parameters that received a basis, as one fp64 matrix (every field is an
+    int32, a float32 or an fp64 value, so fp64 holds it exactly): what a rank contributes to the diagnostics
+    gather of a parameter-sharded merge (ONE flat all-gather instead of pickled dicts), and what
+    diagnostics_from_records needs.  -> (names in sorted order, [P, record_width(N)])."""
+    fetched = job._fetch()
+    names = sorted(index)
+    N = job.N
+    rec = np.zeros((len(names), record_width(N)), np.float64)
+    for i, name in enumerate(names):
+        dt, p = index[name]
+        g, f = job.groups[dt], fetched[dt]
+        info = f["info"][p]
+        shape = list(g.shapes[p])
+        if len(shape) > REC_MAX_DIMS:
+            raise ValueError(f"{name}: more than {REC_MAX_DIMS} dimensions")
+        rec[i, :4] = info[:4]
+        rec[i, 4] = int(f["dm"][p])
+        rec[i, 5] = int(g.host["has_mask"][p])
+        rec[i, 6] = int(g.host["present"][p])
+        rec[i, 7] = int(g.numel[p])
+        rec[i, 8] = float(f["scal"][p, 0])
+        rec[i, 9] = len(shape)
+        rec[i, 10: 10 + len(shape)] = shape
+        if job.want_diag:
+            rec[i, REC_HEAD:] = f["diag_out"][p].reshape(-1)
+    return names, rec
+
+
+def diagnostics_from_records(cfg, tasks, bits: int, stages: int, names, rec: np.ndarray, want_diag: bool = True) -> Dict:
+    """diagnostics.py:234-321 schema from per-parameter records (pack_records)."""
     out = {"config": {"svd_energy_threshold": cfg.svd_energy_threshold, "svd_max_rank": cfg.svd_max_rank,
                       "svd_low_bits": cfg.svd_low_bits, "svd_rtvq_stages": cfg.svd_rtvq_stages,
                       "svd_mask_strategy": cfg.svd_mask_strategy, "svd_weighting": cfg.svd_weighting},
            "per_parameter": {}, "summary": {}}
-    fetched = job._fetch()
+    N = len(tasks)
     ranks, energy, errs, ratios = [], [], [], []
-    for name in sorted(index):
-        dt, p = index[name]
-        g, f = job.groups[dt], fetched[dt]
-        info = f["info"][p]
-        r, k, dm = int(info[2]), int(info[3]), int(f["dm"][p])
-        has_mask = bool(g.host["has_mask"][p])
-        present = int(g.host["present"][p])
-        shape = list(g.shapes[p])
+    order = sorted(range(len(names)), key=lambda i: names[i])
+    for i in order:
+        name, row = names[i], rec[i]
+        n_active, r, k, dm = int(row[1]), int(row[2]), int(row[3]), int(row[4])
+        has_mask, present, numel = bool(row[5]), int(row[6]), int(row[7])
+        shape = [int(x) for x in row[10: 10 + int(row[9])]]
         d = {"param_name": name, "original_shape": shape,
              "masked_size": dm if has_mask else np.prod(shape),
-             "unmasked_size": (g.numel[p] - dm) if has_mask else 0,
+             "unmasked_size": (numel - dm) if has_mask else 0,
              "reconstruction_errors": {}, "compression_ratios": {},
-             "basis": {"k": k, "D": dm, "N": int(info[1]), "energy_retained": float(f["scal"][p, 0])}}
+             "basis": {"k": k, "D": dm, "N": n_active, "energy_retained": float(row[8])}}
         rel = []
-        ratio = estimate_ratio(r - k, job.bits, job.stages)
-        for t, task in enumerate(job.tasks):
+        ratio = estimate_ratio(r - k, bits, stages)
+        dg = row[REC_HEAD:].reshape(N, 6)
+        for t, task in enumerate(tasks):
             if not (present >> t) & 1:
                 continue
-            row = f["diag_out"][p, t]
-            d["reconstruction_errors"][task] = {key: float(row[i]) for i, key in enumerate(_ERR_KEYS)}
+            d["reconstruction_errors"][task] = {key: float(dg[t, j]) for j, key in enumerate(_ERR_KEYS)}
             d["compression_ratios"][task] = ratio
-            rel.append(float(row[1]))
+            rel.append(float(dg[t, 1]))
         if rel:
             d["mean_relative_error"] = float(np.mean(rel))
             d["std_relative_error"] = float(np.std(rel))
@@ -180,3 +214,9 @@ def build_diagnostics(job, index) -> Dict:
                       "average_reconstruction_error": float(np.mean(errs)) if errs else 0,
                       "average_compression_ratio": float(np.mean(ratios)) if ratios else 0}
     return out
+
+
+def build_diagnostics(job, index) -> Dict:
+    """diagnostics.py:234-321 schema from the fused K3 reductions."""
+    names, rec = pack_records(job, index)
+    return diagnostics_from_records(job.cfg, job.tasks, job.bits, job.stages, names, rec)

@@ -4,8 +4,9 @@ Every parameter tensor is an independent unit of work from task-vector construct
 weight (reference: the sequential loops of src/svd_hybrid/cli.py:317, compress.py:189, merge.py:371),
 so the path shards with NO data-path collective.  NCCL (torch.distributed) is used only
   * to all-reduce the N x N whole-model task Gram (fp64) when cluster weighting needs it,
-  * to gather the per-parameter records / diagnostics, and
-  * optionally to replicate the merged tensors (one broadcast of a flat buffer per owner).
+  * to gather the per-parameter records / diagnostics (one flat fp64 all_gather_into_tensor), and
+  * optionally to replicate the merged tensors (one broadcast of a flat buffer per owner, or one padded
+    all_gather_into_tensor of the ranks' output arenas).
 Results are bit-identical for any world size: the reduction order inside a parameter is fixed by
 the tile size, never by the placement.
 """
@@ -84,40 +85,95 @@ def replicate_tensors(local: Mapping[str, torch.Tensor], owner: Mapping[str, int
     return out
 
 
-def merge_state_dicts_sharded(base, finetuned, task_masks, config, device: Optional[str] = None, group=None,
-                              replicate_merged: bool = False, **kw) -> Dict:
-    """Parameter-sharded SVD-Hybrid merge.  Every rank passes the same (or at least its own shard of
-    the) inputs; rank r processes the parameters ``lpt_partition`` assigns to it.
+def gather_records(local: "np.ndarray", rows_per_rank: Sequence[int], device, group=None) -> List["np.ndarray"]:
+    """Per-parameter fp64 records of every rank with ONE collective: each rank contributes a [rows_per_rank[r], W]
+    matrix, padded to the longest, through all_gather_into_tensor.  -> list of [rows_r, W] arrays in rank order."""
+    import numpy as np
+    world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+    if world == 1:
+        return [np.asarray(local, np.float64)]
+    width = int(local.shape[1])
+    pmax = max(int(n) for n in rows_per_rank)
+    buf = torch.zeros(max(pmax, 1), width, dtype=torch.float64, device=device)
+    if local.shape[0]:
+        buf[: local.shape[0]] = torch.from_numpy(np.ascontiguousarray(local, np.float64)).to(device)
+    out = torch.empty(world * max(pmax, 1), width, dtype=torch.float64, device=device)
+    dist.all_gather_into_tensor(out, buf, group=group)
+    host = out.view(world, max(pmax, 1), width).cpu().numpy()
+    return [host[r, : int(rows_per_rank[r])] for r in range(world)]
 
-    Returns this rank's result dict (merged tensors of its shard; diagnostics and per-parameter
-    records gathered from all ranks on every rank; all merged tensors when ``replicate_merged``)."""
+
+def gather_merged(local_flat: torch.Tensor, sizes_per_rank: Sequence[int], group=None) -> torch.Tensor:
+    """All ranks' merged shards with ONE padded all_gather_into_tensor over NVLink: rank r contributes its flat fp32
+    arena (sizes_per_rank[r] elements).  -> [world, max size] tensor; row r's first sizes_per_rank[r] elements are
+    rank r's arena."""
+    world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+    smax = max(int(x) for x in sizes_per_rank)
+    if world == 1:
+        return local_flat.view(1, -1)
+    buf = local_flat
+    if buf.numel() != smax:
+        buf = torch.zeros(smax, dtype=local_flat.dtype, device=local_flat.device)
+        buf[: local_flat.numel()] = local_flat
+    out = torch.empty(world * smax, dtype=local_flat.dtype, device=local_flat.device)
+    dist.all_gather_into_tensor(out, buf, group=group)
+    return out.view(world, smax)
+
+
+def merge_state_dicts_sharded(base, finetuned, task_masks, config, device: Optional[str] = None, group=None,
+                              replicate_merged: bool = False, owner: Optional[Mapping[str, int]] = None,
+                              to_host=False, **kw) -> Dict:
+    """Parameter-sharded SVD-Hybrid merge.  Every rank passes the same inputs, or just its own shard of them
+    together with the global ``owner`` map; rank r processes the parameters ``lpt_partition`` assigns to it and
+    uploads only those (engine: the filter is applied before any host->device copy).
+
+    Collectives: the N x N fp64 whole-model Gram all-reduce of cluster weighting (on the job's side stream), ONE
+    flat all-gather of the per-parameter records / diagnostics, and -- only with ``replicate_merged`` -- one
+    broadcast of a flat buffer per owner.  Returns this rank's result dict (merged tensors of its shard;
+    diagnostics gathered from all ranks on every rank; all merged tensors when ``replicate_merged``)."""
     from .engine import MergeJob
+    from .results import diagnostics_from_records, pack_records, record_width
+    import numpy as np
     world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
     rank = dist.get_rank(group) if world > 1 else 0
     n_tasks = len(config.tasks) if config.tasks else len(finetuned)
-    cost = {k: int(v.numel()) * (n_tasks + 1) for k, v in base.items() if torch.is_tensor(v) and v.is_floating_point()}
-    owner = lpt_partition(cost, world)
-    mine = [n for n, r in owner.items() if r == rank]
+    if owner is None:
+        cost = {k: int(v.numel()) * (n_tasks + 1) for k, v in base.items()
+                if torch.is_tensor(v) and v.is_floating_point()}
+        owner = lpt_partition(cost, world)
+    by_rank = [sorted(n for n, r in owner.items() if r == q) for q in range(world)]
+    mine = by_rank[rank]
     job = MergeJob(base, finetuned, task_masks, config, device, param_filter=mine, **kw)
     if world > 1 and job.cluster_mode:
         job.gram_reduce_hook = lambda g: allreduce_gram(g, group)
     job.run()
-    res = job.results()
+    res = job.results(to_host=to_host)
     local_merged = {n: res["merged_state_dict"][n] for n in mine if n in res["merged_state_dict"]}
-    records = {"rank": rank, "params": {n: res["bases"].meta(n) for n in res["bases"]},
-               "per_parameter": res["diagnostics"].get("per_parameter", {})}
-    gathered = gather_objects(records, group)
-    per_parameter, meta = {}, {}
-    for rec in gathered:
-        per_parameter.update(rec["per_parameter"])
-        meta.update(rec["params"])
+    # one fp64 record per owned parameter, rows in sorted-name order (status -1: no basis), gathered flat
+    index = res["bases"]._index
+    names_l, rec_l = pack_records(job, index)
+    width = record_width(job.N)
+    local = np.full((len(mine), width), -1.0, np.float64)
+    pos = {n: i for i, n in enumerate(mine)}
+    for n, row in zip(names_l, rec_l):
+        local[pos[n]] = row
+    gathered = gather_records(local, [len(b) for b in by_rank], job.device, group)
+    names_all, rows = [], []
+    for q in range(world):
+        for n, row in zip(by_rank[q], gathered[q]):
+            if row[0] >= 0:
+                names_all.append(n)
+                rows.append(row)
+    rec_all = np.stack(rows) if rows else np.zeros((0, width))
+    meta = {n: {"k": int(r[3]), "r": int(r[2]), "D": int(r[4]), "N": int(r[1]), "energy_retained": float(r[8]),
+                "solved": int(r[0]) == 0} for n, r in zip(names_all, rec_all)}
     diag = dict(res["diagnostics"])
-    if per_parameter:
-        from .svd_hybrid.diagnostics import summarize
-        diag["per_parameter"] = OrderedDict(sorted(per_parameter.items()))
-        diag["summary"] = summarize(diag["per_parameter"])
+    if job.want_diag:
+        full = diagnostics_from_records(job.cfg, job.tasks, job.bits, job.stages, names_all, rec_all)
+        diag["per_parameter"] = full["per_parameter"]
+        diag["summary"] = full["summary"]
     out = {"merged_state_dict": local_merged, "diagnostics": diag, "bases": res["bases"],
-           "compressed": res["compressed"], "owner": owner, "basis_meta": meta, "job": job}
+           "compressed": res["compressed"], "owner": dict(owner), "basis_meta": meta, "job": job}
     if replicate_merged:
         shapes = {n: tuple(base[n].shape) for n in owner}
         full = replicate_tensors({n: t.float() for n, t in local_merged.items()}, owner, shapes, torch.float32,

@@ -3,7 +3,10 @@
 The reference flattens every task vector into an [N x P_total] fp32 matrix on the host and runs
 sklearn KMeans on it (742 s of an 863 s ViT-L-14 run).  K-means only sees pairwise geometry, so
 the N x N whole-model task Gram -- a free by-product of the K1 streaming pass -- is enough: the
-same sklearn call is run on an N x N embedding E with E E^T = normalised Gram (host side, ms).
+reference's k-means procedure (KMeans(k, random_state=42, n_init=10): numpy RandomState stream,
+k-means++ seeding, float32 Lloyd iterations, best-of-10) is run on an N x N embedding E with
+E E^T = normalised Gram by libsvdq's host routine svdq_host_kmeans (~30 us; label-identical to
+the sklearn call on the same embedding, tests/test_kmeans_native.py).
 """
 import functools
 from typing import Dict, List, Tuple
@@ -22,6 +25,21 @@ def embedding_from_gram(gram: np.ndarray) -> np.ndarray:
 
 
 def compute_kmeans_clustering(features: np.ndarray, k: int, random_state: int = 42) -> np.ndarray:
+    """clustering.py:123-156: KMeans(n_clusters=k, random_state=random_state, n_init=10).fit_predict(features),
+    restated in libsvdq (svdq_host_kmeans): same labels, without sklearn's per-call overhead."""
+    features = np.asarray(features)
+    if k <= 0 or k > features.shape[0]:
+        raise ValueError(f"Invalid k={k} for {features.shape[0]} samples")
+    from .. import _native
+    f = np.ascontiguousarray(features, np.float32)
+    labels = np.empty(f.shape[0], np.int32)
+    _native.call("svdq_host_kmeans", f.ctypes.data, f.shape[0], f.shape[1], int(k), int(random_state) & 0xFFFFFFFF,
+                 10, 300, 1e-4, labels.ctypes.data, None)
+    return labels
+
+
+def compute_kmeans_clustering_sklearn(features: np.ndarray, k: int, random_state: int = 42) -> np.ndarray:
+    """The reference's very call (cross-check for compute_kmeans_clustering; needs scikit-learn)."""
     if k <= 0 or k > features.shape[0]:
         raise ValueError(f"Invalid k={k} for {features.shape[0]} samples")
     from sklearn.cluster import KMeans
@@ -129,14 +147,16 @@ def kmeans_partition_from_gram(gram_normalised: np.ndarray, k: int, exact_limit:
 
 
 def cluster_from_gram(gram: np.ndarray, task_names_in_gram_order: List[str], k: int,
-                      method: str = "kmeans", backend: str = "exact") -> Dict[str, int]:
+                      method: str = "kmeans", backend: str = "kmeans") -> Dict[str, int]:
     """Cluster tasks from the whole-model task Gram.  Rows are re-ordered to sorted task names
     first, because the reference builds its feature matrix in sorted order (clustering.py:87).
 
-    backend "exact"  : deterministic k-means on the Gram (global optimum for small N; 0.1 ms);
-    backend "sklearn": the reference's very call, KMeans(k, random_state=42, n_init=10), on an
-                       isometric N x N embedding (23 ms -- 3x the whole GPU merge of ViT-L-14).
-    Both give the same partition whenever sklearn's best-of-10 reaches the global optimum.
+    backend "kmeans" (default): the reference's procedure, KMeans(k, random_state=42, n_init=10), restated in
+                       libsvdq (svdq_host_kmeans) on an isometric N x N embedding -- the labels sklearn gives;
+    backend "sklearn": the same call made through scikit-learn itself (8-23 ms; cross-check);
+    backend "exact"  : opt-in, NOT the reference's algorithm: the global k-means optimum by enumeration.  It
+                       differs from the reference partition whenever sklearn's best-of-10 stops in a local
+                       optimum (about one unclustered 8-task input in five).
     """
     names = list(task_names_in_gram_order)
     order = sorted(range(len(names)), key=lambda i: names[i])
@@ -145,7 +165,11 @@ def cluster_from_gram(gram: np.ndarray, task_names_in_gram_order: List[str], k: 
         labels = kmeans_partition_from_gram(normalised_gram(g), k)
         return {names[i]: int(l) for i, l in zip(order, labels)}
     feats = embedding_from_gram(g)
-    if method == "kmeans":
+    if method == "kmeans" and backend == "sklearn":
+        labels = compute_kmeans_clustering_sklearn(feats, k)
+    elif method == "kmeans":
+        if backend != "kmeans":
+            raise ValueError(f"Unknown cluster backend: {backend}")
         labels = compute_kmeans_clustering(feats, k)
     elif method == "hierarchical":
         labels = compute_hierarchical_clustering(feats, k)

@@ -100,9 +100,31 @@ def get_weight_statistics(weights: Dict[str, float]) -> Dict[str, float]:
             "entropy": -sum(w * np.log(w + 1e-10) for w in v)}
 
 
+def cluster_omega(weights: Dict[str, float], cluster_assignments: Dict[str, int]) -> Dict[int, float]:
+    """Cross-cluster weights of merge_with_clustering: every cluster is scored by the mean weight of its members
+    (src/svd_hybrid/merge.py:614-618), the scores go through an fp32 softmax in cluster-dict order and the fp32
+    renormalisation of apply_weights_to_tensors in sorted-id order (src/svd_hybrid/clustering.py:399-423,
+    weighting.py:362-366)."""
+    clusters: Dict[int, List[str]] = {}
+    for n, c in cluster_assignments.items():
+        clusters.setdefault(c, []).append(n)
+    ids = list(clusters.keys())
+    score = np.asarray([sum(weights.get(n, 1.0) for n in clusters[c]) / len(clusters[c]) for c in ids], np.float32)
+    # numpy instead of torch.softmax keeps this off the critical path (a last-ulp difference in exp changes
+    # a weight by ~1e-8 relative)
+    ex = np.exp(score - score.max(), dtype=np.float32)
+    sm = (ex / ex.sum(dtype=np.float32)).astype(np.float32)
+    order = sorted(range(len(ids)), key=lambda i: ids[i])
+    wt = sm[order]
+    wt = (wt / wt.sum(dtype=np.float32)).astype(np.float32)
+    return {ids[i]: float(wt[j]) for j, i in enumerate(order)}
+
+
 def effective_merge_weights(task_names: List[str], weights: Dict[str, float],
                             cluster_assignments: Optional[Dict[str, int]] = None) -> Dict[str, float]:
-    """Per-task weights that make ONE weighted average equal to the reference's merge.
+    """Per-task weights that make ONE weighted average equal to the reference's merge WHEN EVERY TASK HAS THE
+    PARAMETER (the per-parameter form, which also covers missing parameters, is K2's average_param fed by
+    cluster_omega; this closed form is what tests compare it with).
 
     Without clustering this is ``weights``.  With clustering the reference merges per cluster with
     member weights renormalised inside the cluster, scores each cluster by the mean member weight,
@@ -115,17 +137,7 @@ def effective_merge_weights(task_names: List[str], weights: Dict[str, float],
     clusters: Dict[int, List[str]] = {}
     for n, c in cluster_assignments.items():
         clusters.setdefault(c, []).append(n)
-    ids = list(clusters.keys())
-    score = np.asarray([sum(weights.get(n, 1.0) for n in clusters[c]) / len(clusters[c]) for c in ids], np.float32)
-    # fp32 softmax, then the fp32 renormalisation apply_weights_to_tensors performs (sorted cluster ids);
-    # numpy instead of torch.softmax keeps this off the critical path (a last-ulp difference in exp changes
-    # a weight by ~1e-8 relative)
-    ex = np.exp(score - score.max(), dtype=np.float32)
-    sm = (ex / ex.sum(dtype=np.float32)).astype(np.float32)
-    order = sorted(range(len(ids)), key=lambda i: ids[i])
-    wt = sm[order]
-    wt = (wt / wt.sum(dtype=np.float32)).astype(np.float32)
-    omega = {ids[i]: float(wt[j]) for j, i in enumerate(order)}
+    omega = cluster_omega(weights, cluster_assignments)
     out = {}
     for c, members in clusters.items():
         tot = sum(weights.get(n, 1.0) for n in members)

@@ -11,6 +11,7 @@ HF Llama layout for the capacity config.  Two input families:
 """
 from __future__ import annotations
 
+import zlib
 from collections import OrderedDict
 from typing import Dict, List, Optional, Tuple
 
@@ -103,10 +104,17 @@ def task_names(n: int) -> List[str]:
     return STANDARD_8_TASKS + [f"Task{i:02d}" for i in range(len(STANDARD_8_TASKS), n)]
 
 
+def _tensor_seed(seed: int, name: str) -> int:
+    return (seed * 1000003 + zlib.crc32(name.encode())) & 0x7FFFFFFFFFFFFFFF
+
+
 def make_checkpoints(shapes, tasks: List[str], family: str = "throughput", seed: int = 1234,
-                     device: str = "cpu", dtype: torch.dtype = torch.float32,
+                     device: str = "cpu", dtype: torch.dtype = torch.float32, per_tensor: bool = False,
                      ) -> Tuple[Dict[str, torch.Tensor], Dict[str, Dict[str, torch.Tensor]]]:
-    """-> (base_state_dict, {task: finetuned_state_dict}) of random-init weights of the given shapes."""
+    """-> (base_state_dict, {task: finetuned_state_dict}) of random-init weights of the given shapes.
+
+    per_tensor: every tensor draws from its own stream seeded by (seed, name), so that a rank that generates
+    only its shard of the model gets exactly the tensors a rank generating the whole model gets."""
     g = torch.Generator(device=device).manual_seed(seed)
     n = len(tasks)
     base: Dict[str, torch.Tensor] = OrderedDict()
@@ -123,6 +131,8 @@ def make_checkpoints(shapes, tasks: List[str], family: str = "throughput", seed:
         numel = 1
         for d in shp:
             numel *= d
+        if per_tensor:
+            g.manual_seed(_tensor_seed(seed, name))
         b = torch.randn(numel, generator=g, device=device, dtype=torch.float32) * 0.02
         if family == "parity":
             c = torch.randn(n, numel, generator=g, device=device, dtype=torch.float32) * 0.01
@@ -138,13 +148,17 @@ def make_checkpoints(shapes, tasks: List[str], family: str = "throughput", seed:
     return base, fts
 
 
-def make_masks(shapes, tasks: List[str], p: float, seed: int = 4321, device: str = "cpu",
+def make_masks(shapes, tasks: List[str], p: float, seed: int = 4321, device: str = "cpu", per_tensor: bool = False,
                ) -> Dict[str, Dict[str, torch.Tensor]]:
-    """Per-task Bernoulli(p) tall masks as torch.bool state dicts."""
+    """Per-task Bernoulli(p) tall masks as torch.bool state dicts (per_tensor: see make_checkpoints)."""
     g = torch.Generator(device=device).manual_seed(seed)
     out: Dict[str, Dict[str, torch.Tensor]] = OrderedDict()
-    for t in tasks:
-        out[t] = OrderedDict((name, torch.rand(shp, generator=g, device=device) < p) for name, shp in shapes.items())
+    for i, t in enumerate(tasks):
+        out[t] = OrderedDict()
+        for name, shp in shapes.items():
+            if per_tensor:
+                g.manual_seed(_tensor_seed(seed + 7919 * (i + 1), name))
+            out[t][name] = torch.rand(shp, generator=g, device=device) < p
     return out
 
 

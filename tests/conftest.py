@@ -18,3 +18,20 @@ def cuda_device():
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
     return torch.device("cuda:0")
+
+
+def pytest_sessionfinish(session, exitstatus):
+    """Observed c_high / RTVQ-code equality rates of the parity runs of this session -> gpurun_out/parity_rates.json
+    (copied to profiles/parity_rates.json when committed)."""
+    try:
+        from tests import parity
+    except Exception:
+        return
+    if not parity.RATES:
+        return
+    import json
+    out = os.path.join(ROOT, "gpurun_out")
+    os.makedirs(out, exist_ok=True)
+    tot = {k: sum(r[k] for r in parity.RATES) for k in ("c_high_equal", "c_high_total", "codes_equal", "codes_total")}
+    with open(os.path.join(out, "parity_rates.json"), "w") as f:
+        json.dump({"totals": tot, "runs": parity.RATES}, f, indent=1)

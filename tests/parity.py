@@ -28,6 +28,10 @@ TOL_COEF = 1e-5         # raw coefficients, abs relative to ||c||_inf
 TOL_DIAG = 1e-4         # diagnostics floats, relative
 TOL_ANGLE = 1e-5        # sine of the largest principal angle between spans
 
+# observed equality rates of every compare_run call of the session (written to gpurun_out/parity_rates.json by
+# tests/conftest.py; the committed copy is profiles/parity_rates.json)
+RATES = []
+
 MEDIUM_SHAPES = OrderedDict([
     ("blk.attn.weight", (300, 70)), ("blk.bias", (4099,)), ("conv.weight", (17, 33, 5)),
     ("wide.weight", (1, 1, 40000)), ("ln.weight", (768,)), ("tiny", (7,)), ("scalar_like", (1,)),
@@ -219,6 +223,13 @@ def compare_run(ref: Dict, res: Dict, check_diag: bool = True, tol_merged: Optio
             assert torch.equal(m_new.cpu(), m_ref), f"untouched parameter changed: {name}"
     report["flipped_params"] = sorted(flipped)
     report["dust_params"] = sorted(dust)
+    import os
+    RATES.append({"test": os.environ.get("PYTEST_CURRENT_TEST", "").split(" ")[0], "params": report["params"],
+                  "n_tasks": job.N, "fp16_bases": bool(job.cfg.svd_fp16), "bits": job.bits, "stages": job.stages,
+                  "projection": job.projection, "c_high_equal": report["chigh_equal"],
+                  "c_high_total": report["chigh_total"], "codes_equal": report["code_equal"],
+                  "codes_total": report["code_total"], "max_merged_rel": report["max_merged_rel"],
+                  "flipped_params": len(flipped), "dust_params": len(dust)})
     flipped = flipped | dust
     if check_diag and ref["diagnostics"].get("per_parameter") is not None and "per_parameter" in res["diagnostics"]:
         compare_diagnostics(ref["diagnostics"], res["diagnostics"], flipped=flipped, dust=dust,

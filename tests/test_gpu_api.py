@@ -54,10 +54,10 @@ def test_cluster_partition_golden_from_gram(cuda_device):
     case = _gold("intersection_cluster")
     cfg = SVDHybridConfig(tasks=case["tasks"], svd_max_rank=64, svd_store_artifacts=False, **case["config"])
     gold = case["diagnostics"]["cluster_assignments"]
-    # backend "sklearn" = the reference's very call on an isometric embedding of the Gram.  (The default
-    # "exact" backend returns the global k-means optimum, which coincides with sklearn's best-of-10 whenever
-    # the tasks really form clusters -- tests/test_host_logic.py -- but not on these unclustered toy tasks.)
-    job = MergeJob(case["base"], case["finetuned"], case["masks"], cfg, "cuda", cluster_backend="sklearn").run()
+    # default backend = the reference's KMeans(k, random_state=42, n_init=10) procedure restated in libsvdq
+    # (svdq_host_kmeans) on an isometric embedding of the Gram; these toy tasks are unclustered, so only the
+    # reference's own procedure (local optimum included) reproduces its partition
+    job = MergeJob(case["base"], case["finetuned"], case["masks"], cfg, "cuda").run()
     mine, ts = job.cluster_assignments, case["tasks"]
     assert all((mine[a] == mine[b]) == (gold[a] == gold[b]) for a in ts for b in ts)
     assert mine == gold                                  # same label numbering as well
@@ -196,7 +196,6 @@ def _write_case(tmp, case):
 @pytest.mark.parametrize("name", ["union_uniform", "intersection_cluster", "majority_noise_uniform"])
 def test_pipeline_on_disk_writes_reference_layout(cuda_device, tmp_path, name, monkeypatch):
     from src.svd_hybrid.cli import run_svd_hybrid_pipeline
-    monkeypatch.setenv("SVDQ_CLUSTER_BACKEND", "sklearn")      # label-exact parity with the reference's k-means
     from src.svd_hybrid.storage import load_all_artifacts
     case = _gold(name)
     ck, md = _write_case(tmp_path, case)

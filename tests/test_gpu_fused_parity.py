@@ -57,7 +57,7 @@ def test_cluster_partition_from_gram_matches_full_kmeans(cuda_device):
     masks = synth.make_masks(parity.MEDIUM_SHAPES, tasks, 0.9, seed=78)
     cfg = SVDHybridConfig(tasks=tasks, svd_weighting="cluster", svd_mask_strategy="intersection",
                           svd_energy_threshold=0.9, svd_store_artifacts=False)
-    job = MergeJob(base, fts, masks, cfg, "cuda", cluster_backend="sklearn").run()
+    job = MergeJob(base, fts, masks, cfg, "cuda").run()      # default cluster backend
     tvs = {t: R.task_vector(base, fts[t]) for t in tasks}
     full = R.cluster_tasks_full(tvs, 2)
     mine = job.cluster_assignments
@@ -143,6 +143,85 @@ def test_missing_task_parameter_and_partial_masks(cuda_device):
     res = merge_state_dicts(base, fts, masks, cfg, "cuda", sign_ref=sign_ref)
     rep = parity.compare_run(ref, res)
     print(_summary(rep))
+
+
+@pytest.mark.parametrize("n_tasks,noise", [(6, False), (6, True), (18, False)])
+def test_cluster_weighting_with_missing_parameters(cuda_device, n_tasks, noise):
+    """merge_with_clustering (merge.py:586-626) renormalises the member weights inside each cluster over the members
+    that HAVE the parameter, and a cluster none of whose members has it contributes zeros -- mean included.
+    Parameter "b" is missing in one member of cluster 0; parameter "c" in ALL members of cluster 1."""
+    from oracle import svd_hybrid_ref as R
+    from svd_quantization_task_merging_b200.engine import merge_state_dicts
+    tasks = synth.task_names(n_tasks)
+    shapes = {"a": (90, 41), "b": (3000,), "c": (64, 70)}
+    base, fts = synth.make_checkpoints(shapes, tasks, family="parity", seed=19)
+    masks = synth.make_masks(shapes, tasks, 0.6, seed=20)
+    assign = {t: (0 if i % 3 else 1) for i, t in enumerate(tasks)}          # cluster 1: tasks 0, 3, ...
+    cl0 = [t for t in tasks if assign[t] == 0]
+    del fts[cl0[1]]["b"]
+    for t in tasks:
+        if assign[t] == 1:
+            del fts[t]["c"]
+    ref_cfg, cfg = parity.make_cfgs(tasks, svd_energy_threshold=0.85, svd_mask_strategy="union", svd_weighting="cluster",
+                                    svd_include_noise=noise)
+    ref = R.run_reference_path(base, fts, masks, ref_cfg, assignments=assign)
+    ref["_base"] = base
+
+    def scatter(bases):
+        out = {}
+        for p, b in bases.items():
+            active = [i for i, t in enumerate(tasks) if p in fts[t]]
+            vh = torch.zeros(len(tasks), len(tasks), dtype=torch.float64)
+            vh[: b["Vh"].shape[0], active] = b["Vh"].double()
+            out[p] = vh
+        return out
+    res = merge_state_dicts(base, fts, masks, cfg, "cuda", sign_ref=scatter(ref["bases"]),
+                            sign_ref_noise=scatter(ref.get("bases_noise") or {}), cluster_assignments=assign)
+    rep = parity.compare_run(ref, res)
+    print(_summary(rep))
+    # the quirk is really exercised: the reference's "c" differs from an all-clusters-present merge of the same inputs
+    scal = res["job"]._fetch()[torch.float32]["scal"]
+    names = res["job"].groups[torch.float32].names
+    assert scal[names.index("c"), 2] < 0.999 and abs(scal[names.index("a"), 2] - 1.0) < 1e-6
+
+
+def test_sharded_upload_moves_only_the_shard(cuda_device):
+    """Host (packed, pinned) state dicts + param_filter: only the owned tensors cross PCIe, and the result equals
+    the unfiltered merge bit for bit; a rank with an EMPTY shard still runs (and would join the collectives)."""
+    from svd_quantization_task_merging_b200 import sharding
+    from svd_quantization_task_merging_b200.engine import MergeJob, merge_state_dicts, pack_state_dict
+    tasks = synth.task_names(8)
+    shapes = dict(parity.MEDIUM_SHAPES)
+    base, fts = synth.make_checkpoints(shapes, tasks, family="parity", seed=41)
+    masks = synth.make_masks(shapes, tasks, 0.7, seed=42)
+    _, cfg = parity.make_cfgs(tasks, svd_energy_threshold=0.9, svd_mask_strategy="intersection", svd_weighting="cluster")
+    assign = {t: i % 2 for i, t in enumerate(tasks)}
+    full = merge_state_dicts(base, fts, masks, cfg, "cuda", cluster_assignments=assign)
+    hb = pack_state_dict(base, pin=True)
+    hf = {t: pack_state_dict(fts[t], pin=True) for t in tasks}
+    hm = {t: pack_state_dict(masks[t], pin=True) for t in tasks}
+    whole = MergeJob(hb, hf, hm, cfg, "cuda", cluster_assignments=assign).h2d_bytes
+    cost = {k: int(np.prod(v)) * 9 for k, v in shapes.items()}
+    world = 3
+    owner = sharding.lpt_partition(cost, world)
+    moved = 0
+    for r in range(world):
+        mine = [n for n, o in owner.items() if o == r]
+        job = MergeJob(hb, hf, hm, cfg, "cuda", cluster_assignments=assign, param_filter=mine)
+        moved += job.h2d_bytes
+        job.run()
+        got = job.merged_state_dict()
+        assert sorted(got) == sorted(mine)
+        for n in mine:
+            assert torch.equal(got[n], full["merged_state_dict"][n]), n
+        # upload accounting: this shard's tensors (+ alignment padding) and its bit-packed masks, nothing else
+        own = sum(int(np.prod(shapes[n])) for n in mine)
+        assert job.h2d_bytes <= own * 4 * 9 + own * 8 // 8 + 4096 * len(mine) * 17
+    assert moved <= whole * 1.02 + 65536
+    empty = MergeJob(hb, hf, hm, cfg, "cuda", param_filter=[])
+    empty.gram_reduce_hook = lambda g: g
+    empty.run()
+    assert empty.merged_state_dict() == {} and empty.h2d_bytes <= 64
 
 
 def test_without_sign_hint_matches_at_quantisation_noise_level(cuda_device):

@@ -1,0 +1,69 @@
+"""Oracle parity at REAL tensor sizes: the closed-form coefficient regime (parameters above
+engine.EXACT_MAX_NUMEL = 262,144 elements take c = Sigma V^T instead of a re-projection on the stored fp16
+basis) carries > 99 % of ViT-L-14's and Llama's bytes.  The oracle (reference path: fp32 LAPACK SVD, cast of the
+bases to fp16 -- src/svd_hybrid/cli.py:355-361 -- BEFORE the projection of src/svd_hybrid/compress.py:10-19) runs on
+real ViT-L-14 tensors x 8 and x 20 tasks with intersection masks; asserted: rank k, fp16 c_high BITS, RTVQ codes
+(flip count reported, expected 0) and merged weights <= 1e-4 relative L2."""
+import json
+import os
+from collections import OrderedDict
+
+import numpy as np
+import pytest
+import torch
+
+from svd_quantization_task_merging_b200 import synth
+from tests import parity
+
+pytestmark = pytest.mark.gpu
+
+# real ViT-L-14 tensor shapes (open_clip visual tower, width 1024)
+REAL = OrderedDict([
+    ("transformer.resblocks.0.attn.in_proj_weight", (3072, 1024)),     # 3,145,728
+    ("transformer.resblocks.0.mlp.c_fc.weight", (4096, 1024)),         # 4,194,304
+    ("transformer.resblocks.0.ln_1.weight", (1024,)),
+])
+
+
+def _run(n_tasks, projection, strategy="intersection", mask_p=0.9, seed=2024, **kw):
+    from oracle import svd_hybrid_ref as R
+    from svd_quantization_task_merging_b200.engine import merge_state_dicts
+    tasks = synth.task_names(n_tasks)
+    base, fts = synth.make_checkpoints(REAL, tasks, family="parity", seed=seed)
+    masks = synth.make_masks(REAL, tasks, mask_p, seed=seed + 1)
+    ref_cfg, cfg = parity.make_cfgs(tasks, svd_energy_threshold=0.9, svd_mask_strategy=strategy, svd_fp16=True,
+                                    svd_low_bits=4, svd_rtvq_stages=2, **kw)
+    ref = R.run_reference_path(base, fts, masks, ref_cfg)
+    ref["_base"] = base
+    res = merge_state_dicts(base, fts, masks, cfg, "cuda", sign_ref={p: b["Vh"] for p, b in ref["bases"].items()},
+                            projection=projection)
+    return ref, res
+
+
+@pytest.mark.parametrize("n_tasks,mask_p", [(8, 0.9), (20, 0.97)])
+@pytest.mark.parametrize("projection", ["auto", "closed"])
+def test_closed_form_regime_matches_oracle_at_vit_l_14_sizes(cuda_device, n_tasks, mask_p, projection):
+    ref, res = _run(n_tasks, projection, mask_p=mask_p)
+    rep = parity.compare_run(ref, res)
+    big = [n for n, s in REAL.items() if int(np.prod(s)) > 262144]
+    flips = {"codes": rep["code_total"] - rep["code_equal"], "c_high": rep["chigh_total"] - rep["chigh_equal"]}
+    print(f"n_tasks={n_tasks} projection={projection}: c_high {rep['chigh_equal']}/{rep['chigh_total']} "
+          f"codes {rep['code_equal']}/{rep['code_total']} max merged rel {rep['max_merged_rel']:.2e} "
+          f"flipped={rep['flipped_params']}")
+    # the big tensors (closed form in both modes): identical stored artifacts, merged within 1e-4
+    for name in big:
+        assert res["bases"].meta(name)["k"] == ref["bases"][name]["k"]
+        for task, rc in ref["compressed"][name].items():
+            nc = res["compressed"][name][task]["masked"]
+            assert torch.equal(nc["c_high_fp16"].view(torch.int16), rc["c_high_fp16"].view(torch.int16)), (name, task)
+            for a, b in zip(rc["c_low_quant"]["payloads"], nc["c_low_quant"]["payloads"]):
+                assert torch.equal(a["quantized"], b["quantized"]), (name, task, a["stage"])
+        d_ref = ref["merged_deltas"][name].double()
+        d_new = (res["merged_state_dict"][name].cpu() - ref["_base"][name]).double()
+        assert (d_new - d_ref).norm() / d_ref.norm() <= 1e-4, name
+    out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    os.makedirs(out, exist_ok=True)
+    with open(os.path.join(out, f"realsize_parity_{n_tasks}tasks_{projection}.json"), "w") as f:
+        json.dump({"n_tasks": n_tasks, "projection": projection, "shapes": {k: list(v) for k, v in REAL.items()},
+                   "flips": flips, "report": {k: v for k, v in rep.items()}}, f, indent=1)
+    assert flips["codes"] == 0 or projection == "closed" or not set(rep["flipped_params"]) & set(big)

@@ -198,6 +198,18 @@ def _gloo_worker(rank, world, port, q):
         ok = ok and bool((g == sum(range(1, world + 1))).all())
         recs = sharding.gather_objects({"rank": rank, "n": len(local)})
         ok = ok and [r["rank"] for r in recs] == list(range(world)) and sum(r["n"] for r in recs) == len(shapes)
+        # flat record gather: ragged row counts (rank r contributes r + 1 rows), one collective
+        rows = [q + 1 for q in range(world)]
+        mine = np.full((rows[rank], 5), float(rank)) + np.arange(5)[None, :]
+        got = sharding.gather_records(mine, rows, "cpu")
+        ok = ok and len(got) == world and all(g.shape == (rows[q], 5) and (g == q + np.arange(5)[None, :]).all()
+                                              for q, g in enumerate(got))
+        # padded all-gather of the ranks' merged arenas
+        sizes = [3 + 2 * q for q in range(world)]
+        flat = torch.arange(sizes[rank], dtype=torch.float32) + 10 * rank
+        allm = sharding.gather_merged(flat, sizes)
+        ok = ok and all(torch.equal(allm[q, : sizes[q]], torch.arange(sizes[q], dtype=torch.float32) + 10 * q)
+                        for q in range(world))
         q.put((rank, ok))
     finally:
         dist.destroy_process_group()
