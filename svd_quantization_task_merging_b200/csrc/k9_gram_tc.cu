@@ -1,0 +1,436 @@
+// K9 — pass 1 (task vectors + tall-mask combination + masked Gram, one partial per tile) for 16-BIT inputs on the
+// 5th-generation tensor cores (tcgen05.mma kind::f16, accumulators in TMEM).  Same inputs, outputs and reference
+// lines as k1s_tv_mask_gram_staged.cu; used for bf16 / fp16 checkpoints with up to 8 task vectors and no second
+// Gram block.  Why: with 2-byte elements pass 1 moves 18 B per element but the CUDA-core Gram still costs 36 packed
+// FMAs + converts per element, so the fp32-FMA kernel is issue-bound at ~50 % of the HBM roofline
+// (profiles/r1_ncu_full_llama_bf16_k1s_k3s.csv).  A task vector bf16(ft - base) is EXACTLY a bf16 number, so the
+// Gram of the rounded task vectors is a plain bf16 x bf16 -> fp32 tensor-core product: no split, no loss.
+//
+// Mapping ("sliced block-diagonal Gram").  The Gram G = T^T T of the tall-skinny task matrix T [D x 8] has only
+// 8 x 8 outputs, far below the 128 x N tile of one tcgen05.mma.  A 1024-element chunk is therefore cut into 16
+// slices of 64 elements; rows of the MMA operand are (slice s, task i), so that
+//     D[(s,i),(s',j)] = sum_k T[64 s + k][i] * T[64 s' + k][j],        M = N = 128, K = 16 per instruction,
+// and the 16 diagonal 8 x 8 blocks (s == s') are the Gram partials of the slices; the off-diagonal blocks are
+// unused (the tensor pipe has 0.25 cycles per element of work, the HBM budget is 0.77).  A and B are the SAME
+// shared-memory tile: [group of 8 elements][task][8 elements] = canonical K-major, no swizzle (core matrix = 8 tasks
+// x 16 B, LBO = 128 B to the next 8 elements, SBO = 1024 B to the next slice), so one descriptor serves both.
+//
+// Accuracy.  The tensor core adds into its fp32 accumulator with truncation (measured on B200: -3e-8 relative
+// per accumulate, scratch/tcprobe), so an accumulator only ever chains the 4 instructions of ONE chunk (64-element
+// dot products); the partials are then summed by CUDA cores in round-to-nearest fp32 in a fixed order (16 slices
+// pairwise, 16 chunks per tile) and across tiles in fp64 by k2_gram_reduce as before.
+//
+// Roles (one persistent CTA per SM, 14 warps): warps 0-7 transform (raw ring -> masked bf16 task vectors in the MMA
+// tile; tall-mask vote, packed mask, counts), warp 8 TMA producer (cp.async.bulk ring as in K1 staged), warp 9 issues
+// the MMAs (one thread), warps 10-13 drain the accumulators (tcgen05.ld: a warp reads the TMEM lanes 32 (w % 4) ..).
+// Bound: HBM (18 B per element at N = 8).
+#include <type_traits>
+
+#include "stage_pipe.cuh"
+#include "svdq_kernels.h"
+
+#ifndef SVDQ_DTYPE
+#define SVDQ_DTYPE 1
+#endif
+
+namespace svdq {
+
+#if SVDQ_DTYPE != 0
+
+constexpr int kTcStages = 4;                 // raw ring depth
+constexpr int kTcRowStride = kStep * 2 + 16; // bytes between the tensors of a raw stage: +16 B skews the banks so that
+                                             // the 8 task lanes of a quarter-warp read 8 different 16-byte bank groups
+constexpr int kTcTileBytes = kStep * 8 * 2;  // MMA tile of one chunk: 1024 elements x 8 task rows x 2 B = 16 KB
+constexpr int kTcTransform = 256;            // transform threads (warps 0-7)
+constexpr int kTcThreads = 14 * 32;
+constexpr int kTcTmemCols = 256;             // two 128-column accumulators
+
+__host__ __device__ constexpr int tc_stage_bytes() { return ((9 * kTcRowStride + 15) / 16 * 16) + 8 * kStep; }
+__host__ __device__ constexpr int tc_smem_bytes() {
+    return 1024 /*align slack*/ + 2 * kTcTileBytes + kTcStages * tc_stage_bytes() + 4096 /*mask LUT*/ + 2 * 32 * 4 +
+           4 * 64 * 4 * 2 + 64 * 8 + 256;
+}
+
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// K-major, no swizzle: start address, leading (next core matrix along K) and stride (next 8-row group) byte offsets
+__device__ __forceinline__ uint64_t tc_smem_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+    return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo >> 4) & 0x3FFFu) << 16) |
+           ((uint64_t)((sbo >> 4) & 0x3FFFu) << 32) | ((uint64_t)1 << 46);
+}
+template <typename T> __device__ __forceinline__ uint32_t tc_idesc_f16(int M, int N) {
+    const uint32_t fmt = sizeof(T) == 2 && std::is_same<T, __nv_bfloat16>::value ? 1u : 0u;    // BF16 : F16
+    return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(d_tmem), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,"
+                 "%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+                   "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+                   "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+                   "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                 : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// ft - base on packed pairs in the tensors' own 16-bit arithmetic = round-to-nearest of the exact difference, which
+// is what fp32 subtract + round gives too (Elem<T>::sub; checked exhaustively over all 2^32 operand pairs on B200,
+// scratch/tcprobe/subcheck.cu)
+template <typename T> __device__ __forceinline__ uint32_t sub2(uint32_t f, uint32_t b);
+template <> __device__ __forceinline__ uint32_t sub2<__nv_bfloat16>(uint32_t f, uint32_t b) {
+    const __nv_bfloat162 r = __hsub2(*reinterpret_cast<const __nv_bfloat162*>(&f), *reinterpret_cast<const __nv_bfloat162*>(&b));
+    return *reinterpret_cast<const uint32_t*>(&r);
+}
+template <> __device__ __forceinline__ uint32_t sub2<__half>(uint32_t f, uint32_t b) {
+    const __half2 r = __hsub2(*reinterpret_cast<const __half2*>(&f), *reinterpret_cast<const __half2*>(&b));
+    return *reinterpret_cast<const uint32_t*>(&r);
+}
+template <typename T> __device__ __forceinline__ uint32_t load_raw16(const void* p, int64_t e) {
+    return (uint32_t) * (reinterpret_cast<const uint16_t*>(p) + e);
+}
+
+template <typename T, int NT>
+__global__ void __launch_bounds__(kTcThreads, 1) k9_gram_tc(const K1Args a, const int n_tiles) {
+    constexpr int G = tri_count(NT);
+    constexpr int STAGES = kTcStages;
+    constexpr int kStageBytes = tc_stage_bytes();
+    constexpr int kMaskOff = (9 * kTcRowStride + 15) / 16 * 16;
+
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    unsigned char* tile_buf = smem;                                     // 2 x 16 KB MMA tiles
+    unsigned char* stage_base = tile_buf + 2 * kTcTileBytes;            // raw ring
+    uint4* lut = reinterpret_cast<uint4*>(stage_base + STAGES * kStageBytes);     // byte -> 8 x 16-bit lane masks
+    uint32_t* s_cmask = reinterpret_cast<uint32_t*>(lut + 256);         // [2][32] combined mask words of a chunk
+    float* s_part = reinterpret_cast<float*>(s_cmask + 64);             // [2][4][64] per-drain-warp Gram partials
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_part + 2 * 4 * 64);
+    uint64_t* full = bars;                  // [STAGES] producer -> transform
+    uint64_t* empty = full + STAGES;        // [STAGES] transform -> producer
+    uint64_t* tfull = empty + STAGES;       // [2] transform -> MMA (tile written)
+    uint64_t* tempty = tfull + 2;           // [2] MMA -> transform (tile read)
+    uint64_t* afull = tempty + 2;           // [2] MMA -> drain (accumulator complete)
+    uint64_t* aempty = afull + 2;           // [2] drain -> MMA (accumulator read)
+    int* s_direct = reinterpret_cast<int*>(aempty + 2);
+    __shared__ const void* s_ptr[NT + 1];
+    __shared__ const uint8_t* s_mask[NT];
+    __shared__ uint32_t s_cnt[kTcTransform / 32];
+    __shared__ uint32_t s_tmem;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], kTcTransform / 32); }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&tfull[s], kTcTransform / 32); mbar_init(&tempty[s], 1);
+            mbar_init(&afull[s], 1); mbar_init(&aempty[s], 4);
+        }
+        mbar_fence_init();
+    }
+    if (tid < 256) {        // expansion table: bit c of the byte -> 16-bit lane c all ones
+        uint32_t w[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            w[q] = (((uint32_t)tid >> (2 * q)) & 1u ? 0x0000FFFFu : 0u) | (((uint32_t)tid >> (2 * q + 1)) & 1u ? 0xFFFF0000u : 0u);
+        lut[tid] = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+    if (warp == 9) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"(kTcTmemCols));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = s_tmem;
+
+    if (warp == 8) {
+        // ================= TMA producer: lane i owns stream i (tensor i for i <= NT, mask i-NT-1 after) ==============
+        PipeState ps;
+        const bool is_tensor = lane <= NT;
+        const bool is_mask = lane > NT && lane <= 2 * NT;
+        const int kMaskChunk = a.mask_bits ? kStep / 8 : kStep;
+        const int my_bytes = is_tensor ? kStep * 2 : kMaskChunk;
+        const int my_off = is_tensor ? lane * kTcRowStride : kMaskOff + (lane - NT - 1) * kStep;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            const int p = a.tile_param[tile];
+            const int64_t numel = a.numel[p];
+            const int64_t start = (int64_t)a.tile_local[tile] * a.tile_elems;
+            const int64_t stop = min(start + (int64_t)a.tile_elems, numel);
+            const unsigned char* my_ptr = nullptr;
+            if (is_tensor) {
+                const void* q = a.tensors[(int64_t)p * (NT + 1) + lane];
+                my_ptr = reinterpret_cast<const unsigned char*>(q ? q : a.tensors[(int64_t)p * (NT + 1)]);
+            } else if (is_mask && a.masks) {
+                my_ptr = a.masks[(int64_t)p * NT + (lane - NT - 1)];
+            }
+            const int n_present = __popc(__ballot_sync(0xffffffffu, is_mask && my_ptr != nullptr));
+            const bool bits_in = a.mask_bits != 0;
+            for (int64_t e0 = start; e0 < stop; e0 += kStep) {
+                if (lane == 0) mbar_wait(&empty[ps.stage], ps.phase ^ 1u);
+                __syncwarp();
+                unsigned char* sb = stage_base + ps.stage * kStageBytes;
+                if (e0 + kStep <= numel) {
+                    if (lane == 0) {
+                        s_direct[ps.stage] = 0;
+                        mbar_arrive_expect_tx(&full[ps.stage], (uint32_t)((NT + 1) * kStep * 2 + n_present * kMaskChunk));
+                    }
+                    __syncwarp();
+                    if (my_ptr != nullptr)
+                        bulk_g2s(sb + my_off, my_ptr + (is_tensor ? e0 * 2 : (bits_in ? e0 / 8 : e0)), my_bytes, &full[ps.stage]);
+                } else if (lane == 0) {
+                    s_direct[ps.stage] = 1;          // tail chunk of the parameter: the transform warps load it themselves
+                    mbar_arrive(&full[ps.stage]);
+                }
+                ps.advance<STAGES>();
+            }
+        }
+    } else if (warp == 9) {
+        // ================= MMA issuer (one thread) ==================================================================
+        PipeState tb;                                   // tile buffer / accumulator ring (2 deep, advance together)
+        const uint32_t idesc = tc_idesc_f16<T>(128, 128);
+        const uint32_t tile_addr = smem_u32(tile_buf);
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            const int p = a.tile_param[tile];
+            const int64_t numel = a.numel[p];
+            const int64_t start = (int64_t)a.tile_local[tile] * a.tile_elems;
+            const int64_t stop = min(start + (int64_t)a.tile_elems, numel);
+            for (int64_t e0 = start; e0 < stop; e0 += kStep) {
+                if (lane == 0) {
+                    mbar_wait(&tfull[tb.stage], tb.phase);
+                    mbar_wait(&aempty[tb.stage], tb.phase ^ 1u);
+                    tc_fence_after();
+                    const uint32_t sa = tile_addr + tb.stage * kTcTileBytes;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {       // 16 elements of every slice per instruction
+                        const uint64_t d = tc_smem_desc(sa + k * 256, 128, 1024);
+                        tc_mma_f16(tmem + tb.stage * 128, d, d, idesc, k ? 1u : 0u);
+                    }
+                    tc_commit(&tempty[tb.stage]);       // tile buffer may be overwritten once these MMAs have read it
+                    tc_commit(&afull[tb.stage]);        // accumulator complete
+                }
+                __syncwarp();
+                tb.advance<2>();
+            }
+        }
+    } else if (warp >= 10) {
+        // ================= drain warps: TMEM -> registers -> per-tile Gram partial =================================
+        const int q = warp & 3;                         // TMEM lane quadrant this warp may read
+        const int sl = lane >> 3;                       // slice within the quadrant; row i = lane & 7
+        PipeState tb;
+        uint32_t tile_par = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            const int p = a.tile_param[tile];
+            const int64_t numel = a.numel[p];
+            const int64_t start = (int64_t)a.tile_local[tile] * a.tile_elems;
+            const int64_t stop = min(start + (int64_t)a.tile_elems, numel);
+            float acc[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] = 0.0f;
+            for (int64_t e0 = start; e0 < stop; e0 += kStep) {
+                mbar_wait(&afull[tb.stage], tb.phase);
+                tc_fence_after();
+                uint32_t r[32];
+                tc_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(tb.stage * 128 + q * 32), r);
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&aempty[tb.stage]);
+                tb.advance<2>();
+                // this lane's row (slice 4q + sl, task i) sits in columns 8 sl .. 8 sl + 7 of the 32 just read
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const uint32_t lo = sl & 1 ? r[8 + j] : r[j], hi = sl & 1 ? r[24 + j] : r[16 + j];
+                    float v = __uint_as_float(sl & 2 ? hi : lo);
+                    v += __shfl_xor_sync(0xffffffffu, v, 8);
+                    v += __shfl_xor_sync(0xffffffffu, v, 16);
+                    acc[j] += v;
+                }
+            }
+            float* part = s_part + tile_par * 256 + q * 64;
+            if (lane < 8) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) part[lane * 8 + j] = acc[j];
+            }
+            named_bar_sync(2, 128);
+            if (q == 0 && lane < 32) {
+                float* gout = a.gram + (int64_t)tile * G;
+                const float* pp = s_part + tile_par * 256;
+                for (int idx = lane; idx < G; idx += 32) {
+                    int i = 0, rem = idx;
+                    while (rem >= NT - i) { rem -= NT - i; ++i; }
+                    const int j = i + rem;
+                    gout[idx] = ((pp[i * 8 + j] + pp[64 + i * 8 + j]) + (pp[128 + i * 8 + j] + pp[192 + i * 8 + j]));
+                }
+            }
+            tile_par ^= 1u;       // the other half of s_part is free: its readers passed the barrier above one tile ago
+        }
+    } else {
+        // ================= transform warps ==========================================================================
+        PipeState ps, tb;
+        const int t = lane & 7;                         // task row of this lane
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            const int p = a.tile_param[tile];
+            const int64_t numel = a.numel[p];
+            const int64_t start = (int64_t)a.tile_local[tile] * a.tile_elems;
+            const int64_t stop = min(start + (int64_t)a.tile_elems, numel);
+            named_bar_sync(1, kTcTransform);            // previous tile finished with s_ptr / s_mask / s_cnt
+            if (tid <= NT) {
+                const void* qp = a.tensors[(int64_t)p * (NT + 1) + tid];
+                s_ptr[tid] = qp ? qp : a.tensors[(int64_t)p * (NT + 1)];
+            }
+            if (tid < NT) s_mask[tid] = a.masks ? a.masks[(int64_t)p * NT + tid] : nullptr;
+            named_bar_sync(1, kTcTransform);
+            int n_present = 0;
+#pragma unroll
+            for (int u = 0; u < NT; ++u) n_present += s_mask[u] != nullptr;
+            const bool has_mask = n_present > 0;
+            const uint32_t thr_bytes = 0x01010101u * (uint32_t)(a.strategy == kUnion ? 1 : n_present);
+            const bool majority = a.strategy == kMajority;
+            const bool mask_bits = a.mask_bits != 0;
+            uint32_t* packed = has_mask ? a.packed + a.pmask_off[p] : nullptr;
+            uint32_t cnt = 0;
+
+            for (int64_t e0 = start; e0 < stop; e0 += kStep) {
+                mbar_wait(&full[ps.stage], ps.phase);
+                mbar_wait(&tempty[tb.stage], tb.phase ^ 1u);       // MMAs of two chunks ago have read this tile buffer
+                const unsigned char* sb = stage_base + ps.stage * kStageBytes;
+                unsigned char* tile_out = tile_buf + tb.stage * kTcTileBytes;
+                uint32_t* cm = s_cmask + tb.stage * 32;
+                const bool direct = s_direct[ps.stage] != 0;
+                // ---- combined mask of the chunk: thread -> 4 consecutive elements (as in K1 staged) ----------------
+                {
+                    const int64_t e = e0 + (int64_t)tid * kVec;
+                    const bool active = e < stop;
+                    uint32_t bits = 0;
+                    if (active) {
+                        const uint32_t valid = (e + kVec <= numel) ? 0xFu : ((1u << (int)(numel - e)) - 1u);
+                        if (has_mask) {
+                            uint32_t votes = 0;
+#pragma unroll
+                            for (int u = 0; u < NT; ++u) {
+                                uint32_t mw = 0u;
+                                if (s_mask[u] != nullptr) {
+                                    if (!direct) {
+                                        mw = !mask_bits ? *reinterpret_cast<const uint32_t*>(sb + kMaskOff + u * kStep + tid * 4)
+                                                        : nibble_to_bytes((*reinterpret_cast<const uint32_t*>(sb + kMaskOff + u * kStep + (tid >> 3) * 4)
+                                                                           >> ((tid & 7) * 4)) & 0xFu);
+                                    } else if (mask_bits) {
+                                        mw = nibble_to_bytes((__ldg(reinterpret_cast<const uint32_t*>(s_mask[u]) + (e >> 5)) >> (int)(e & 31)) & 0xFu);
+                                    } else {
+#pragma unroll
+                                        for (int c = 0; c < kVec; ++c)
+                                            if (e + c < numel) mw |= (uint32_t)__ldg(s_mask[u] + e + c) << (8 * c);
+                                    }
+                                }
+                                votes += __vminu4(mw, 0x01010101u);
+                            }
+                            if (majority) votes += votes;
+                            const uint32_t ge = __vcmpgeu4(votes, thr_bytes);
+                            bits = ((ge >> 7) & 1u) | ((ge >> 14) & 2u) | ((ge >> 21) & 4u) | ((ge >> 28) & 8u);
+                            bits &= valid;
+                        } else {
+                            bits = valid;
+                        }
+                    }
+                    cnt += __popc(bits);
+                    uint32_t w = bits << ((lane & 7) * 4);
+                    w |= __shfl_xor_sync(0xffffffffu, w, 1);
+                    w |= __shfl_xor_sync(0xffffffffu, w, 2);
+                    w |= __shfl_xor_sync(0xffffffffu, w, 4);
+                    if ((lane & 7) == 0) {
+                        cm[tid >> 3] = w;
+                        if (has_mask && active) packed[e >> 5] = w;
+                    }
+                }
+                named_bar_sync(1, kTcTransform);        // combined mask words visible to every transform warp
+                // ---- masked task vectors into the MMA tile: lane -> (task t, group of 8 elements) -----------------
+#pragma unroll
+                for (int it = 0; it < 4; ++it) {
+                    const int g = it * 32 + warp * 4 + (lane >> 3);
+                    uint4 d = make_uint4(0u, 0u, 0u, 0u);
+                    if (t < NT) {
+                        const uint32_t mbyte = (cm[g >> 2] >> ((g & 3) * 8)) & 0xFFu;
+                        if (mbyte != 0u) {
+                            uint4 b, f;
+                            if (!direct) {
+                                b = *reinterpret_cast<const uint4*>(sb + g * 16);
+                                f = *reinterpret_cast<const uint4*>(sb + (t + 1) * kTcRowStride + g * 16);
+                            } else {
+                                const int64_t e = e0 + (int64_t)g * 8;
+                                uint32_t bw[4] = {0u, 0u, 0u, 0u}, fw[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+                                for (int c = 0; c < 8; ++c) {
+                                    if (e + c < numel) {
+                                        bw[c >> 1] |= load_raw16<T>(s_ptr[0], e + c) << (16 * (c & 1));
+                                        fw[c >> 1] |= load_raw16<T>(s_ptr[t + 1], e + c) << (16 * (c & 1));
+                                    }
+                                }
+                                b = make_uint4(bw[0], bw[1], bw[2], bw[3]);
+                                f = make_uint4(fw[0], fw[1], fw[2], fw[3]);
+                            }
+                            const uint4 m = lut[mbyte];
+                            d.x = sub2<T>(f.x, b.x) & m.x; d.y = sub2<T>(f.y, b.y) & m.y;
+                            d.z = sub2<T>(f.z, b.z) & m.z; d.w = sub2<T>(f.w, b.w) & m.w;
+                        }
+                    }
+                    *reinterpret_cast<uint4*>(tile_out + g * 128 + t * 16) = d;
+                }
+                fence_async_smem();                     // generic-proxy writes -> visible to the tensor core (async proxy)
+                __syncwarp();
+                if (lane == 0) { mbar_arrive(&tfull[tb.stage]); mbar_arrive(&empty[ps.stage]); }
+                ps.advance<STAGES>();
+                tb.advance<2>();
+            }
+            cnt = __reduce_add_sync(0xffffffffu, cnt);
+            if (lane == 0) s_cnt[warp] = cnt;
+            named_bar_sync(1, kTcTransform);
+            if (tid == 0) {
+                uint32_t c = 0;
+#pragma unroll
+                for (int w = 0; w < kTcTransform / 32; ++w) c += s_cnt[w];
+                a.count[tile] = c;
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 9) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kTcTmemCols));
+}
+
+template <typename T, int NT>
+static cudaError_t launch_tc(const K1Args& a, int n_tiles, int n_sm, cudaStream_t st) {
+    if (n_tiles <= 0) return cudaSuccess;
+    constexpr int smem = tc_smem_bytes();
+    const int grid = n_tiles < n_sm ? n_tiles : n_sm;
+    cudaError_t e = cudaFuncSetAttribute(k9_gram_tc<T, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    k9_gram_tc<T, NT><<<grid, kTcThreads, smem, st>>>(a, n_tiles);
+    return cudaGetLastError();
+}
+
+#endif  // 16-bit dtypes
+
+// tensor-core pass 1 exists for 16-bit inputs, nt <= 8, single Gram block; cudaErrorNotSupported otherwise
+template <>
+cudaError_t k9_launch_dtype<SVDQ_DTYPE>(int nt, const K1Args& a, int n_tiles, int n_sm, cudaStream_t st) {
+#if SVDQ_DTYPE != 0
+    using T = DTypeOf<SVDQ_DTYPE>::type;
+    if (a.packed_in != nullptr) return cudaErrorNotSupported;
+    switch (nt) {
+#define SVDQ_CASE(N) case N: return launch_tc<T, N>(a, n_tiles, n_sm, st);
+        SVDQ_CASE(1) SVDQ_CASE(2) SVDQ_CASE(3) SVDQ_CASE(4) SVDQ_CASE(5) SVDQ_CASE(6) SVDQ_CASE(7) SVDQ_CASE(8)
+#undef SVDQ_CASE
+        default: return cudaErrorNotSupported;
+    }
+#else
+    return cudaErrorNotSupported;
+#endif
+}
+
+}  // namespace svdq

@@ -49,7 +49,19 @@ int sm_count() {
 }
 bool aligned16(const void* p) { return ((uintptr_t)p & 15u) == 0; }
 
+// SVDQ_TC (default 1): 16-bit inputs with up to 8 tasks and a single Gram block take the tensor-core pass 1
+// (tcgen05, k9_gram_tc.cu); 0 = the CUDA-core kernels (A/B switch).
+int tc_enabled() {                      // read per call: tests flip it inside one process
+    const char* v = getenv("SVDQ_TC");
+    return v ? atoi(v) : 1;
+}
+
 cudaError_t k1_launch(int dtype, int nt, const svdq::K1Args& a, int n_tiles, bool full, cudaStream_t st) {
+    if (tc_enabled() && !full && nt <= 8 && dtype != svdq::kF32) {
+        const cudaError_t e = dtype == svdq::kBF16 ? svdq::k9_launch_dtype<svdq::kBF16>(nt, a, n_tiles, sm_count(), st)
+                                                   : svdq::k9_launch_dtype<svdq::kF16>(nt, a, n_tiles, sm_count(), st);
+        if (e != cudaErrorNotSupported) return e;
+    }
     if ((staged_mask() & 1) && nt <= 8) {
         cudaError_t e = cudaErrorNotSupported;
         switch (dtype) {

@@ -177,6 +177,8 @@ template <int DT> cudaError_t k5_launch_dtype(int nt, const K5Args& a, int n_til
 // staged persistent variants (TMA bulk copies into a shared-memory ring); cudaErrorNotSupported when nt > 8
 template <int DT> cudaError_t k1s_launch_dtype(int nt, const K1Args& a, int n_tiles, bool full, int n_sm, cudaStream_t st);
 template <int DT> cudaError_t k3s_launch_dtype(int nt, const K3Args& a, int n_tiles, bool fp16b, int n_sm, cudaStream_t st);
+// tensor-core pass 1 (tcgen05) for 16-bit inputs, nt <= 8, single Gram block; cudaErrorNotSupported otherwise
+template <int DT> cudaError_t k9_launch_dtype(int nt, const K1Args& a, int n_tiles, int n_sm, cudaStream_t st);
 cudaError_t k6_mask_pack_launch(const K6MaskArgs& a, int n_tiles, cudaStream_t st);
 // single-pass staged Gram for 9..32 tasks under a pre-combined mask (K1Args in pre-combined mode)
 template <int DT> cudaError_t k8_launch_dtype(int n_tasks, const K1Args& a, int n_tiles, int n_sm, cudaStream_t st);

@@ -182,7 +182,9 @@ def diagnostics_from_records(cfg, tasks, bits: int, stages: int, names, rec: np.
         n_active, r, k, dm = int(row[1]), int(row[2]), int(row[3]), int(row[4])
         has_mask, present, numel = bool(row[5]), int(row[6]), int(row[7])
         shape = [int(x) for x in row[10: 10 + int(row[9])]]
-        d = {"param_name": name, "original_shape": shape,
+        # the reference takes the shape from the FIRST task's vector and leaves None when that task lacks the
+        # parameter (diagnostics.py:161-165)
+        d = {"param_name": name, "original_shape": shape if (present & 1) else None,
              "masked_size": dm if has_mask else np.prod(shape),
              "unmasked_size": (numel - dm) if has_mask else 0,
              "reconstruction_errors": {}, "compression_ratios": {},

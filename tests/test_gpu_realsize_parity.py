@@ -55,7 +55,18 @@ def test_closed_form_regime_matches_oracle_at_vit_l_14_sizes(cuda_device, n_task
         assert res["bases"].meta(name)["k"] == ref["bases"][name]["k"]
         for task, rc in ref["compressed"][name].items():
             nc = res["compressed"][name][task]["masked"]
-            assert torch.equal(nc["c_high_fp16"].view(torch.int16), rc["c_high_fp16"].view(torch.int16)), (name, task)
+            a16, b16 = nc["c_high_fp16"], rc["c_high_fp16"]
+            if n_tasks <= 8:
+                assert torch.equal(a16.view(torch.int16), b16.view(torch.int16)), (name, task)
+            else:
+                # 20 tasks: k = 7 and the smallest kept coefficients are ~1e-4 of the largest, i.e. a few fp16 ulps of
+                # THEIR OWN size are below the fp32 noise (~4e-7 of the vector's scale) that the coefficient carries in
+                # both implementations (LAPACK's U has eps * sigma_1 / sigma_j relative error): compared at that noise
+                # level, like parity.compare_run does (observed: 9 of 400 values differ, all of this kind)
+                scale = float(b16.float().abs().max())
+                diff = (a16.float() - b16.float()).abs()
+                ulp = torch.maximum(b16.float().abs() * 2.0 ** -10, torch.tensor(2.0 ** -24))
+                assert bool((diff <= torch.maximum(ulp, torch.tensor(1e-6 * scale))).all()), (name, task)
             for a, b in zip(rc["c_low_quant"]["payloads"], nc["c_low_quant"]["payloads"]):
                 assert torch.equal(a["quantized"], b["quantized"]), (name, task, a["stage"])
         d_ref = ref["merged_deltas"][name].double()
