@@ -37,17 +37,21 @@ namespace svdq {
 
 #if SVDQ_DTYPE != 0
 
-constexpr int kTcStages = 4;                 // raw ring depth
-constexpr int kTcRowStride = kStep * 2 + 16; // bytes between the tensors of a raw stage: +16 B skews the banks so that
-                                             // the 8 task lanes of a quarter-warp read 8 different 16-byte bank groups
+constexpr int kTcStages = 3;                 // raw ring depth (stages of kTcStageElems elements)
+constexpr int kTcStageElems = 2 * kStep;     // one raw stage = two 1024-element chunks: 4 KB per bulk copy (the producer
+                                             // issues its copies one at a time, so 2 KB copies capped it near 4.7 TB/s)
+constexpr int kTcTiles = 3;                  // MMA tile ring depth (accumulators: 2)
+constexpr int kTcRowStride = kTcStageElems * 2 + 16;   // bytes between the tensors of a raw stage: +16 B skews the banks
+                                             // so that the 8 task lanes of a quarter-warp read 8 different bank groups
+constexpr int kTcMaskStride = kTcStageElems; // bytes between the task masks of a raw stage
 constexpr int kTcTileBytes = kStep * 8 * 2;  // MMA tile of one chunk: 1024 elements x 8 task rows x 2 B = 16 KB
 constexpr int kTcTransform = 256;            // transform threads (warps 0-7)
 constexpr int kTcThreads = 14 * 32;
 constexpr int kTcTmemCols = 256;             // two 128-column accumulators
 
-__host__ __device__ constexpr int tc_stage_bytes() { return ((9 * kTcRowStride + 15) / 16 * 16) + 8 * kStep; }
+__host__ __device__ constexpr int tc_stage_bytes() { return ((9 * kTcRowStride + 15) / 16 * 16) + 8 * kTcMaskStride; }
 __host__ __device__ constexpr int tc_smem_bytes() {
-    return 1024 /*align slack*/ + 2 * kTcTileBytes + kTcStages * tc_stage_bytes() + 4096 /*mask LUT*/ + 2 * 32 * 4 +
+    return kTcTiles * kTcTileBytes + kTcStages * tc_stage_bytes() + 4096 /*mask LUT*/ +
            4 * 64 * 4 * 2 + 64 * 8 + 256;
 }
 
@@ -105,19 +109,19 @@ __global__ void __launch_bounds__(kTcThreads, 1) k9_gram_tc(const K1Args a, cons
     constexpr int kStageBytes = tc_stage_bytes();
     constexpr int kMaskOff = (9 * kTcRowStride + 15) / 16 * 16;
 
-    extern __shared__ unsigned char smem_raw[];
-    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    unsigned char* tile_buf = smem;                                     // 2 x 16 KB MMA tiles
-    unsigned char* stage_base = tile_buf + 2 * kTcTileBytes;            // raw ring
+    // (no swizzle: the MMA descriptors need 16-byte alignment only; keeping the pointer arithmetic on the __shared__
+    // array itself lets the compiler emit LDS / STS instead of generic loads and stores)
+    extern __shared__ __align__(128) unsigned char smem[];
+    unsigned char* tile_buf = smem;                                     // kTcTiles x 16 KB MMA tiles
+    unsigned char* stage_base = tile_buf + kTcTiles * kTcTileBytes;     // raw ring
     uint4* lut = reinterpret_cast<uint4*>(stage_base + STAGES * kStageBytes);     // byte -> 8 x 16-bit lane masks
-    uint32_t* s_cmask = reinterpret_cast<uint32_t*>(lut + 256);         // [2][32] combined mask words of a chunk
-    float* s_part = reinterpret_cast<float*>(s_cmask + 64);             // [2][4][64] per-drain-warp Gram partials
+    float* s_part = reinterpret_cast<float*>(lut + 256);                // [2][4][64] per-drain-warp Gram partials
     uint64_t* bars = reinterpret_cast<uint64_t*>(s_part + 2 * 4 * 64);
     uint64_t* full = bars;                  // [STAGES] producer -> transform
     uint64_t* empty = full + STAGES;        // [STAGES] transform -> producer
-    uint64_t* tfull = empty + STAGES;       // [2] transform -> MMA (tile written)
-    uint64_t* tempty = tfull + 2;           // [2] MMA -> transform (tile read)
-    uint64_t* afull = tempty + 2;           // [2] MMA -> drain (accumulator complete)
+    uint64_t* tfull = empty + STAGES;       // [kTcTiles] transform -> MMA (tile written)
+    uint64_t* tempty = tfull + kTcTiles;    // [kTcTiles] MMA -> transform (tile read)
+    uint64_t* afull = tempty + kTcTiles;    // [2] MMA -> drain (accumulator complete)
     uint64_t* aempty = afull + 2;           // [2] drain -> MMA (accumulator read)
     int* s_direct = reinterpret_cast<int*>(aempty + 2);
     __shared__ const void* s_ptr[NT + 1];
@@ -128,10 +132,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) k9_gram_tc(const K1Args a, cons
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], kTcTransform / 32); }
-        for (int s = 0; s < 2; ++s) {
-            mbar_init(&tfull[s], kTcTransform / 32); mbar_init(&tempty[s], 1);
-            mbar_init(&afull[s], 1); mbar_init(&aempty[s], 4);
-        }
+        for (int s = 0; s < kTcTiles; ++s) { mbar_init(&tfull[s], kTcTransform / 32); mbar_init(&tempty[s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&afull[s], 1); mbar_init(&aempty[s], 4); }
         mbar_fence_init();
     }
     if (tid < 256) {        // expansion table: bit c of the byte -> 16-bit lane c all ones
@@ -155,9 +157,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) k9_gram_tc(const K1Args a, cons
         PipeState ps;
         const bool is_tensor = lane <= NT;
         const bool is_mask = lane > NT && lane <= 2 * NT;
-        const int kMaskChunk = a.mask_bits ? kStep / 8 : kStep;
-        const int my_bytes = is_tensor ? kStep * 2 : kMaskChunk;
-        const int my_off = is_tensor ? lane * kTcRowStride : kMaskOff + (lane - NT - 1) * kStep;
+        const bool bits_in = a.mask_bits != 0;
+        const int kMaskBytes = bits_in ? kTcStageElems / 8 : kTcStageElems;     // one task's mask bytes per stage
+        const int my_bytes = is_tensor ? kTcStageElems * 2 : kMaskBytes;
+        const int my_off = is_tensor ? lane * kTcRowStride : kMaskOff + (lane - NT - 1) * kTcMaskStride;
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
             const int p = a.tile_param[tile];
             const int64_t numel = a.numel[p];
@@ -171,21 +174,20 @@ __global__ void __launch_bounds__(kTcThreads, 1) k9_gram_tc(const K1Args a, cons
                 my_ptr = a.masks[(int64_t)p * NT + (lane - NT - 1)];
             }
             const int n_present = __popc(__ballot_sync(0xffffffffu, is_mask && my_ptr != nullptr));
-            const bool bits_in = a.mask_bits != 0;
-            for (int64_t e0 = start; e0 < stop; e0 += kStep) {
+            for (int64_t e0 = start; e0 < stop; e0 += kTcStageElems) {
                 if (lane == 0) mbar_wait(&empty[ps.stage], ps.phase ^ 1u);
                 __syncwarp();
                 unsigned char* sb = stage_base + ps.stage * kStageBytes;
-                if (e0 + kStep <= numel) {
+                if (e0 + kTcStageElems <= numel) {
                     if (lane == 0) {
                         s_direct[ps.stage] = 0;
-                        mbar_arrive_expect_tx(&full[ps.stage], (uint32_t)((NT + 1) * kStep * 2 + n_present * kMaskChunk));
+                        mbar_arrive_expect_tx(&full[ps.stage], (uint32_t)((NT + 1) * kTcStageElems * 2 + n_present * kMaskBytes));
                     }
                     __syncwarp();
                     if (my_ptr != nullptr)
                         bulk_g2s(sb + my_off, my_ptr + (is_tensor ? e0 * 2 : (bits_in ? e0 / 8 : e0)), my_bytes, &full[ps.stage]);
                 } else if (lane == 0) {
-                    s_direct[ps.stage] = 1;          // tail chunk of the parameter: the transform warps load it themselves
+                    s_direct[ps.stage] = 1;          // tail of the parameter: the transform warps load it themselves
                     mbar_arrive(&full[ps.stage]);
                 }
                 ps.advance<STAGES>();
@@ -193,7 +195,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k9_gram_tc(const K1Args a, cons
         }
     } else if (warp == 9) {
         // ================= MMA issuer (one thread) ==================================================================
-        PipeState tb;                                   // tile buffer / accumulator ring (2 deep, advance together)
+        PipeState tb, ab;                               // tile-buffer ring, accumulator ring
         const uint32_t idesc = tc_idesc_f16<T>(128, 128);
         const uint32_t tile_addr = smem_u32(tile_buf);
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -204,19 +206,20 @@ __global__ void __launch_bounds__(kTcThreads, 1) k9_gram_tc(const K1Args a, cons
             for (int64_t e0 = start; e0 < stop; e0 += kStep) {
                 if (lane == 0) {
                     mbar_wait(&tfull[tb.stage], tb.phase);
-                    mbar_wait(&aempty[tb.stage], tb.phase ^ 1u);
+                    mbar_wait(&aempty[ab.stage], ab.phase ^ 1u);
                     tc_fence_after();
                     const uint32_t sa = tile_addr + tb.stage * kTcTileBytes;
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {       // 16 elements of every slice per instruction
                         const uint64_t d = tc_smem_desc(sa + k * 256, 128, 1024);
-                        tc_mma_f16(tmem + tb.stage * 128, d, d, idesc, k ? 1u : 0u);
+                        tc_mma_f16(tmem + ab.stage * 128, d, d, idesc, k ? 1u : 0u);
                     }
                     tc_commit(&tempty[tb.stage]);       // tile buffer may be overwritten once these MMAs have read it
-                    tc_commit(&afull[tb.stage]);        // accumulator complete
+                    tc_commit(&afull[ab.stage]);        // accumulator complete
                 }
                 __syncwarp();
-                tb.advance<2>();
+                tb.advance<kTcTiles>();
+                ab.advance<2>();
             }
         }
     } else if (warp >= 10) {
@@ -274,6 +277,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k9_gram_tc(const K1Args a, cons
         // ================= transform warps ==========================================================================
         PipeState ps, tb;
         const int t = lane & 7;                         // task row of this lane
+        int pending = -1;                               // tile buffer written but not yet handed to the MMA warp
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
             const int p = a.tile_param[tile];
             const int64_t numel = a.numel[p];
@@ -296,67 +300,118 @@ __global__ void __launch_bounds__(kTcThreads, 1) k9_gram_tc(const K1Args a, cons
             uint32_t* packed = has_mask ? a.packed + a.pmask_off[p] : nullptr;
             uint32_t cnt = 0;
 
-            for (int64_t e0 = start; e0 < stop; e0 += kStep) {
+            for (int64_t s0 = start; s0 < stop; s0 += kTcStageElems) {
                 mbar_wait(&full[ps.stage], ps.phase);
-                mbar_wait(&tempty[tb.stage], tb.phase ^ 1u);       // MMAs of two chunks ago have read this tile buffer
-                const unsigned char* sb = stage_base + ps.stage * kStageBytes;
-                unsigned char* tile_out = tile_buf + tb.stage * kTcTileBytes;
-                uint32_t* cm = s_cmask + tb.stage * 32;
+                const unsigned char* sbase = stage_base + ps.stage * kStageBytes;
                 const bool direct = s_direct[ps.stage] != 0;
-                // ---- combined mask of the chunk: thread -> 4 consecutive elements (as in K1 staged) ----------------
-                {
-                    const int64_t e = e0 + (int64_t)tid * kVec;
-                    const bool active = e < stop;
-                    uint32_t bits = 0;
-                    if (active) {
-                        const uint32_t valid = (e + kVec <= numel) ? 0xFu : ((1u << (int)(numel - e)) - 1u);
-                        if (has_mask) {
-                            uint32_t votes = 0;
+#pragma unroll 1
+                for (int sub = 0; sub < kTcStageElems / kStep; ++sub) {
+                    const int64_t e0 = s0 + (int64_t)sub * kStep;
+                    if (e0 >= stop) break;
+                    const bool last_sub = sub == kTcStageElems / kStep - 1 || e0 + kStep >= stop;
+                    mbar_wait(&tempty[tb.stage], tb.phase ^ 1u);   // the MMAs that read this tile buffer have finished
+                    const unsigned char* sb = sbase + sub * (kStep * 2);          // this chunk inside the tensors' rows
+                    unsigned char* tile_out = tile_buf + tb.stage * kTcTileBytes;
+                    // Warp w owns elements 128 w .. 128 w + 127 of the chunk for every step, so the transform warps
+                    // never wait for one another inside a tile.
+                    if (!has_mask && !direct) {
+                        // ---- fast path (whole chunk, no masks): all loads first; the async-proxy fence + hand-over of
+                        // the PREVIOUS chunk's tile overlaps their latency
+                        uint4 b[4], f[4];
 #pragma unroll
-                            for (int u = 0; u < NT; ++u) {
-                                uint32_t mw = 0u;
-                                if (s_mask[u] != nullptr) {
-                                    if (!direct) {
-                                        mw = !mask_bits ? *reinterpret_cast<const uint32_t*>(sb + kMaskOff + u * kStep + tid * 4)
-                                                        : nibble_to_bytes((*reinterpret_cast<const uint32_t*>(sb + kMaskOff + u * kStep + (tid >> 3) * 4)
-                                                                           >> ((tid & 7) * 4)) & 0xFu);
-                                    } else if (mask_bits) {
-                                        mw = nibble_to_bytes((__ldg(reinterpret_cast<const uint32_t*>(s_mask[u]) + (e >> 5)) >> (int)(e & 31)) & 0xFu);
-                                    } else {
-#pragma unroll
-                                        for (int c = 0; c < kVec; ++c)
-                                            if (e + c < numel) mw |= (uint32_t)__ldg(s_mask[u] + e + c) << (8 * c);
-                                    }
-                                }
-                                votes += __vminu4(mw, 0x01010101u);
-                            }
-                            if (majority) votes += votes;
-                            const uint32_t ge = __vcmpgeu4(votes, thr_bytes);
-                            bits = ((ge >> 7) & 1u) | ((ge >> 14) & 2u) | ((ge >> 21) & 4u) | ((ge >> 28) & 8u);
-                            bits &= valid;
-                        } else {
-                            bits = valid;
+                        for (int it = 0; it < 4; ++it) {
+                            const int g = warp * 16 + it * 4 + (lane >> 3);
+                            b[it] = *reinterpret_cast<const uint4*>(sb + g * 16);
+                            f[it] = *reinterpret_cast<const uint4*>(sb + (t + 1) * kTcRowStride + g * 16);
                         }
-                    }
-                    cnt += __popc(bits);
-                    uint32_t w = bits << ((lane & 7) * 4);
-                    w |= __shfl_xor_sync(0xffffffffu, w, 1);
-                    w |= __shfl_xor_sync(0xffffffffu, w, 2);
-                    w |= __shfl_xor_sync(0xffffffffu, w, 4);
-                    if ((lane & 7) == 0) {
-                        cm[tid >> 3] = w;
-                        if (has_mask && active) packed[e >> 5] = w;
-                    }
-                }
-                named_bar_sync(1, kTcTransform);        // combined mask words visible to every transform warp
-                // ---- masked task vectors into the MMA tile: lane -> (task t, group of 8 elements) -----------------
+                        if (pending >= 0) {
+                            fence_async_smem();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(&tfull[pending]);
+                            pending = -1;
+                        }
+                        uint4 d[4];
 #pragma unroll
-                for (int it = 0; it < 4; ++it) {
-                    const int g = it * 32 + warp * 4 + (lane >> 3);
-                    uint4 d = make_uint4(0u, 0u, 0u, 0u);
-                    if (t < NT) {
-                        const uint32_t mbyte = (cm[g >> 2] >> ((g & 3) * 8)) & 0xFFu;
-                        if (mbyte != 0u) {
+                        for (int it = 0; it < 4; ++it) {
+                            d[it] = make_uint4(0u, 0u, 0u, 0u);
+                            if (t < NT) {
+                                d[it].x = sub2<T>(f[it].x, b[it].x); d[it].y = sub2<T>(f[it].y, b[it].y);
+                                d[it].z = sub2<T>(f[it].z, b[it].z); d[it].w = sub2<T>(f[it].w, b[it].w);
+                            }
+                        }
+                        if (last_sub) {                  // the raw stage lives in registers now: hand it back
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(&empty[ps.stage]);
+                        }
+#pragma unroll
+                        for (int it = 0; it < 4; ++it) {
+                            const int g = warp * 16 + it * 4 + (lane >> 3);
+                            *reinterpret_cast<uint4*>(tile_out + g * 128 + t * 16) = d[it];
+                        }
+                        cnt += kVec;                    // every element of the chunk counts
+                        pending = (int)tb.stage;
+                        tb.advance<kTcTiles>();
+                        continue;
+                    }
+                    if (pending >= 0) {
+                        fence_async_smem();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&tfull[pending]);
+                        pending = -1;
+                    }
+                    // ---- combined mask: lane -> 4 consecutive elements; the 8 lanes of an octet end up with the same word
+                    uint32_t w = 0xFFFFFFFFu;
+                    {
+                        const int64_t e = e0 + (int64_t)warp * 128 + lane * kVec;
+                        const bool active = e < stop;
+                        uint32_t bits = 0;
+                        if (active) {
+                            const uint32_t valid = (e + kVec <= numel) ? 0xFu : ((1u << (int)(numel - e)) - 1u);
+                            if (has_mask) {
+                                const int mt = warp * 32 + lane;       // this thread's word / nibble index in the chunk
+                                const unsigned char* mb = sbase + kMaskOff + sub * (mask_bits ? kStep / 8 : kStep);
+                                uint32_t votes = 0;
+#pragma unroll
+                                for (int u = 0; u < NT; ++u) {
+                                    uint32_t mw = 0u;
+                                    if (s_mask[u] != nullptr) {
+                                        if (!direct) {
+                                            mw = !mask_bits ? *reinterpret_cast<const uint32_t*>(mb + u * kTcMaskStride + mt * 4)
+                                                            : nibble_to_bytes((*reinterpret_cast<const uint32_t*>(mb + u * kTcMaskStride + (mt >> 3) * 4)
+                                                                               >> ((mt & 7) * 4)) & 0xFu);
+                                        } else if (mask_bits) {
+                                            mw = nibble_to_bytes((__ldg(reinterpret_cast<const uint32_t*>(s_mask[u]) + (e >> 5)) >> (int)(e & 31)) & 0xFu);
+                                        } else {
+#pragma unroll
+                                            for (int c = 0; c < kVec; ++c)
+                                                if (e + c < numel) mw |= (uint32_t)__ldg(s_mask[u] + e + c) << (8 * c);
+                                        }
+                                    }
+                                    votes += __vminu4(mw, 0x01010101u);
+                                }
+                                if (majority) votes += votes;
+                                const uint32_t ge = __vcmpgeu4(votes, thr_bytes);
+                                bits = ((ge >> 7) & 1u) | ((ge >> 14) & 2u) | ((ge >> 21) & 4u) | ((ge >> 28) & 8u);
+                                bits &= valid;
+                            } else {
+                                bits = valid;
+                            }
+                        }
+                        cnt += __popc(bits);
+                        w = bits << ((lane & 7) * 4);
+                        w |= __shfl_xor_sync(0xffffffffu, w, 1);
+                        w |= __shfl_xor_sync(0xffffffffu, w, 2);
+                        w |= __shfl_xor_sync(0xffffffffu, w, 4);
+                        if ((lane & 7) == 0 && has_mask && active) packed[e >> 5] = w;
+                    }
+                    // ---- masked task vectors into the MMA tile: lane -> (task t, group of 8 elements) -------------
+#pragma unroll
+                    for (int it = 0; it < 4; ++it) {
+                        const int g = warp * 16 + it * 4 + (lane >> 3);
+                        // elements 8 g .. 8 g + 7 sit in byte (lane >> 3) of the word held by octet `it`
+                        const uint32_t mbyte = (__shfl_sync(0xffffffffu, w, it * 8) >> ((lane >> 3) * 8)) & 0xFFu;
+                        uint4 d = make_uint4(0u, 0u, 0u, 0u);
+                        if (t < NT && mbyte != 0u) {
                             uint4 b, f;
                             if (!direct) {
                                 b = *reinterpret_cast<const uint4*>(sb + g * 16);
@@ -374,18 +429,22 @@ __global__ void __launch_bounds__(kTcThreads, 1) k9_gram_tc(const K1Args a, cons
                                 b = make_uint4(bw[0], bw[1], bw[2], bw[3]);
                                 f = make_uint4(fw[0], fw[1], fw[2], fw[3]);
                             }
-                            const uint4 m = lut[mbyte];
-                            d.x = sub2<T>(f.x, b.x) & m.x; d.y = sub2<T>(f.y, b.y) & m.y;
-                            d.z = sub2<T>(f.z, b.z) & m.z; d.w = sub2<T>(f.w, b.w) & m.w;
+                            d.x = sub2<T>(f.x, b.x); d.y = sub2<T>(f.y, b.y); d.z = sub2<T>(f.z, b.z); d.w = sub2<T>(f.w, b.w);
+                            if (mbyte != 0xFFu) {
+                                const uint4 m = lut[mbyte];
+                                d.x &= m.x; d.y &= m.y; d.z &= m.z; d.w &= m.w;
+                            }
                         }
+                        *reinterpret_cast<uint4*>(tile_out + g * 128 + t * 16) = d;
                     }
-                    *reinterpret_cast<uint4*>(tile_out + g * 128 + t * 16) = d;
+                    if (last_sub) {
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&empty[ps.stage]);
+                    }
+                    pending = (int)tb.stage;
+                    tb.advance<kTcTiles>();
                 }
-                fence_async_smem();                     // generic-proxy writes -> visible to the tensor core (async proxy)
-                __syncwarp();
-                if (lane == 0) { mbar_arrive(&tfull[tb.stage]); mbar_arrive(&empty[ps.stage]); }
                 ps.advance<STAGES>();
-                tb.advance<2>();
             }
             cnt = __reduce_add_sync(0xffffffffu, cnt);
             if (lane == 0) s_cnt[warp] = cnt;
@@ -396,6 +455,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) k9_gram_tc(const K1Args a, cons
                 for (int w = 0; w < kTcTransform / 32; ++w) c += s_cnt[w];
                 a.count[tile] = c;
             }
+        }
+        if (pending >= 0) {
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tfull[pending]);
         }
     }
     tc_fence_before();
