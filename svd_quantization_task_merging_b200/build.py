@@ -33,6 +33,7 @@ UNITS: List[Tuple[str, object]] = (
     + [("k7_project_exact.cu", d) for d in (0, 1, 2)]
     + [("k8_gram_staged.cu", d) for d in (0, 1, 2)]
     + [("k9_gram_tc.cu", d) for d in (0, 1, 2)]
+    + [("k10_merge_tc.cu", d) for d in (0, 1, 2)]
     + [("k2_param_solve.cu", None), ("k4_rtvq_large.cu", None), ("svdq_capi.cu", None), ("host_kmeans.cpp", None)]
 )
 HEADERS = ["svdq_common.cuh", "svdq_kernels.h", "k2_core.h", "k3_body.cuh", "stage_pipe.cuh", os.path.join("..", "..", "include", "svdq.h")]

@@ -49,15 +49,16 @@ int sm_count() {
 }
 bool aligned16(const void* p) { return ((uintptr_t)p & 15u) == 0; }
 
-// SVDQ_TC (default 1): 16-bit inputs with up to 8 tasks and a single Gram block take the tensor-core pass 1
-// (tcgen05, k9_gram_tc.cu); 0 = the CUDA-core kernels (A/B switch).
+// SVDQ_TC (bit mask, default 3): bit 0 = tensor-core pass 1 for 16-bit inputs (tcgen05, k9_gram_tc.cu; up to 8 tasks,
+// single Gram block), bit 1 = tensor-core pass 2 for bf16 inputs (k10_merge_tc.cu; up to 8 tasks, no diagnostics /
+// noise region); 0 = the CUDA-core kernels (A/B switch).
 int tc_enabled() {                      // read per call: tests flip it inside one process
     const char* v = getenv("SVDQ_TC");
-    return v ? atoi(v) : 1;
+    return v ? atoi(v) : 3;
 }
 
 cudaError_t k1_launch(int dtype, int nt, const svdq::K1Args& a, int n_tiles, bool full, cudaStream_t st) {
-    if (tc_enabled() && !full && nt <= 8 && dtype != svdq::kF32) {
+    if ((tc_enabled() & 1) && !full && nt <= 8 && dtype != svdq::kF32) {
         const cudaError_t e = dtype == svdq::kBF16 ? svdq::k9_launch_dtype<svdq::kBF16>(nt, a, n_tiles, sm_count(), st)
                                                    : svdq::k9_launch_dtype<svdq::kF16>(nt, a, n_tiles, sm_count(), st);
         if (e != cudaErrorNotSupported) return e;
@@ -87,6 +88,10 @@ cudaError_t k3_launch(int dtype, int nt, const svdq::K3Args& a, int n_tiles, boo
             case svdq::kF16:  return svdq::k6_merge_launch_dtype<svdq::kF16>(nt, a, n_tiles, fp16b, diag, st);
             default:          return cudaErrorInvalidValue;
         }
+    }
+    if ((tc_enabled() & 2) && dtype == svdq::kBF16 && nt <= 8 && !diag && a.info_n == nullptr) {
+        const cudaError_t e = svdq::k10_launch_dtype<svdq::kBF16>(nt, a, n_tiles, fp16b, sm_count(), st);
+        if (e != cudaErrorNotSupported) return e;
     }
     if ((staged_mask() & 2) && nt <= 8 && !diag && a.info_n == nullptr) {
         cudaError_t e = cudaErrorNotSupported;

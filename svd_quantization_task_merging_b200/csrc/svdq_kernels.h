@@ -179,6 +179,8 @@ template <int DT> cudaError_t k1s_launch_dtype(int nt, const K1Args& a, int n_ti
 template <int DT> cudaError_t k3s_launch_dtype(int nt, const K3Args& a, int n_tiles, bool fp16b, int n_sm, cudaStream_t st);
 // tensor-core pass 1 (tcgen05) for 16-bit inputs, nt <= 8, single Gram block; cudaErrorNotSupported otherwise
 template <int DT> cudaError_t k9_launch_dtype(int nt, const K1Args& a, int n_tiles, int n_sm, cudaStream_t st);
+// tensor-core pass 2 (tcgen05) for bf16 inputs, nt <= 8, no diagnostics / noise; cudaErrorNotSupported otherwise
+template <int DT> cudaError_t k10_launch_dtype(int nt, const K3Args& a, int n_tiles, bool fp16b, int n_sm, cudaStream_t st);
 cudaError_t k6_mask_pack_launch(const K6MaskArgs& a, int n_tiles, cudaStream_t st);
 // single-pass staged Gram for 9..32 tasks under a pre-combined mask (K1Args in pre-combined mode)
 template <int DT> cudaError_t k8_launch_dtype(int n_tasks, const K1Args& a, int n_tiles, int n_sm, cudaStream_t st);

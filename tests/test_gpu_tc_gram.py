@@ -96,3 +96,47 @@ def test_tc_gram_is_deterministic_and_placement_independent(cuda_device, monkeyp
         assert torch.equal(gc.t["gram_masked"][gc.names.index(name)], ga.t["gram_masked"][ga.names.index(name)])
     ma, mc = a.merged_state_dict(), c.merged_state_dict()
     assert all(torch.equal(ma[k], mc[k]) for k in mc)
+
+
+@pytest.mark.parametrize("fp16_bases", [True, False])
+@pytest.mark.parametrize("n_tasks,strategy,mask_p,weighting", [
+    (8, "union", None, "uniform"), (8, "intersection", 0.9, "performance"), (5, "majority", 0.5, "uniform"),
+    (3, "union", 0.5, "uniform"), (1, "union", None, "uniform")])
+def test_tc_merge_matches_cuda_core_merge(cuda_device, monkeypatch, fp16_bases, n_tasks, strategy, mask_p, weighting):
+    """Tensor-core pass 2 (k10_merge_tc.cu, SVDQ_TC bit 1) against the CUDA-core pass 2 on identical coefficients
+    (pass 1 on CUDA cores in both runs): same ranks / codes by construction, merged weights equal to fp32 round-off
+    of the basis rows (an fp16 rounding of a basis entry may land on the other side: 5e-4 relative on that entry),
+    untouched elements bit-identical."""
+    from svd_quantization_task_merging_b200.engine import MergeJob
+    tasks = synth.task_names(n_tasks)
+    dtype = torch.bfloat16
+    base, fts = synth.make_checkpoints(SHAPES, tasks, family="parity", seed=13, dtype=dtype, device="cuda")
+    if n_tasks >= 3:
+        del fts[tasks[1]]["two"]
+    masks = synth.make_masks(SHAPES, tasks, mask_p, seed=14, device="cuda") if mask_p is not None else None
+    perf = synth.performance_table(tasks) if weighting == "performance" else None
+    cfg = SVDHybridConfig(tasks=tasks, svd_energy_threshold=0.9, svd_mask_strategy=strategy, svd_weighting=weighting,
+                          svd_fp16=fp16_bases, svd_store_artifacts=False, svd_eval_reconstruction=False)
+    out = {}
+    for mode in ("2", "0"):
+        monkeypatch.setenv("SVDQ_TC", mode)
+        job = MergeJob(base, fts, masks, cfg, "cuda", diagnostics=False, performance=perf).run()
+        out[mode] = (job, job.merged_state_dict())
+    (ja, ma), (jb, mb) = out["2"], out["0"]
+    fa, fb = ja._fetch()[dtype], jb._fetch()[dtype]
+    for key in ("info", "chigh", "codes", "cbar"):
+        assert np.array_equal(fa[key], fb[key], equal_nan=True), key
+    cm = ja.combined_masks()
+    worst = 0.0
+    for k in mb:
+        a32, b32, base32 = ma[k].float(), mb[k].float(), base[k].float()
+        fin = torch.isfinite(b32)
+        assert torch.equal(torch.isfinite(a32), fin), k
+        if k in cm:
+            assert torch.equal(a32[~cm[k]], base32[~cm[k]]), k            # outside the mask: merged == base exactly
+        da, db = (a32 - base32)[fin].double(), (b32 - base32)[fin].double()
+        if db.numel() and db.norm() > 0:
+            err = float((da - db).norm() / db.norm())
+            worst = max(worst, err)
+            assert err <= (2e-5 if fp16_bases else 2e-6), (k, err)
+    print(f"tensor-core pass 2 vs CUDA-core pass 2: max rel L2 of the merged delta {worst:.2e}")
