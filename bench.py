@@ -198,7 +198,7 @@ def run_reference_arm(args):
                                    f" (bounded CPU sample per step)"},
             "cpu_baseline": base,
             "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    _emit(json.dumps(line))
 
 
 def _bind_to_gpu_numa_node(gpu_index: int):
@@ -502,9 +502,18 @@ def run_ours(args):
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             dist.all_reduce(hb)
+        # one more call with per-phase synchronisation: where the end-to-end time goes on rank 0 (not part of the timing)
+        os.environ["SVDQ_PROFILE"] = "1"
+        t0 = time.perf_counter()
+        r = e2e_call()
+        phases = dict(r["job"].timing)
+        phases["total_s"] = time.perf_counter() - t0
+        del r
+        os.environ["SVDQ_PROFILE"] = "0"
+        barrier()
         e2e = {"value": n_total / float(tt.item()), "unit": UNIT, "h2d_bytes_per_step": int(hb[0].item()),
                "d2h_bytes_per_step": int(hb[1].item()), "ms_per_step": float(tt.item()) * 1e3, "steps": e_steps,
-               "bytes_are": "summed over all ranks"}
+               "bytes_are": "summed over all ranks", "phases_rank0_synchronised": phases}
 
     if rank == 0:
         cpu = None
@@ -533,9 +542,29 @@ def run_ours(args):
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
                 "gpu_launches": launches_per_step * args.steps, "params_per_rank": params_per_rank,
                 "params_with_basis_per_rank": solved_all, "sharded": sharded, "secondary": secondary}
-        print(json.dumps(line))
+        _emit(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+_REAL_STDOUT = None
+
+
+def _claim_stdout():
+    """The bench prints ONE JSON line on stdout.  Native libraries write to file descriptor 1 directly (NCCL's
+    version banner), so fd 1 is pointed at stderr for the duration of the run and the line goes to the saved fd."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
+
+
+def _emit(text: str):
+    if _REAL_STDOUT is None:
+        print(text)
+        return
+    sys.stdout.flush()
+    os.write(_REAL_STDOUT, (text + "\n").encode())
 
 
 def main():
@@ -556,6 +585,7 @@ def main():
                     help="synthetic input family (SURVEY 8d): decaying spectrum | iid")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    _claim_stdout()
     if args.impl == "reference":
         run_reference_arm(args)
     else:

@@ -82,6 +82,10 @@ int svdq_tv_mask_gram_bits(int dtype, int n_tasks, int mask_strategy, int full, 
                            const int32_t* tile_param, const int32_t* tile_local, const int64_t* pmask_off,
                            uint32_t* packed, float* gram, uint32_t* count, void* stream);
 int svdq_host_pack_mask(const uint8_t* src_host, int64_t n, uint8_t* dst_host, int n_threads);
+/* the same for a batch of masks (what one rank of a parameter-sharded merge owns): src_host[i] / n[i] / dst_host[i],
+ * i < count; the batch's bytes are split evenly over n_threads host threads spawned once */
+int svdq_host_pack_mask_batch(const uint8_t* const* src_host, const int64_t* n, uint8_t* const* dst_host, int64_t count,
+                              int n_threads);
 
 /*
  * Host-side k-means of cluster weighting (all pointers are HOST pointers; no CUDA call).

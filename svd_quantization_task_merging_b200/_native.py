@@ -28,6 +28,7 @@ _SIGNATURES = {
     "svdq_tv_mask_gram": (C.c_int, [_i32, _i32, _i32, _i32, _i64, _i32] + [_vp] * 10),
     "svdq_tv_mask_gram_bits": (C.c_int, [_i32, _i32, _i32, _i32, _i64, _i32] + [_vp] * 10),
     "svdq_host_pack_mask": (C.c_int, [_vp, _i64, _vp, _i32]),
+    "svdq_host_pack_mask_batch": (C.c_int, [_vp, _vp, _vp, _i64, _i32]),
     "svdq_host_kmeans": (C.c_int, [_vp, _i32, _i32, _i32, C.c_uint32, _i32, _i32, C.c_double, _vp, _vp]),
     "svdq_mask_pack": (C.c_int, [_i32, _i32, _i64, _i32] + [_vp] * 8),
     "svdq_gram_staged": (C.c_int, [_i32, _i32, _i32, _i64, _i32] + [_vp] * 9),

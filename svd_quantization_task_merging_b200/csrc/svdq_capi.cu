@@ -167,34 +167,45 @@ int svdq_tv_mask_gram_bits(int dtype, int n_tasks, int mask_strategy, int full, 
                              numel, tile_param, tile_local, pmask_off, packed, gram, count, stream);
 }
 
-// Host-side transfer encoding of one task mask: torch.bool bytes -> bits (element 8k+i = bit i of byte k).  Eight
-// input bytes become one output byte with one multiply; the range is split across n_threads host threads.
-int svdq_host_pack_mask(const uint8_t* src, int64_t n, uint8_t* dst, int n_threads) {
-    REQUIRE(n >= 0 && (n == 0 || (src && dst)), "null pointer");
+// Host-side transfer encoding of task masks: torch.bool bytes -> bits (element 8k+i = bit i of byte k).  The work of
+// a whole batch of masks is cut into equal byte ranges over n_threads host threads (spawned once per call); the
+// inner loop is in host_pack.cpp (AVX2 when the CPU has it: 32 mask bytes -> one 32-bit word per instruction pair).
+extern "C" void svdq_host_pack_range(const uint8_t* src, int64_t n, uint8_t* dst, int64_t lo, int64_t hi);
+
+int svdq_host_pack_mask_batch(const uint8_t* const* src, const int64_t* n, uint8_t* const* dst, int64_t count, int n_threads) {
+    REQUIRE(count >= 0 && (count == 0 || (src && n && dst)), "null pointer");
     REQUIRE(n_threads >= 1 && n_threads <= 256, "n_threads must be in [1, 256]");
-    const int64_t n_out = (n + 7) / 8;
-    auto work = [src, dst, n](int64_t lo, int64_t hi) {          // output bytes [lo, hi)
-        for (int64_t k = lo; k < hi; ++k) {
-            const int64_t e = k * 8;
-            uint64_t x = 0;
-            if (e + 8 <= n) memcpy(&x, src + e, 8);
-            else memcpy(&x, src + e, (size_t)(n - e));
-            // any non-zero byte counts as set (torch.bool storage is 0/1, be safe): fold every bit of a byte into bit 0
-            x |= x >> 4; x |= x >> 2; x |= x >> 1;
-            x &= 0x0101010101010101ull;
-            dst[k] = (uint8_t)((x * 0x0102040810204080ull) >> 56);
+    int64_t total = 0;
+    for (int64_t i = 0; i < count; ++i) {
+        REQUIRE(n[i] >= 0 && (n[i] == 0 || (src[i] && dst[i])), "null mask pointer");
+        total += (n[i] + 7) / 8;
+    }
+    if (total == 0) return 0;
+    // output bytes [lo, hi) of the concatenation of all masks' packed images, 64-byte granules
+    auto work = [&](int64_t lo, int64_t hi) {
+        int64_t off = 0;
+        for (int64_t i = 0; i < count && off < hi; ++i) {
+            const int64_t n_out = (n[i] + 7) / 8;
+            const int64_t a = lo > off ? lo - off : 0, b = (hi - off) < n_out ? (hi - off) : n_out;
+            if (a < b) svdq_host_pack_range(src[i], n[i], dst[i], a, b);
+            off += n_out;
         }
     };
-    const int64_t per = ((n_out + n_threads - 1) / n_threads + 63) & ~(int64_t)63;
-    if (n_threads == 1 || n_out < (1 << 16)) { work(0, n_out); return 0; }
+    if (n_threads == 1 || total < (1 << 16)) { work(0, total); return 0; }
+    const int64_t per = ((total + n_threads - 1) / n_threads + 63) & ~(int64_t)63;
     std::vector<std::thread> pool;
     for (int t = 0; t < n_threads; ++t) {
-        const int64_t lo = (int64_t)t * per, hi = lo + per < n_out ? lo + per : n_out;
+        const int64_t lo = (int64_t)t * per, hi = lo + per < total ? lo + per : total;
         if (lo >= hi) break;
         pool.emplace_back(work, lo, hi);
     }
     for (auto& th : pool) th.join();
     return 0;
+}
+
+int svdq_host_pack_mask(const uint8_t* src, int64_t n, uint8_t* dst, int n_threads) {
+    REQUIRE(n >= 0 && (n == 0 || (src && dst)), "null pointer");
+    return svdq_host_pack_mask_batch(&src, &n, &dst, 1, n_threads);
 }
 
 extern "C" int svdq_host_kmeans_impl(const float*, int, int, int, uint32_t, int, int, double, int32_t*, double*);

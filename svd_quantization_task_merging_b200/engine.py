@@ -203,12 +203,12 @@ def _upload_mask_bits(task_masks: Sequence[Optional[Mapping[str, torch.Tensor]]]
         plan.append(entry)
     stage = _pinned_staging(max(total, 16))
     base_ptr = stage.data_ptr()
-    keep = []
+    keep, src, cnt, dst = [], [], [], []
     for m, entry in zip(task_masks, plan):
         if m is None:
             continue
         if entry["whole"]:
-            _native.call("svdq_host_pack_mask", m.flat.data_ptr(), m.flat.numel(), base_ptr + entry["base"], n_threads)
+            src.append(m.flat.data_ptr()); cnt.append(m.flat.numel()); dst.append(base_ptr + entry["base"])
         else:
             for k, v in m.items():
                 v = v.detach()
@@ -216,8 +216,10 @@ def _upload_mask_bits(task_masks: Sequence[Optional[Mapping[str, torch.Tensor]]]
                     v = v.bool()
                 v = v.contiguous()
                 keep.append(v)
-                _native.call("svdq_host_pack_mask", v.data_ptr(), v.numel(), base_ptr + entry["base"] + entry["offs"][k],
-                             n_threads)
+                src.append(v.data_ptr()); cnt.append(v.numel()); dst.append(base_ptr + entry["base"] + entry["offs"][k])
+    if src:          # one call for the whole batch: its bytes are split evenly over the host threads
+        a_src, a_cnt, a_dst = (np.asarray(x, np.int64) for x in (src, cnt, dst))
+        _native.call("svdq_host_pack_mask_batch", a_src.ctypes.data, a_cnt.ctypes.data, a_dst.ctypes.data, len(src), n_threads)
     dev_bits = torch.empty(max(total, 16), dtype=torch.uint8, device=device)
     dev_bits.copy_(stage[: dev_bits.numel()], non_blocking=True)
     ev = torch.cuda.Event()
@@ -310,10 +312,22 @@ class MergeJob:
         if self.stages > 8:
             raise ValueError("RTVQ stages must be <= 8 in this build")
 
+        # SVDQ_PROFILE=1: host wall-clock of the phases, each closed by a device synchronise (diagnostic runs only)
+        self._profile = os.environ.get("SVDQ_PROFILE", "0") == "1"
+        self.timing: Dict[str, float] = {}
+        import time as _time
         with torch.cuda.device(self.device):
+            t0 = _time.perf_counter()
             self._stage_inputs(base, finetuned, task_masks, param_filter)
+            if self._profile:
+                torch.cuda.synchronize(self.device)
+                self.timing["stage_inputs_s"] = _time.perf_counter() - t0
+                t0 = _time.perf_counter()
             for g in self.groups.values():
                 self._build_group(g)
+            if self._profile:
+                torch.cuda.synchronize(self.device)
+                self.timing["build_tables_s"] = _time.perf_counter() - t0
         self._ran = False
         self._side = None
         self._order_dev = _dev(np.asarray(sorted(range(self.N), key=lambda i: self.tasks[i]), np.int32), self.device)
@@ -321,7 +335,6 @@ class MergeJob:
         self._fetched: Optional[Dict[str, Dict[str, np.ndarray]]] = None
         self.weights: Optional[Dict[str, float]] = None
         self.cluster_assignments: Optional[Dict[str, int]] = None
-        self.timing: Dict[str, float] = {}
 
     # ------------------------------------------------------------------------------------------
     def _stage_inputs(self, base, finetuned, task_masks, param_filter):
@@ -339,6 +352,8 @@ class MergeJob:
             else:
                 sd = {}
             fts_d.append(sd)
+        import time as _time
+        _t_issue = _time.perf_counter()
         masks_h = [(task_masks.get(t) if task_masks else None) for t in self.tasks]
         # masks that all sit in host memory (what load_task_masks yields) cross PCIe bit-packed: 1/8 of the bytes
         self.mask_bits = (not self.wide and any(m is not None for m in masks_h) and
@@ -348,6 +363,8 @@ class MergeJob:
         if self.mask_bits:
             masks_d, nbytes = _upload_mask_bits(masks_h, dev, wanted)
             self.h2d_bytes += nbytes
+            if getattr(self, "_profile", False):
+                self.timing["host_mask_pack_s"] = _time.perf_counter() - _t_issue
         else:
             for m in masks_h:
                 if m is not None:
@@ -896,10 +913,19 @@ class MergeJob:
 def merge_state_dicts(base, finetuned, task_masks, config, device: Optional[str] = None, **kw) -> Dict:
     """Fused fast path: the whole of run_svd_hybrid_pipeline steps 1-9 (cli.py:146-722) on in-memory
     state dicts.  Returns the reference's result dict (cli.py:773-778)."""
+    import time as _time
     to_host = kw.pop("to_host", False)
     job = MergeJob(base, finetuned, task_masks, config, device, **kw)
+    t0 = _time.perf_counter()
     job.run()
+    if job._profile:
+        torch.cuda.synchronize(job.device)
+        job.timing["run_s"] = _time.perf_counter() - t0
+        t0 = _time.perf_counter()
     res = job.results(to_host=to_host)
+    if job._profile:
+        torch.cuda.synchronize(job.device)
+        job.timing["results_s"] = _time.perf_counter() - t0
     res["job"] = job
     return res
 

@@ -143,11 +143,21 @@ def merge_state_dicts_sharded(base, finetuned, task_masks, config, device: Optio
         owner = lpt_partition(cost, world)
     by_rank = [sorted(n for n, r in owner.items() if r == q) for q in range(world)]
     mine = by_rank[rank]
+    import time as _time
     job = MergeJob(base, finetuned, task_masks, config, device, param_filter=mine, **kw)
     if world > 1 and job.cluster_mode:
         job.gram_reduce_hook = lambda g: allreduce_gram(g, group)
+    t0 = _time.perf_counter()
     job.run()
+    if job._profile:
+        torch.cuda.synchronize(job.device)
+        job.timing["run_s"] = _time.perf_counter() - t0
+        t0 = _time.perf_counter()
     res = job.results(to_host=to_host)
+    if job._profile:
+        torch.cuda.synchronize(job.device)
+        job.timing["results_s"] = _time.perf_counter() - t0
+        t0 = _time.perf_counter()
     local_merged = {n: res["merged_state_dict"][n] for n in mine if n in res["merged_state_dict"]}
     # one fp64 record per owned parameter, rows in sorted-name order (status -1: no basis), gathered flat
     index = res["bases"]._index
@@ -172,6 +182,8 @@ def merge_state_dicts_sharded(base, finetuned, task_masks, config, device: Optio
         full = diagnostics_from_records(job.cfg, job.tasks, job.bits, job.stages, names_all, rec_all)
         diag["per_parameter"] = full["per_parameter"]
         diag["summary"] = full["summary"]
+    if job._profile:
+        job.timing["gather_records_s"] = _time.perf_counter() - t0
     out = {"merged_state_dict": local_merged, "diagnostics": diag, "bases": res["bases"],
            "compressed": res["compressed"], "owner": dict(owner), "basis_meta": meta, "job": job}
     if replicate_merged:
