@@ -11,9 +11,14 @@
 // quantises stage q-1, and reduces min / max / sum-of-squares of the new residual for stage q
 // in the same pass.  S stages cost S+1 reads of x and S code writes; all scalars stay on the
 // device (no host synchronisation between stages).  Bound: HBM.
+#include <cooperative_groups.h>
+#include <stdlib.h>
+
 #include "svdq_kernels.h"
 
 namespace svdq {
+
+namespace cg = cooperative_groups;
 
 
 
@@ -258,6 +263,174 @@ __global__ void __launch_bounds__(kBlock) k4_absmax_quant(const float* x, int64_
     }
 }
 
+// ---- single-kernel path for tensors that fit the register file of the whole GPU (<= ~4.8 M elements) ---------
+// One cooperative launch: every thread loads its R elements ONCE and keeps the residual in registers across all
+// stages; per stage the CTAs publish min / max / sum-of-squares partials, meet at a grid barrier, every CTA
+// reduces the (few hundred) partials in the same fixed order, then quantises, writes the codes and updates the
+// residual.  x is read once, the codes are written once per stage, nothing else touches memory -- and the
+// S + 1 pass launches + S finalize launches of the multi-pass path (launch-latency-bound below ~20 M elements:
+// 74 us for one stage of 4.19 M elements) become one launch with S grid barriers.  Bit-identical codes / scale /
+// zero point (min / max are order-free, the quantiser arithmetic is the same code); the residual norm is summed
+// in fp64 in a different order (same value to ~1e-16 relative).
+constexpr int kK4fThreads = 512;
+
+template <int R>     // R = elements per thread, a multiple of 4
+__global__ void __launch_bounds__(kK4fThreads, 2) k4_rtvq_fused(const K4PassArgs a, float* scale_out, float* zp_out,
+                                                                float* resnorm_out) {
+    cg::grid_group grid = cg::this_grid();
+    __shared__ float s_lut[256];
+    __shared__ K4Stats s_w[kK4fThreads / 32];
+    __shared__ QuantScalars s_q;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int64_t nvec = (a.n + kVec - 1) / kVec;
+    const int64_t vstride = (int64_t)gridDim.x * kK4fThreads;
+    float r[R];
+#pragma unroll
+    for (int k = 0; k < R / kVec; ++k) {
+        const int64_t v = (int64_t)k * vstride + (int64_t)blockIdx.x * kK4fThreads + tid;
+        const int64_t e = v * kVec;
+        if (v < nvec && e + kVec <= a.n) {
+            const float4 t = ldg_stream_f4(a.x + e);
+            r[k * 4 + 0] = t.x; r[k * 4 + 1] = t.y; r[k * 4 + 2] = t.z; r[k * 4 + 3] = t.w;
+        } else {
+#pragma unroll
+            for (int c = 0; c < kVec; ++c) r[k * 4 + c] = (v < nvec && e + c < a.n) ? __ldg(a.x + e + c) : 0.0f;
+        }
+    }
+    const float qmax = (float)((1 << a.bits) - 1);
+    const int levels = 1 << a.bits;
+    for (int s = 0; s < a.stages; ++s) {
+        // ---- statistics of the residual before stage s ----------------------------------------------------------
+        float lo = __int_as_float(0x7f800000), hi = __int_as_float(0xff800000);
+        int nan = 0;
+        double ss = 0.0;
+#pragma unroll
+        for (int k = 0; k < R / kVec; ++k) {
+            const int64_t e = ((int64_t)k * vstride + (int64_t)blockIdx.x * kK4fThreads + tid) * kVec;
+#pragma unroll
+            for (int c = 0; c < kVec; ++c)
+                if (e + c < a.n) stats_update(r[k * 4 + c], lo, hi, nan, ss);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+            hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+            nan |= __shfl_xor_sync(0xffffffffu, nan, o);
+            ss += __shfl_xor_sync(0xffffffffu, ss, o);
+        }
+        if (lane == 0) { s_w[tid >> 5].lo = lo; s_w[tid >> 5].hi = hi; s_w[tid >> 5].nan = nan; s_w[tid >> 5].sumsq = ss; }
+        __syncthreads();
+        if (tid == 0) {
+            K4Stats t = s_w[0];
+            for (int w = 1; w < kK4fThreads / 32; ++w) {
+                t.lo = fminf(t.lo, s_w[w].lo); t.hi = fmaxf(t.hi, s_w[w].hi); t.nan |= s_w[w].nan; t.sumsq += s_w[w].sumsq;
+            }
+            t.pad = 0;
+            a.part[(int64_t)(s & 1) * gridDim.x + blockIdx.x] = t;      // double-buffered: one barrier per stage
+            __threadfence();
+        }
+        grid.sync();
+        // ---- every CTA reduces the partials in the same fixed order: one partial per thread (gridDim.x <= 512) ------
+        {
+            const K4Stats* part = a.part + (int64_t)(s & 1) * gridDim.x;
+            float glo = __int_as_float(0x7f800000), ghi = __int_as_float(0xff800000);
+            int gnan = 0;
+            double gss = 0.0;
+            if (tid < (int)gridDim.x) { const K4Stats t = part[tid]; glo = t.lo; ghi = t.hi; gnan = t.nan; gss = t.sumsq; }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                glo = fminf(glo, __shfl_xor_sync(0xffffffffu, glo, o));
+                ghi = fmaxf(ghi, __shfl_xor_sync(0xffffffffu, ghi, o));
+                gnan |= __shfl_xor_sync(0xffffffffu, gnan, o);
+                gss += __shfl_xor_sync(0xffffffffu, gss, o);
+            }
+            __syncthreads();                       // s_w is free (its readers finished before the grid barrier)
+            if (lane == 0) { s_w[tid >> 5].lo = glo; s_w[tid >> 5].hi = ghi; s_w[tid >> 5].nan = gnan; s_w[tid >> 5].sumsq = gss; }
+            __syncthreads();
+            if (tid == 0) {
+                K4Stats t = s_w[0];
+                for (int w = 1; w < kK4fThreads / 32; ++w) {
+                    t.lo = fminf(t.lo, s_w[w].lo); t.hi = fmaxf(t.hi, s_w[w].hi); t.nan |= s_w[w].nan; t.sumsq += s_w[w].sumsq;
+                }
+                if (t.nan) { t.lo = __int_as_float(0x7fc00000); t.hi = t.lo; }
+                s_q = asym_scalars(t.lo, t.hi, a.bits);
+                if (blockIdx.x == 0) { scale_out[s] = s_q.scale; zp_out[s] = s_q.zp; resnorm_out[s] = (float)sqrt(t.sumsq); }
+            }
+        }
+        __syncthreads();
+        const QuantScalars qs = s_q;
+        for (int i = tid; i < levels; i += kK4fThreads) s_lut[i] = asym_decode(i, qs);
+        __syncthreads();
+        // ---- quantise stage s, write its codes, update the residual ----------------------------------------------
+        uint8_t* crow = reinterpret_cast<uint8_t*>(a.codes) + (int64_t)s * a.codes_ld;
+        const bool need_res = s + 1 < a.stages;
+#pragma unroll
+        for (int k = 0; k < R / kVec; ++k) {
+            const int64_t v = (int64_t)k * vstride + (int64_t)blockIdx.x * kK4fThreads + tid;
+            const int64_t e = v * kVec;
+            int code[kVec];
+#pragma unroll
+            for (int c = 0; c < kVec; ++c) {
+                float t = rintf(f_add(f_mul(qs.scale, r[k * 4 + c]), qs.zp));
+                t = (t != t) ? 0.0f : fminf(fmaxf(t, 0.0f), qmax);           // NaN -> code 0 (torch .to(uint8))
+                code[c] = (int)t;
+                if (need_res) r[k * 4 + c] = f_sub(r[k * 4 + c], s_lut[code[c]]);
+            }
+            if (v < nvec) {
+                if (e + kVec <= a.n) {
+                    *reinterpret_cast<uint32_t*>(crow + e) = (uint32_t)code[0] | ((uint32_t)code[1] << 8) |
+                                                             ((uint32_t)code[2] << 16) | ((uint32_t)code[3] << 24);
+                } else {
+#pragma unroll
+                    for (int c = 0; c < kVec; ++c)
+                        if (e + c < a.n) crow[e + c] = (uint8_t)code[c];
+                }
+            }
+            if (a.packed != nullptr) {           // bit-packed copy: 32 / (4 bits) neighbouring lanes share a word
+                const int per_thread = kVec * a.bits, lanes_per_word = 32 / per_thread;
+                uint32_t w = 0;
+                if (v < nvec) {
+#pragma unroll
+                    for (int c = 0; c < kVec; ++c)
+                        if (e + c < a.n) w |= (uint32_t)code[c] << (c * a.bits);
+                    w <<= (lane % lanes_per_word) * per_thread;
+                }
+                for (int o = 1; o < lanes_per_word; o <<= 1) w |= __shfl_xor_sync(0xffffffffu, w, o);
+                if (v < nvec && (lane % lanes_per_word) == 0) a.packed[(int64_t)s * a.packed_ld + v / lanes_per_word] = w;
+            }
+        }
+    }
+}
+
+// largest tensor the fused path takes (elements): all CTAs must be co-resident (cooperative launch)
+static int64_t k4_fused_capacity(int* grid_max) {
+    static int g = -1;
+    if (g < 0) {
+        int dev = 0, sms = 0, occ = 0;
+        g = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess &&
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess &&
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k4_rtvq_fused<32>, kK4fThreads, 0) == cudaSuccess && occ > 0) {
+            int coop = 0;
+            cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+            if (coop) g = sms * (occ < 2 ? occ : 2);
+        }
+        const char* v = getenv("SVDQ_K4_FUSED");
+        if (v && atoi(v) == 0) g = 0;                 // A/B switch
+    }
+    *grid_max = g;
+    return (int64_t)g * kK4fThreads * 32;
+}
+
+template <int R>
+static cudaError_t k4_fused_launch(K4PassArgs a, float* scale, float* zp, float* resnorm, int grid_max, cudaStream_t st) {
+    int64_t g = (a.n + (int64_t)kK4fThreads * R - 1) / ((int64_t)kK4fThreads * R);
+    if (g < 1) g = 1;
+    if (g > grid_max) return cudaErrorInvalidValue;
+    void* args[] = {&a, &scale, &zp, &resnorm};
+    return cudaLaunchCooperativeKernel((void*)k4_rtvq_fused<R>, dim3((unsigned)g), dim3(kK4fThreads), args, 0, st);
+}
+
 static int grid_for(int64_t n_threads_needed) {
     int64_t g = (n_threads_needed + kBlock - 1) / kBlock;
     if (g < 1) g = 1;
@@ -281,6 +454,16 @@ cudaError_t k4_rtvq_launch(const float* x, int64_t n, int bits, int stages, void
     const bool packable = code_bytes == 1 && (bits == 1 || bits == 2 || bits == 4 || bits == 8);
     if (packed != nullptr && !packable) return cudaErrorInvalidValue;
     a.packed = packed; a.packed_ld = packed_ld;
+    // small / medium tensors: one cooperative launch with the residual resident in registers
+    int grid_max = 0;
+    const int64_t cap = k4_fused_capacity(&grid_max);
+    if (code_bytes == 1 && n <= cap && grid_max > 0 && 2 * grid_max <= kK4MaxGrid) {
+        a.pass = 0;
+        const int64_t per8 = (int64_t)grid_max * kK4fThreads * 8, per16 = per8 * 2;
+        if (n <= per8) return k4_fused_launch<8>(a, scale, zp, resnorm, grid_max, st);
+        if (n <= per16) return k4_fused_launch<16>(a, scale, zp, resnorm, grid_max, st);
+        return k4_fused_launch<32>(a, scale, zp, resnorm, grid_max, st);
+    }
     for (int q = 0; q <= stages; ++q) {
         a.pass = q;
         if (code_bytes == 1) k4_rtvq_pass<uint8_t><<<grid, kBlock, 0, st>>>(a);
