@@ -248,6 +248,29 @@ int svdq_diag_finalize(int n_tasks, int64_t n_params, const float* diag_partials
  * region: 0 = the rows inside the combined mask; 1 = the rows outside it (the "noise" basis of
  * src/svd_hybrid/basis.py:455-466, with info / W of the noise solve; numel is needed for the offsets).
  */
+/*
+ * K11 -- merge from STORED artifacts (the reload path).
+ * Replaces: merge_all_parameters / merge_parameter / reconstruct_from_coefficients (src/svd_hybrid/merge.py:144-426)
+ *           as called by reconstruct_from_artifacts (src/svd_hybrid/reload.py:142-238), and the scatter of
+ *           reconstruct_from_masked (src/svd_hybrid/mask_loader.py:712-763), for ALL parameters in one launch.
+ * svdq_mask_tile_counts: masked elements per tile from the packed combined masks (count [n_tiles]); feed it to
+ *           svdq_basis_offsets for tile_row_off.
+ * svdq_reload_merge: kr [P][2] = (k, r) per parameter ((0, 0) = no basis -> zeros); u_high / u_low / mean [P] point to
+ *           the stored bases (fp16 when basis_fp16 else fp32; mean fp32 or NULL), rows compacted to the region's
+ *           elements; cbar [P][n_tasks] = averaged coefficients, c_high then c_low (dequantize_and_average,
+ *           merge.py:61-141, on the host: a few numbers per parameter); out [P] = fp32 deltas.
+ *           region 0: delta at the rows inside the mask, zeros elsewhere; region 1 (noise basis, merge.py:257-284):
+ *           scale * value at the rows outside the mask, the rest of out untouched (call after region 0).
+ */
+int svdq_mask_tile_counts(int64_t n_tiles, int tile_elems, const int64_t* numel, const int32_t* tile_param,
+                          const int32_t* tile_local, const int64_t* pmask_off, const uint8_t* has_mask,
+                          const uint32_t* packed, uint32_t* count, void* stream);
+int svdq_reload_merge(int basis_fp16, int n_tasks, int region, float scale, int64_t n_tiles, int tile_elems,
+                      const int64_t* numel, const int32_t* tile_param, const int32_t* tile_local,
+                      const int64_t* pmask_off, const uint8_t* has_mask, const uint32_t* packed, const int32_t* kr,
+                      const void* const* u_high, const void* const* u_low, const float* const* mean, const float* cbar,
+                      const int64_t* tile_row_off, float* const* out, void* stream);
+
 int svdq_basis_offsets(int64_t n_params, int region, int tile_elems, const uint32_t* count, const int64_t* tile_begin,
                        const int64_t* numel, int64_t* tile_row_off, void* stream);
 int svdq_write_basis(int dtype, int n_tasks, int fp16_basis, int center, int region, int64_t n_tiles, int tile_elems,

@@ -39,6 +39,8 @@ _SIGNATURES = {
     "svdq_param_requantize": (C.c_int, [_i32, _i64, _i32, _i32] + [_vp] * 12),
     "svdq_reconstruct_merge": (C.c_int, [_i32, _i32, _i32, _i32, _i32, _i64, _i32] + [_vp] * 20 + [_f32, _vp]),
     "svdq_diag_finalize": (C.c_int, [_i32, _i64] + [_vp] * 7),
+    "svdq_mask_tile_counts": (C.c_int, [_i64, _i32] + [_vp] * 8),
+    "svdq_reload_merge": (C.c_int, [_i32, _i32, _i32, _f32, _i64, _i32] + [_vp] * 14),
     "svdq_basis_offsets": (C.c_int, [_i64, _i32, _i32] + [_vp] * 5),
     "svdq_write_basis": (C.c_int, [_i32, _i32, _i32, _i32, _i32, _i64, _i32] + [_vp] * 14),
     "svdq_rtvq_quantize": (C.c_int, [_vp, _i64, _i32, _i32, _vp, _i64, _i32] + [_vp] * 5 + [_i64, _vp]),

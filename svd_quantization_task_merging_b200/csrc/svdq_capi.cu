@@ -441,6 +441,38 @@ int svdq_write_basis(int dtype, int n_tasks, int fp16_basis, int center, int reg
     return finish(__func__, k5_launch(dtype, n_tasks, a, (int)n_tiles, (cudaStream_t)stream));
 }
 
+int svdq_mask_tile_counts(int64_t n_tiles, int tile_elems, const int64_t* numel, const int32_t* tile_param,
+                          const int32_t* tile_local, const int64_t* pmask_off, const uint8_t* has_mask,
+                          const uint32_t* packed, uint32_t* count, void* stream) {
+    REQUIRE(tile_elems > 0 && tile_elems % svdq::kStep == 0, "tile_elems must be a positive multiple of 1024");
+    REQUIRE(n_tiles >= 0 && n_tiles < (1ll << 31), "n_tiles");
+    if (n_tiles == 0) return 0;
+    REQUIRE(numel && tile_param && tile_local && has_mask && count, "null pointer");
+    svdq::K11Args a = {};
+    a.numel = numel; a.tile_param = tile_param; a.tile_local = tile_local; a.pmask_off = pmask_off; a.has_mask = has_mask;
+    a.packed = packed; a.count = count; a.tile_elems = tile_elems;
+    return finish(__func__, svdq::k11_counts_launch(a, (int)n_tiles, (cudaStream_t)stream));
+}
+
+int svdq_reload_merge(int basis_fp16, int n_tasks, int region, float scale, int64_t n_tiles, int tile_elems,
+                      const int64_t* numel, const int32_t* tile_param, const int32_t* tile_local,
+                      const int64_t* pmask_off, const uint8_t* has_mask, const uint32_t* packed, const int32_t* kr,
+                      const void* const* u_high, const void* const* u_low, const float* const* mean, const float* cbar,
+                      const int64_t* tile_row_off, float* const* out, void* stream) {
+    REQUIRE(n_tasks >= 1 && n_tasks <= SVDQ_MAX_TASKS, "n_tasks must be in [1, 32]");
+    REQUIRE(region == 0 || region == 1, "region");
+    REQUIRE(tile_elems > 0 && tile_elems % svdq::kStep == 0, "tile_elems must be a positive multiple of 1024");
+    REQUIRE(n_tiles >= 0 && n_tiles < (1ll << 31), "n_tiles");
+    if (n_tiles == 0) return 0;
+    REQUIRE(numel && tile_param && tile_local && has_mask && kr && u_high && u_low && cbar && tile_row_off && out, "null pointer");
+    svdq::K11Args a = {};
+    a.numel = numel; a.tile_param = tile_param; a.tile_local = tile_local; a.pmask_off = pmask_off; a.has_mask = has_mask;
+    a.packed = packed; a.kr = kr; a.u_high = u_high; a.u_low = u_low; a.mean = mean; a.cbar = cbar;
+    a.tile_row_off = tile_row_off; a.out = out; a.tile_elems = tile_elems; a.n_tasks = n_tasks; a.region = region;
+    a.scale = scale;
+    return finish(__func__, svdq::k11_merge_launch(a, (int)n_tiles, basis_fp16 != 0, (cudaStream_t)stream));
+}
+
 int svdq_rtvq_quantize(const float* x, int64_t n, int bits, int stages, void* codes, int64_t codes_ld,
                        int code_bytes, float* scale, float* zp, float* resnorm, void* scratch, uint32_t* packed,
                        int64_t packed_ld, void* stream) {

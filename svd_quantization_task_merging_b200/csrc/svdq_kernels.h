@@ -170,6 +170,25 @@ struct K5Args {
     int n_tasks;                  // stride of the per-task tables (<= the kernel's compile-time task bound)
 };
 
+struct K11Args {                 // merge from stored artifacts (reload path)
+    const int64_t* numel;           // [P]
+    const int32_t* tile_param;      // [n_tiles]
+    const int32_t* tile_local;
+    const int64_t* pmask_off;       // [P] word offset of the parameter's packed combined mask
+    const uint8_t* has_mask;        // [P]
+    const uint32_t* packed;
+    uint32_t* count;                // [n_tiles] (k11_tile_counts output)
+    const int32_t* kr;              // [P][2]: k, r (0, 0: the parameter has no basis -> zeros)
+    const void* const* u_high;      // [P] [Dm x k]     fp16 or fp32, rows compacted to the region's elements
+    const void* const* u_low;       // [P] [Dm x (r-k)]
+    const float* const* mean;       // [P] [Dm] or null entries / null table
+    const float* cbar;              // [P][n_tasks] averaged coefficients (c_high then c_low)
+    const int64_t* tile_row_off;    // [n_tiles]
+    float* const* out;              // [P] fp32 deltas
+    int tile_elems, n_tasks, region;
+    float scale;                    // svd_noise_shrink for region 1, 1 otherwise
+};
+
 // launchers (one translation unit per kernel family; K1/K3/K5 additionally one per dtype)
 template <int DT> cudaError_t k1_launch_dtype(int nt, const K1Args& a, int n_tiles, bool full, cudaStream_t st);
 template <int DT> cudaError_t k3_launch_dtype(int nt, const K3Args& a, int n_tiles, bool fp16b, bool diag, cudaStream_t st);
@@ -181,6 +200,8 @@ template <int DT> cudaError_t k3s_launch_dtype(int nt, const K3Args& a, int n_ti
 template <int DT> cudaError_t k9_launch_dtype(int nt, const K1Args& a, int n_tiles, int n_sm, cudaStream_t st);
 // tensor-core pass 2 (tcgen05) for bf16 inputs, nt <= 8, no diagnostics / noise; cudaErrorNotSupported otherwise
 template <int DT> cudaError_t k10_launch_dtype(int nt, const K3Args& a, int n_tiles, bool fp16b, int n_sm, cudaStream_t st);
+cudaError_t k11_counts_launch(const K11Args& a, int n_tiles, cudaStream_t st);
+cudaError_t k11_merge_launch(const K11Args& a, int n_tiles, bool basis_fp16, cudaStream_t st);
 cudaError_t k6_mask_pack_launch(const K6MaskArgs& a, int n_tiles, cudaStream_t st);
 // single-pass staged Gram for 9..32 tasks under a pre-combined mask (K1Args in pre-combined mode)
 template <int DT> cudaError_t k8_launch_dtype(int n_tasks, const K1Args& a, int n_tiles, int n_sm, cudaStream_t st);

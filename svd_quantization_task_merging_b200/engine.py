@@ -150,6 +150,53 @@ def _to_device_state_dict(sd: Mapping[str, torch.Tensor], device, wanted=None) -
     return out, nbytes
 
 
+def upload_state_dicts(sds: Sequence[Mapping[str, torch.Tensor]], device, n_buffers: int = 2) -> List[Mapping[str, torch.Tensor]]:
+    """Pageable host state dicts (what torch.load yields; reference: load_checkpoint / load_task_vectors,
+    src/svd_hybrid/task_vector_loader.py:56-189) -> device, PIPELINED: while the DMA of state dict t runs out of one
+    pinned staging buffer, the host packs state dict t+1 into the other.  Each state dict arrives as one flat device
+    buffer (PackedStateDict).  State dicts with mixed dtypes, or already on the device, are passed through."""
+    device = torch.device(device)
+    out: List[Mapping[str, torch.Tensor]] = []
+    staging: List[Optional[torch.Tensor]] = [None] * n_buffers
+    events: List[Optional[torch.cuda.Event]] = [None] * n_buffers
+    slot = 0
+    for sd in sds:
+        tensors = [(k, v) for k, v in sd.items() if torch.is_tensor(v)]
+        dtypes = {v.dtype for _, v in tensors}
+        if (len(dtypes) != 1 or len(tensors) != len(sd) or any(v.device.type != "cpu" for _, v in tensors)
+                or isinstance(sd, PackedStateDict)):
+            out.append(sd)
+            continue
+        dtype = next(iter(dtypes))
+        al = 128 if dtype == torch.bool else 64
+        offs, n = {}, 0
+        for k, v in tensors:
+            offs[k] = n
+            n += (v.numel() + al - 1) // al * al
+        if events[slot] is not None:
+            events[slot].synchronize()                      # the previous upload out of this buffer has finished
+        buf = staging[slot]
+        nbytes = n * torch.empty(0, dtype=dtype).element_size()
+        if buf is None or buf.numel() < nbytes:
+            buf = staging[slot] = torch.empty(nbytes + nbytes // 16, dtype=torch.uint8).pin_memory()
+        host = buf[:nbytes].view(dtype)
+        for k, v in tensors:
+            host[offs[k]: offs[k] + v.numel()].copy_(v.detach().reshape(-1))
+        flat = torch.empty(n, dtype=dtype, device=device)
+        flat.copy_(host, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        events[slot] = ev
+        slot = (slot + 1) % n_buffers
+        d = PackedStateDict((k, flat[offs[k]: offs[k] + v.numel()].view(v.shape)) for k, v in tensors)
+        d.flat, d.offsets = flat, offs
+        out.append(d)
+    for ev in events:
+        if ev is not None:
+            ev.synchronize()                                # staging buffers are released on return
+    return out
+
+
 @dataclass
 class _PackedBits:
     """One task mask as it sits on the device after a host-side bit pack: ``bits`` = ceil(numel/8) bytes."""

@@ -41,7 +41,13 @@ def run_svd_hybrid_pipeline(config: SVDHybridConfig, verbose: bool = True) -> Di
                                      verbose=verbose)
     say(f"[svd-hybrid] {len(config.tasks)} tasks, {len(base)} base tensors, masks: {'yes' if task_masks else 'no'}")
 
-    job = MergeJob(base, finetuned, task_masks, config, device, materialize_bases=bool(config.svd_store_artifacts))
+    # checkpoint ingest (steps 0-1 end here): pageable torch.load dicts -> pinned staging -> device, the packing of
+    # state dict t+1 overlapped with the DMA of state dict t (engine.upload_state_dicts)
+    from ..engine import upload_state_dicts
+    order = [t for t in config.tasks if t in finetuned]
+    staged = upload_state_dicts([base] + [finetuned[t] for t in order], device)
+    base_d, finetuned_d = staged[0], dict(zip(order, staged[1:]))
+    job = MergeJob(base_d, finetuned_d, task_masks, config, device, materialize_bases=bool(config.svd_store_artifacts))
     job.run()                                                                          # steps 3-9 on the GPU
     res = job.results()
     merged, bases, compressed, diagnostics = (res["merged_state_dict"], res["bases"], res["compressed"],

@@ -434,3 +434,32 @@ def test_two_level_gram_reduction_of_many_tile_parameters(cuda_device, weighting
         j = g.names.index(k)
         assert torch.equal(gp.t["gram_masked"].view(-1, 8, 8)[i], got[j]), k
         assert torch.equal(part.merged_state_dict()[k].view(torch.int32), merged[k].view(torch.int32)), k
+
+
+def test_reload_with_noise_region_and_batched_merge_matches_per_parameter(cuda_device, tmp_path):
+    """Artifacts of a masked run with svd_include_noise: the batched reload merge (K11, one launch over the stored
+    bases) reproduces the pipeline's merged model and equals the per-parameter operator merge_parameter."""
+    from src.svd_hybrid.cli import run_svd_hybrid_pipeline
+    from src.svd_hybrid.reload import reconstruct_from_artifacts
+    from src.svd_hybrid.merge import merge_all_parameters, merge_parameter
+    from src.svd_hybrid.rtvq import RTVQQuantizer
+    from src.svd_hybrid.storage import load_all_artifacts, load_combined_masks
+    case = _gold("majority_noise_uniform")
+    ck, md = _write_case(tmp_path, case)
+    cfg = SVDHybridConfig(tasks=case["tasks"], checkpoint_dir=str(ck), base_model_path=str(tmp_path / "base.pt"),
+                          mask_dir=str(md), svd_store_artifacts=True, svd_max_rank=64, output_dir=str(tmp_path / "out"),
+                          artifact_dir=str(tmp_path / "art"), device="cuda", **case["config"])
+    res = run_svd_hybrid_pipeline(cfg, verbose=False)
+    out = reconstruct_from_artifacts(str(tmp_path / "art"), str(tmp_path / "base.pt"), str(tmp_path / "re.pt"), "cpu")
+    for p, m in res["merged_state_dict"].items():
+        assert torch.allclose(out["merged_state_dict"][p], m.cpu(), rtol=1e-4, atol=1e-6), p
+    art = load_all_artifacts(str(tmp_path / "art"), device="cpu")
+    masks = load_combined_masks(str(tmp_path / "art"), device="cpu")
+    weights = art["diagnostics"]["task_weights"]
+    shapes = {p: torch.Size(d["original_shape"]) for p, d in art["diagnostics"]["per_parameter"].items()}
+    batched = merge_all_parameters(art["compressed"], art["bases"], masks, weights, shapes, art["config"], "cpu", verbose=False)
+    q = RTVQQuantizer(num_bits=art["config"].svd_low_bits, num_stages=art["config"].svd_rtvq_stages)
+    for p in batched:
+        one = merge_parameter(p, art["compressed"][p], art["bases"][p], weights, q, shapes[p], mask=masks.get(p),
+                              include_noise=True, noise_shrink=art["config"].svd_noise_shrink, device="cpu")
+        assert torch.allclose(batched[p], one, rtol=1e-5, atol=1e-8), p
