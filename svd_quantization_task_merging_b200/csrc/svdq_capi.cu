@@ -51,10 +51,15 @@ bool aligned16(const void* p) { return ((uintptr_t)p & 15u) == 0; }
 
 // SVDQ_TC (bit mask, default 3): bit 0 = tensor-core pass 1 for 16-bit inputs (tcgen05, k9_gram_tc.cu; up to 8 tasks,
 // single Gram block), bit 1 = tensor-core pass 2 for bf16 inputs (k10_merge_tc.cu; up to 8 tasks, no diagnostics /
-// noise region); 0 = the CUDA-core kernels (A/B switch).
+// noise region), bit 2 = tensor-core single-pass Gram of the wide path for fp32 inputs (k12_gram_wide_tc.cu; 3-piece
+// bf16 split); 0 = the CUDA-core kernels (A/B switch).  SVDQ_TC_CHAIN = MMA steps per short accumulator chain of K12.
 int tc_enabled() {                      // read per call: tests flip it inside one process
     const char* v = getenv("SVDQ_TC");
-    return v ? atoi(v) : 3;
+    return v ? atoi(v) : 7;
+}
+int tc_chain() {
+    const char* v = getenv("SVDQ_TC_CHAIN");
+    return v ? atoi(v) : 4;
 }
 
 cudaError_t k1_launch(int dtype, int nt, const svdq::K1Args& a, int n_tiles, bool full, cudaStream_t st) {
@@ -252,6 +257,10 @@ int svdq_gram_staged(int dtype, int n_tasks, int mask_mode, int64_t n_tiles, int
     a.strategy = 0; a.packed_in = packed; a.has_mask_in = has_mask; a.second_complement = 0; a.mask_mode = mask_mode;
     a.mask_bits = 0;
     cudaError_t e;
+    if ((tc_enabled() & 4) && dtype == svdq::kF32) {
+        e = svdq::k12_launch_dtype<svdq::kF32>(n_tasks, a, (int)n_tiles, sm_count(), tc_chain(), (cudaStream_t)stream);
+        if (e != cudaErrorNotSupported) return finish(__func__, e);
+    }
     switch (dtype) {
         case svdq::kF32:  e = svdq::k8_launch_dtype<svdq::kF32>(n_tasks, a, (int)n_tiles, sm_count(), (cudaStream_t)stream); break;
         case svdq::kBF16: e = svdq::k8_launch_dtype<svdq::kBF16>(n_tasks, a, (int)n_tiles, sm_count(), (cudaStream_t)stream); break;

@@ -140,3 +140,91 @@ def test_tc_merge_matches_cuda_core_merge(cuda_device, monkeypatch, fp16_bases, 
             worst = max(worst, err)
             assert err <= (2e-5 if fp16_bases else 2e-6), (k, err)
     print(f"tensor-core pass 2 vs CUDA-core pass 2: max rel L2 of the merged delta {worst:.2e}")
+
+
+WIDE_SHAPES = {"big": (3, 12288 + 1024 + 40), "chunk": (1024,), "odd": (1531,), "tiny": (7,), "tile": (12288,),
+               "two_tiles": (2 * 12288 + 128,), "mid": (130, 257), "stage": (512,), "sub": (128,)}
+
+
+@pytest.mark.parametrize("n_tasks,strategy,mask_p,weighting,noise", [
+    (20, "union", 0.5, "uniform", False), (17, "intersection", 0.97, "cluster", False),
+    (21, "majority", 0.5, "uniform", True), (18, "union", None, "uniform", False),
+    (19, "union", 0.3, "cluster", False), (20, "union", None, "cluster", False),
+    (24, "majority", 0.5, "uniform", False)])        # above 21 tasks: the CUDA-core kernel serves both runs
+def test_wide_tc_gram_matches_fp64_and_cuda_core(cuda_device, monkeypatch, n_tasks, strategy, mask_p, weighting, noise):
+    """Tensor-core single-pass Gram of the wide path (k12_gram_wide_tc.cu, SVDQ_TC bit 2: fp32 task vectors as three
+    exact bf16 pieces on tcgen05) against an fp64 Gram of the masked task vectors and against the CUDA-core kernel
+    (k8_gram_staged.cu) on the same inputs: same accuracy class, same ranks, merged weights equal at the round-off
+    of the Gram.  Covers all three mask modes (rows inside the mask, all rows for cluster weighting, rows outside
+    for the noise region), parameters that end inside a stage / a tile buffer, and tasks that lack a parameter."""
+    from svd_quantization_task_merging_b200.engine import MergeJob
+    tasks = synth.task_names(n_tasks)
+    base, fts = synth.make_checkpoints(WIDE_SHAPES, tasks, family="parity", seed=23, device="cuda")
+    del fts[tasks[1]]["odd"]
+    masks = synth.make_masks(WIDE_SHAPES, tasks, mask_p, seed=24, device="cuda") if mask_p is not None else None
+    cfg = SVDHybridConfig(tasks=tasks, svd_energy_threshold=0.9, svd_mask_strategy=strategy or "union",
+                          svd_weighting=weighting, svd_include_noise=noise, svd_store_artifacts=False,
+                          svd_eval_reconstruction=False)
+    out = {}
+    for mode in ("4", "0"):
+        monkeypatch.setenv("SVDQ_TC", mode)
+        out[mode] = MergeJob(base, fts, masks, cfg, "cuda", diagnostics=False).run()
+    a, b = out["4"], out["0"]
+    ga, gb = a.groups[torch.float32], b.groups[torch.float32]
+    cm = a.combined_masks()
+    worst_a = worst_b = 0.0
+    keys = ["gram_masked"] + (["gram_all"] if weighting == "cluster" else [])
+    for key in keys:
+        Ga = ga.t[key].cpu().numpy().reshape(-1, n_tasks, n_tasks)
+        Gb = gb.t[key].cpu().numpy().reshape(-1, n_tasks, n_tasks)
+        if key == "gram_all":                               # one whole-model Gram
+            Ga, Gb = Ga.sum(0, keepdims=True), Gb.sum(0, keepdims=True)
+        acc = np.zeros((n_tasks, n_tasks))
+        for p, name in enumerate(ga.names):
+            cols = []
+            for t in tasks:
+                d = (fts[t][name] - base[name]).double().flatten() if name in fts[t] else \
+                    torch.zeros(base[name].numel(), dtype=torch.float64, device="cuda")
+                if key == "gram_masked" and name in cm:
+                    d = d * cm[name].flatten().double()
+                cols.append(d)
+            T = torch.stack(cols, 1)
+            G = (T.T @ T).cpu().numpy()
+            if key == "gram_all":
+                acc += G
+                continue
+            scale = np.sqrt(np.outer(np.diag(G), np.diag(G))) + 1e-300
+            ea, eb = (np.abs(Ga[p] - G) / scale).max(), (np.abs(Gb[p] - G) / scale).max()
+            worst_a, worst_b = max(worst_a, ea), max(worst_b, eb)
+            assert ea <= 4e-7, (key, name, ea, eb)
+        if key == "gram_all":
+            scale = np.sqrt(np.outer(np.diag(acc), np.diag(acc)))
+            assert (np.abs(Ga[0] - acc) / scale).max() <= 4e-7
+    print(f"wide Gram vs fp64, max relative error: tensor cores {worst_a:.2e}, CUDA cores {worst_b:.2e}")
+    fa, fb = a._fetch()[torch.float32], b._fetch()[torch.float32]
+    assert (fa["info"][:, :4] == fb["info"][:, :4]).all()
+    ma, mb = a.merged_state_dict(), b.merged_state_dict()
+    for k in ma:
+        fin = torch.isfinite(mb[k])
+        assert torch.equal(torch.isfinite(ma[k]), fin), k
+        if fin.any() and k != "tiny":
+            da, db = (ma[k] - base[k])[fin].double(), (mb[k] - base[k])[fin].double()
+            assert (da - db).norm() <= 2e-3 * db.norm() + 1e-12, k
+
+
+def test_wide_tc_gram_is_deterministic_and_placement_independent(cuda_device, monkeypatch):
+    from svd_quantization_task_merging_b200.engine import MergeJob
+    monkeypatch.setenv("SVDQ_TC", "4")
+    tasks = synth.task_names(20)
+    base, fts = synth.make_checkpoints(WIDE_SHAPES, tasks, family="parity", seed=5, device="cuda")
+    masks = synth.make_masks(WIDE_SHAPES, tasks, 0.5, seed=6, device="cuda")
+    cfg = SVDHybridConfig(tasks=tasks, svd_energy_threshold=0.9, svd_store_artifacts=False, svd_eval_reconstruction=False)
+    a = MergeJob(base, fts, masks, cfg, "cuda", diagnostics=False).run()
+    b = MergeJob(base, fts, masks, cfg, "cuda", diagnostics=False).run()
+    c = MergeJob(base, fts, masks, cfg, "cuda", diagnostics=False, param_filter=["big", "odd", "two_tiles"]).run()
+    ga, gb, gc = (j.groups[torch.float32] for j in (a, b, c))
+    assert torch.equal(ga.t["gram_masked"], gb.t["gram_masked"])
+    for name in gc.names:
+        assert torch.equal(gc.t["gram_masked"][gc.names.index(name)], ga.t["gram_masked"][ga.names.index(name)])
+    ma, mc = a.merged_state_dict(), c.merged_state_dict()
+    assert all(torch.equal(ma[k], mc[k]) for k in mc)
