@@ -18,7 +18,7 @@
 // 16 elements of EACH slice; these tiny-N MMAs are bound by the issue rate of the one thread that launches them and by
 // their shared-memory operand reads, not by the tensor pipe, hence two slices per instruction and one issuing warp
 // per instruction kind):
-//     MMA 1: A = rows 0..127, B = rows 0..47   (h_s0, h_s1)              -> D1[h_s,i][h_s,j]              = hh per slice
+//     MMA 1: A = rows 0..63 (M = 64), B = rows 0..47 (h_s0, h_s1)        -> D1[h_s,i][h_s,j]              = hh per slice
 //     MMA 2: A = rows 0..127, B = rows 42..137 (m_s0, m_s1, l_s0, l_s1)  -> D2[h_s,i | m_s,i][m_s,j | l_s,j] = hm hl / mm ml
 // (blocks that pair different slices, and rows past 125, are never read).
 //
@@ -71,15 +71,16 @@ constexpr int kWXRows = 4 * kWNP, kWHLd = 22, kWHRows = 2 * kWNP;
 constexpr int kWFixed = kWBufs * kWTileBytes + kWPad + 4096 /*lut*/ + kWXRows * kWXLd * 4 + kWHRows * kWHLd * 4 + 512 /*barriers*/;
 static_assert((kWXRows * kWXLd * 4 + kWHRows * kWHLd * 4) % 16 == 0, "barrier block alignment");
 
-// Two fp32 values -> the three bf16 pieces of each, packed (low half = first value).  The pieces are cut by
-// TRUNCATION: h = the top 16 bits of x (sign, exponent, 7 mantissa bits), x - h is exact and has at most 16
-// significant bits, m = its top 16 bits, and what is left has at most 8 significant bits, i.e. IS a bf16 number.
-// Packed arithmetic (one FFMA2 per pair), byte permutes to gather the high halves.
+// Two fp32 values -> the three bf16 pieces of each, packed (low half = first value).  h = bf16(x) rounded to NEAREST, so
+// that the residual x - h (exact, at most 16 significant bits) has a random sign and the cross terms h m stay sums of
+// random-sign products (their long accumulator chains would otherwise collect the truncation bias of a same-sign
+// sum); m = the top 16 bits of the residual (truncation), and what is left has at most 8 significant bits, i.e. IS a
+// bf16 number.  Packed arithmetic (one F2FP / FFMA2 per pair), byte permutes to gather the high halves.
 __device__ __forceinline__ void split2(float2 x, uint32_t& h, uint32_t& m, uint32_t& l) {
     const float2 neg1 = make_float2(-1.0f, -1.0f);
-    const uint32_t xa = __float_as_uint(x.x), xb = __float_as_uint(x.y);
-    h = __byte_perm(xa, xb, 0x7632);
-    const float2 hf = make_float2(__uint_as_float(xa & 0xffff0000u), __uint_as_float(xb & 0xffff0000u));
+    const __nv_bfloat162 hb = __floats2bfloat162_rn(x.x, x.y);
+    h = *reinterpret_cast<const uint32_t*>(&hb);
+    const float2 hf = make_float2(__uint_as_float(h << 16), __uint_as_float(h & 0xffff0000u));
     const float2 r = __ffma2_rn(hf, neg1, x);                                   // x - h, exact
     const uint32_t ra = __float_as_uint(r.x), rb = __float_as_uint(r.y);
     m = __byte_perm(ra, rb, 0x7632);
@@ -121,7 +122,7 @@ __global__ void __launch_bounds__(kWThreads, 1) k12_gram_wide_tc(const K1Args a,
     if (tid == 0) {
         for (int s = 0; s < 4; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], kWTransformWarps); }
         for (int s = 0; s < kWBufs; ++s) { mbar_init(&tfull[s], 4); mbar_init(&tempty[s], 2); }
-        for (int s = 0; s < kWD1Bufs; ++s) { mbar_init(&d1full[s], 1); mbar_init(&d1empty[s], 2); }
+        for (int s = 0; s < kWD1Bufs; ++s) { mbar_init(&d1full[s], 1); mbar_init(&d1empty[s], 3); }
         for (int s = 0; s < 2; ++s) { mbar_init(&d2full[s], 1); mbar_init(&d2empty[s], 3); }
         mbar_fence_init();
     }
@@ -185,7 +186,7 @@ __global__ void __launch_bounds__(kWThreads, 1) k12_gram_wide_tc(const K1Args a,
         const bool second = warp == kWMma + 1;
         const bool leader = elect_one();
         PipeState tb, d1, d2;
-        const uint32_t idesc = tc_idesc(1u, 1u, 128, second ? kWN2 : kWN1);
+        const uint32_t idesc = second ? tc_idesc(1u, 1u, 128, kWN2) : tc_idesc(1u, 1u, 64, kWN1);   // MMA 1 needs the h rows (0..41) only
         const uint64_t desc0 = tc_smem_desc(smem_u32(tile_buf), kWGroupBytes, 128);    // buffer 0, step 0, row 0
         const uint64_t b_row = second ? (uint64_t)(2 * kWNP) : 0ull;                  // start address field: 16-byte units
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -243,8 +244,11 @@ __global__ void __launch_bounds__(kWThreads, 1) k12_gram_wide_tc(const K1Args a,
         // D1 rows: h_s,i = 21 s + i (42 rows: quadrants 0, 1).  D2 rows: h_s,i = 21 s + i, m_s,i = 42 + 21 s + i (84 rows);
         // D2 columns: m_s,j = 21 s + j, l_s,j = 42 + 21 s + j.
         const int q = warp - kWDrain0;                      // == warp % 4: the TMEM lane quadrant this warp may read
-        const int row = 32 * q + lane;
+        const int row = 32 * q + lane;                      // D2 (M = 128): row r in TMEM lane r
         const bool slice1 = (row / kWNP) & 1;               // rows of slice 1 pair with the columns of slice 1
+        const int row1 = 16 * q + (lane & 15);              // D1 (M = 64): row r in TMEM lane 32 (r / 16) + r % 16
+        const bool row1_ok = lane < 16 && row1 < kWHRows;
+        const bool slice1_d1 = row1 >= kWNP;
         const uint32_t lane_base = (uint32_t)(32 * q) << 16;
         PipeState d1, d2;
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -253,7 +257,7 @@ __global__ void __launch_bounds__(kWThreads, 1) k12_gram_wide_tc(const K1Args a,
             const int64_t start = (int64_t)a.tile_local[tile] * a.tile_elems;
             const int64_t stop = min(start + (int64_t)a.tile_elems, numel);
             const int nsub = (int)((stop - start + kWTB - 1) / kWTB);
-            if (q < 2) {                                    // hh rows live in quadrants 0 and 1
+            {                                               // hh rows 0..41 live in lanes 0..15 of quadrants 0, 1, 2
                 float hi[kWNP], lo[kWNP];
 #pragma unroll
                 for (int j = 0; j < kWNP; ++j) { hi[j] = 0.0f; lo[j] = 0.0f; }
@@ -275,15 +279,15 @@ __global__ void __launch_bounds__(kWThreads, 1) k12_gram_wide_tc(const K1Args a,
                     if (lane == 0) mbar_arrive(&d1empty[d1.stage]);
                     d1.advance<kWD1Bufs>();
 #pragma unroll
-                    for (int j = 0; j < kWNP; ++j) lo[j] += __uint_as_float(slice1 ? r[kWNP + j] : r[j]);
+                    for (int j = 0; j < kWNP; ++j) lo[j] += __uint_as_float(slice1_d1 ? r[kWNP + j] : r[j]);
                     if ((c & 15) == 15) {                   // two-level sum: 16 chains per low accumulator
 #pragma unroll
                         for (int j = 0; j < kWNP; ++j) { hi[j] += lo[j]; lo[j] = 0.0f; }
                     }
                 }
-                if (row < kWHRows) {
+                if (row1_ok) {
 #pragma unroll
-                    for (int j = 0; j < kWNP; ++j) s_hh[row * kWHLd + j] = hi[j] + lo[j];
+                    for (int j = 0; j < kWNP; ++j) s_hh[row1 * kWHLd + j] = hi[j] + lo[j];
                 }
             }
             // ---- tile end: D2 (whole-tile sums of the cross terms) -----------------------------------------------
