@@ -34,7 +34,7 @@ UNITS: List[Tuple[str, object]] = (
     + [("k8_gram_staged.cu", d) for d in (0, 1, 2)]
     + [("k9_gram_tc.cu", d) for d in (0, 1, 2)]
     + [("k10_merge_tc.cu", d) for d in (0, 1, 2)]
-    + [("k12_gram_wide_tc.cu", 0)]
+    + [("k12_gram_wide_tc.cu", 0), ("k13_merge_wide_tc.cu", 0)]
     + [("k2_param_solve.cu", None), ("k11_reload_merge.cu", None), ("k4_rtvq_large.cu", None), ("svdq_capi.cu", None), ("host_kmeans.cpp", None), ("host_pack.cpp", None)]
 )
 HEADERS = ["svdq_common.cuh", "svdq_kernels.h", "k2_core.h", "k3_body.cuh", "stage_pipe.cuh", os.path.join("..", "..", "include", "svdq.h")]

@@ -52,10 +52,11 @@ bool aligned16(const void* p) { return ((uintptr_t)p & 15u) == 0; }
 // SVDQ_TC (bit mask, default 3): bit 0 = tensor-core pass 1 for 16-bit inputs (tcgen05, k9_gram_tc.cu; up to 8 tasks,
 // single Gram block), bit 1 = tensor-core pass 2 for bf16 inputs (k10_merge_tc.cu; up to 8 tasks, no diagnostics /
 // noise region), bit 2 = tensor-core single-pass Gram of the wide path for fp32 inputs (k12_gram_wide_tc.cu; 3-piece
-// bf16 split); 0 = the CUDA-core kernels (A/B switch).  SVDQ_TC_CHAIN = MMA steps per short accumulator chain of K12.
+// bf16 split), bit 3 = tensor-core pass 2 of the wide path for fp32 inputs and fp16 bases (k13_merge_wide_tc.cu);
+// 0 = the CUDA-core kernels (A/B switch).  SVDQ_TC_CHAIN = MMA steps per short accumulator chain of K12.
 int tc_enabled() {                      // read per call: tests flip it inside one process
     const char* v = getenv("SVDQ_TC");
-    return v ? atoi(v) : 7;
+    return v ? atoi(v) : 15;
 }
 int tc_chain() {
     const char* v = getenv("SVDQ_TC_CHAIN");
@@ -86,6 +87,10 @@ cudaError_t k1_launch(int dtype, int nt, const svdq::K1Args& a, int n_tiles, boo
     }
 }
 cudaError_t k3_launch(int dtype, int nt, const svdq::K3Args& a, int n_tiles, bool fp16b, bool diag, cudaStream_t st) {
+    if ((tc_enabled() & 8) && dtype == svdq::kF32 && nt > 16 && fp16b && !diag && a.info_n == nullptr) {
+        const cudaError_t e = svdq::k13_launch_dtype<svdq::kF32>(nt, a, n_tiles, fp16b, sm_count(), st);
+        if (e != cudaErrorNotSupported) return e;
+    }
     if (nt > SVDQ_MAX_STREAM_TASKS) {           // 17..32 tasks: runtime-N kernel
         switch (dtype) {
             case svdq::kF32:  return svdq::k6_merge_launch_dtype<svdq::kF32>(nt, a, n_tiles, fp16b, diag, st);

@@ -203,6 +203,9 @@ template <int DT> cudaError_t k10_launch_dtype(int nt, const K3Args& a, int n_ti
 // tensor-core single-pass Gram (tcgen05, 3-piece bf16 split) for fp32 inputs under a pre-combined mask, 1..32 tasks;
 // cudaErrorNotSupported otherwise.  chain = MMA steps per short accumulator chain (2, 4 or 8)
 template <int DT> cudaError_t k12_launch_dtype(int n_tasks, const K1Args& a, int n_tiles, int n_sm, int chain, cudaStream_t st);
+// tensor-core pass 2 of the wide path (tcgen05) for fp32 inputs, 2..21 tasks, no diagnostics / noise region;
+// cudaErrorNotSupported otherwise
+template <int DT> cudaError_t k13_launch_dtype(int n_tasks, const K3Args& a, int n_tiles, bool fp16b, int n_sm, cudaStream_t st);
 cudaError_t k11_counts_launch(const K11Args& a, int n_tiles, cudaStream_t st);
 cudaError_t k11_merge_launch(const K11Args& a, int n_tiles, bool basis_fp16, cudaStream_t st);
 cudaError_t k6_mask_pack_launch(const K6MaskArgs& a, int n_tiles, cudaStream_t st);

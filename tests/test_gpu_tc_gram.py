@@ -228,3 +228,47 @@ def test_wide_tc_gram_is_deterministic_and_placement_independent(cuda_device, mo
         assert torch.equal(gc.t["gram_masked"][gc.names.index(name)], ga.t["gram_masked"][ga.names.index(name)])
     ma, mc = a.merged_state_dict(), c.merged_state_dict()
     assert all(torch.equal(ma[k], mc[k]) for k in mc)
+
+
+@pytest.mark.parametrize("n_tasks,strategy,mask_p,weighting,center", [
+    (20, "union", 0.5, "uniform", True), (17, "intersection", 0.97, "cluster", True),
+    (21, "majority", 0.5, "performance", True), (18, "union", None, "uniform", True),
+    (19, "union", 0.3, "uniform", False)])
+def test_wide_tc_merge_matches_cuda_core_merge(cuda_device, monkeypatch, n_tasks, strategy, mask_p, weighting, center):
+    """Tensor-core pass 2 of the wide path (k13_merge_wide_tc.cu, SVDQ_TC bit 3: tau as three exact bf16 pieces times
+    the centred projection matrix as three bf16 pieces on tcgen05, TMEM epilogue) against the CUDA-core pass 2
+    (k6_reconstruct_merge) on identical coefficients (pass 1 on CUDA cores in both runs): same ranks / codes by
+    construction, merged weights equal to fp32 round-off of the basis rows (an fp16 rounding of a basis entry may land
+    on the other side: 5e-4 relative on that entry), untouched elements bit-identical.  Covers parameters that end
+    inside a stage / a tile buffer, a task that lacks a parameter, and parameters without a basis."""
+    from svd_quantization_task_merging_b200.engine import MergeJob
+    tasks = synth.task_names(n_tasks)
+    base, fts = synth.make_checkpoints(WIDE_SHAPES, tasks, family="parity", seed=33, device="cuda")
+    del fts[tasks[1]]["odd"]
+    masks = synth.make_masks(WIDE_SHAPES, tasks, mask_p, seed=34, device="cuda") if mask_p is not None else None
+    perf = synth.performance_table(tasks) if weighting == "performance" else None
+    cfg = SVDHybridConfig(tasks=tasks, svd_energy_threshold=0.9, svd_mask_strategy=strategy, svd_weighting=weighting,
+                          svd_center=center, svd_fp16=True, svd_store_artifacts=False, svd_eval_reconstruction=False)
+    out = {}
+    for mode in ("8", "0"):
+        monkeypatch.setenv("SVDQ_TC", mode)
+        job = MergeJob(base, fts, masks, cfg, "cuda", diagnostics=False, performance=perf).run()
+        out[mode] = (job, job.merged_state_dict())
+    (ja, ma), (jb, mb) = out["8"], out["0"]
+    fa, fb = ja._fetch()[torch.float32], jb._fetch()[torch.float32]
+    for key in ("info", "chigh", "codes", "cbar"):
+        assert np.array_equal(fa[key], fb[key], equal_nan=True), key
+    cm = ja.combined_masks()
+    worst = 0.0
+    for k in mb:
+        a32, b32 = ma[k], mb[k]
+        fin = torch.isfinite(b32)
+        assert torch.equal(torch.isfinite(a32), fin), k
+        if k in cm:
+            assert torch.equal(a32[~cm[k]], base[k][~cm[k]]), k            # outside the mask: merged == base exactly
+        da, db = (a32 - base[k])[fin].double(), (b32 - base[k])[fin].double()
+        if db.numel() and db.norm() > 0:
+            err = float((da - db).norm() / db.norm())
+            worst = max(worst, err)
+            assert err <= 2e-5, (k, err)
+    print(f"wide tensor-core pass 2 vs CUDA-core pass 2: max rel L2 of the merged delta {worst:.2e}")
