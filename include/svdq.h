@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define SVDQ_ABI_VERSION 4   /* 4: svdq_host_kmeans, per-cluster svdq_param_average; 3: svdq_tv_mask_gram_bits, svdq_host_pack_mask */
+#define SVDQ_ABI_VERSION 5   /* 5: svdq_mask_tile_counts, svdq_reload_merge; 4: svdq_host_kmeans, per-cluster svdq_param_average; 3: svdq_tv_mask_gram_bits, svdq_host_pack_mask */
 #define SVDQ_MAX_STREAM_TASKS 16
 #define SVDQ_MAX_TASKS 32
 #define SVDQ_MAX_STAGES 8

@@ -12,7 +12,7 @@ from typing import Optional
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libsvdq.so")
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 DTYPE_CODE = {"float32": 0, "bfloat16": 1, "float16": 2}
 STRATEGY_CODE = {"union": 0, "intersection": 1, "majority": 2}
