@@ -36,14 +36,21 @@ __device__ __forceinline__ void k3_step(const float (&b)[VEC], float (&x)[NT][VE
                                         float (&dacc)[DIAG ? kDiagRows * NT : 1],
                                         const K3NoiseSet<NT>& ns = K3NoiseSet<NT>()) {
     struct { int center; } a{center};
+    constexpr int kH = VEC / 2;
     float mean[VEC];
+    {
+        // sum over the tasks in task order, two elements per packed add (same rounding as the scalar adds)
+        float2 m2[kH];
 #pragma unroll
-    for (int c = 0; c < VEC; ++c) mean[c] = 0.0f;
+        for (int h = 0; h < kH; ++h) m2[h] = make_float2(0.0f, 0.0f);
 #pragma unroll
-    for (int t = 0; t < NT; ++t) {
-        Elem<T>::template subv<VEC>(x[t], b, x[t]);
+        for (int t = 0; t < NT; ++t) {
+            Elem<T>::template subv<VEC>(x[t], b, x[t]);
 #pragma unroll
-        for (int c = 0; c < VEC; ++c) mean[c] += x[t][c];
+            for (int h = 0; h < kH; ++h) m2[h] = __fadd2_rn(m2[h], make_float2(x[t][2 * h], x[t][2 * h + 1]));
+        }
+#pragma unroll
+        for (int h = 0; h < kH; ++h) { mean[2 * h] = m2[h].x; mean[2 * h + 1] = m2[h].y; }
     }
     const uint32_t bits = (pword >> (int)(e & 31)) & ((1u << VEC) - 1u);
 
@@ -60,11 +67,17 @@ __device__ __forceinline__ void k3_step(const float (&b)[VEC], float (&x)[NT][VE
     const float inv_n = __fdiv_rn(1.0f, n_f);
 #pragma unroll
     for (int c = 0; c < VEC; ++c) mean[c] = a.center ? (pow2 ? mean[c] * inv_n : __fdiv_rn(mean[c], n_f)) : 0.0f;
-    if (present_bits == ((1u << NT) - 1u)) {
+    const bool all_present = present_bits == ((1u << NT) - 1u);
+    if (all_present) {
+        // x - mean as mean * -1 + x: one packed instruction per element pair, same single rounding
+        const float2 neg1 = make_float2(-1.0f, -1.0f);
 #pragma unroll
         for (int t = 0; t < NT; ++t)
 #pragma unroll
-            for (int c = 0; c < VEC; ++c) x[t][c] = x[t][c] - mean[c];
+            for (int h = 0; h < VEC / 2; ++h) {
+                const float2 d = __ffma2_rn(make_float2(mean[2 * h], mean[2 * h + 1]), neg1, make_float2(x[t][2 * h], x[t][2 * h + 1]));
+                x[t][2 * h] = d.x; x[t][2 * h + 1] = d.y;
+            }
     } else {
 #pragma unroll
         for (int t = 0; t < NT; ++t)
@@ -74,7 +87,6 @@ __device__ __forceinline__ void k3_step(const float (&b)[VEC], float (&x)[NT][VE
 
     // The two tall-skinny contractions run as packed 2-wide FMAs (fma.rn.f32x2): elements (0,1) and (2,3)
     // of the thread share an instruction; the fp16 round trip of the basis row uses the packed converts.
-    constexpr int kH = VEC / 2;
     float2 x2[NT][kH];
 #pragma unroll
     for (int t = 0; t < NT; ++t)
@@ -91,9 +103,8 @@ __device__ __forceinline__ void k3_step(const float (&b)[VEC], float (&x)[NT][VE
             for (int h = 0; h < kH; ++h) rec2[t][h] = make_float2(0.0f, 0.0f);
     }
     if (FP16B || DIAG) {
-#pragma unroll
-        for (int j = 0; j < NT; ++j) {               // r <= NT columns; unrolled, uniform early exit
-            if (j >= r) break;
+        // r <= NT columns, unrolled
+        auto column = [&](const int j) {
             float2 u2[kH];
 #pragma unroll
             for (int h = 0; h < kH; ++h) u2[h] = make_float2(0.0f, 0.0f);
@@ -119,6 +130,19 @@ __device__ __forceinline__ void k3_step(const float (&b)[VEC], float (&x)[NT][VE
 #pragma unroll
                     for (int h = 0; h < kH; ++h) rec2[t][h] = __ffma2_rn(u2[h], ch2, rec2[t][h]);
                 }
+            }
+        };
+        if (DIAG && NT > 1 && r >= NT - 1) {
+            // the common case (full rank, or full rank minus the centring direction): straight-line code, one
+            // uniform test instead of an exit test per column
+#pragma unroll
+            for (int j = 0; j < NT - 1; ++j) column(j);
+            if (r == NT) column(NT - 1);
+        } else {
+#pragma unroll
+            for (int j = 0; j < NT; ++j) {            // uniform early exit
+                if (j >= r) break;
+                column(j);
             }
         }
     } else {
@@ -199,7 +223,7 @@ __device__ __forceinline__ void k3_step(const float (&b)[VEC], float (&x)[NT][VE
         const uint32_t mb = bits & (left >= (int64_t)VEC ? ((1u << VEC) - 1u) : ((1u << (int)(left > 0 ? left : 0)) - 1u));
 #pragma unroll
         for (int t = 0; t < NT; ++t) {
-            if (!((present_bits >> t) & 1u)) continue;
+            if (!all_present && !((present_bits >> t) & 1u)) continue;
 #pragma unroll
             for (int c = 0; c < VEC; ++c) {
                 if ((mb >> c) & 1u) {
