@@ -34,4 +34,4 @@ def pytest_sessionfinish(session, exitstatus):
     os.makedirs(out, exist_ok=True)
     tot = {k: sum(r[k] for r in parity.RATES) for k in ("c_high_equal", "c_high_total", "codes_equal", "codes_total")}
     with open(os.path.join(out, "parity_rates.json"), "w") as f:
-        json.dump({"totals": tot, "runs": parity.RATES}, f, indent=1)
+        json.dump({"totals": tot, "max_absolute_error_rel_dev_fp16_bases": parity.MAX_ABS_DEV, "runs": parity.RATES}, f, indent=1)

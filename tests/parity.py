@@ -233,13 +233,17 @@ def compare_run(ref: Dict, res: Dict, check_diag: bool = True, tol_merged: Optio
     flipped = flipped | dust
     if check_diag and ref["diagnostics"].get("per_parameter") is not None and "per_parameter" in res["diagnostics"]:
         compare_diagnostics(ref["diagnostics"], res["diagnostics"], flipped=flipped, dust=dust,
-                            max_abs_tol=0.3 if job.cfg.svd_fp16 else 0.0, fp16_bases=bool(job.cfg.svd_fp16),
+                            max_abs_tol=0.2 if job.cfg.svd_fp16 else 0.0, fp16_bases=bool(job.cfg.svd_fp16),
                             flipped_tol=5e-2 if job.bits >= 4 else (0.3 if job.bits == 3 else 1.0))
     return report
 
 
 def _base_of(ref, name):
     return ref["_base"][name].float()
+
+
+# observed relative deviation of max_absolute_error (fp16 bases, parameters whose stored artifacts equal the oracle's)
+MAX_ABS_DEV = {"worst": 0.0, "n": 0}
 
 
 def compare_diagnostics(d_ref: Dict, d_new: Dict, tol_exact: float = TOL_DIAG, flipped=(), dust=(),
@@ -281,6 +285,9 @@ def compare_diagnostics(d_ref: Dict, d_new: Dict, tol_exact: float = TOL_DIAG, f
                     tol_k = tol
                     if key == "max_absolute_error":
                         tol_k = 0.5 if name in flipped else max(tol, max_abs_tol)
+                        if name not in flipped and fp16_bases and abs(v) > floor:
+                            MAX_ABS_DEV["worst"] = max(MAX_ABS_DEV["worst"], abs(w - v) / abs(v))
+                            MAX_ABS_DEV["n"] += 1
                     assert abs(w - v) <= tol_k * abs(v) + floor + 1e-12, f"{name}/{task}/{key}: {w} vs {v}"
     tol = flipped_tol if flipped else tol_exact
     for key, v in d_ref["summary"].items():

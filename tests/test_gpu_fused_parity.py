@@ -23,7 +23,7 @@ def test_medium_shapes_masks(cuda_device, strategy, mask_p):
                                   svd_energy_threshold=0.9, svd_low_bits=4, svd_rtvq_stages=2)
     rep = parity.compare_run(ref, res)
     print(_summary(rep))
-    assert rep["code_equal"] >= 0.95 * rep["code_total"]
+    assert rep["code_equal"] >= 0.99 * rep["code_total"]          # observed 0.995 .. 1.0 (profiles/parity_rates.json)
 
 
 def test_performance_weighting_three_stages(cuda_device):
@@ -269,7 +269,7 @@ def test_wide_path_20_tasks_rtvq_sweep(cuda_device, n_tasks, bits, stages, strat
                                   svd_energy_threshold=0.9, svd_low_bits=bits, svd_rtvq_stages=stages)
     rep = parity.compare_run(ref, res)
     print(_summary(rep))
-    assert rep["code_equal"] >= 0.9 * rep["code_total"]
+    assert rep["code_equal"] >= 0.98 * rep["code_total"]          # observed 0.9888 .. 1.0 (profiles/parity_rates.json)
 
 
 def test_wide_path_cluster_and_fp32_basis(cuda_device):
@@ -299,7 +299,7 @@ def test_noise_region(cuda_device, strategy, mask_p, shrink, weighting, n_tasks,
     assert ref["bases_noise"], "the case must exercise the noise region"
     rep = parity.compare_run(ref, res)
     print(_summary(rep))
-    assert rep["code_equal"] >= 0.9 * rep["code_total"]
+    assert rep["code_equal"] >= 0.99 * rep["code_total"]          # observed 0.9975 .. 1.0
     # unmasked positions are no longer zero deltas
     name = "blk.attn.weight"
     m = ref["combined_masks"][name]
@@ -346,7 +346,7 @@ def test_noise_region_wide_path(cuda_device):
     assert ref["bases_noise"]
     rep = parity.compare_run(ref, res)
     print(_summary(rep))
-    assert rep["code_equal"] >= 0.9 * rep["code_total"]
+    assert rep["code_equal"] >= 0.99 * rep["code_total"]          # observed 1.0
 
 
 def test_noise_region_materialised_bases(cuda_device):
@@ -388,7 +388,7 @@ def test_task_count_sweep_with_tiny_parameters(cuda_device, n_tasks, mask_p):
                                   svd_energy_threshold=0.9)
     rep = parity.compare_run(ref, res)
     print(_summary(rep), rep["dust_params"])
-    assert rep["chigh_equal"] >= 0.9 * rep["chigh_total"]
+    assert rep["chigh_equal"] >= 0.95 * rep["chigh_total"]        # observed 0.963 .. 1.0 (3 of 81 values one fp16 ulp off)
 
 
 @pytest.mark.parametrize("dtype,n_tasks", [(torch.bfloat16, 20), (torch.float16, 20), (torch.bfloat16, 12),
