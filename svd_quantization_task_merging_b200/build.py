@@ -20,7 +20,9 @@ LIB = os.path.join(HERE, "libsvdq.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 
 ARCH_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a"]
-COMMON = ["-std=c++17", "-O3", "-lineinfo", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"] + ARCH_FLAGS
+# -Xfatbin -compress-all: the library instantiates every (kernel family x task count x dtype x flag) combination; the
+# compressed device images are a third of the size (the library travels to the GPU box with every snapshot)
+COMMON = ["-std=c++17", "-O3", "-lineinfo", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xfatbin", "-compress-all"] + ARCH_FLAGS
 
 # (source, SVDQ_DTYPE or None)
 UNITS: List[Tuple[str, object]] = (

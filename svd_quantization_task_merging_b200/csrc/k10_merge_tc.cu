@@ -158,28 +158,27 @@ __global__ void __launch_bounds__(kMtThreads, 1) k10_merge_tc(const K3Args a, co
             }
         }
     } else if (warp == 9) {
-        // ================= MMA issuer ===============================================================================
+        // ================= MMA issuer: the whole warp walks the loops, one elected lane issues ==========================
+        const bool leader = elect_one();
         PipeState tb, ab;
         const uint32_t idesc = tc_idesc(1u, 1u, 128, 32, /*a_mn=*/1u, /*b_mn=*/0u);
-        const uint32_t tile_addr = smem_u32(tile_buf);
+        const uint64_t desc_a0 = tc_smem_desc(smem_u32(tile_buf), /*lbo (K groups)=*/0, /*sbo (M groups)=*/128);
+        const uint64_t desc_b0 = tc_smem_desc(smem_u32(tile_buf) + kMtBOff, /*lbo (K chunks)=*/128, /*sbo (N groups)=*/256);
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
             const int p = a.tile_param[tile];
             const int64_t numel = a.numel[p];
             const int64_t start = (int64_t)a.tile_local[tile] * a.tile_elems;
             const int64_t stop = min(start + (int64_t)a.tile_elems, numel);
             for (int64_t e0 = start; e0 < stop; e0 += kStep) {
-                if (lane == 0) {
-                    mbar_wait(&tfull[tb.stage], tb.phase);
-                    mbar_wait(&aempty[ab.stage], ab.phase ^ 1u);
-                    tc_fence_after();
-                    const uint32_t sa = tile_addr + tb.stage * kMtTileBytes;
-                    const uint64_t db = tc_smem_desc(sa + kMtBOff, /*lbo (K chunks)=*/128, /*sbo (N groups)=*/256);
+                mbar_wait(&tfull[tb.stage], tb.phase);
+                mbar_wait(&aempty[ab.stage], ab.phase ^ 1u);
+                tc_fence_after();
+                if (leader) {
+                    const uint64_t da = desc_a0 + (uint64_t)(tb.stage * (kMtTileBytes >> 4));
+                    const uint64_t db = desc_b0 + (uint64_t)(tb.stage * (kMtTileBytes >> 4));
+                    const uint32_t td = tmem + ab.stage * 256;
 #pragma unroll
-                    for (int m = 0; m < 8; ++m) {       // 128 elements per instruction
-                        // A, MN-major: M groups of 8 elements 128 B apart; the second K group aliases the first
-                        const uint64_t da = tc_smem_desc(sa + m * 2048, /*lbo (K groups)=*/0, /*sbo (M groups)=*/128);
-                        tc_mma_f16(tmem + ab.stage * 256 + m * 32, da, db, idesc, 0u);
-                    }
+                    for (int m = 0; m < 8; ++m) tc_mma_f16(td + m * 32, da + (uint64_t)(m * (2048 >> 4)), db, idesc, 0u);
                     tc_commit(&tempty[tb.stage]);
                     tc_commit(&afull[ab.stage]);
                 }
