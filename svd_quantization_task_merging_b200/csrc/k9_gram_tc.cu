@@ -152,24 +152,26 @@ __global__ void __launch_bounds__(kTcThreads, 1) k9_gram_tc(const K1Args a, cons
             }
         }
     } else if (warp == 9) {
-        // ================= MMA issuer (one thread) ==================================================================
+        // ================= MMA issuer: the whole warp walks the loops, one elected lane issues ==========================
+        // (uniform control flow: the compiler needs no divergent-operand loops around the tcgen05 instructions)
+        const bool leader = elect_one();
         PipeState tb, ab;                               // tile-buffer ring, accumulator ring
         const uint32_t idesc = tc_idesc_f16<T>(128, 128);
-        const uint32_t tile_addr = smem_u32(tile_buf);
+        const uint64_t desc0 = tc_smem_desc(smem_u32(tile_buf), 128, 1024);
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
             const int p = a.tile_param[tile];
             const int64_t numel = a.numel[p];
             const int64_t start = (int64_t)a.tile_local[tile] * a.tile_elems;
             const int64_t stop = min(start + (int64_t)a.tile_elems, numel);
             for (int64_t e0 = start; e0 < stop; e0 += kStep) {
-                if (lane == 0) {
-                    mbar_wait(&tfull[tb.stage], tb.phase);
-                    mbar_wait(&aempty[ab.stage], ab.phase ^ 1u);
-                    tc_fence_after();
-                    const uint32_t sa = tile_addr + tb.stage * kTcTileBytes;
+                mbar_wait(&tfull[tb.stage], tb.phase);
+                mbar_wait(&aempty[ab.stage], ab.phase ^ 1u);
+                tc_fence_after();
+                if (leader) {
+                    const uint64_t d0 = desc0 + (uint64_t)(tb.stage * (kTcTileBytes >> 4));
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {       // 16 elements of every slice per instruction
-                        const uint64_t d = tc_smem_desc(sa + k * 256, 128, 1024);
+                        const uint64_t d = d0 + (uint64_t)(k * (256 >> 4));
                         tc_mma_f16(tmem + ab.stage * 128, d, d, idesc, k ? 1u : 0u);
                     }
                     tc_commit(&tempty[tb.stage]);       // tile buffer may be overwritten once these MMAs have read it
