@@ -455,7 +455,7 @@ def run_ours(args):
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath) and world == 1:
         try:
-            traffic = json.load(open(tpath)).get(dom)
+            traffic = (json.load(open(tpath)).get(args.workload) or {}).get(dom)      # null for workloads without a capture
         except Exception:
             traffic = None
     whole_bytes = (bytes_k1 + bytes_k3) / n_params * n_total        # all ranks' algorithmic bytes per step
