@@ -120,6 +120,21 @@ def _make_cfg(workload):
     return cfg, tasks, model, p
 
 
+def _workload_string(workload: str, family: str = "parity") -> str:
+    """The workload as both arms name it in config.workload (what is merged; not where or on what sample)."""
+    import torch
+    from svd_quantization_task_merging_b200 import synth
+    cfg, tasks, model, p = _make_cfg(workload)
+    shapes_all = synth.model_shapes(model)
+    in_dtype = WORKLOAD_EXTRA.get(workload, {}).get("dtype", "float32")
+    return (f"{workload}: {model} {'image encoder' if model.startswith('ViT') else 'weights'} "
+            f"({len(shapes_all)} tensors, {synth.total_params(shapes_all)} params, {in_dtype}) x {len(tasks)} random-init "
+            f"task vectors ({'decaying spectrum' if family == 'parity' else 'iid'}), "
+            + (f"{cfg.svd_mask_strategy} tall masks (Bernoulli {p}), " if p is not None else "no masks, ")
+            + f"{cfg.svd_weighting} weighting, energy {cfg.svd_energy_threshold}, {cfg.svd_low_bits}-bit x "
+            f"{cfg.svd_rtvq_stages}-stage RTVQ, fp16 bases")
+
+
 def _cpu_sample_names(shapes, model):
     """Bounded CPU sample: the tensors of the first four transformer blocks (the whole toy model)."""
     if model == "toy":
@@ -192,10 +207,9 @@ def run_reference_arm(args):
     line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": dt * 1e3, "higher_is_better": True,
             "scaling": "weak" if (WORKLOAD_EXTRA.get(args.workload, {}).get("shard_world") or args.replicas) else "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{args.workload}: {model} x {len(tasks)} tasks, "
-                                   f"{cfg.svd_mask_strategy + ' masks' if p is not None else 'no masks'}, "
-                                   f"{cfg.svd_weighting} weighting, {cfg.svd_low_bits}-bit x {cfg.svd_rtvq_stages} RTVQ"
-                                   f" (bounded CPU sample per step)"},
+            "config": {"workload": _workload_string(args.workload, getattr(args, "family", "parity")),
+                       "placement": "host cores of the box; every step = one pass over the bounded sample named in "
+                                    "cpu_baseline.sample"},
             "cpu_baseline": base,
             "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     _emit(json.dumps(line))
@@ -524,14 +538,8 @@ def run_ours(args):
                 "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
                 "scaling": "weak" if mode in ("shard", "replicas") else "strong",
                 "vs_baseline": None, "dtype": dt_name, "data": "synthetic",
-                "config": {"workload": f"{args.workload}: {model} {'image encoder' if model.startswith('ViT') else 'weights'} "
-                                       f"({len(shapes_all)} tensors, {synth.total_params(shapes_all)} params, "
-                                       f"{str(in_dtype).split('.')[-1]}) x {N} random-init task vectors "
-                                       f"({'decaying spectrum' if args.family == 'parity' else 'iid'}), "
-                                       + (f"{cfg.svd_mask_strategy} tall masks (Bernoulli {p}), " if has_masks else "no masks, ")
-                                       + f"{cfg.svd_weighting} "
-                                       f"weighting, energy {cfg.svd_energy_threshold}, {cfg.svd_low_bits}-bit x "
-                                       f"{cfg.svd_rtvq_stages}-stage RTVQ, fp16 bases; " + shard_note,
+                "config": {"workload": _workload_string(args.workload, args.family),
+                           "placement": shard_note,
                            "l2": f"inputs ({bytes_k1 / 1e9:.1f} GB per rank and step) "
                                  + ("are larger than the 126 MB L2; no flush needed" if bytes_k1 > 4e8 else
                                     "-- see DESIGN.md section 7 on L2 residency at high rank counts"),
