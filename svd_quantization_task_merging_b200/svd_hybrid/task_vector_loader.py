@@ -14,6 +14,11 @@ def load_checkpoint(checkpoint_path: str, device: str = "cpu") -> Dict[str, torc
     """task_vector_loader.py:56-100: torch.load, unwrap nn.Module / {"state_dict"|"model"|"model_state_dict"}."""
     if not os.path.exists(checkpoint_path):
         raise FileNotFoundError(f"Checkpoint not found: {checkpoint_path}")
+    if checkpoint_path.endswith(".safetensors"):
+        # additive input format (the reference reads pickles only): memory-mapped tensors, no unpickling pass --
+        # engine.upload_state_dicts then packs them straight from the page cache into its pinned staging buffers
+        from safetensors.torch import load_file
+        return load_file(checkpoint_path, device=device)
     ckpt = torch.load(checkpoint_path, map_location=device, weights_only=False)
     if isinstance(ckpt, torch.nn.Module):
         return ckpt.state_dict()
@@ -72,12 +77,15 @@ def flatten_task_deltas(task_vectors: Dict[str, Dict[str, torch.Tensor]], param_
 
 
 def get_task_checkpoint_paths(checkpoint_dir: str, task_names: List[str]) -> Dict[str, str]:
-    """task_vector_loader.py:258-291: {t}.pt, {t}.pth, {t}/checkpoint.pt, {t}/model.pt, {t}/finetuned.pt."""
+    """task_vector_loader.py:258-291: {t}.pt, {t}.pth, {t}/checkpoint.pt, {t}/model.pt, {t}/finetuned.pt; then, as an
+    additive format, {t}.safetensors and {t}/model.safetensors."""
     out = {}
     for t in task_names:
         cands = [os.path.join(checkpoint_dir, f"{t}.pt"), os.path.join(checkpoint_dir, f"{t}.pth"),
                  os.path.join(checkpoint_dir, t, "checkpoint.pt"), os.path.join(checkpoint_dir, t, "model.pt"),
-                 os.path.join(checkpoint_dir, t, "finetuned.pt")]
+                 os.path.join(checkpoint_dir, t, "finetuned.pt"),
+                 os.path.join(checkpoint_dir, f"{t}.safetensors"),                 # additive, tried last
+                 os.path.join(checkpoint_dir, t, "model.safetensors")]
         hit = next((c for c in cands if os.path.exists(c)), None)
         if hit is None:
             raise FileNotFoundError(f"No checkpoint found for task {t} in {checkpoint_dir}")

@@ -227,3 +227,24 @@ def test_sharded_collectives_world_size_2_gloo():
     for p in procs:
         p.join(timeout=60)
     assert res == [(0, True), (1, True)]
+
+
+def test_safetensors_checkpoints_are_an_additive_input_format(tmp_path):
+    """load_checkpoint (reference: task_vector_loader.py:56-100 reads pickles only) also accepts .safetensors files,
+    and get_task_checkpoint_paths finds them after the reference's own candidates."""
+    from safetensors.torch import save_file
+    from svd_quantization_task_merging_b200.svd_hybrid.task_vector_loader import (get_task_checkpoint_paths,
+                                                                                   load_checkpoint, load_task_vectors)
+    g = torch.Generator().manual_seed(0)
+    base = {"a.weight": torch.randn(4, 5, generator=g), "b": torch.randn(7, generator=g)}
+    ft = {k: v + 0.01 * torch.randn(v.shape, generator=g) for k, v in base.items()}
+    torch.save(base, tmp_path / "base.pt")
+    os.makedirs(tmp_path / "ck")
+    save_file(ft, str(tmp_path / "ck" / "A.safetensors"))
+    torch.save(ft, tmp_path / "ck" / "B.pt")
+    paths = get_task_checkpoint_paths(str(tmp_path / "ck"), ["A", "B"])
+    assert paths["A"].endswith("A.safetensors") and paths["B"].endswith("B.pt")
+    sd = load_checkpoint(paths["A"])
+    assert sorted(sd) == sorted(ft) and all(torch.equal(sd[k], ft[k]) for k in ft)
+    tv = load_task_vectors(str(tmp_path / "base.pt"), paths)
+    assert all(torch.equal(tv["A"][k], tv["B"][k]) for k in base)
