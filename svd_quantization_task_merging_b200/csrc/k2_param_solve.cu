@@ -140,8 +140,17 @@ struct WarpLanes {
     static constexpr int nl = 32;
     __device__ __forceinline__ void sync() { __syncwarp(); }
 };
+// a whole CTA as the lane set: above 8 tasks a Jacobi round has more (pair, row) items than a warp has lanes, and the
+// solve of the 17..32-task merges is pure latency (one CTA per parameter, 296 parameters); every sync() of the
+// lane-SPMD code is reached uniformly, and no value depends on the number of lanes, so the results are the same bits
+template <int THREADS> struct BlockLanes {
+    int lane;
+    static constexpr int nl = THREADS;
+    __device__ __forceinline__ void sync() { __syncthreads(); }
+};
 
-__global__ void __launch_bounds__(32) k2_param_solve(const K2SolveArgs a) {
+template <class LN, int THREADS>
+__global__ void __launch_bounds__(THREADS) k2_param_solve(const K2SolveArgs a) {
     __shared__ SolveScratch sc;
     const int p = blockIdx.x;
     const int NT = a.cfg.n_tasks, S = a.cfg.stages;
@@ -169,7 +178,7 @@ __global__ void __launch_bounds__(32) k2_param_solve(const K2SolveArgs a) {
     out.W = a.W + p * nn;
     out.gvec = a.gvec + (int64_t)p * NT;
     out.V = a.V + p * nn;
-    WarpLanes ln{(int)threadIdx.x};
+    LN ln{(int)threadIdx.x};
     solve_param(a.cfg, in, out, sc, ln);
 }
 
@@ -259,7 +268,9 @@ cudaError_t k2_solve_launch(const K2SolveArgs& a, int n_params, cudaStream_t st)
     if (a.cfg.n_tasks < 1 || a.cfg.n_tasks > kCoreMaxTasks) return cudaErrorInvalidValue;
     if (a.cfg.stages < 1 || a.cfg.stages > kCoreMaxStages || a.cfg.bits < 1 || a.cfg.bits > 8)
         return cudaErrorInvalidValue;
-    k2_param_solve<<<n_params, 32, 0, st>>>(a);
+    if (a.cfg.n_tasks <= 8) k2_param_solve<WarpLanes, 32><<<n_params, 32, 0, st>>>(a);
+    else if (a.cfg.n_tasks <= 16) k2_param_solve<BlockLanes<128>, 128><<<n_params, 128, 0, st>>>(a);     // 8 pairs x 16 rows
+    else k2_param_solve<BlockLanes<256>, 256><<<n_params, 256, 0, st>>>(a);
     return cudaGetLastError();
 }
 
