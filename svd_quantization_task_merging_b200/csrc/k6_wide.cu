@@ -35,7 +35,8 @@ __global__ void __launch_bounds__(kBlock) k6_mask_pack(const K6MaskArgs a) {
     const bool majority = a.strategy == kMajority;
     uint32_t* packed = has_mask ? a.packed + a.pmask_off[p] : nullptr;
     uint32_t cnt = 0;
-    // 16 elements (one 128-bit mask load per task) per thread and step, eight tasks' loads in flight
+    // 16 elements (one 128-bit mask load per task) per thread and step, up to twenty tasks' loads in flight
+    // (measured on ViT-L-14 x 20: 8 in flight 1.355 ms, 10: 1.185 ms, 20: 1.169 ms)
     constexpr int kMV = 16;
     for (int64_t e0 = start; e0 < stop; e0 += (int64_t)kBlock * kMV) {
         const int64_t e = e0 + (int64_t)tid * kMV;
@@ -45,7 +46,7 @@ __global__ void __launch_bounds__(kBlock) k6_mask_pack(const K6MaskArgs a) {
             const uint32_t valid = full ? 0xFFFFu : ((1u << (int)(numel - e)) - 1u);
             if (has_mask) {
                 uint32_t votes[4] = {0u, 0u, 0u, 0u};
-                constexpr int kUT = 8;
+                constexpr int kUT = 20;
                 for (int t0 = 0; t0 < a.n_tasks; t0 += kUT) {
                     uint4 w[kUT];
 #pragma unroll
