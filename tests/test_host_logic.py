@@ -248,3 +248,25 @@ def test_safetensors_checkpoints_are_an_additive_input_format(tmp_path):
     assert sorted(sd) == sorted(ft) and all(torch.equal(sd[k], ft[k]) for k in ft)
     tv = load_task_vectors(str(tmp_path / "base.pt"), paths)
     assert all(torch.equal(tv["A"][k], tv["B"][k]) for k in base)
+
+
+def test_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (CPU arm: the oracle port on the box's host cores) prints ONE JSON line with the
+    keys the driver reads, names the workload exactly as the GPU arm does, and needs no GPU."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--workload", "toy",
+                        "--steps", "1", "--warmup", "0"], capture_output=True, text=True, timeout=600, cwd=root)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["higher_is_better"] is True and d["unit"] == "params/s"
+    assert d["metric"].startswith("task-vector params merged/sec")
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(root, "bench.py"))
+    b = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(b)
+    assert d["config"]["workload"] == b._workload_string("toy")
