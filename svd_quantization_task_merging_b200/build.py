@@ -28,6 +28,7 @@ COMMON = ["-std=c++17", "-O3", "-lineinfo", "-Xcompiler", "-fPIC", "--expt-relax
 UNITS: List[Tuple[str, object]] = (
     [("k1_tv_mask_gram.cu", d) for d in (0, 1, 2)]
     + [("k3_reconstruct_merge.cu", d) for d in (0, 1, 2)]
+    + [("k3c_merge_diag_compact.cu", d) for d in (0, 1, 2)]
     + [("k5_basis_misc.cu", d) for d in (0, 1, 2)]
     + [("k1s_tv_mask_gram_staged.cu", d) for d in (0, 1, 2)]
     + [("k3s_reconstruct_merge_staged.cu", d) for d in (0, 1, 2)]

@@ -58,6 +58,12 @@ int tc_enabled() {                      // read per call: tests flip it inside o
     const char* v = getenv("SVDQ_TC");
     return v ? atoi(v) : 15;
 }
+// SVDQ_COMPACT_DIAG (default 1): pass 2 with fused diagnostics compacts the elements inside the combined mask before
+// the arithmetic (k3c_merge_diag_compact.cu); 0 = the non-compacting kernel (A/B switch)
+bool compact_diag() {
+    const char* v = getenv("SVDQ_COMPACT_DIAG");
+    return v ? atoi(v) != 0 : true;
+}
 int tc_chain() {
     const char* v = getenv("SVDQ_TC_CHAIN");
     return v ? atoi(v) : 4;
@@ -101,6 +107,16 @@ cudaError_t k3_launch(int dtype, int nt, const svdq::K3Args& a, int n_tiles, boo
     }
     if ((tc_enabled() & 2) && dtype == svdq::kBF16 && nt <= 8 && !diag && a.info_n == nullptr) {
         const cudaError_t e = svdq::k10_launch_dtype<svdq::kBF16>(nt, a, n_tiles, fp16b, sm_count(), st);
+        if (e != cudaErrorNotSupported) return e;
+    }
+    if (diag && nt <= 8 && a.info_n == nullptr && compact_diag()) {
+        cudaError_t e = cudaErrorNotSupported;
+        switch (dtype) {
+            case svdq::kF32:  e = svdq::k3c_launch_dtype<svdq::kF32>(nt, a, n_tiles, fp16b, st); break;
+            case svdq::kBF16: e = svdq::k3c_launch_dtype<svdq::kBF16>(nt, a, n_tiles, fp16b, st); break;
+            case svdq::kF16:  e = svdq::k3c_launch_dtype<svdq::kF16>(nt, a, n_tiles, fp16b, st); break;
+            default: break;
+        }
         if (e != cudaErrorNotSupported) return e;
     }
     if ((staged_mask() & 2) && nt <= 8 && !diag && a.info_n == nullptr) {

@@ -206,6 +206,9 @@ template <int DT> cudaError_t k12_launch_dtype(int n_tasks, const K1Args& a, int
 // tensor-core pass 2 of the wide path (tcgen05) for fp32 inputs, 2..21 tasks, no diagnostics / noise region;
 // cudaErrorNotSupported otherwise
 template <int DT> cudaError_t k13_launch_dtype(int n_tasks, const K3Args& a, int n_tiles, bool fp16b, int n_sm, cudaStream_t st);
+// compacting pass 2 with fused diagnostics (only the elements inside the combined mask go through the arithmetic):
+// up to 8 tasks, no noise region; cudaErrorNotSupported otherwise
+template <int DT> cudaError_t k3c_launch_dtype(int nt, const K3Args& a, int n_tiles, bool fp16b, cudaStream_t st);
 cudaError_t k11_counts_launch(const K11Args& a, int n_tiles, cudaStream_t st);
 cudaError_t k11_merge_launch(const K11Args& a, int n_tiles, bool basis_fp16, cudaStream_t st);
 cudaError_t k6_mask_pack_launch(const K6MaskArgs& a, int n_tiles, cudaStream_t st);
