@@ -93,6 +93,10 @@ __global__ void __launch_bounds__(kBlock, 2) k3c_merge_diag_compact(const K3Args
     const float tail_add = a.scal[(int64_t)p * 4 + 1];
     const float mean_scale = a.scal[(int64_t)p * 4 + 2];
     const bool has_mask = a.has_mask[p] != 0;
+    // automatic mode (diag_select == 2): per tile -- compaction where the mask keeps fewer than 55 % of the elements, the
+    // plain two-elements-per-thread walk (the loop of k3_reconstruct_merge) elsewhere and for parameters without a basis
+    const bool compact = a.diag_select != 2 ||
+                         (status == kSolved && k3_tile_is_sparse(has_mask ? a.packed + a.pmask_off[p] : nullptr, start, stop, numel));
 
     if (tid <= NT) s_ptr[tid] = a.tensors[(int64_t)p * (NT + 1) + tid];
     for (int i = tid; i < NT * NTP; i += kBlock) {
@@ -130,6 +134,27 @@ __global__ void __launch_bounds__(kBlock, 2) k3c_merge_diag_compact(const K3Args
             }
         }
     };
+    if (!compact) {
+        constexpr int kStepV = kBlock * 2;
+        for (int64_t e0 = start; e0 < stop; e0 += kStepV) {
+            const int64_t e = e0 + (int64_t)tid * 2;
+            if (e >= stop) continue;
+            const bool full = e + 2 <= numel;
+            float b[2], res[2];
+            ElemPair<T>::load(s_ptr[0], e, full, numel, b);
+            if (!solved) { res[0] = b[0]; res[1] = b[1]; }
+            else {
+                float x[NT][2];
+#pragma unroll
+                for (int t = 0; t < NT; ++t) ElemPair<T>::load(s_ptr[t + 1], e, full, numel, x[t]);
+                const uint32_t pword = has_mask ? __ldg(packed + (e >> 5)) : 0xffffffffu;
+                k3_step<T, NT, FP16B, true, false, 2>(b, x, pword, e, numel, r, present_bits, a.center, n_f, tail_add, mean_scale,
+                                                      sWT, sChatT, sCbar, sG, res, dacc);
+            }
+            if (full) stg_stream_f2(outp + e, make_float2(res[0], res[1]));
+            else if (e < numel) outp[e] = res[0];
+        }
+    } else {
     stage(start);
 
     for (int64_t e0 = start; e0 < stop; e0 += kCStep) {
@@ -224,6 +249,7 @@ __global__ void __launch_bounds__(kBlock, 2) k3c_merge_diag_compact(const K3Args
         // (the next step's first barrier separates these reads of s_x / s_idx from its writes)
     }
     cp_async_commit_wait_all();
+    }
 
     // ---- CTA reduction of the 4*NT diagnostic rows: sums for rows < 3*NT, max for the rest --------------------------
     __syncthreads();

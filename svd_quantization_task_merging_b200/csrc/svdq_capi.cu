@@ -58,11 +58,13 @@ int tc_enabled() {                      // read per call: tests flip it inside o
     const char* v = getenv("SVDQ_TC");
     return v ? atoi(v) : 15;
 }
-// SVDQ_COMPACT_DIAG (default 1): pass 2 with fused diagnostics compacts the elements inside the combined mask before
-// the arithmetic (k3c_merge_diag_compact.cu); 0 = the non-compacting kernel (A/B switch)
-bool compact_diag() {
+// SVDQ_COMPACT_DIAG: pass 2 with fused diagnostics (up to 8 tasks) compacts the elements inside the combined mask before
+// the arithmetic (k3c_merge_diag_compact.cu).  1 (default) = per tile inside that kernel: compaction where the mask
+// keeps fewer than 55 % of the elements, the plain walk elsewhere; 2 = compaction for every tile;
+// 0 = non-compacting kernel for every tile (A/B switches)
+int compact_diag() {
     const char* v = getenv("SVDQ_COMPACT_DIAG");
-    return v ? atoi(v) != 0 : true;
+    return v ? atoi(v) : 1;
 }
 int tc_chain() {
     const char* v = getenv("SVDQ_TC_CHAIN");
@@ -109,15 +111,20 @@ cudaError_t k3_launch(int dtype, int nt, const svdq::K3Args& a, int n_tiles, boo
         const cudaError_t e = svdq::k10_launch_dtype<svdq::kBF16>(nt, a, n_tiles, fp16b, sm_count(), st);
         if (e != cudaErrorNotSupported) return e;
     }
-    if (diag && nt <= 8 && a.info_n == nullptr && compact_diag()) {
-        cudaError_t e = cudaErrorNotSupported;
-        switch (dtype) {
-            case svdq::kF32:  e = svdq::k3c_launch_dtype<svdq::kF32>(nt, a, n_tiles, fp16b, st); break;
-            case svdq::kBF16: e = svdq::k3c_launch_dtype<svdq::kBF16>(nt, a, n_tiles, fp16b, st); break;
-            case svdq::kF16:  e = svdq::k3c_launch_dtype<svdq::kF16>(nt, a, n_tiles, fp16b, st); break;
-            default: break;
+    if (diag && nt <= 8 && a.info_n == nullptr && compact_diag() != 0) {
+        const bool split = compact_diag() == 1 && a.packed != nullptr;      // without packed masks nothing is sparse
+        if (split || compact_diag() == 2) {
+            svdq::K3Args c = a;
+            c.diag_select = split ? 2 : 0;
+            cudaError_t e = cudaErrorNotSupported;
+            switch (dtype) {
+                case svdq::kF32:  e = svdq::k3c_launch_dtype<svdq::kF32>(nt, c, n_tiles, fp16b, st); break;
+                case svdq::kBF16: e = svdq::k3c_launch_dtype<svdq::kBF16>(nt, c, n_tiles, fp16b, st); break;
+                case svdq::kF16:  e = svdq::k3c_launch_dtype<svdq::kF16>(nt, c, n_tiles, fp16b, st); break;
+                default: break;
+            }
+            if (e != cudaErrorNotSupported) return e;
         }
-        if (e != cudaErrorNotSupported) return e;
     }
     if ((staged_mask() & 2) && nt <= 8 && !diag && a.info_n == nullptr) {
         cudaError_t e = cudaErrorNotSupported;
@@ -422,6 +429,7 @@ int svdq_reconstruct_merge(int dtype, int n_tasks, int fp16_basis, int diag, int
             "noise region requested without its W / cbar / gvec / scal tables or without packed masks");
     a.info_n = noise_info; a.W_n = noise_W; a.cbar_n = noise_cbar; a.gvec_n = noise_gvec; a.scal_n = noise_scal;
     a.noise_shrink = noise_shrink;
+    a.diag_select = 0;
     return finish(__func__, k3_launch(dtype, n_tasks, a, (int)n_tiles, fp16_basis != 0, diag != 0,
                                             (cudaStream_t)stream));
 }

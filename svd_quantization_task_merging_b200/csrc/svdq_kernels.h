@@ -92,6 +92,9 @@ struct K3Args {
     const float* gvec_n;          // [P][NT]
     const float* scal_n;          // [P][4]
     float noise_shrink;
+    // fused diagnostics, up to 8 tasks (k3c_merge_diag_compact): 0 = compact every tile; 2 = per tile, compaction only
+    // where the combined mask keeps fewer than 55 % of the elements
+    int diag_select;
 };
 
 struct K3DiagArgs {
