@@ -272,3 +272,40 @@ def test_wide_tc_merge_matches_cuda_core_merge(cuda_device, monkeypatch, n_tasks
             worst = max(worst, err)
             assert err <= 2e-5, (k, err)
     print(f"wide tensor-core pass 2 vs CUDA-core pass 2: max rel L2 of the merged delta {worst:.2e}")
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("n_tasks,strategy,mask_p", [(8, "intersection", 0.9), (5, "majority", 0.5), (8, "union", None), (3, "intersection", 0.6)])
+def test_compacting_diag_pass_matches_plain_walk(cuda_device, monkeypatch, dtype, n_tasks, strategy, mask_p):
+    """Pass 2 with fused diagnostics, compacting kernel (k3c_merge_diag_compact.cu: only the elements inside the combined
+    mask go through the arithmetic) against the non-compacting kernel on identical coefficients: merged weights
+    bit-identical (same per-element instruction sequence), per-task error figures equal to the fp32 round-off of a
+    different summation order.  SVDQ_COMPACT_DIAG = 2 forces compaction for every tile, 1 chooses per tile, 0 never."""
+    from svd_quantization_task_merging_b200.engine import MergeJob
+    tasks = synth.task_names(n_tasks)
+    base, fts = synth.make_checkpoints(SHAPES, tasks, family="parity", seed=43, dtype=dtype, device="cuda")
+    if n_tasks >= 3:
+        del fts[tasks[1]]["two"]
+    masks = synth.make_masks(SHAPES, tasks, mask_p, seed=44, device="cuda") if mask_p is not None else None
+    cfg = SVDHybridConfig(tasks=tasks, svd_energy_threshold=0.9, svd_mask_strategy=strategy, svd_store_artifacts=False,
+                          svd_eval_reconstruction=True)
+    out = {}
+    for mode in ("2", "1", "0"):
+        monkeypatch.setenv("SVDQ_COMPACT_DIAG", mode)
+        job = MergeJob(base, fts, masks, cfg, "cuda", diagnostics=True).run()
+        res = job.results()
+        out[mode] = (job.merged_state_dict(), res["diagnostics"]["per_parameter"])
+    for mode in ("2", "1"):
+        ma, da = out[mode]
+        mb, db = out["0"]
+        for k in mb:
+            assert torch.equal(ma[k].view(torch.int32 if ma[k].element_size() == 4 else torch.int16),
+                               mb[k].view(torch.int32 if mb[k].element_size() == 4 else torch.int16)), (mode, k)
+        for name, pr in db.items():
+            for task, er in pr["reconstruction_errors"].items():
+                for key, v in er.items():
+                    w = da[name]["reconstruction_errors"][task][key]
+                    if v != v:
+                        assert w != w, (mode, name, task, key)
+                    else:
+                        assert abs(w - v) <= 2e-5 * abs(v) + 1e-12, (mode, name, task, key, w, v)
