@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define SVDQ_ABI_VERSION 5   /* 5: svdq_mask_tile_counts, svdq_reload_merge; 4: svdq_host_kmeans, per-cluster svdq_param_average; 3: svdq_tv_mask_gram_bits, svdq_host_pack_mask */
+#define SVDQ_ABI_VERSION 6   /* 6: svdq_reconstruct_merge_basis; 5: svdq_mask_tile_counts, svdq_reload_merge; 4: svdq_host_kmeans, per-cluster svdq_param_average; 3: svdq_tv_mask_gram_bits, svdq_host_pack_mask */
 #define SVDQ_MAX_STREAM_TASKS 16
 #define SVDQ_MAX_TASKS 32
 #define SVDQ_MAX_STAGES 8
@@ -237,6 +237,22 @@ int svdq_reconstruct_merge(int dtype, int n_tasks, int fp16_basis, int diag, int
  * max_absolute_error, mean_absolute_error, original_norm, reconstructed_norm
  * (src/svd_hybrid/diagnostics.py:110-117).  original_norm^2 is read off the diagonal of gram_masked
  * (the masked task vector's squared norm, already reduced in fp64 by svdq_gram_reduce). */
+/*
+ * K3c with the basis write-out fused in (the reference's default settings: svd_eval_reconstruction AND
+ * svd_store_artifacts): svdq_reconstruct_merge(diag = 1) that ALSO stores the artifact bases of the masked region --
+ * U_high [Dm x k], U_low [Dm x (r-k)] (fp16 when fp16_basis else fp32) and mean [Dm] (NULL table = no mean), rows
+ * compacted to the elements inside the combined mask, exactly what svdq_write_basis would store (construct_basis
+ * src/svd_hybrid/basis.py:363-364,398-407 after apply_mask_to_tensor src/svd_hybrid/mask_loader.py:675-679) -- so the
+ * inputs are not read a third time.  tile_row_off from svdq_basis_offsets(region = 0).  Up to 8 tasks, no noise region.
+ */
+int svdq_reconstruct_merge_basis(int dtype, int n_tasks, int fp16_basis, int center, int64_t n_tiles, int tile_elems,
+                                 const void* const* tensors, const int64_t* numel, const int32_t* tile_param,
+                                 const int32_t* tile_local, const int64_t* pmask_off, const uint8_t* has_mask,
+                                 const uint32_t* packed, const int32_t* info, const float* W, const float* cbar,
+                                 const float* gvec, const float* scal, const float* chat, float* const* out,
+                                 float* diag_partials, const int64_t* tile_row_off, void* const* u_high,
+                                 void* const* u_low, float* const* mean, void* stream);
+
 int svdq_diag_finalize(int n_tasks, int64_t n_params, const float* diag_partials, const int64_t* tile_begin,
                        const int64_t* dm, const int32_t* info, const double* gram_masked, double* out, void* stream);
 

@@ -12,7 +12,7 @@ from typing import Optional
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libsvdq.so")
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 DTYPE_CODE = {"float32": 0, "bfloat16": 1, "float16": 2}
 STRATEGY_CODE = {"union": 0, "intersection": 1, "majority": 2}
@@ -38,6 +38,7 @@ _SIGNATURES = {
     "svdq_project_exact": (C.c_int, [_i32, _i32, _i32, _i32, _i32, _i64, _i32] + [_vp] * 11),
     "svdq_param_requantize": (C.c_int, [_i32, _i64, _i32, _i32] + [_vp] * 12),
     "svdq_reconstruct_merge": (C.c_int, [_i32, _i32, _i32, _i32, _i32, _i64, _i32] + [_vp] * 20 + [_f32, _vp]),
+    "svdq_reconstruct_merge_basis": (C.c_int, [_i32, _i32, _i32, _i32, _i64, _i32] + [_vp] * 20),
     "svdq_diag_finalize": (C.c_int, [_i32, _i64] + [_vp] * 7),
     "svdq_mask_tile_counts": (C.c_int, [_i64, _i32] + [_vp] * 8),
     "svdq_reload_merge": (C.c_int, [_i32, _i32, _i32, _f32, _i64, _i32] + [_vp] * 14),

@@ -47,9 +47,18 @@ template <int NT> struct K3NoiseSet {
     bool on = false;
 };
 
+// Optional observer of pass 2's intermediate values (VEC = 2 only): the basis-row entries u_dj of the thread's two
+// elements, after the fp16 round trip when the bases are stored in fp16, and the per-element mean across tasks.  The
+// compacting diagnostics kernel uses it to write the artifact bases in the same pass (K3NoSink: nothing).
+struct K3NoSink {
+    static constexpr bool on = false;
+    __device__ __forceinline__ void col(int, float2) const {}
+    __device__ __forceinline__ void mean2(float, float) const {}
+};
+
 // x: in = fine-tuned values, scratch afterwards.  res: out = merged values.  VEC = elements per thread and call
 // (4; 2 for the kernel with fused diagnostics, whose 4*NT running reductions otherwise cap it at 8 warps per SM).
-template <typename T, int NT, bool FP16B, bool DIAG, bool NOISE = false, int VEC = kVec>
+template <typename T, int NT, bool FP16B, bool DIAG, bool NOISE = false, int VEC = kVec, class SINK = K3NoSink>
 __device__ __forceinline__ void k3_step(const float (&b)[VEC], float (&x)[NT][VEC], const uint32_t pword,
                                         const int64_t e, const int64_t numel, const int r, const uint32_t present_bits,
                                         const int center, const float n_f, const float tail_add,
@@ -57,7 +66,8 @@ __device__ __forceinline__ void k3_step(const float (&b)[VEC], float (&x)[NT][VE
                                         const float (*sWT)[(NT + 3) & ~3], const float (*sChatT)[(NT + 3) & ~3],
                                         const float* sCbar, const float* sG, float (&res)[VEC],
                                         float (&dacc)[DIAG ? kDiagRows * NT : 1],
-                                        const K3NoiseSet<NT>& ns = K3NoiseSet<NT>()) {
+                                        const K3NoiseSet<NT>& ns = K3NoiseSet<NT>(), const SINK& sink = SINK()) {
+    static_assert(!SINK::on || VEC == 2, "the sink sees two elements per call");
     struct { int center; } a{center};
     constexpr int kH = VEC / 2;
     float mean[VEC];
@@ -90,6 +100,7 @@ __device__ __forceinline__ void k3_step(const float (&b)[VEC], float (&x)[NT][VE
     const float inv_n = __fdiv_rn(1.0f, n_f);
 #pragma unroll
     for (int c = 0; c < VEC; ++c) mean[c] = a.center ? (pow2 ? mean[c] * inv_n : __fdiv_rn(mean[c], n_f)) : 0.0f;
+    if constexpr (SINK::on) sink.mean2(mean[0], mean[1]);
     const bool all_present = present_bits == ((1u << NT) - 1u);
     if (all_present) {
         // x - mean as mean * -1 + x: one packed instruction per element pair, same single rounding
@@ -145,6 +156,7 @@ __device__ __forceinline__ void k3_step(const float (&b)[VEC], float (&x)[NT][VE
                 if (FP16B) u2[h] = __half22float2(__float22half2_rn(u2[h]));
                 acc2[h] = __ffma2_rn(u2[h], cb2, acc2[h]);
             }
+            if constexpr (SINK::on) sink.col(j, u2[0]);
             if (DIAG) {
 #pragma unroll
                 for (int t = 0; t < NT; ++t) {

@@ -16,6 +16,8 @@
 // bit-identical to the non-compacting kernel) and store merged = base + delta at the elements' positions.  The
 // diagnostics partials of a tile are summed in a different (still fixed, placement-independent) order.
 // Bound: HBM ((N+1) s + 1/8 + 4 B per element) once the mask is sparse enough; issue otherwise.
+#include <type_traits>
+
 #include "k3_body.cuh"
 
 #ifndef SVDQ_DTYPE
@@ -63,6 +65,29 @@ template <> struct StagedQuad<__half> {
     }
 };
 
+// writes the basis rows of the thread's two compacted elements straight into the artifact arrays (rows row0, row0 + 1:
+// consecutive threads hold consecutive rows, so the stores of a warp fall into a few adjacent lines)
+template <typename OUT> struct K3BasisSink {
+    static constexpr bool on = true;
+    OUT* uh; OUT* ul; float* mn;
+    int64_t row0;
+    int k, nlow;
+    bool two;
+    static __device__ __forceinline__ OUT cvt(float v) {
+        if constexpr (sizeof(OUT) == 2) return __float2half_rn(v); else return v;
+    }
+    __device__ __forceinline__ void col(int j, float2 u) const {
+        if (uh == nullptr) return;
+        if (j < k) { uh[row0 * k + j] = cvt(u.x); if (two) uh[(row0 + 1) * k + j] = cvt(u.y); }
+        else { ul[row0 * nlow + (j - k)] = cvt(u.x); if (two) ul[(row0 + 1) * nlow + (j - k)] = cvt(u.y); }
+    }
+    __device__ __forceinline__ void mean2(float m0, float m1) const {
+        if (mn == nullptr) return;
+        mn[row0] = m0;
+        if (two) mn[row0 + 1] = m1;
+    }
+};
+
 template <typename T, int NT, bool FP16B>
 __global__ void __launch_bounds__(kBlock, 2) k3c_merge_diag_compact(const K3Args a) {
     constexpr int NTP = (NT + 3) & ~3;
@@ -95,7 +120,8 @@ __global__ void __launch_bounds__(kBlock, 2) k3c_merge_diag_compact(const K3Args
     const bool has_mask = a.has_mask[p] != 0;
     // automatic mode (diag_select == 2): per tile -- compaction where the mask keeps fewer than 55 % of the elements, the
     // plain two-elements-per-thread walk (the loop of k3_reconstruct_merge) elsewhere and for parameters without a basis
-    const bool compact = a.diag_select != 2 ||
+    const bool write_basis = a.u_high != nullptr;         // every solved tile is compacted then (rows = compacted slots)
+    const bool compact = a.diag_select != 2 || (write_basis && status == kSolved) ||
                          (status == kSolved && k3_tile_is_sparse(has_mask ? a.packed + a.pmask_off[p] : nullptr, start, stop, numel));
 
     if (tid <= NT) s_ptr[tid] = a.tensors[(int64_t)p * (NT + 1) + tid];
@@ -155,6 +181,14 @@ __global__ void __launch_bounds__(kBlock, 2) k3c_merge_diag_compact(const K3Args
             else if (e < numel) outp[e] = res[0];
         }
     } else {
+    using OUT = typename std::conditional<FP16B, __half, float>::type;
+    K3BasisSink<OUT> sink;
+    sink.uh = write_basis ? reinterpret_cast<OUT*>(a.u_high[p]) : nullptr;
+    sink.ul = write_basis ? reinterpret_cast<OUT*>(a.u_low[p]) : nullptr;
+    sink.mn = (write_basis && a.mean_out) ? a.mean_out[p] : nullptr;
+    sink.k = a.info[(int64_t)p * 8 + 3];
+    sink.nlow = r - sink.k;
+    int64_t row_base = write_basis ? a.tile_row_off[tile] : 0;
     stage(start);
 
     for (int64_t e0 = start; e0 < stop; e0 += kCStep) {
@@ -241,11 +275,15 @@ __global__ void __launch_bounds__(kBlock, 2) k3c_merge_diag_compact(const K3Args
             }
             const uint32_t i0 = s_idx[2 * it], i1 = two ? s_idx[2 * it + 1] : 0u;
             // both elements are inside the mask and inside the tensor: pword = 0b11 (0b01), "numel" = their count
-            k3_step<T, NT, FP16B, true, false, 2>(b2, x2, two ? 3u : 1u, (int64_t)0, (int64_t)(two ? 2 : 1), r, present_bits,
-                                                  a.center, n_f, tail_add, mean_scale, sWT, sChatT, sCbar, sG, res, dacc);
+            sink.row0 = row_base + 2 * it;
+            sink.two = two;
+            k3_step<T, NT, FP16B, true, false, 2, K3BasisSink<OUT>>(b2, x2, two ? 3u : 1u, (int64_t)0, (int64_t)(two ? 2 : 1), r,
+                                                                   present_bits, a.center, n_f, tail_add, mean_scale, sWT,
+                                                                   sChatT, sCbar, sG, res, dacc, K3NoiseSet<NT>(), sink);
             outp[e0 + i0] = res[0];
             if (two) outp[e0 + i1] = res[1];
         }
+        row_base += kept;
         // (the next step's first barrier separates these reads of s_x / s_idx from its writes)
     }
     cp_async_commit_wait_all();

@@ -430,8 +430,40 @@ int svdq_reconstruct_merge(int dtype, int n_tasks, int fp16_basis, int diag, int
     a.info_n = noise_info; a.W_n = noise_W; a.cbar_n = noise_cbar; a.gvec_n = noise_gvec; a.scal_n = noise_scal;
     a.noise_shrink = noise_shrink;
     a.diag_select = 0;
+    a.tile_row_off = nullptr; a.u_high = nullptr; a.u_low = nullptr; a.mean_out = nullptr;
     return finish(__func__, k3_launch(dtype, n_tasks, a, (int)n_tiles, fp16_basis != 0, diag != 0,
                                             (cudaStream_t)stream));
+}
+
+int svdq_reconstruct_merge_basis(int dtype, int n_tasks, int fp16_basis, int center, int64_t n_tiles, int tile_elems,
+                                 const void* const* tensors, const int64_t* numel, const int32_t* tile_param,
+                                 const int32_t* tile_local, const int64_t* pmask_off, const uint8_t* has_mask,
+                                 const uint32_t* packed, const int32_t* info, const float* W, const float* cbar,
+                                 const float* gvec, const float* scal, const float* chat, float* const* out,
+                                 float* diag_partials, const int64_t* tile_row_off, void* const* u_high,
+                                 void* const* u_low, float* const* mean, void* stream) {
+    REQUIRE(n_tasks >= 1 && n_tasks <= 8, "n_tasks must be in [1, 8] (use svdq_reconstruct_merge + svdq_write_basis above)");
+    REQUIRE(dtype >= 0 && dtype <= 2, "dtype");
+    REQUIRE(tile_elems > 0 && tile_elems % svdq::kStep == 0, "tile_elems must be a positive multiple of 1024");
+    REQUIRE(n_tiles >= 0 && n_tiles < (1ll << 31), "n_tiles");
+    if (n_tiles == 0) return 0;
+    REQUIRE(tensors && numel && tile_param && tile_local && has_mask && info && W && cbar && gvec && scal && chat && out &&
+            diag_partials && tile_row_off && u_high && u_low, "null pointer");
+    svdq::K3Args a;
+    a.tensors = tensors; a.numel = numel; a.tile_param = tile_param; a.tile_local = tile_local;
+    a.pmask_off = pmask_off; a.has_mask = has_mask; a.packed = packed; a.info = info; a.W = W; a.cbar = cbar;
+    a.gvec = gvec; a.scal = scal; a.chat = chat; a.out = out; a.diag = diag_partials; a.tile_elems = tile_elems;
+    a.center = center;
+    a.info_n = nullptr; a.W_n = nullptr; a.cbar_n = nullptr; a.gvec_n = nullptr; a.scal_n = nullptr; a.noise_shrink = 1.0f;
+    a.diag_select = 0;
+    a.tile_row_off = tile_row_off; a.u_high = u_high; a.u_low = u_low; a.mean_out = mean;
+    cudaError_t e;
+    switch (dtype) {
+        case svdq::kF32:  e = svdq::k3c_launch_dtype<svdq::kF32>(n_tasks, a, (int)n_tiles, fp16_basis != 0, (cudaStream_t)stream); break;
+        case svdq::kBF16: e = svdq::k3c_launch_dtype<svdq::kBF16>(n_tasks, a, (int)n_tiles, fp16_basis != 0, (cudaStream_t)stream); break;
+        default:          e = svdq::k3c_launch_dtype<svdq::kF16>(n_tasks, a, (int)n_tiles, fp16_basis != 0, (cudaStream_t)stream); break;
+    }
+    return finish(__func__, e);
 }
 
 int svdq_diag_finalize(int n_tasks, int64_t n_params, const float* diag_partials, const int64_t* tile_begin,

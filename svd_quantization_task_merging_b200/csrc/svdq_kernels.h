@@ -95,6 +95,13 @@ struct K3Args {
     // fused diagnostics, up to 8 tasks (k3c_merge_diag_compact): 0 = compact every tile; 2 = per tile, compaction only
     // where the combined mask keeps fewer than 55 % of the elements
     int diag_select;
+    // optional (k3c_merge_diag_compact only): write the artifact bases in the same pass -- U_high [Dm x k], U_low
+    // [Dm x (r-k)] (fp16 when the bases are stored in fp16, else fp32), mean [Dm], rows compacted to the masked
+    // elements (the layout of svdq_write_basis); tile_row_off from svdq_basis_offsets.  All null = off.
+    const int64_t* tile_row_off;
+    void* const* u_high;
+    void* const* u_low;
+    float* const* mean_out;
 };
 
 struct K3DiagArgs {

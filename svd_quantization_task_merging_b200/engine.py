@@ -759,8 +759,21 @@ class MergeJob:
                 solve(w_dev, order_dev)
             self._w_keep = (w_dev, order_dev)
             mark("k2")
+            fused = self._fused_basis_buffers()             # None unless artifacts + diagnostics of <= 8 tasks are wanted
             for g in self.groups.values():
                 t, tn = g.t, (g.tn or {})
+                if fused is not None:
+                    # the reference's default settings (diagnostics AND stored artifacts): pass 2 writes the bases too
+                    fb = fused[g.dtype]
+                    _native.call("svdq_basis_offsets", len(g.names), 0, te, _ptr(t["count"]), _ptr(t["tile_begin"]),
+                                 _ptr(t["numel"]), _ptr(fb["row_off"]), st)
+                    _native.call("svdq_reconstruct_merge_basis", _FLOAT_DTYPES[g.dtype], N, int(bool(cfg.svd_fp16)),
+                                 int(bool(cfg.svd_center)), g.n_tiles, te, _ptr(t["tptr"]), _ptr(t["numel"]),
+                                 _ptr(t["tile_param"]), _ptr(t["tile_local"]), _ptr(t["pm_off"]), _ptr(t["has_mask"]),
+                                 _ptr(t["packed"]), _ptr(t["info"]), _ptr(t["W"]), _ptr(t["cbar"]), _ptr(t["gvec"]),
+                                 _ptr(t["scal"]), _ptr(t["chat"]), _ptr(t["optr"]), _ptr(t["diag"]), _ptr(fb["row_off"]),
+                                 _ptr(fb["uh_d"]), _ptr(fb["ul_d"]), _ptr(fb["mn_d"]), st)
+                    continue
                 _native.call("svdq_reconstruct_merge", _FLOAT_DTYPES[g.dtype], N, int(bool(cfg.svd_fp16)),
                              int(self.want_diag), int(bool(cfg.svd_center)), g.n_tiles, te, _ptr(t["tptr"]),
                              _ptr(t["numel"]), _ptr(t["tile_param"]), _ptr(t["tile_local"]), _ptr(t["pm_off"]),
@@ -851,11 +864,59 @@ class MergeJob:
         return out
 
     # ------------------------------------------------------------------------------------------
+    def _fused_basis_buffers(self):
+        """Worst-case sized U_high / U_low / mean buffers for the fused write-out of pass 2 (svdq_reconstruct_merge_basis):
+        k, r and the masked row count of a parameter are only known on the device when pass 2 is launched, so every
+        parameter gets room for numel x N entries per block (views of the real size are cut after the fetch).
+        None when the fused path does not apply (then K5 materialises the bases in a pass of its own)."""
+        if not (self.materialize and self.want_diag and not self.wide and self.N <= 8 and not self.noise
+                and os.environ.get("SVDQ_FUSED_BASIS", "1") != "0"):
+            return None
+        if getattr(self, "_fused", None) is not None:
+            return self._fused
+        cfg, N = self.cfg, self.N
+        udt = torch.float16 if cfg.svd_fp16 else torch.float32
+        esz = 2 if cfg.svd_fp16 else 4
+        need = sum(2 * int(sum(g.numel)) * N * esz + 4 * int(sum(g.numel)) for g in self.groups.values())
+        free, _ = torch.cuda.mem_get_info(self.device)
+        if need > free // 3:
+            self._fused = None
+            self.materialize_fused_skipped = f"worst-case basis buffers ({need / 1e9:.1f} GB) do not fit"
+            return None
+        out = {}
+        for dt, g in self.groups.items():
+            numel = np.asarray(g.numel, np.int64)
+            al = 16 // esz
+            nh = (numel * N + al - 1) // al * al
+            nm = (numel + 3) // 4 * 4
+            oh = np.concatenate([[0], np.cumsum(nh)]).astype(np.int64)
+            om = np.concatenate([[0], np.cumsum(nm)]).astype(np.int64)
+            uh = torch.empty(max(int(oh[-1]), 1), dtype=udt, device=self.device)
+            ul = torch.empty(max(int(oh[-1]), 1), dtype=udt, device=self.device)
+            mn = torch.empty(max(int(om[-1]), 1), dtype=torch.float32, device=self.device) if cfg.svd_center else None
+            out[dt] = dict(uh=uh, ul=ul, mn=mn, oh=oh, ol=oh, om=om,
+                           uh_d=_dev((uh.data_ptr() + oh[:-1] * esz).astype(np.int64), self.device),
+                           ul_d=_dev((ul.data_ptr() + oh[:-1] * esz).astype(np.int64), self.device),
+                           mn_d=_dev((mn.data_ptr() + om[:-1] * 4).astype(np.int64), self.device) if mn is not None else None,
+                           row_off=torch.empty(max(g.n_tiles, 1), dtype=torch.int64, device=self.device))
+        self._fused = out
+        return out
+
     def _materialize_bases(self):
-        """K5: U_high / U_low / mean compacted to the masked rows, in the artifact dtype."""
+        """K5: U_high / U_low / mean compacted to the masked rows, in the artifact dtype (already written by pass 2
+        when the fused write-out applied)."""
         if self._bases_done:
             return
         fetched = self._fetch()
+        if getattr(self, "_fused", None) is not None:
+            self._basis_store = {}
+            for dt, fb in self._fused.items():
+                info, dm = fetched[dt]["info"], fetched[dt]["dm"].astype(np.int64)
+                self._basis_store[(dt, "masked")] = dict(
+                    uh=fb["uh"], ul=fb["ul"], mn=fb["mn"], oh=fb["oh"], ol=fb["ol"], om=fb["om"], dm=dm,
+                    r=info[:, 2].astype(np.int64), k=info[:, 3].astype(np.int64), ok=info[:, 0] == 0)
+            self._bases_done = True
+            return
         cfg, N, te = self.cfg, self.N, self.tile_elems
         st = _native.stream_ptr()
         udt = torch.float16 if cfg.svd_fp16 else torch.float32

@@ -309,3 +309,47 @@ def test_compacting_diag_pass_matches_plain_walk(cuda_device, monkeypatch, dtype
                         assert w != w, (mode, name, task, key)
                     else:
                         assert abs(w - v) <= 2e-5 * abs(v) + 1e-12, (mode, name, task, key, w, v)
+
+
+@pytest.mark.parametrize("dtype,fp16_bases", [(torch.float32, True), (torch.float32, False), (torch.bfloat16, True)])
+@pytest.mark.parametrize("n_tasks,strategy,mask_p,center", [(8, "intersection", 0.9, True), (5, "majority", 0.5, True),
+                                                            (8, "union", None, True), (3, "union", 0.3, False)])
+def test_fused_basis_write_out_equals_k5(cuda_device, monkeypatch, dtype, fp16_bases, n_tasks, strategy, mask_p, center):
+    """The reference's default settings (svd_eval_reconstruction AND svd_store_artifacts): pass 2 writes the artifact
+    bases itself (svdq_reconstruct_merge_basis: U_high / U_low / mean compacted to the masked rows) instead of a third
+    pass over the inputs (K5, svdq_write_basis).  Same bits in the bases, the merged model and the coefficients;
+    diagnostics equal to the round-off of the summation order."""
+    from svd_quantization_task_merging_b200.engine import MergeJob
+    tasks = synth.task_names(n_tasks)
+    base, fts = synth.make_checkpoints(SHAPES, tasks, family="parity", seed=53, dtype=dtype, device="cuda")
+    if n_tasks >= 3:
+        del fts[tasks[1]]["two"]
+    masks = synth.make_masks(SHAPES, tasks, mask_p, seed=54, device="cuda") if mask_p is not None else None
+    cfg = SVDHybridConfig(tasks=tasks, svd_energy_threshold=0.9, svd_mask_strategy=strategy, svd_center=center,
+                          svd_fp16=fp16_bases, svd_store_artifacts=True, svd_eval_reconstruction=True)
+    out = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("SVDQ_FUSED_BASIS", mode)
+        job = MergeJob(base, fts, masks, cfg, "cuda", diagnostics=True, materialize_bases=True).run()
+        assert (job._fused_basis_buffers() is not None) == (mode == "1")
+        res = job.results()
+        out[mode] = (job, res)
+    (ja, ra), (jb, rb) = out["1"], out["0"]
+    n_checked = 0
+    for name in rb["bases"]:
+        ba, bb = ra["bases"][name]["masked"], rb["bases"][name]["masked"]
+        assert ba["k"] == bb["k"] and ba["D"] == bb["D"]
+        for key in ("U_high", "U_low"):
+            assert ba[key].shape == bb[key].shape and ba[key].dtype == bb[key].dtype, (name, key)
+            bits = torch.int16 if ba[key].element_size() == 2 else torch.int32
+            assert torch.equal(ba[key].contiguous().view(bits), bb[key].contiguous().view(bits)), (name, key)
+        if bb.get("mean") is not None:
+            assert torch.equal(ba["mean"].view(torch.int32), bb["mean"].view(torch.int32)), name
+        else:
+            assert ba.get("mean") is None
+        n_checked += 1
+    assert n_checked >= 4
+    for k in rb["merged_state_dict"]:
+        a_, b_ = ra["merged_state_dict"][k], rb["merged_state_dict"][k]
+        bits = torch.int16 if a_.element_size() == 2 else torch.int32
+        assert torch.equal(a_.view(bits), b_.view(bits)), k
