@@ -244,6 +244,7 @@ int svdq_reconstruct_merge(int dtype, int n_tasks, int fp16_basis, int diag, int
  * compacted to the elements inside the combined mask, exactly what svdq_write_basis would store (construct_basis
  * src/svd_hybrid/basis.py:363-364,398-407 after apply_mask_to_tensor src/svd_hybrid/mask_loader.py:675-679) -- so the
  * inputs are not read a third time.  tile_row_off from svdq_basis_offsets(region = 0).  Up to 8 tasks, no noise region.
+ * chat and diag_partials both NULL = no diagnostics (svd_store_artifacts alone).
  */
 int svdq_reconstruct_merge_basis(int dtype, int n_tasks, int fp16_basis, int center, int64_t n_tiles, int tile_elems,
                                  const void* const* tensors, const int64_t* numel, const int32_t* tile_param,

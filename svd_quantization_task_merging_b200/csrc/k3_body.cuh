@@ -136,7 +136,7 @@ __device__ __forceinline__ void k3_step(const float (&b)[VEC], float (&x)[NT][VE
 #pragma unroll
             for (int h = 0; h < kH; ++h) rec2[t][h] = make_float2(0.0f, 0.0f);
     }
-    if (FP16B || DIAG) {
+    if (FP16B || DIAG || SINK::on) {
         // r <= NT columns, unrolled
         auto column = [&](const int j) {
             float2 u2[kH];

@@ -19,6 +19,7 @@
 #include <type_traits>
 
 #include "k3_body.cuh"
+#include "copy_out.cuh"
 
 #ifndef SVDQ_DTYPE
 #define SVDQ_DTYPE 0
@@ -65,36 +66,32 @@ template <> struct StagedQuad<__half> {
     }
 };
 
-// writes the basis rows of the thread's two compacted elements straight into the artifact arrays (rows row0, row0 + 1:
-// consecutive threads hold consecutive rows, so the stores of a warp fall into a few adjacent lines)
+// drops the basis rows of the thread's two compacted elements into the shared-memory image of the step's slice of
+// U_high / U_low / mean (rows lr, lr + 1 of the step); the CTA copies the slices out with 16-byte stores afterwards
 template <typename OUT> struct K3BasisSink {
     static constexpr bool on = true;
-    OUT* uh; OUT* ul; float* mn;
-    int64_t row0;
-    int k, nlow;
+    OUT* s_h; OUT* s_l; float* s_m;         // images, already re-based to the step (null s_h: off)
+    int lr, k, nlow;
     bool two;
-    static __device__ __forceinline__ OUT cvt(float v) {
-        if constexpr (sizeof(OUT) == 2) return __float2half_rn(v); else return v;
-    }
     __device__ __forceinline__ void col(int j, float2 u) const {
-        if (uh == nullptr) return;
-        if (j < k) { uh[row0 * k + j] = cvt(u.x); if (two) uh[(row0 + 1) * k + j] = cvt(u.y); }
-        else { ul[row0 * nlow + (j - k)] = cvt(u.x); if (two) ul[(row0 + 1) * nlow + (j - k)] = cvt(u.y); }
+        if (s_h == nullptr) return;
+        if (j < k) { s_h[lr * k + j] = OutCvt<OUT>::cvt(u.x); if (two) s_h[(lr + 1) * k + j] = OutCvt<OUT>::cvt(u.y); }
+        else { s_l[lr * nlow + (j - k)] = OutCvt<OUT>::cvt(u.x); if (two) s_l[(lr + 1) * nlow + (j - k)] = OutCvt<OUT>::cvt(u.y); }
     }
     __device__ __forceinline__ void mean2(float m0, float m1) const {
-        if (mn == nullptr) return;
-        mn[row0] = m0;
-        if (two) mn[row0 + 1] = m1;
+        if (s_m == nullptr) return;
+        s_m[lr] = m0;
+        if (two) s_m[lr + 1] = m1;
     }
 };
 
-template <typename T, int NT, bool FP16B>
+template <typename T, int NT, bool FP16B, bool DIAG, bool BASIS>
 __global__ void __launch_bounds__(kBlock, 2) k3c_merge_diag_compact(const K3Args a) {
     constexpr int NTP = (NT + 3) & ~3;
-    constexpr int NR = kDiagRows * NT;
+    constexpr int NR = DIAG ? kDiagRows * NT : 1;
     constexpr int ES = (int)sizeof(T);
     __shared__ __align__(16) float sWT[NT][NTP];        // sWT[j][t] = W[t][j]
-    __shared__ __align__(16) float sChatT[NT][NTP];     // sChatT[j][t] = chat[t][j]
+    __shared__ __align__(16) float sChatT[DIAG ? NT : 1][NTP];     // sChatT[j][t] = chat[t][j]
     __shared__ float sCbar[NT], sG[NT];
     __shared__ const void* s_ptr[NT + 1];
     __shared__ uint32_t s_wtot[kBlock / 32];
@@ -114,13 +111,15 @@ __global__ void __launch_bounds__(kBlock, 2) k3c_merge_diag_compact(const K3Args
     const int64_t stop = min(start + (int64_t)a.tile_elems, numel);
     const int status = a.info[(int64_t)p * 8 + 0];
     const int n_active = a.info[(int64_t)p * 8 + 1];
-    const int r = a.info[(int64_t)p * 8 + 2];           // diagnostics walk all r columns (NaN coefficients show up as in the reference)
+    // with diagnostics or a basis write-out all r columns are walked (NaN coefficients show up as in the reference;
+    // the artifacts hold all r columns), otherwise only the r_eff that are not numerically null
+    const int r = a.info[(int64_t)p * 8 + ((DIAG || BASIS) ? 2 : 4)];
     const float tail_add = a.scal[(int64_t)p * 4 + 1];
     const float mean_scale = a.scal[(int64_t)p * 4 + 2];
     const bool has_mask = a.has_mask[p] != 0;
     // automatic mode (diag_select == 2): per tile -- compaction where the mask keeps fewer than 55 % of the elements, the
     // plain two-elements-per-thread walk (the loop of k3_reconstruct_merge) elsewhere and for parameters without a basis
-    const bool write_basis = a.u_high != nullptr;         // every solved tile is compacted then (rows = compacted slots)
+    constexpr bool write_basis = BASIS;                   // every solved tile is compacted then (rows = compacted slots)
     const bool compact = a.diag_select != 2 || (write_basis && status == kSolved) ||
                          (status == kSolved && k3_tile_is_sparse(has_mask ? a.packed + a.pmask_off[p] : nullptr, start, stop, numel));
 
@@ -128,7 +127,7 @@ __global__ void __launch_bounds__(kBlock, 2) k3c_merge_diag_compact(const K3Args
     for (int i = tid; i < NT * NTP; i += kBlock) {
         const int j = i / NTP, t = i % NTP;
         sWT[j][t] = (t < NT) ? a.W[(int64_t)p * NT * NT + t * NT + j] : 0.0f;
-        sChatT[j][t] = (t < NT) ? a.chat[(int64_t)p * NT * NT + t * NT + j] : 0.0f;
+        if (DIAG) sChatT[j][t] = (t < NT) ? a.chat[(int64_t)p * NT * NT + t * NT + j] : 0.0f;
     }
     if (tid < NT) { sCbar[tid] = a.cbar[(int64_t)p * NT + tid]; sG[tid] = a.gvec[(int64_t)p * NT + tid]; }
     __syncthreads();
@@ -174,7 +173,7 @@ __global__ void __launch_bounds__(kBlock, 2) k3c_merge_diag_compact(const K3Args
 #pragma unroll
                 for (int t = 0; t < NT; ++t) ElemPair<T>::load(s_ptr[t + 1], e, full, numel, x[t]);
                 const uint32_t pword = has_mask ? __ldg(packed + (e >> 5)) : 0xffffffffu;
-                k3_step<T, NT, FP16B, true, false, 2>(b, x, pword, e, numel, r, present_bits, a.center, n_f, tail_add, mean_scale,
+                k3_step<T, NT, FP16B, DIAG, false, 2>(b, x, pword, e, numel, r, present_bits, a.center, n_f, tail_add, mean_scale,
                                                       sWT, sChatT, sCbar, sG, res, dacc);
             }
             if (full) stg_stream_f2(outp + e, make_float2(res[0], res[1]));
@@ -182,10 +181,15 @@ __global__ void __launch_bounds__(kBlock, 2) k3c_merge_diag_compact(const K3Args
         }
     } else {
     using OUT = typename std::conditional<FP16B, __half, float>::type;
+    constexpr int V = 16 / (int)sizeof(OUT);
+    OUT* uh_out = write_basis ? reinterpret_cast<OUT*>(a.u_high[p]) : nullptr;
+    OUT* ul_out = write_basis ? reinterpret_cast<OUT*>(a.u_low[p]) : nullptr;
+    float* mean_out = (write_basis && a.mean_out) ? a.mean_out[p] : nullptr;
+    // image of the step's artifact slices behind the staging area (allocated only when the bases are written)
+    OUT* s_u = reinterpret_cast<OUT*>(s_raw + (size_t)(NT + 1) * kCStep * ES);
+    float* s_mean = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(s_u) +
+                                             ((size_t)(kCStep * NT + 3 * V) * sizeof(OUT) + 15) / 16 * 16);
     K3BasisSink<OUT> sink;
-    sink.uh = write_basis ? reinterpret_cast<OUT*>(a.u_high[p]) : nullptr;
-    sink.ul = write_basis ? reinterpret_cast<OUT*>(a.u_low[p]) : nullptr;
-    sink.mn = (write_basis && a.mean_out) ? a.mean_out[p] : nullptr;
     sink.k = a.info[(int64_t)p * 8 + 3];
     sink.nlow = r - sink.k;
     int64_t row_base = write_basis ? a.tile_row_off[tile] : 0;
@@ -263,6 +267,10 @@ __global__ void __launch_bounds__(kBlock, 2) k3c_merge_diag_compact(const K3Args
         if (!solved) continue;                              // uniform: parameter without a basis, merged = base
         // ---- B: the kept elements, two at a time, through the unchanged per-element arithmetic ----------------------
         const int items = (int)(kept + 1) >> 1;
+        const int64_t gh = row_base * sink.k, gl = row_base * sink.nlow, gm = row_base;
+        sink.s_h = write_basis ? s_u + (gh % V) : nullptr;
+        sink.s_l = s_u + ((gh % V) + (int64_t)kept * sink.k + V - 1) / V * V + (gl % V);
+        sink.s_m = mean_out ? s_mean + (gm % 4) : nullptr;
         for (int it = tid; it < items; it += kBlock) {
             const bool two = 2 * it + 1 < (int)kept;
             float b2[2], x2[NT][2], res[2];
@@ -275,20 +283,32 @@ __global__ void __launch_bounds__(kBlock, 2) k3c_merge_diag_compact(const K3Args
             }
             const uint32_t i0 = s_idx[2 * it], i1 = two ? s_idx[2 * it + 1] : 0u;
             // both elements are inside the mask and inside the tensor: pword = 0b11 (0b01), "numel" = their count
-            sink.row0 = row_base + 2 * it;
+            sink.lr = 2 * it;
             sink.two = two;
-            k3_step<T, NT, FP16B, true, false, 2, K3BasisSink<OUT>>(b2, x2, two ? 3u : 1u, (int64_t)0, (int64_t)(two ? 2 : 1), r,
-                                                                   present_bits, a.center, n_f, tail_add, mean_scale, sWT,
-                                                                   sChatT, sCbar, sG, res, dacc, K3NoiseSet<NT>(), sink);
+            if constexpr (BASIS)
+                k3_step<T, NT, FP16B, DIAG, false, 2, K3BasisSink<OUT>>(b2, x2, two ? 3u : 1u, (int64_t)0, (int64_t)(two ? 2 : 1), r,
+                                                                       present_bits, a.center, n_f, tail_add, mean_scale, sWT,
+                                                                       sChatT, sCbar, sG, res, dacc, K3NoiseSet<NT>(), sink);
+            else
+                k3_step<T, NT, FP16B, DIAG, false, 2>(b2, x2, two ? 3u : 1u, (int64_t)0, (int64_t)(two ? 2 : 1), r, present_bits,
+                                                      a.center, n_f, tail_add, mean_scale, sWT, sChatT, sCbar, sG, res, dacc);
             outp[e0 + i0] = res[0];
             if (two) outp[e0 + i1] = res[1];
         }
-        row_base += kept;
+        if (write_basis) {
+            __syncthreads();                                // the step's image is complete
+            k5_copy_out<OUT>(uh_out, sink.s_h, gh, (int)kept * sink.k, tid);
+            k5_copy_out<OUT>(ul_out, sink.s_l, gl, (int)kept * sink.nlow, tid);
+            if (mean_out) k5_copy_out<float>(mean_out, sink.s_m, gm, (int)kept, tid);
+            row_base += kept;
+            // (the image is rewritten two barriers from here, in phase B of the next step)
+        }
         // (the next step's first barrier separates these reads of s_x / s_idx from its writes)
     }
     cp_async_commit_wait_all();
     }
 
+    if (!DIAG) return;
     // ---- CTA reduction of the 4*NT diagnostic rows: sums for rows < 3*NT, max for the rest --------------------------
     __syncthreads();
     constexpr int kRows = 16;
@@ -323,32 +343,40 @@ __global__ void __launch_bounds__(kBlock, 2) k3c_merge_diag_compact(const K3Args
     }
 }
 
-template <typename T, int NT>
+template <typename T, int NT, bool DIAG, bool BASIS>
 static cudaError_t launch_c(const K3Args& a, int n_tiles, bool fp16b, cudaStream_t st) {
     if (n_tiles <= 0) return cudaSuccess;
     constexpr size_t kCompact = (size_t)(NT + 1) * kCStep * 4 + kCStep * 2 + (size_t)(NT + 1) * kCStep * sizeof(T),
                      kRed = 16 * (kBlock + 1) * 4;
-    constexpr size_t dsm = kCompact > kRed ? kCompact : kRed;      // the reduction scratch reuses the compaction buffer
+    // + the image of a step's artifact slices when the bases are written (U entries of NT columns, then the means)
+    const size_t esz = fp16b ? 2 : 4, vv = 16 / esz;
+    const size_t image = BASIS ? ((kCStep * NT + 3 * vv) * esz + 15) / 16 * 16 + (kCStep + 4) * 4 : 0;
+    const size_t dsm = (kCompact > kRed ? kCompact : kRed) + image;      // the reduction scratch reuses the compaction buffer
     cudaError_t e;
     if (fp16b) {
-        e = cudaFuncSetAttribute(k3c_merge_diag_compact<T, NT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm);
+        e = cudaFuncSetAttribute(k3c_merge_diag_compact<T, NT, true, DIAG, BASIS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm);
         if (e != cudaSuccess) return e;
-        k3c_merge_diag_compact<T, NT, true><<<n_tiles, kBlock, dsm, st>>>(a);
+        k3c_merge_diag_compact<T, NT, true, DIAG, BASIS><<<n_tiles, kBlock, dsm, st>>>(a);
     } else {
-        e = cudaFuncSetAttribute(k3c_merge_diag_compact<T, NT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm);
+        e = cudaFuncSetAttribute(k3c_merge_diag_compact<T, NT, false, DIAG, BASIS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm);
         if (e != cudaSuccess) return e;
-        k3c_merge_diag_compact<T, NT, false><<<n_tiles, kBlock, dsm, st>>>(a);
+        k3c_merge_diag_compact<T, NT, false, DIAG, BASIS><<<n_tiles, kBlock, dsm, st>>>(a);
     }
     return cudaGetLastError();
 }
 
-// compacting pass 2 with fused diagnostics: up to 8 tasks, no noise region; cudaErrorNotSupported otherwise
+// compacting pass 2 with fused diagnostics and / or the basis write-out: up to 8 tasks, no noise region;
+// cudaErrorNotSupported otherwise
 template <>
 cudaError_t k3c_launch_dtype<SVDQ_DTYPE>(int nt, const K3Args& a, int n_tiles, bool fp16b, cudaStream_t st) {
     using T = DTypeOf<SVDQ_DTYPE>::type;
-    if (a.info_n != nullptr || a.diag == nullptr || a.chat == nullptr || a.tile_elems % kCStep != 0) return cudaErrorNotSupported;
+    if (a.info_n != nullptr || a.tile_elems % kCStep != 0) return cudaErrorNotSupported;
+    const bool diag = a.diag != nullptr && a.chat != nullptr;
+    const bool basis = a.u_high != nullptr;
+    if (!diag && !basis) return cudaErrorNotSupported;                     // without diagnostics only the basis write-out uses it
     switch (nt) {
-#define SVDQ_CASE(N) case N: return launch_c<T, N>(a, n_tiles, fp16b, st);
+#define SVDQ_CASE(N) case N: return !basis ? launch_c<T, N, true, false>(a, n_tiles, fp16b, st) \
+                                   : diag ? launch_c<T, N, true, true>(a, n_tiles, fp16b, st) : launch_c<T, N, false, true>(a, n_tiles, fp16b, st);
         SVDQ_CASE(1) SVDQ_CASE(2) SVDQ_CASE(3) SVDQ_CASE(4) SVDQ_CASE(5) SVDQ_CASE(6) SVDQ_CASE(7) SVDQ_CASE(8)
 #undef SVDQ_CASE
         default: return cudaErrorNotSupported;

@@ -11,6 +11,7 @@
 //                     (src/svd_hybrid/mask_loader.py:412-485) -> torch.bool
 //   k_unpack_mask     packed combined mask -> torch.bool
 #include "svdq_kernels.h"
+#include "copy_out.cuh"
 
 #ifndef SVDQ_DTYPE
 #define SVDQ_DTYPE 0
@@ -43,25 +44,6 @@ __global__ void __launch_bounds__(32) k5_tile_offsets(const uint32_t* count, con
 // U_low / mean -- the kept rows of a step are consecutive rows of the artifacts -- and then copies the three
 // slices out with 16-byte coalesced stores (the smem image starts at the same offset modulo 16 bytes as the
 // global slice, so head / tail handling is a few scalar elements).
-template <typename OUT> struct OutCvt;
-template <> struct OutCvt<__half> { static __device__ __forceinline__ __half cvt(float v) { return __float2half_rn(v); } };
-template <> struct OutCvt<float> { static __device__ __forceinline__ float cvt(float v) { return v; } };
-
-template <typename OUT>
-__device__ __forceinline__ void k5_copy_out(OUT* __restrict__ dst, const OUT* __restrict__ src, int64_t g0, int n,
-                                            int tid) {
-    // dst + g0 .. + n  <-  src[0 .. n);  src is placed so that (src address) == (dst + g0 address) mod 16
-    constexpr int V = 16 / (int)sizeof(OUT);
-    const int head = min(n, (int)((V - (g0 % V)) % V));
-    if (tid < head) dst[g0 + tid] = src[tid];
-    const int nvec = (n - head) / V;
-    const uint4* s4 = reinterpret_cast<const uint4*>(src + head);
-    uint4* d4 = reinterpret_cast<uint4*>(dst + g0 + head);
-    for (int i = tid; i < nvec; i += kBlock) d4[i] = s4[i];
-    const int done = head + nvec * V;
-    if (tid < n - done) dst[g0 + done + tid] = src[done + tid];
-}
-
 // NT bounds the unrolled task loops (n = a.n_tasks <= NT tasks are real); VEC elements per thread and step: 4 up to
 // 16 tasks, 2 above (the task values of a thread's elements stay in registers).
 template <typename T, int NT, typename OUT, int VEC>

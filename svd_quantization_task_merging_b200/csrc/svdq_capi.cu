@@ -447,8 +447,9 @@ int svdq_reconstruct_merge_basis(int dtype, int n_tasks, int fp16_basis, int cen
     REQUIRE(tile_elems > 0 && tile_elems % svdq::kStep == 0, "tile_elems must be a positive multiple of 1024");
     REQUIRE(n_tiles >= 0 && n_tiles < (1ll << 31), "n_tiles");
     if (n_tiles == 0) return 0;
-    REQUIRE(tensors && numel && tile_param && tile_local && has_mask && info && W && cbar && gvec && scal && chat && out &&
-            diag_partials && tile_row_off && u_high && u_low, "null pointer");
+    REQUIRE(tensors && numel && tile_param && tile_local && has_mask && info && W && cbar && gvec && scal && out &&
+            tile_row_off && u_high && u_low, "null pointer");
+    REQUIRE((chat != nullptr) == (diag_partials != nullptr), "chat and diag_partials go together (both NULL = no diagnostics)");
     svdq::K3Args a;
     a.tensors = tensors; a.numel = numel; a.tile_param = tile_param; a.tile_local = tile_local;
     a.pmask_off = pmask_off; a.has_mask = has_mask; a.packed = packed; a.info = info; a.W = W; a.cbar = cbar;

@@ -759,7 +759,7 @@ class MergeJob:
                 solve(w_dev, order_dev)
             self._w_keep = (w_dev, order_dev)
             mark("k2")
-            fused = self._fused_basis_buffers()             # None unless artifacts + diagnostics of <= 8 tasks are wanted
+            fused = self._fused_basis_buffers()             # None unless artifacts of <= 8 tasks are wanted
             for g in self.groups.values():
                 t, tn = g.t, (g.tn or {})
                 if fused is not None:
@@ -771,7 +771,8 @@ class MergeJob:
                                  int(bool(cfg.svd_center)), g.n_tiles, te, _ptr(t["tptr"]), _ptr(t["numel"]),
                                  _ptr(t["tile_param"]), _ptr(t["tile_local"]), _ptr(t["pm_off"]), _ptr(t["has_mask"]),
                                  _ptr(t["packed"]), _ptr(t["info"]), _ptr(t["W"]), _ptr(t["cbar"]), _ptr(t["gvec"]),
-                                 _ptr(t["scal"]), _ptr(t["chat"]), _ptr(t["optr"]), _ptr(t["diag"]), _ptr(fb["row_off"]),
+                                 _ptr(t["scal"]), _ptr(t["chat"]) if self.want_diag else None, _ptr(t["optr"]),
+                                 _ptr(t["diag"]) if self.want_diag else None, _ptr(fb["row_off"]),
                                  _ptr(fb["uh_d"]), _ptr(fb["ul_d"]), _ptr(fb["mn_d"]), st)
                     continue
                 _native.call("svdq_reconstruct_merge", _FLOAT_DTYPES[g.dtype], N, int(bool(cfg.svd_fp16)),
@@ -869,7 +870,7 @@ class MergeJob:
         k, r and the masked row count of a parameter are only known on the device when pass 2 is launched, so every
         parameter gets room for numel x N entries per block (views of the real size are cut after the fetch).
         None when the fused path does not apply (then K5 materialises the bases in a pass of its own)."""
-        if not (self.materialize and self.want_diag and not self.wide and self.N <= 8 and not self.noise
+        if not (self.materialize and not self.wide and self.N <= 8 and not self.noise
                 and os.environ.get("SVDQ_FUSED_BASIS", "1") != "0"):
             return None
         if getattr(self, "_fused", None) is not None:
