@@ -40,7 +40,7 @@ def _case(rng):
     return n, shapes, mask_p, kw, rng.randint(0, 10 ** 6)
 
 
-@pytest.mark.parametrize("block", range(4))
+@pytest.mark.parametrize("block", range(8))
 def test_random_configurations_against_oracle(cuda_device, block):
     failures = []
     for it in range(15):
