@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define SVDQ_ABI_VERSION 6   /* 6: svdq_reconstruct_merge_basis; 5: svdq_mask_tile_counts, svdq_reload_merge; 4: svdq_host_kmeans, per-cluster svdq_param_average; 3: svdq_tv_mask_gram_bits, svdq_host_pack_mask */
+#define SVDQ_ABI_VERSION 7   /* 7: K14 operators (svdq_basis_project/expand, svdq_mask_offsets/select/scatter); 6: svdq_reconstruct_merge_basis; 5: svdq_mask_tile_counts, svdq_reload_merge; 4: svdq_host_kmeans, per-cluster svdq_param_average; 3: svdq_tv_mask_gram_bits, svdq_host_pack_mask */
 #define SVDQ_MAX_STREAM_TASKS 16
 #define SVDQ_MAX_TASKS 32
 #define SVDQ_MAX_STAGES 8
@@ -327,6 +327,34 @@ int svdq_absmax_quantize(const float* x, int64_t n, int bits, void* q, int code_
  */
 int svdq_combine_masks(const uint8_t* const* masks, int n_masks, int64_t n, int strategy, uint8_t* out, void* stream);
 int svdq_unpack_mask(const uint32_t* packed, int64_t n, uint8_t* out, void* stream);
+
+/*
+ * K14 -- the operator-by-operator API of the artifact tools (fine-grained mirrors of the reference functions).
+ * svdq_basis_project : c[cols] = U^T (delta - mean), U = rows x cols (fp16 or fp32, row-major, leading dimension ld),
+ *                      cols <= 32 per call; project_to_basis (src/svd_hybrid/compress.py:6-21) with the centring of
+ *                      compress_single_task (:24-56; mean may be NULL).  Fixed-order reduction (fp64 above the
+ *                      per-thread partial sums).  scratch: svdq_project_scratch_bytes() bytes.
+ * svdq_basis_expand  : out[rows] = scale * (U_high c_high + U_low c_low + mean); reconstruct_from_coefficients
+ *                      (src/svd_hybrid/merge.py:144-194); n_low may be 0, mean may be NULL.
+ * svdq_mask_offsets  : chunk_off[i] = number of kept elements before chunk i (chunks of svdq_select_chunk_elems()
+ *                      elements), chunk_off[n_chunks] = total; kept(i) = (mask[i] != 0) != invert.
+ * svdq_mask_select   : out = x.flatten()[mask] in ascending element order (apply_mask_to_tensor /
+ *                      get_unmasked_portion, src/svd_hybrid/mask_loader.py:665-709); elem_bytes in {1, 2, 4, 8}.
+ * svdq_mask_scatter  : the inverse, out[i] = values[rank of i among the kept elements]; other elements of out are left
+ *                      as they are (reconstruct_from_masked, src/svd_hybrid/mask_loader.py:712-763).
+ */
+size_t svdq_project_scratch_bytes(void);
+int svdq_select_chunk_elems(void);
+int svdq_basis_project(int basis_fp16, const void* u, int64_t ld, int cols, int64_t rows, const float* delta,
+                       const float* mean, float* c, void* scratch, void* stream);
+int svdq_basis_expand(int basis_fp16, const void* u_high, int64_t ld_high, int k, const void* u_low, int64_t ld_low,
+                      int n_low, int64_t rows, const float* c_high, const float* c_low, const float* mean, float scale,
+                      float* out, void* stream);
+int svdq_mask_offsets(const uint8_t* mask, int64_t n, int invert, int64_t* chunk_off, void* stream);
+int svdq_mask_select(const void* x, int elem_bytes, const uint8_t* mask, int64_t n, int invert, const int64_t* chunk_off,
+                     void* out, void* stream);
+int svdq_mask_scatter(const void* values, int elem_bytes, const uint8_t* mask, int64_t n, int invert,
+                      const int64_t* chunk_off, void* out, void* stream);
 
 #ifdef __cplusplus
 }

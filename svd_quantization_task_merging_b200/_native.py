@@ -12,7 +12,7 @@ from typing import Optional
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libsvdq.so")
-ABI_VERSION = 6
+ABI_VERSION = 7
 
 DTYPE_CODE = {"float32": 0, "bfloat16": 1, "float16": 2}
 STRATEGY_CODE = {"union": 0, "intersection": 1, "majority": 2}
@@ -49,6 +49,13 @@ _SIGNATURES = {
     "svdq_absmax_quantize": (C.c_int, [_vp, _i64, _i32, _vp, _i32] + [_vp] * 3),
     "svdq_combine_masks": (C.c_int, [_vp, _i32, _i64, _i32, _vp, _vp]),
     "svdq_unpack_mask": (C.c_int, [_vp, _i64, _vp, _vp]),
+    "svdq_project_scratch_bytes": (C.c_size_t, []),
+    "svdq_select_chunk_elems": (C.c_int, []),
+    "svdq_basis_project": (C.c_int, [_i32, _vp, _i64, _i32, _i64] + [_vp] * 5),
+    "svdq_basis_expand": (C.c_int, [_i32, _vp, _i64, _i32, _vp, _i64, _i32, _i64, _vp, _vp, _vp, _f32, _vp, _vp]),
+    "svdq_mask_offsets": (C.c_int, [_vp, _i64, _i32, _vp, _vp]),
+    "svdq_mask_select": (C.c_int, [_vp, _i32, _vp, _i64, _i32, _vp, _vp, _vp]),
+    "svdq_mask_scatter": (C.c_int, [_vp, _i32, _vp, _i64, _i32, _vp, _vp, _vp]),
 }
 
 EXPORTS = tuple(_SIGNATURES.keys())

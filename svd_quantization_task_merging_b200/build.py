@@ -38,7 +38,7 @@ UNITS: List[Tuple[str, object]] = (
     + [("k9_gram_tc.cu", d) for d in (0, 1, 2)]
     + [("k10_merge_tc.cu", d) for d in (0, 1, 2)]
     + [("k12_gram_wide_tc.cu", 0), ("k13_merge_wide_tc.cu", 0)]
-    + [("k2_param_solve.cu", None), ("k11_reload_merge.cu", None), ("k4_rtvq_large.cu", None), ("svdq_capi.cu", None), ("host_kmeans.cpp", None), ("host_pack.cpp", None)]
+    + [("k2_param_solve.cu", None), ("k11_reload_merge.cu", None), ("k14_operators.cu", None), ("k4_rtvq_large.cu", None), ("svdq_capi.cu", None), ("host_kmeans.cpp", None), ("host_pack.cpp", None)]
 )
 HEADERS = ["svdq_common.cuh", "svdq_kernels.h", "k2_core.h", "k3_body.cuh", "stage_pipe.cuh", os.path.join("..", "..", "include", "svdq.h")]
 

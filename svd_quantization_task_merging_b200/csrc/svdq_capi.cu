@@ -600,4 +600,54 @@ int svdq_unpack_mask(const uint32_t* packed, int64_t n, uint8_t* out, void* stre
     return finish(__func__, svdq::unpack_mask_launch(packed, n, out, (cudaStream_t)stream));
 }
 
+size_t svdq_project_scratch_bytes(void) { return svdq::k14_project_scratch_bytes(); }
+int svdq_select_chunk_elems(void) { return svdq::k14_select_chunk(); }
+
+int svdq_basis_project(int basis_fp16, const void* u, int64_t ld, int cols, int64_t rows, const float* delta,
+                       const float* mean, float* c, void* scratch, void* stream) {
+    REQUIRE(cols >= 1 && cols <= 32, "cols must be 1..32 (call once per block of 32 columns)");
+    REQUIRE(rows >= 0 && ld >= cols, "rows / ld");
+    REQUIRE(c && scratch, "null pointer");
+    REQUIRE(rows == 0 || (u && delta), "null pointer");
+    return finish(__func__, svdq::k14_project_launch(basis_fp16 != 0, u, ld, cols, rows, delta, mean, c, scratch,
+                                                     (cudaStream_t)stream));
+}
+
+int svdq_basis_expand(int basis_fp16, const void* u_high, int64_t ld_high, int k, const void* u_low, int64_t ld_low,
+                      int n_low, int64_t rows, const float* c_high, const float* c_low, const float* mean, float scale,
+                      float* out, void* stream) {
+    REQUIRE(k >= 0 && n_low >= 0 && k + n_low <= 8192, "column counts");
+    REQUIRE(rows >= 0, "rows");
+    if (rows == 0) return 0;
+    REQUIRE(out, "null pointer");
+    REQUIRE(k == 0 || (u_high && c_high && ld_high >= k), "high block");
+    REQUIRE(n_low == 0 || (u_low && c_low && ld_low >= n_low), "low block");
+    return finish(__func__, svdq::k14_expand_launch(basis_fp16 != 0, u_high, ld_high, k, u_low, ld_low, n_low, rows,
+                                                    c_high, c_low, mean, scale, out, (cudaStream_t)stream));
+}
+
+int svdq_mask_offsets(const uint8_t* mask, int64_t n, int invert, int64_t* chunk_off, void* stream) {
+    REQUIRE(n >= 0 && chunk_off, "n / chunk_off");
+    REQUIRE(n == 0 || mask, "null pointer");
+    return finish(__func__, svdq::k14_mask_offsets_launch(mask, n, invert != 0, chunk_off, (cudaStream_t)stream));
+}
+
+int svdq_mask_select(const void* x, int elem_bytes, const uint8_t* mask, int64_t n, int invert, const int64_t* chunk_off,
+                     void* out, void* stream) {
+    REQUIRE(n >= 0, "n");
+    if (n == 0) return 0;
+    REQUIRE(x && mask && chunk_off && out, "null pointer");
+    return finish(__func__, svdq::k14_select_launch(false, elem_bytes, x, mask, n, invert != 0, chunk_off, out,
+                                                    (cudaStream_t)stream));
+}
+
+int svdq_mask_scatter(const void* values, int elem_bytes, const uint8_t* mask, int64_t n, int invert,
+                      const int64_t* chunk_off, void* out, void* stream) {
+    REQUIRE(n >= 0, "n");
+    if (n == 0) return 0;
+    REQUIRE(values && mask && chunk_off && out, "null pointer");
+    return finish(__func__, svdq::k14_select_launch(true, elem_bytes, values, mask, n, invert != 0, chunk_off, out,
+                                                    (cudaStream_t)stream));
+}
+
 }  // extern "C"

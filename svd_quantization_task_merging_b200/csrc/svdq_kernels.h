@@ -244,6 +244,17 @@ cudaError_t k4_absmax_launch(const float* x, int64_t n, int bits, void* q, int c
 cudaError_t combine_masks_launch(const uint8_t* const* masks, int n_masks, int64_t n, int strategy, uint8_t* out,
                                  cudaStream_t st);
 cudaError_t unpack_mask_launch(const uint32_t* packed, int64_t n, uint8_t* out, cudaStream_t st);
+// K14: the operator-by-operator API (k14_operators.cu)
+size_t k14_project_scratch_bytes();
+int k14_select_chunk();
+cudaError_t k14_project_launch(bool fp16, const void* U, int64_t ld, int cols, int64_t rows, const float* delta,
+                               const float* mean, float* c, void* scratch, cudaStream_t st);
+cudaError_t k14_expand_launch(bool fp16, const void* Uh, int64_t ldh, int k, const void* Ul, int64_t ldl, int nl,
+                              int64_t rows, const float* ch, const float* cl, const float* mean, float scale,
+                              float* out, cudaStream_t st);
+cudaError_t k14_mask_offsets_launch(const uint8_t* mask, int64_t n, int invert, int64_t* chunk_off, cudaStream_t st);
+cudaError_t k14_select_launch(bool scatter, int elem_bytes, const void* src, const uint8_t* mask, int64_t n, int invert,
+                              const int64_t* chunk_off, void* dst, cudaStream_t st);
 
 template <int DT> struct DTypeOf;
 template <> struct DTypeOf<kF32> { using type = float; };

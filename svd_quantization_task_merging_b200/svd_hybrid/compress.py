@@ -2,34 +2,27 @@
 
 Fine-grained operator API kept for parity tests and the artifact tools; ``compress_all_parameters``
 on whole state dicts is served by the fused engine (closed-form coefficients in K2).  The explicit
-projections here are plain tall-skinny matrix-vector products executed on the GPU."""
+projections here are tall-skinny matrix-vector products run by K14 (csrc/k14_operators.cu) on the device."""
 from typing import Dict, Optional, Tuple
 
 import torch
 
-from .. import _native
+from . import _ops
 from .rtvq import RTVQQuantizer
 
 
-def _gpu(t: torch.Tensor) -> torch.Tensor:
-    return t if t.is_cuda else t.to("cuda")
-
-
-def project_to_basis(delta: torch.Tensor, U_high: torch.Tensor, U_low: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
-    """c_high = U_high^T delta, c_low = U_low^T delta in fp32 (compress.py:6-21).  Results on delta's device."""
-    _native.require_cuda()
+def project_to_basis(delta: torch.Tensor, U_high: torch.Tensor, U_low: torch.Tensor,
+                     mean: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """c_high = U_high^T delta, c_low = U_low^T delta in fp32 (compress.py:6-21) on the device (K14,
+    svdq_basis_project).  ``mean`` (extension) is subtracted inside the kernel.  Results on delta's device."""
     dev = delta.device
-    d = _gpu(delta).float()
-    return (_gpu(U_high).float().T @ d).to(dev), (_gpu(U_low).float().T @ d).to(dev)
+    return _ops.project(delta, U_high, mean).to(dev), _ops.project(delta, U_low, mean).to(dev)
 
 
 def compress_single_task(task_delta: torch.Tensor, U_high: torch.Tensor, U_low: torch.Tensor, quantizer: RTVQQuantizer,
                          device: str = "cpu", mean: Optional[torch.Tensor] = None) -> Dict:
     """compress.py:24-56 -> {"c_high_fp16": fp16 CPU tensor, "c_low_quant": RTVQ object}."""
-    x = task_delta
-    if mean is not None:
-        x = task_delta - mean.squeeze().to(task_delta.device)
-    c_high, c_low = project_to_basis(x, U_high, U_low)
+    c_high, c_low = project_to_basis(task_delta, U_high, U_low, mean=mean)
     c_high_fp16 = c_high if c_high.dtype == torch.float16 else c_high.half()
     return {"c_high_fp16": c_high_fp16.cpu(), "c_low_quant": quantizer.quantize(c_low.cpu())}
 

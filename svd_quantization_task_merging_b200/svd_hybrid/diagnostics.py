@@ -9,6 +9,7 @@ import numpy as np
 import torch
 
 from .. import _native
+from . import _ops
 from .rtvq import RTVQQuantizer, estimate_compression_ratio
 
 
@@ -42,7 +43,6 @@ def compute_parameter_diagnostics(param_name: str, task_vectors: Dict[str, Dict[
     else:
         d["masked_size"] = np.prod(d["original_shape"])
     d["basis"] = {"k": bm["k"], "D": bm["D"], "N": bm["N"], "energy_retained": bm["energy_retained"]}
-    uh, ul = bm["U_high"].to(g).float(), bm["U_low"].to(g).float()
     rel = []
     for task, tv in task_vectors.items():
         if param_name not in tv or task not in compressed_params:
@@ -55,7 +55,7 @@ def compute_parameter_diagnostics(param_name: str, task_vectors: Dict[str, Dict[
         c_hi = art["masked"]["c_high_fp16"].to(g).float()
         c_lo_obj = art["masked"]["c_low_quant"]
         c_lo = quantizer.dequantize(c_lo_obj, device="cuda").float()
-        rec = uh @ c_hi + ul @ c_lo
+        rec = _ops.expand(c_hi, c_lo, bm["U_high"], bm["U_low"])
         em = compute_reconstruction_error(orig.to(g).float(), rec)
         rel.append(em["relative_error"])
         d["reconstruction_errors"][task] = em

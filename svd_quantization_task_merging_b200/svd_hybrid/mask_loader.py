@@ -12,6 +12,7 @@ import numpy as np
 import torch
 
 from .. import _native
+from . import _ops
 
 _STRATEGIES = ("union", "intersection", "majority")
 
@@ -152,23 +153,28 @@ def combine_masks(task_masks: Dict[str, Optional[Dict[str, torch.Tensor]]], stra
 
 
 def apply_mask_to_tensor(tensor: torch.Tensor, mask: torch.Tensor) -> torch.Tensor:
+    """tensor.flatten()[mask.flatten()] (mask_loader.py:665-686) by the device selection kernels (K14)."""
     if tensor.shape != mask.shape:
         raise ValueError(f"Shape mismatch: tensor {tensor.shape} vs mask {mask.shape}")
-    return tensor.flatten()[mask.flatten()]
+    return _ops.mask_select(tensor, mask)
 
 
 def get_unmasked_portion(tensor: torch.Tensor, mask: torch.Tensor) -> torch.Tensor:
+    """tensor.flatten()[~mask.flatten()] (mask_loader.py:689-709)."""
     if tensor.shape != mask.shape:
         raise ValueError(f"Shape mismatch: tensor {tensor.shape} vs mask {mask.shape}")
-    return tensor.flatten()[~mask.flatten()]
+    return _ops.mask_select(tensor, mask, invert=True)
 
 
 def reconstruct_from_masked(masked_values: torch.Tensor, unmasked_values: Optional[torch.Tensor], mask: torch.Tensor,
                             original_shape: torch.Size) -> torch.Tensor:
-    """Scatter back through the mask, zeros elsewhere unless a noise part is given (mask_loader.py:712-763)."""
-    flat = mask.flatten().to(masked_values.device)
-    out = torch.zeros(flat.shape, dtype=masked_values.dtype, device=masked_values.device)
-    out[flat] = masked_values
+    """Scatter back through the mask, zeros elsewhere unless a noise part is given (mask_loader.py:712-763).
+    Result on masked_values' device."""
+    home = masked_values.device
+    dev = home if home.type == "cuda" else torch.device("cuda")
+    _native.require_cuda()
+    out = torch.zeros(mask.numel(), dtype=masked_values.dtype, device=dev)
+    _ops.mask_scatter(masked_values, mask, out)
     if unmasked_values is not None:
-        out[~flat] = unmasked_values
-    return out.view(original_shape)
+        _ops.mask_scatter(unmasked_values, mask, out, invert=True)
+    return out.view(original_shape).to(home)

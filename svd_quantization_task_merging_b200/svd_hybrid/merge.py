@@ -9,6 +9,7 @@ from typing import Dict, List, Optional, Tuple
 import torch
 
 from .. import _native
+from . import _ops
 from .rtvq import RTVQQuantizer
 
 
@@ -34,13 +35,8 @@ def dequantize_and_average(compressed_coeffs: Dict[str, Dict], weights: Dict[str
 
 def reconstruct_from_coefficients(avg_c_high: torch.Tensor, avg_c_low: torch.Tensor, U_high: torch.Tensor,
                                   U_low: torch.Tensor, device: str = "cpu", mean: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """U_high c_high + U_low c_low (+ mean) in fp32 (merge.py:144-194), computed on the GPU."""
-    _native.require_cuda()
-    g = torch.device("cuda")
-    out = U_high.to(g).float() @ avg_c_high.to(g).float() + U_low.to(g).float() @ avg_c_low.to(g).float()
-    if mean is not None:
-        out = out + mean.squeeze().to(g).float()
-    return out.to(device)
+    """U_high c_high + U_low c_low (+ mean) in fp32 (merge.py:144-194) on the device (K14, svdq_basis_expand)."""
+    return _ops.expand(avg_c_high, avg_c_low, U_high, U_low, mean=mean).to(device)
 
 
 def merge_parameter(param_name: str, compressed_params: Dict[str, Dict], basis: Dict, weights: Dict[str, float],

@@ -463,3 +463,72 @@ def test_reload_with_noise_region_and_batched_merge_matches_per_parameter(cuda_d
         one = merge_parameter(p, art["compressed"][p], art["bases"][p], weights, q, shapes[p], mask=masks.get(p),
                               include_noise=True, noise_shrink=art["config"].svd_noise_shrink, device="cpu")
         assert torch.allclose(batched[p], one, rtol=1e-5, atol=1e-8), p
+
+
+def test_k14_projection_and_expansion(cuda_device):
+    """project_to_basis / reconstruct_from_coefficients on K14 (no library matmul): against fp64 torch on fp16 and
+    fp32 bases, strided column slices, more than 32 columns, with and without a mean; launch-independent results."""
+    from svd_quantization_task_merging_b200.svd_hybrid import _ops
+    from src.svd_hybrid.compress import project_to_basis
+    from src.svd_hybrid.merge import reconstruct_from_coefficients
+    g = torch.Generator().manual_seed(5)
+    for rows, cols, dt in ((1, 1, torch.float32), (257, 3, torch.float16), (70001, 8, torch.float16),
+                           (300000, 20, torch.float32), (5000, 50, torch.float32), (1000003, 32, torch.float16)):
+        U = (torch.randn(rows, cols, generator=g) / rows ** 0.5).to(dt)
+        x = torch.randn(rows, generator=g)
+        m = torch.randn(rows, 1, generator=g) * 0.1
+        k = max(1, cols // 3) if cols > 1 else 1
+        Uh, Ul = U[:, :k], U[:, k:]                              # column slices: leading dimension = cols
+        ch, cl = project_to_basis(x, Uh, Ul)
+        ref = U.double().T @ x.double()
+        scale = (U.double().abs().T @ x.double().abs()).clamp_min(1e-30)
+        assert ch.dtype == torch.float32 and ch.device.type == "cpu" and ch.shape == (k,) and cl.shape == (cols - k,)
+        assert ((torch.cat([ch, cl]).double() - ref).abs() / scale).max().item() < 2e-6
+        chm, clm = project_to_basis(x, Uh, Ul, mean=m)
+        refm = U.double().T @ (x.double() - m.squeeze(1).double())
+        scale_m = (U.double().abs().T @ (x.double() - m.squeeze(1).double()).abs()).clamp_min(1e-30)
+        assert ((torch.cat([chm, clm]).double() - refm).abs() / scale_m).max().item() < 2e-6
+        again = _ops.project(x.cuda(), U.cuda())
+        assert torch.equal(again.cpu(), torch.cat([ch, cl]))                  # fixed reduction order
+        c = torch.randn(cols, generator=g)
+        rec = reconstruct_from_coefficients(c[:k], c[k:], Uh, Ul, "cpu", mean=m)
+        want = U.double() @ c.double() + m.squeeze(1).double()
+        bound = U.double().abs() @ c.double().abs() + m.squeeze(1).double().abs()
+        assert rec.dtype == torch.float32 and rec.shape == (rows,)
+        assert ((rec.double() - want).abs() / bound.clamp_min(1e-30)).max().item() < 2e-6
+        rec0 = reconstruct_from_coefficients(c[:k], c[k:], Uh, Ul, "cuda")
+        assert rec0.is_cuda
+        assert ((rec0.cpu().double() - U.double() @ c.double()).abs() / bound.clamp_min(1e-30)).max().item() < 2e-6
+    with pytest.raises(ValueError):
+        _ops.project(torch.zeros(5), torch.zeros(6, 2))
+
+
+def test_k14_mask_select_and_scatter(cuda_device):
+    """apply_mask_to_tensor / get_unmasked_portion / reconstruct_from_masked on the K14 selection kernels: bit-equal
+    to torch boolean indexing for every element size, ragged sizes, unaligned mask storage, empty / full masks."""
+    from src.svd_hybrid.mask_loader import apply_mask_to_tensor, get_unmasked_portion, reconstruct_from_masked
+    g = torch.Generator().manual_seed(9)
+    for n in (1, 15, 16, 4095, 4096, 4097, 100003, 3 * 4096 * 257 + 5):
+        for dt in (torch.float32, torch.float16, torch.float64, torch.uint8, torch.bfloat16):
+            if n > 200000 and dt not in (torch.float32, torch.float16):
+                continue
+            x = (torch.randn(n, generator=g) * 50).to(dt)
+            for p in (0.0, 0.3, 1.0):
+                store = torch.rand(n + 3, generator=g) < p
+                mask = store[3:] if n % 2 else store[:n]          # odd sizes: mask storage off 16-byte alignment
+                kept = apply_mask_to_tensor(x, mask)
+                rest = get_unmasked_portion(x, mask)
+                assert kept.dtype == dt and kept.device.type == "cpu"
+                assert torch.equal(kept, x[mask]) and torch.equal(rest, x[~mask])
+                back = reconstruct_from_masked(kept, rest, mask, x.shape)
+                assert torch.equal(back, x)
+                only = reconstruct_from_masked(kept, None, mask, x.shape)
+                assert torch.equal(only, torch.where(mask, x, torch.zeros_like(x)))
+    x = torch.randn(6, 7, 11, generator=g).cuda()
+    mask = (torch.rand(6, 7, 11, generator=g) < 0.5).cuda()
+    assert apply_mask_to_tensor(x, mask).is_cuda and torch.equal(apply_mask_to_tensor(x, mask), x.flatten()[mask.flatten()])
+    assert torch.equal(reconstruct_from_masked(apply_mask_to_tensor(x, mask), get_unmasked_portion(x, mask), mask, x.shape), x)
+    with pytest.raises(ValueError):
+        apply_mask_to_tensor(torch.zeros(4), torch.zeros(5, dtype=torch.bool))
+    with pytest.raises(ValueError):
+        reconstruct_from_masked(torch.zeros(3), None, torch.ones(5, dtype=torch.bool), torch.Size([5]))
