@@ -129,16 +129,29 @@ __global__ void __launch_bounds__(kMtThreads, 1) k10_merge_tc(const K3Args a, co
         // ================= TMA producer: lane i streams tensor i (base, then the NT fine-tuned tensors) ============
         PipeState ps;
         const bool is_tensor = lane <= NT;
+        // Per-parameter values are re-read only when the CTA's next tile belongs to another parameter: consecutive
+        // tiles of a CTA mostly come from the same (large) tensor, and the dependent global loads of a tile boundary
+        // otherwise cost every role a few hundred nanoseconds per tile.
+        int prev_p = -1;
+        int64_t numel = 0;
+        const unsigned char* my_ptr = nullptr;
+        int p_ahead = a.tile_param[blockIdx.x], local_ahead = a.tile_local[blockIdx.x];    // grid <= n_tiles
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-            const int p = a.tile_param[tile];
-            const int64_t numel = a.numel[p];
-            const int64_t start = (int64_t)a.tile_local[tile] * a.tile_elems;
-            const int64_t stop = min(start + (int64_t)a.tile_elems, numel);
-            const unsigned char* my_ptr = nullptr;
-            if (is_tensor) {
-                const void* q = a.tensors[(int64_t)p * (NT + 1) + lane];
-                my_ptr = reinterpret_cast<const unsigned char*>(q ? q : a.tensors[(int64_t)p * (NT + 1)]);
+            const int p = p_ahead;                      // tile -> (parameter, position) is read one tile ahead
+            const int64_t start = (int64_t)local_ahead * a.tile_elems;
+            if (tile + (int)gridDim.x < n_tiles) {
+                p_ahead = a.tile_param[tile + gridDim.x];
+                local_ahead = a.tile_local[tile + gridDim.x];
             }
+            if (p != prev_p) {
+                prev_p = p;
+                numel = a.numel[p];
+                if (is_tensor) {
+                    const void* q = a.tensors[(int64_t)p * (NT + 1) + lane];
+                    my_ptr = reinterpret_cast<const unsigned char*>(q ? q : a.tensors[(int64_t)p * (NT + 1)]);
+                }
+            }
+            const int64_t stop = min(start + (int64_t)a.tile_elems, numel);
             for (int64_t e0 = start; e0 < stop; e0 += kMtStageElems) {
                 if (lane == 0) mbar_wait(&empty[ps.stage], ps.phase ^ 1u);
                 __syncwarp();
@@ -164,10 +177,17 @@ __global__ void __launch_bounds__(kMtThreads, 1) k10_merge_tc(const K3Args a, co
         const uint32_t idesc = tc_idesc(1u, 1u, 128, 32, /*a_mn=*/1u, /*b_mn=*/0u);
         const uint64_t desc_a0 = tc_smem_desc(smem_u32(tile_buf), /*lbo (K groups)=*/0, /*sbo (M groups)=*/128);
         const uint64_t desc_b0 = tc_smem_desc(smem_u32(tile_buf) + kMtBOff, /*lbo (K chunks)=*/128, /*sbo (N groups)=*/256);
+        int prev_p = -1;
+        int64_t numel = 0;
+        int p_ahead = a.tile_param[blockIdx.x], local_ahead = a.tile_local[blockIdx.x];    // grid <= n_tiles
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-            const int p = a.tile_param[tile];
-            const int64_t numel = a.numel[p];
-            const int64_t start = (int64_t)a.tile_local[tile] * a.tile_elems;
+            const int p = p_ahead;                      // tile -> (parameter, position) is read one tile ahead
+            const int64_t start = (int64_t)local_ahead * a.tile_elems;
+            if (tile + (int)gridDim.x < n_tiles) {
+                p_ahead = a.tile_param[tile + gridDim.x];
+                local_ahead = a.tile_local[tile + gridDim.x];
+            }
+            if (p != prev_p) { prev_p = p; numel = a.numel[p]; }
             const int64_t stop = min(start + (int64_t)a.tile_elems, numel);
             for (int64_t e0 = start; e0 < stop; e0 += kStep) {
                 mbar_wait(&tfull[tb.stage], tb.phase);
@@ -193,26 +213,42 @@ __global__ void __launch_bounds__(kMtThreads, 1) k10_merge_tc(const K3Args a, co
         constexpr int kSets = kMtEpiWarps / 4;          // row blocks m = mset, mset + kSets, ... belong to this warp
         const int mset = (warp - 10) >> 2;
         PipeState bb, ab;
-        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-            const int p = a.tile_param[tile];
-            const int64_t numel = a.numel[p];
-            const int64_t start = (int64_t)a.tile_local[tile] * a.tile_elems;
-            const int64_t stop = min(start + (int64_t)a.tile_elems, numel);
-            const bool solved = a.info[(int64_t)p * 8 + 0] == kSolved;
-            const int n_active = a.info[(int64_t)p * 8 + 1];
-            const int r = a.info[(int64_t)p * 8 + 4];
-            const float tail_add = a.scal[(int64_t)p * 4 + 1];
-            const float mean_scale = a.scal[(int64_t)p * 4 + 2];
-            const bool has_mask = a.has_mask[p] != 0;
-            const uint32_t* packed = has_mask ? a.packed + a.pmask_off[p] : nullptr;
-            float* outp = a.out[p];
-            const float n_f = (float)(n_active > 0 ? n_active : 1);
-            const bool pow2 = (n_active & (n_active - 1)) == 0;
-            const float inv_n = __fdiv_rn(1.0f, n_f);
-            float cb[8];
+        const bool center = a.center != 0;
+        int prev_p = -1;
+        int64_t numel = 0;
+        bool solved = false, has_mask = false, pow2 = true;
+        float tail_add = 0.0f, mean_scale = 0.0f, n_f = 1.0f, inv_n = 1.0f;
+        const uint32_t* packed = nullptr;
+        float* outp = nullptr;
+        float cb[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) cb[j] = (j < NT && j < r && solved) ? a.cbar[(int64_t)p * NT + j] : 0.0f;
-            const bool center = a.center != 0;
+        for (int j = 0; j < 8; ++j) cb[j] = 0.0f;
+        int p_ahead = a.tile_param[blockIdx.x], local_ahead = a.tile_local[blockIdx.x];    // grid <= n_tiles
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            const int p = p_ahead;                      // tile -> (parameter, position) is read one tile ahead
+            const int64_t start = (int64_t)local_ahead * a.tile_elems;
+            if (tile + (int)gridDim.x < n_tiles) {
+                p_ahead = a.tile_param[tile + gridDim.x];
+                local_ahead = a.tile_local[tile + gridDim.x];
+            }
+            if (p != prev_p) {
+                prev_p = p;
+                numel = a.numel[p];
+                solved = a.info[(int64_t)p * 8 + 0] == kSolved;
+                const int n_active = a.info[(int64_t)p * 8 + 1];
+                const int r = a.info[(int64_t)p * 8 + 4];
+                tail_add = a.scal[(int64_t)p * 4 + 1];
+                mean_scale = a.scal[(int64_t)p * 4 + 2];
+                has_mask = a.has_mask[p] != 0;
+                packed = has_mask ? a.packed + a.pmask_off[p] : nullptr;
+                outp = a.out[p];
+                n_f = (float)(n_active > 0 ? n_active : 1);
+                pow2 = (n_active & (n_active - 1)) == 0;
+                inv_n = __fdiv_rn(1.0f, n_f);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) cb[j] = (j < NT && j < r && solved) ? a.cbar[(int64_t)p * NT + j] : 0.0f;
+            }
+            const int64_t stop = min(start + (int64_t)a.tile_elems, numel);
             for (int64_t e0 = start; e0 < stop; e0 += kStep) {
                 // this thread's elements of the chunk: loc = m * 128 + q * 32 + lane for m = mset, mset + kSets, ...
                 const int left = (int)min(stop - e0, (int64_t)kStep) - (q * 32 + lane);       // element m valid iff m * 128 < left
@@ -283,21 +319,32 @@ __global__ void __launch_bounds__(kMtThreads, 1) k10_merge_tc(const K3Args a, co
         PipeState ps, tb, bb;
         const int t = lane & 7;
         int pending = -1;
+        int prev_p = -1;
+        int64_t numel = 0;
+        uint4 bfrag[2] = {make_uint4(0u, 0u, 0u, 0u), make_uint4(0u, 0u, 0u, 0u)};
+        int p_ahead = a.tile_param[blockIdx.x], local_ahead = a.tile_local[blockIdx.x];    // grid <= n_tiles
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-            const int p = a.tile_param[tile];
-            const int64_t numel = a.numel[p];
-            const int64_t start = (int64_t)a.tile_local[tile] * a.tile_elems;
-            const int64_t stop = min(start + (int64_t)a.tile_elems, numel);
-            named_bar_sync(1, kMtTransform);            // previous tile finished with s_ptr
-            if (tid <= NT) {
-                const void* qp = a.tensors[(int64_t)p * (NT + 1) + tid];
-                s_ptr[tid] = qp ? qp : a.tensors[(int64_t)p * (NT + 1)];
+            const int p = p_ahead;                      // tile -> (parameter, position) is read one tile ahead
+            const int64_t start = (int64_t)local_ahead * a.tile_elems;
+            if (tile + (int)gridDim.x < n_tiles) {
+                p_ahead = a.tile_param[tile + gridDim.x];
+                local_ahead = a.tile_local[tile + gridDim.x];
             }
-            named_bar_sync(1, kMtTransform);
+            const bool new_param = p != prev_p;         // same decision in every transform warp (same tile sequence)
+            if (new_param) {
+                prev_p = p;
+                numel = a.numel[p];
+                named_bar_sync(1, kMtTransform);        // previous parameter finished with s_ptr
+                if (tid <= NT) {
+                    const void* qp = a.tensors[(int64_t)p * (NT + 1) + tid];
+                    s_ptr[tid] = qp ? qp : a.tensors[(int64_t)p * (NT + 1)];
+                }
+                named_bar_sync(1, kMtTransform);
+            }
+            const int64_t stop = min(start + (int64_t)a.tile_elems, numel);
             // B operand of this parameter: warp 0 keeps its 1 KB image in registers (lane -> rows lane, lane + 32 of
             // the 64 sixteen-byte rows) and drops it into every tile buffer of the tile
-            uint4 bfrag[2] = {make_uint4(0u, 0u, 0u, 0u), make_uint4(0u, 0u, 0u, 0u)};
-            if (warp == 0) {
+            if (warp == 0 && new_param) {
                 const bool solved = a.info[(int64_t)p * 8 + 0] == kSolved;
                 const int r = solved ? a.info[(int64_t)p * 8 + 4] : 0;
                 const int n_active = a.info[(int64_t)p * 8 + 1];

@@ -38,58 +38,62 @@ namespace svdq {
 
 #if SVDQ_DTYPE != 0
 
-constexpr int kTcStages = 3;                 // raw ring depth (stages of kTcStageElems elements)
+constexpr int kTcMaxStages = 4;              // raw ring depth (stages of kTcStageElems elements): as many as fit next to
+                                             // the fixed regions -- 4 without masks or with bit-packed masks, 3 with byte
+                                             // masks (launch_tc); a 4th stage is worth 4 % on the mask-free Llama shard
 constexpr int kTcStageElems = 2 * kStep;     // one raw stage = two 1024-element chunks: 4 KB per bulk copy (the producer
                                              // issues its copies one at a time, so 2 KB copies capped it near 4.7 TB/s)
 constexpr int kTcTiles = 3;                  // MMA tile ring depth (accumulators: 2)
 constexpr int kTcRowStride = kTcStageElems * 2 + 16;   // bytes between the tensors of a raw stage: +16 B skews the banks
                                              // so that the 8 task lanes of a quarter-warp read 8 different bank groups
-constexpr int kTcMaskStride = kTcStageElems; // bytes between the task masks of a raw stage
+// bytes between the task masks of a raw stage (runtime: 0 without masks, kTcStageElems / 8 for bit-packed masks,
+// kTcStageElems for byte masks)
 constexpr int kTcTileBytes = kStep * 8 * 2;  // MMA tile of one chunk: 1024 elements x 8 task rows x 2 B = 16 KB
 constexpr int kTcTransform = 256;            // transform threads (warps 0-7)
 constexpr int kTcThreads = 14 * 32;
 constexpr int kTcTmemCols = 256;             // two 128-column accumulators
 
-__host__ __device__ constexpr int tc_stage_bytes() { return ((9 * kTcRowStride + 15) / 16 * 16) + 8 * kTcMaskStride; }
-__host__ __device__ constexpr int tc_smem_bytes() {
-    return kTcTiles * kTcTileBytes + kTcStages * tc_stage_bytes() + 4096 /*mask LUT*/ +
-           4 * 64 * 4 * 2 + 64 * 8 + 256;
-}
+constexpr int kTcMaskOff = (9 * kTcRowStride + 15) / 16 * 16;      // the masks follow the 9 tensor rows of a stage
+__host__ __device__ constexpr int tc_stage_bytes(int mask_stride) { return kTcMaskOff + 8 * mask_stride; }
+// tiles + mask LUT + drain partials + barriers / flags; the raw ring follows
+constexpr int kTcFixedBytes = kTcTiles * kTcTileBytes + 4096 + 4 * 64 * 4 * 2 + 512;
+constexpr int kTcSmemLimit = 227 * 1024 - 1024;      // opt-in limit minus the static __shared__ variables
 
 template <typename T> __device__ __forceinline__ uint32_t load_raw16(const void* p, int64_t e) {
     return (uint32_t) * (reinterpret_cast<const uint16_t*>(p) + e);
 }
 
 template <typename T, int NT>
-__global__ void __launch_bounds__(kTcThreads, 1) k9_gram_tc(const K1Args a, const int n_tiles) {
+__global__ void __launch_bounds__(kTcThreads, 1) k9_gram_tc(const K1Args a, const int n_tiles, const int n_stages,
+                                                            const int mask_stride) {
     constexpr int G = tri_count(NT);
-    constexpr int STAGES = kTcStages;
-    constexpr int kStageBytes = tc_stage_bytes();
-    constexpr int kMaskOff = (9 * kTcRowStride + 15) / 16 * 16;
+    constexpr int kMaskOff = kTcMaskOff;
+    const uint32_t STAGES = (uint32_t)n_stages;
+    const int kStageBytes = tc_stage_bytes(mask_stride);
 
     // (no swizzle: the MMA descriptors need 16-byte alignment only; keeping the pointer arithmetic on the __shared__
     // array itself lets the compiler emit LDS / STS instead of generic loads and stores)
     extern __shared__ __align__(128) unsigned char smem[];
     unsigned char* tile_buf = smem;                                     // kTcTiles x 16 KB MMA tiles
-    unsigned char* stage_base = tile_buf + kTcTiles * kTcTileBytes;     // raw ring
-    uint4* lut = reinterpret_cast<uint4*>(stage_base + STAGES * kStageBytes);     // byte -> 8 x 16-bit lane masks
+    uint4* lut = reinterpret_cast<uint4*>(tile_buf + kTcTiles * kTcTileBytes);    // byte -> 8 x 16-bit lane masks
+    unsigned char* stage_base = smem + kTcFixedBytes;                   // raw ring: n_stages x kStageBytes
     float* s_part = reinterpret_cast<float*>(lut + 256);                // [2][4][64] per-drain-warp Gram partials
     uint64_t* bars = reinterpret_cast<uint64_t*>(s_part + 2 * 4 * 64);
-    uint64_t* full = bars;                  // [STAGES] producer -> transform
-    uint64_t* empty = full + STAGES;        // [STAGES] transform -> producer
-    uint64_t* tfull = empty + STAGES;       // [kTcTiles] transform -> MMA (tile written)
+    uint64_t* full = bars;                  // [kTcMaxStages] producer -> transform
+    uint64_t* empty = full + kTcMaxStages;  // [kTcMaxStages] transform -> producer
+    uint64_t* tfull = empty + kTcMaxStages; // [kTcTiles] transform -> MMA (tile written)
     uint64_t* tempty = tfull + kTcTiles;    // [kTcTiles] MMA -> transform (tile read)
     uint64_t* afull = tempty + kTcTiles;    // [2] MMA -> drain (accumulator complete)
     uint64_t* aempty = afull + 2;           // [2] drain -> MMA (accumulator read)
     int* s_direct = reinterpret_cast<int*>(aempty + 2);
     __shared__ const void* s_ptr[NT + 1];
     __shared__ const uint8_t* s_mask[NT];
-    __shared__ uint32_t s_cnt[kTcTransform / 32];
+    __shared__ uint32_t s_cnt[2 * (kTcTransform / 32)];
     __shared__ uint32_t s_tmem;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) {
-        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], kTcTransform / 32); }
+        for (int s = 0; s < kTcMaxStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], kTcTransform / 32); }
         for (int s = 0; s < kTcTiles; ++s) { mbar_init(&tfull[s], kTcTransform / 32); mbar_init(&tempty[s], 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(&afull[s], 1); mbar_init(&aempty[s], 4); }
         mbar_fence_init();
@@ -118,20 +122,34 @@ __global__ void __launch_bounds__(kTcThreads, 1) k9_gram_tc(const K1Args a, cons
         const bool bits_in = a.mask_bits != 0;
         const int kMaskBytes = bits_in ? kTcStageElems / 8 : kTcStageElems;     // one task's mask bytes per stage
         const int my_bytes = is_tensor ? kTcStageElems * 2 : kMaskBytes;
-        const int my_off = is_tensor ? lane * kTcRowStride : kMaskOff + (lane - NT - 1) * kTcMaskStride;
+        const int my_off = is_tensor ? lane * kTcRowStride : kMaskOff + (lane - NT - 1) * mask_stride;
+        // Per-parameter values are re-read only when the CTA's next tile belongs to another parameter (consecutive
+        // tiles of a CTA mostly come from the same large tensor): the dependent global loads of a tile boundary cost
+        // every role a few hundred nanoseconds per tile otherwise.
+        int prev_p = -1, n_present = 0;
+        int64_t numel = 0;
+        const unsigned char* my_ptr = nullptr;
+        int p_ahead = a.tile_param[blockIdx.x], local_ahead = a.tile_local[blockIdx.x];    // grid <= n_tiles
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-            const int p = a.tile_param[tile];
-            const int64_t numel = a.numel[p];
-            const int64_t start = (int64_t)a.tile_local[tile] * a.tile_elems;
-            const int64_t stop = min(start + (int64_t)a.tile_elems, numel);
-            const unsigned char* my_ptr = nullptr;
-            if (is_tensor) {
-                const void* q = a.tensors[(int64_t)p * (NT + 1) + lane];
-                my_ptr = reinterpret_cast<const unsigned char*>(q ? q : a.tensors[(int64_t)p * (NT + 1)]);
-            } else if (is_mask && a.masks) {
-                my_ptr = a.masks[(int64_t)p * NT + (lane - NT - 1)];
+            const int p = p_ahead;                      // tile -> (parameter, position) is read one tile ahead
+            const int64_t start = (int64_t)local_ahead * a.tile_elems;
+            if (tile + (int)gridDim.x < n_tiles) {
+                p_ahead = a.tile_param[tile + gridDim.x];
+                local_ahead = a.tile_local[tile + gridDim.x];
             }
-            const int n_present = __popc(__ballot_sync(0xffffffffu, is_mask && my_ptr != nullptr));
+            if (p != prev_p) {
+                prev_p = p;
+                numel = a.numel[p];
+                my_ptr = nullptr;
+                if (is_tensor) {
+                    const void* q = a.tensors[(int64_t)p * (NT + 1) + lane];
+                    my_ptr = reinterpret_cast<const unsigned char*>(q ? q : a.tensors[(int64_t)p * (NT + 1)]);
+                } else if (is_mask && a.masks) {
+                    my_ptr = a.masks[(int64_t)p * NT + (lane - NT - 1)];
+                }
+                n_present = __popc(__ballot_sync(0xffffffffu, is_mask && my_ptr != nullptr));
+            }
+            const int64_t stop = min(start + (int64_t)a.tile_elems, numel);
             for (int64_t e0 = start; e0 < stop; e0 += kTcStageElems) {
                 if (lane == 0) mbar_wait(&empty[ps.stage], ps.phase ^ 1u);
                 __syncwarp();
@@ -148,7 +166,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k9_gram_tc(const K1Args a, cons
                     s_direct[ps.stage] = 1;          // tail of the parameter: the transform warps load it themselves
                     mbar_arrive(&full[ps.stage]);
                 }
-                ps.advance<STAGES>();
+                ps.advance_n(STAGES);
             }
         }
     } else if (warp == 9) {
@@ -158,10 +176,17 @@ __global__ void __launch_bounds__(kTcThreads, 1) k9_gram_tc(const K1Args a, cons
         PipeState tb, ab;                               // tile-buffer ring, accumulator ring
         const uint32_t idesc = tc_idesc_f16<T>(128, 128);
         const uint64_t desc0 = tc_smem_desc(smem_u32(tile_buf), 128, 1024);
+        int prev_p = -1;
+        int64_t numel = 0;
+        int p_ahead = a.tile_param[blockIdx.x], local_ahead = a.tile_local[blockIdx.x];    // grid <= n_tiles
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-            const int p = a.tile_param[tile];
-            const int64_t numel = a.numel[p];
-            const int64_t start = (int64_t)a.tile_local[tile] * a.tile_elems;
+            const int p = p_ahead;                      // tile -> (parameter, position) is read one tile ahead
+            const int64_t start = (int64_t)local_ahead * a.tile_elems;
+            if (tile + (int)gridDim.x < n_tiles) {
+                p_ahead = a.tile_param[tile + gridDim.x];
+                local_ahead = a.tile_local[tile + gridDim.x];
+            }
+            if (p != prev_p) { prev_p = p; numel = a.numel[p]; }
             const int64_t stop = min(start + (int64_t)a.tile_elems, numel);
             for (int64_t e0 = start; e0 < stop; e0 += kStep) {
                 mbar_wait(&tfull[tb.stage], tb.phase);
@@ -188,10 +213,17 @@ __global__ void __launch_bounds__(kTcThreads, 1) k9_gram_tc(const K1Args a, cons
         const int sl = lane >> 3;                       // slice within the quadrant; row i = lane & 7
         PipeState tb;
         uint32_t tile_par = 0;
+        int prev_p = -1;
+        int64_t numel = 0;
+        int p_ahead = a.tile_param[blockIdx.x], local_ahead = a.tile_local[blockIdx.x];    // grid <= n_tiles
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-            const int p = a.tile_param[tile];
-            const int64_t numel = a.numel[p];
-            const int64_t start = (int64_t)a.tile_local[tile] * a.tile_elems;
+            const int p = p_ahead;                      // tile -> (parameter, position) is read one tile ahead
+            const int64_t start = (int64_t)local_ahead * a.tile_elems;
+            if (tile + (int)gridDim.x < n_tiles) {
+                p_ahead = a.tile_param[tile + gridDim.x];
+                local_ahead = a.tile_local[tile + gridDim.x];
+            }
+            if (p != prev_p) { prev_p = p; numel = a.numel[p]; }
             const int64_t stop = min(start + (int64_t)a.tile_elems, numel);
             float acc[8];
 #pragma unroll
@@ -238,26 +270,39 @@ __global__ void __launch_bounds__(kTcThreads, 1) k9_gram_tc(const K1Args a, cons
         PipeState ps, tb;
         const int t = lane & 7;                         // task row of this lane
         int pending = -1;                               // tile buffer written but not yet handed to the MMA warp
+        const bool majority = a.strategy == kMajority;
+        const bool mask_bits = a.mask_bits != 0;
+        int prev_p = -1;
+        int64_t numel = 0;
+        bool has_mask = false;
+        uint32_t thr_bytes = 0, tile_par = 0;
+        uint32_t* packed = nullptr;
+        int p_ahead = a.tile_param[blockIdx.x], local_ahead = a.tile_local[blockIdx.x];    // grid <= n_tiles
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-            const int p = a.tile_param[tile];
-            const int64_t numel = a.numel[p];
-            const int64_t start = (int64_t)a.tile_local[tile] * a.tile_elems;
-            const int64_t stop = min(start + (int64_t)a.tile_elems, numel);
-            named_bar_sync(1, kTcTransform);            // previous tile finished with s_ptr / s_mask / s_cnt
-            if (tid <= NT) {
-                const void* qp = a.tensors[(int64_t)p * (NT + 1) + tid];
-                s_ptr[tid] = qp ? qp : a.tensors[(int64_t)p * (NT + 1)];
+            const int p = p_ahead;                      // tile -> (parameter, position) is read one tile ahead
+            const int64_t start = (int64_t)local_ahead * a.tile_elems;
+            if (tile + (int)gridDim.x < n_tiles) {
+                p_ahead = a.tile_param[tile + gridDim.x];
+                local_ahead = a.tile_local[tile + gridDim.x];
             }
-            if (tid < NT) s_mask[tid] = a.masks ? a.masks[(int64_t)p * NT + tid] : nullptr;
-            named_bar_sync(1, kTcTransform);
-            int n_present = 0;
+            if (p != prev_p) {                          // same decision in every transform warp (same tile sequence)
+                prev_p = p;
+                numel = a.numel[p];
+                named_bar_sync(1, kTcTransform);        // previous parameter finished with s_ptr / s_mask
+                if (tid <= NT) {
+                    const void* qp = a.tensors[(int64_t)p * (NT + 1) + tid];
+                    s_ptr[tid] = qp ? qp : a.tensors[(int64_t)p * (NT + 1)];
+                }
+                if (tid < NT) s_mask[tid] = a.masks ? a.masks[(int64_t)p * NT + tid] : nullptr;
+                named_bar_sync(1, kTcTransform);
+                int n_present = 0;
 #pragma unroll
-            for (int u = 0; u < NT; ++u) n_present += s_mask[u] != nullptr;
-            const bool has_mask = n_present > 0;
-            const uint32_t thr_bytes = 0x01010101u * (uint32_t)(a.strategy == kUnion ? 1 : n_present);
-            const bool majority = a.strategy == kMajority;
-            const bool mask_bits = a.mask_bits != 0;
-            uint32_t* packed = has_mask ? a.packed + a.pmask_off[p] : nullptr;
+                for (int u = 0; u < NT; ++u) n_present += s_mask[u] != nullptr;
+                has_mask = n_present > 0;
+                thr_bytes = 0x01010101u * (uint32_t)(a.strategy == kUnion ? 1 : n_present);
+                packed = has_mask ? a.packed + a.pmask_off[p] : nullptr;
+            }
+            const int64_t stop = min(start + (int64_t)a.tile_elems, numel);
             uint32_t cnt = 0;
 
             for (int64_t s0 = start; s0 < stop; s0 += kTcStageElems) {
@@ -337,8 +382,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) k9_gram_tc(const K1Args a, cons
                                     uint32_t mw = 0u;
                                     if (s_mask[u] != nullptr) {
                                         if (!direct) {
-                                            mw = !mask_bits ? *reinterpret_cast<const uint32_t*>(mb + u * kTcMaskStride + mt * 4)
-                                                            : nibble_to_bytes((*reinterpret_cast<const uint32_t*>(mb + u * kTcMaskStride + (mt >> 3) * 4)
+                                            mw = !mask_bits ? *reinterpret_cast<const uint32_t*>(mb + u * mask_stride + mt * 4)
+                                                            : nibble_to_bytes((*reinterpret_cast<const uint32_t*>(mb + u * mask_stride + (mt >> 3) * 4)
                                                                                >> ((mt & 7) * 4)) & 0xFu);
                                         } else if (mask_bits) {
                                             mw = nibble_to_bytes((__ldg(reinterpret_cast<const uint32_t*>(s_mask[u]) + (e >> 5)) >> (int)(e & 31)) & 0xFu);
@@ -405,17 +450,19 @@ __global__ void __launch_bounds__(kTcThreads, 1) k9_gram_tc(const K1Args a, cons
                     pending = (int)tb.stage;
                     tb.advance<kTcTiles>();
                 }
-                ps.advance<STAGES>();
+                ps.advance_n(STAGES);
             }
             cnt = __reduce_add_sync(0xffffffffu, cnt);
-            if (lane == 0) s_cnt[warp] = cnt;
+            uint32_t* sc = s_cnt + tile_par * (kTcTransform / 32);     // two sets: the other one may still be read
+            if (lane == 0) sc[warp] = cnt;
             named_bar_sync(1, kTcTransform);
             if (tid == 0) {
                 uint32_t c = 0;
 #pragma unroll
-                for (int w = 0; w < kTcTransform / 32; ++w) c += s_cnt[w];
+                for (int w = 0; w < kTcTransform / 32; ++w) c += sc[w];
                 a.count[tile] = c;
             }
+            tile_par ^= 1u;
         }
         if (pending >= 0) {
             fence_async_smem();
@@ -431,11 +478,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) k9_gram_tc(const K1Args a, cons
 template <typename T, int NT>
 static cudaError_t launch_tc(const K1Args& a, int n_tiles, int n_sm, cudaStream_t st) {
     if (n_tiles <= 0) return cudaSuccess;
-    constexpr int smem = tc_smem_bytes();
+    const int mask_stride = a.masks == nullptr ? 0 : (a.mask_bits ? kTcStageElems / 8 : kTcStageElems);
+    int n_stages = (kTcSmemLimit - kTcFixedBytes) / tc_stage_bytes(mask_stride);
+    if (n_stages > kTcMaxStages) n_stages = kTcMaxStages;
+    const int smem = kTcFixedBytes + n_stages * tc_stage_bytes(mask_stride);
     const int grid = n_tiles < n_sm ? n_tiles : n_sm;
-    cudaError_t e = cudaFuncSetAttribute(k9_gram_tc<T, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaError_t e = cudaFuncSetAttribute(k9_gram_tc<T, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemLimit);
     if (e != cudaSuccess) return e;
-    k9_gram_tc<T, NT><<<grid, kTcThreads, smem, st>>>(a, n_tiles);
+    k9_gram_tc<T, NT><<<grid, kTcThreads, smem, st>>>(a, n_tiles, n_stages, mask_stride);
     return cudaGetLastError();
 }
 

@@ -50,6 +50,9 @@ struct PipeState {
     template <int STAGES> __device__ __forceinline__ void advance() {
         if (++stage == STAGES) { stage = 0; phase ^= 1u; }
     }
+    __device__ __forceinline__ void advance_n(uint32_t stages) {       // ring depth chosen at launch
+        if (++stage == stages) { stage = 0; phase ^= 1u; }
+    }
 };
 
 }  // namespace svdq

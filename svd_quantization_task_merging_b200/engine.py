@@ -30,7 +30,7 @@ import torch
 from . import _native
 from .svd_hybrid.weighting import cluster_omega, compute_weights
 
-TILE_ELEMS = 16384          # elements per tile (multiple of 1024); fixes the reduction order
+TILE_ELEMS = int(os.environ.get("SVDQ_TILE_ELEMS", "16384"))          # elements per tile (multiple of 1024); fixes the reduction order
 MAX_STREAM_TASKS = 16      # register-resident Gram (one K1 launch)
 MAX_TASKS = 32             # wide path: mask pack + single-pass staged Gram (K8) + runtime-N pass 2 (K6)
 EXACT_MAX_NUMEL = 262144   # projection="auto": parameters up to this size are re-projected on the stored basis
