@@ -578,20 +578,35 @@ class MergeJob:
                                            performance_file=getattr(cfg, "performance_file", None),
                                            temperature=cfg.svd_weighting_temperature,
                                            cluster_assignments=self.cluster_assignments)
-        w = np.asarray([self.weights.get(t, 1.0) for t in self.tasks], np.float64)
-        order = np.asarray(sorted(range(self.N), key=lambda i: self.tasks[i]), np.int32)
-        self._cluster_tables = (None, None)
-        if self.cluster_mode and self.cluster_assignments:
+        # one pinned staging buffer and ONE asynchronous upload for the three small tables (task weights, cluster
+        # omegas, cluster index per task): this sits on the critical path between the k-means and pass 2
+        N = self.N
+        if getattr(self, "_wt_host", None) is None:
+            self._wt_host = torch.empty(20 * N, dtype=torch.uint8, pin_memory=True)
+            self._wt_dev = torch.empty(20 * N, dtype=torch.uint8, device=self.device)
+            self._wt_event = None
+        if self._wt_event is not None:
+            self._wt_event.synchronize()                 # the previous upload has left the staging buffer
+        host = self._wt_host.numpy()
+        w_h, om_h, cl_h = host[: 8 * N].view(np.float64), host[8 * N: 16 * N].view(np.float64), host[16 * N:].view(np.int32)
+        w_h[:] = [self.weights.get(t, 1.0) for t in self.tasks]
+        om_h[:] = 0.0
+        cl_h[:] = 0
+        clustered = bool(self.cluster_mode and self.cluster_assignments)
+        if clustered:
             # merge_with_clustering (merge.py:586-626): member weights renormalised inside each cluster PER PARAMETER
             # over the members that have it (K2 average_param), clusters averaged with omega
             om = cluster_omega(self.weights, self.cluster_assignments)
             ids = sorted(om.keys())
             index = {c: i for i, c in enumerate(ids)}
-            cl = np.asarray([index[self.cluster_assignments[t]] for t in self.tasks], np.int32)
-            omega = np.zeros(self.N, np.float64)
-            omega[: len(ids)] = [om[c] for c in ids]
-            self._cluster_tables = (_dev(cl, self.device), _dev(omega, self.device))
-        return _dev(w, self.device), _dev(order, self.device)
+            cl_h[:] = [index[self.cluster_assignments[t]] for t in self.tasks]
+            om_h[: len(ids)] = [om[c] for c in ids]
+        self._wt_dev.copy_(self._wt_host, non_blocking=True)
+        self._wt_event = torch.cuda.Event()
+        self._wt_event.record()
+        dev = self._wt_dev
+        self._cluster_tables = (dev[16 * N:].view(torch.int32), dev[8 * N: 16 * N].view(torch.float64)) if clustered else (None, None)
+        return dev[: 8 * N].view(torch.float64), self._order_dev
 
     def _cluster_begin(self):
         """Whole-model task Gram (K1 by-product) -> pinned host copy on a side stream, so that the
@@ -599,9 +614,12 @@ class MergeJob:
         if self.fixed_assignments is not None:
             return
         # a rank whose shard is empty (more ranks than parameters) still joins the all-reduce with zeros
-        tot = torch.zeros(self.N * self.N, dtype=torch.float64, device=self.device)
+        tot = None
         for g in self.groups.values():
-            tot = tot + g.t["gram_all"].sum(dim=0)
+            part = g.t["gram_all"].sum(dim=0)
+            tot = part if tot is None else tot + part
+        if tot is None:
+            tot = torch.zeros(self.N * self.N, dtype=torch.float64, device=self.device)
         if self._side is None:
             self._side = torch.cuda.Stream(device=self.device)
             self._gram_host = torch.empty(self.N * self.N, dtype=torch.float64, pin_memory=True)
