@@ -3,6 +3,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <exception>
 #include <thread>
 #include <vector>
 
@@ -226,12 +227,21 @@ int svdq_host_pack_mask_batch(const uint8_t* const* src, const int64_t* n, uint8
     };
     if (n_threads == 1 || total < (1 << 16)) { work(0, total); return 0; }
     const int64_t per = ((total + n_threads - 1) / n_threads + 63) & ~(int64_t)63;
+    // A thread that cannot be created (EAGAIN under a process / pid limit) must not take the process down: the
+    // calling thread packs whatever has not been handed out.
     std::vector<std::thread> pool;
-    for (int t = 0; t < n_threads; ++t) {
-        const int64_t lo = (int64_t)t * per, hi = lo + per < total ? lo + per : total;
-        if (lo >= hi) break;
-        pool.emplace_back(work, lo, hi);
+    int64_t handed = 0;
+    try {
+        pool.reserve(n_threads);
+        for (int t = 0; t < n_threads; ++t) {
+            const int64_t lo = (int64_t)t * per, hi = lo + per < total ? lo + per : total;
+            if (lo >= hi) break;
+            pool.emplace_back(work, lo, hi);
+            handed = hi;
+        }
+    } catch (...) {
     }
+    if (handed < total) work(handed, total);
     for (auto& th : pool) th.join();
     return 0;
 }
@@ -249,7 +259,12 @@ int svdq_host_kmeans(const float* features, int n, int d, int k, uint32_t seed, 
     REQUIRE(n >= 1 && d >= 1 && n <= 4096 && d <= 65536, "feature matrix shape");
     REQUIRE(k >= 1 && k <= n, "Invalid k for the number of samples");      // clustering.py:147-148
     REQUIRE(n_init >= 1 && max_iter >= 1 && tol >= 0.0, "n_init / max_iter / tol");
-    return svdq_host_kmeans_impl(features, n, d, k, seed, n_init, max_iter, tol, labels, inertia);
+    try {
+        return svdq_host_kmeans_impl(features, n, d, k, seed, n_init, max_iter, tol, labels, inertia);
+    } catch (const std::exception& e) {      // allocation failure: report it, do not unwind through the C ABI
+        snprintf(g_err, sizeof(g_err), "%s: %s", __func__, e.what());
+        return -1;
+    }
 }
 
 int svdq_mask_pack(int n_tasks, int mask_strategy, int64_t n_tiles, int tile_elems, const uint8_t* const* masks,
