@@ -53,6 +53,19 @@ def test_invalid_arguments_are_value_errors_without_touching_the_gpu():
     # zero-sized work is a no-op, not an error
     assert lib.svdq_rtvq_quantize(None, 0, 4, 2, None, 0, 1, None, None, None, None, None, 0, None) == 0
     assert lib.svdq_unpack_mask(None, 0, None, None) == 0
+    # K14 operator entries: shape checks before any launch
+    assert lib.svdq_project_scratch_bytes() >= 32 * 8 and lib.svdq_select_chunk_elems() % 1024 == 0
+    rc = lib.svdq_basis_project(0, None, 0, 0, 10, None, None, None, None, None)
+    assert rc < 0 and b"cols" in lib.svdq_last_error()
+    rc = lib.svdq_basis_project(0, None, 4, 33, 10, None, None, None, None, None)
+    assert rc < 0 and b"cols" in lib.svdq_last_error()
+    rc = lib.svdq_basis_expand(1, None, 0, -1, None, 0, 0, 10, None, None, None, C.c_float(1.0), None, None)
+    assert rc < 0 and b"column counts" in lib.svdq_last_error()
+    assert lib.svdq_basis_expand(1, None, 0, 3, None, 0, 0, 0, None, None, None, C.c_float(1.0), None, None) == 0   # no rows
+    rc = lib.svdq_mask_offsets(None, -1, 0, None, None)
+    assert rc < 0
+    assert lib.svdq_mask_select(None, 4, None, 0, 0, None, None, None) == 0
+    assert lib.svdq_mask_scatter(None, 4, None, 0, 1, None, None, None) == 0
 
 
 def test_host_mask_packer_matches_numpy_packbits():
