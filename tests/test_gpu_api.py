@@ -532,3 +532,24 @@ def test_k14_mask_select_and_scatter(cuda_device):
         apply_mask_to_tensor(torch.zeros(4), torch.zeros(5, dtype=torch.bool))
     with pytest.raises(ValueError):
         reconstruct_from_masked(torch.zeros(3), None, torch.ones(5, dtype=torch.bool), torch.Size([5]))
+
+
+def test_pipeline_device_cpu_means_host_resident_results(cuda_device, tmp_path, capsys):
+    """The reference's integration tests configure device="cpu" (tests/test_integration.py:77,165).  Here the arithmetic
+    runs on the GPU regardless; the setting decides where the returned state dict lives, and the run says so."""
+    from src.svd_hybrid.cli import run_svd_hybrid_pipeline
+    case = _gold("union_uniform")
+    ck, md = _write_case(tmp_path, case)
+    out = {}
+    for dev in ("cpu", "cuda"):
+        cfg = SVDHybridConfig(tasks=case["tasks"], checkpoint_dir=str(ck), base_model_path=str(tmp_path / "base.pt"),
+                              mask_dir=str(md), svd_store_artifacts=False, svd_eval_reconstruction=True, svd_max_rank=64,
+                              output_dir=str(tmp_path / f"out_{dev}"), artifact_dir=str(tmp_path / f"art_{dev}"),
+                              device=dev, **case["config"])
+        out[dev] = run_svd_hybrid_pipeline(cfg, verbose=False)
+        text = capsys.readouterr().out
+        assert ('device="cpu" requested' in text) == (dev == "cpu")
+    for name, t in out["cpu"]["merged_state_dict"].items():
+        assert t.device.type == "cpu"
+        assert torch.equal(t, out["cuda"]["merged_state_dict"][name].cpu()), name
+    assert out["cpu"]["diagnostics"]["task_weights"] == out["cuda"]["diagnostics"]["task_weights"]
