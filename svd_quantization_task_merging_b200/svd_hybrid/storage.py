@@ -164,3 +164,11 @@ def save_merged_model(merged_state_dict: Dict[str, torch.Tensor], output_dir: st
     os.makedirs(output_dir, exist_ok=True)
     torch.save({k: (v.cpu() if torch.is_tensor(v) else v) for k, v in merged_state_dict.items()},
                os.path.join(output_dir, filename))
+
+
+def load_merged_model(path: str, device: str = "cpu", filename: str = "merged_state_dict.pt") -> Dict[str, torch.Tensor]:
+    """Counterpart of save_merged_model; ``path`` is the file or the directory it was saved into.  Additive: the
+    reference's scripts/reload_svd_hybrid.py:18 imports this name, but its storage.py (392-409) only has the saver."""
+    if os.path.isdir(path):
+        path = os.path.join(path, filename)
+    return torch.load(path, map_location=device, weights_only=False)
