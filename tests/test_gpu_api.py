@@ -18,12 +18,14 @@ GOLD = os.path.join(os.path.dirname(__file__), "golden")
 
 
 def _gold(name):
-    return torch.load(os.path.join(GOLD, "pipeline_golden.pt"), weights_only=False)[name]
+    f = "pipeline_golden_wide.pt" if name.startswith("wide") else "pipeline_golden.pt"     # > 16 tasks: own file
+    return torch.load(os.path.join(GOLD, f), weights_only=False)[name]
 
 
 # ---- the CUDA path against the real reference's outputs -------------------------------------------------
 @pytest.mark.parametrize("name", ["union_uniform", "majority_performance_3stage", "intersection_cluster",
-                                  "nomask_fp32_nocenter", "majority_noise_uniform", "union_noise_cluster_3stage"])
+                                  "nomask_fp32_nocenter", "majority_noise_uniform", "union_noise_cluster_3stage",
+                                  "wide20_union_uniform", "wide24_majority_cluster"])
 def test_cuda_path_against_reference_golden(cuda_device, name):
     from svd_quantization_task_merging_b200.engine import merge_state_dicts
     case = _gold(name)

@@ -130,14 +130,19 @@ def _ref_cfg(case):
     return R.RefConfig(tasks=case["tasks"], svd_max_rank=64, performance=case["performance"], **case["config"])
 
 
+def _pipeline_case(name):
+    """Pipeline fixture by name; the cases with more than 16 task vectors live in a file of their own."""
+    return load("pipeline_golden_wide.pt" if name.startswith("wide") else "pipeline_golden.pt")[name]
+
+
 @pytest.mark.parametrize("name", ["union_uniform", "majority_performance_3stage", "intersection_cluster",
                                   "nomask_fp32_nocenter", "iid_degenerate_nan", "majority_noise_uniform",
-                                  "union_noise_cluster_3stage"])
+                                  "union_noise_cluster_3stage", "wide20_union_uniform", "wide24_majority_cluster"])
 def test_pipeline_golden(name):
     """oracle.run_reference_path reproduces run_svd_hybrid_pipeline of the real reference.
     Same torch build -> same LAPACK -> equal to round-off; tolerances only cover a different host CPU
     (MKL code path) on the GPU box."""
-    case = load("pipeline_golden.pt")[name]
+    case = _pipeline_case(name)
     cfg = _ref_cfg(case)
     assign = case["diagnostics"].get("cluster_assignments")
     res = R.run_reference_path(case["base"], case["finetuned"], case["masks"], cfg, assignments=assign)
