@@ -195,7 +195,7 @@ def _write_case(tmp, case):
     return ck, md
 
 
-@pytest.mark.parametrize("name", ["union_uniform", "intersection_cluster", "majority_noise_uniform"])
+@pytest.mark.parametrize("name", ["union_uniform", "intersection_cluster", "majority_noise_uniform", "wide20_union_uniform"])
 def test_pipeline_on_disk_writes_reference_layout(cuda_device, tmp_path, name, monkeypatch):
     from src.svd_hybrid.cli import run_svd_hybrid_pipeline
     from src.svd_hybrid.storage import load_all_artifacts
