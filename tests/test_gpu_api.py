@@ -593,3 +593,33 @@ def test_reload_script_rebuilds_and_verifies(cuda_device, tmp_path):
     # 4. a missing artifact directory is reported, exit code 1
     r = run("--artifact-dir", str(tmp_path / "nope"))
     assert r.returncode == 1 and "Artifact directory not found" in r.stdout
+
+
+@pytest.mark.parametrize("name", ["union_uniform", "majority_performance_3stage", "nomask_fp32_nocenter",
+                                  "majority_noise_uniform", "wide20_union_uniform"])
+def test_reload_of_reference_written_artifacts(cuda_device, tmp_path, name):
+    """Format compatibility of the reload path: the bases, coefficient objects and diagnostics the REAL reference
+    produced (golden fixture) are written in its artifact layout and re-merged by the batched reload kernel (K11).
+    With the reference's own U there is no sign freedom left, so the result must equal the reference's merged model
+    to fp32 round-off (reference reload.py:142-238, merge.py:304-426; the combined masks come from the additive
+    combined_masks.pt, which the reference's reload lacks)."""
+    from src.svd_hybrid.reload import reconstruct_from_artifacts
+    from src.svd_hybrid.storage import save_all_artifacts, save_combined_masks
+    case = _gold(name)
+    torch.save(dict(case["base"]), tmp_path / "base.pt")
+    cfg = SVDHybridConfig(tasks=case["tasks"], base_model_path=str(tmp_path / "base.pt"), svd_max_rank=64,
+                          svd_store_artifacts=True, **case["config"])
+    art = str(tmp_path / "art")
+    save_all_artifacts(case["bases"], case["compressed"], case["diagnostics"], cfg, art)
+    if case["combined_masks"]:
+        save_combined_masks(case["combined_masks"], art)
+    out = reconstruct_from_artifacts(art, str(tmp_path / "base.pt"), str(tmp_path / "re.pt"), "cpu")
+    worst = 0.0
+    for p, gm in case["merged_state_dict"].items():
+        mine = out["merged_state_dict"][p]
+        assert mine.shape == gm.shape and mine.dtype == gm.dtype
+        den = (gm - case["base"][p]).norm().item()
+        err = (mine - gm).norm().item() / max(den, 1e-30)
+        worst = max(worst, err)
+        assert err < 2e-6, (p, err)
+    print(name, "reload of reference artifacts: worst rel L2 of the merged delta", worst)
