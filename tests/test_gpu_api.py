@@ -623,3 +623,43 @@ def test_reload_of_reference_written_artifacts(cuda_device, tmp_path, name):
         worst = max(worst, err)
         assert err < 2e-6, (p, err)
     print(name, "reload of reference artifacts: worst rel L2 of the merged delta", worst)
+
+
+@pytest.mark.parametrize("name", ["union_uniform", "majority_performance_3stage", "nomask_fp32_nocenter",
+                                  "wide20_union_uniform"])
+def test_operator_api_on_reference_bases(cuda_device, name):
+    """The operator-by-operator mirrors (K14 projection / expansion / mask selection, K4 RTVQ) on the REAL reference's
+    stored bases: compress_parameter must reproduce the reference's own fp16 coefficients and RTVQ codes, and
+    compute_parameter_diagnostics its per-task reconstruction errors -- no sign freedom, the basis is the reference's
+    (compress.py:114-170, diagnostics.py:120-231)."""
+    from src.svd_hybrid.compress import compress_parameter
+    from src.svd_hybrid.diagnostics import compute_parameter_diagnostics
+    from src.svd_hybrid.rtvq import RTVQQuantizer
+    case = _gold(name)
+    cfg = SVDHybridConfig(tasks=case["tasks"], svd_max_rank=64, **case["config"])
+    quant = RTVQQuantizer(num_bits=cfg.svd_low_bits, num_stages=cfg.svd_rtvq_stages)
+    tvs = {t: {p: case["finetuned"][t][p] - case["base"][p] for p in case["base"]} for t in case["tasks"]}
+    n_hi = eq_hi = n_code = eq_code = 0
+    for p, basis in case["bases"].items():
+        mask = case["combined_masks"].get(p) if case["combined_masks"] else None
+        mine = compress_parameter(p, tvs, mask, basis, quant, include_noise=False, min_mask_size=cfg.svd_min_mask_size)
+        for t in case["tasks"]:
+            g, m = case["compressed"][p][t]["masked"], mine[t]["masked"]
+            assert m["c_high_fp16"].dtype == torch.float16 and m["c_high_fp16"].shape == g["c_high_fp16"].shape
+            # fp16 values at most one ulp apart (fp32 summation order of U^T d differs from the reference's BLAS)
+            a, b = m["c_high_fp16"].view(torch.int16).int(), g["c_high_fp16"].view(torch.int16).int()
+            assert (a - b).abs().max().item() <= 1, (p, t)
+            n_hi += a.numel()
+            eq_hi += int((a == b).sum())
+            for x, y in zip(m["c_low_quant"]["payloads"], g["c_low_quant"]["payloads"]):
+                n_code += x["quantized"].numel()
+                eq_code += int((x["quantized"] == y["quantized"]).sum())
+        gd = case["diagnostics"]["per_parameter"][p]
+        d = compute_parameter_diagnostics(p, tvs, case["compressed"][p], basis, mask, quant)
+        assert d["masked_size"] == gd["masked_size"] and d["basis"]["k"] == gd["basis"]["k"]
+        for t in case["tasks"]:
+            for key in ("absolute_error", "relative_error", "original_norm", "reconstructed_norm", "mean_absolute_error"):
+                assert d["reconstruction_errors"][t][key] == pytest.approx(gd["reconstruction_errors"][t][key], rel=2e-5), (p, t, key)
+            assert d["compression_ratios"][t] == gd["compression_ratios"][t]
+    print(name, f"c_high fp16 bit-equal {eq_hi}/{n_hi}, RTVQ codes equal {eq_code}/{n_code}")
+    assert eq_hi >= 0.99 * n_hi and eq_code >= 0.99 * n_code         # observed on B200: all of them, in all four cases
