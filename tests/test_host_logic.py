@@ -270,3 +270,20 @@ def test_reference_arm_prints_the_contract_line():
     b = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(b)
     assert d["config"]["workload"] == b._workload_string("toy")
+
+
+def test_entry_scripts_keep_the_reference_command_line():
+    """scripts/reload_svd_hybrid.py and scripts/run_svd_hybrid.py expose the flags of the reference's scripts
+    (scripts/reload_svd_hybrid.py:149-170; run_svd_hybrid.py forwards to the pipeline CLI)."""
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    text = open(os.path.join(root, "scripts", "reload_svd_hybrid.py")).read()
+    flags = set(re.findall(r'add_argument\(\s*"(--[a-z-]+)"', text))
+    assert flags == {"--artifact-dir", "--output-path", "--verify", "--merged-model-path", "--eval", "--eval-script",
+                     "--verbose"}
+    for helper in ("compute_state_dict_checksum", "verify_reconstruction", "run_evaluation", "main"):
+        assert f"def {helper}(" in text
+    run = open(os.path.join(root, "scripts", "run_svd_hybrid.py")).read()
+    assert "from src.svd_hybrid.cli import main" in run
+    from svd_quantization_task_merging_b200.svd_hybrid import storage
+    assert callable(storage.load_merged_model)
